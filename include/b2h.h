@@ -1,0 +1,208 @@
+/* b2h.h — C-ABI of the B200 batched humanoid rollout library (libb2h.so).
+ *
+ * The reference (redradman/MujocoPoseLearning) has no FFI of its own: its hot path is six Python calls
+ * into the third-party `mujoco` wheel plus the SB3 rollout buffer.  Each entry point below names the
+ * reference call site it replaces (paths relative to the reference root):
+ *
+ *   b2h_create            mujoco.MjModel.from_xml_path + mujoco.MjData      custom_env.py:53-54
+ *                         (once per SubprocVecEnv worker, train_sb3.py:203; here once per GPU)
+ *   b2h_reset             HumanoidEnv.reset: mj_resetData, noise, 1 mj_step  custom_env.py:97-150
+ *   b2h_step              HumanoidEnv.step (ctrl write, mj_step x frame_skip, _get_state,
+ *                         _compute_reward, truncation/termination) + the SubprocVecEnv worker's
+ *                         auto-reset / terminal_observation                  custom_env.py:152-261,
+ *                                                                           reward_functions.py:66-211
+ *   b2h_step_host         the same through host buffers (what VecEnv.step_wait returns, train_sb3.py:203)
+ *   b2h_get_state/set     MjData.qpos/qvel/qacc_warmstart/time field access  custom_env.py:105-117,242-246
+ *   b2h_gae               RolloutBuffer.compute_returns_and_advantage (SB3 2.3.2), driven by
+ *                         model.learn()                                      train_sb3.py:228
+ *   b2h_mlp_forward       MlpPolicy forward during collect_rollouts (SB3 2.3.2) train_sb3.py:208-214
+ *
+ * Conventions: every function returns 0 on success or a negative B2H_E* code and never throws; the
+ * message for the last failure on the calling thread is b2h_last_error().  Pointers named *_dev are
+ * caller-owned device pointers (e.g. torch tensor data_ptr()); *_host are host pointers.  All device
+ * work is ordered on the cudaStream_t passed as `void* stream` (NULL = legacy default stream); only the
+ * *_host entry points synchronise that stream.  One handle per GPU, one host thread per handle.
+ */
+#ifndef B2H_H_
+#define B2H_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2H_ABI_VERSION 1
+
+#define B2H_MAX_BODY 32
+#define B2H_MAX_JNT 32
+#define B2H_MAX_DOF 32
+#define B2H_MAX_QPOS 40
+#define B2H_MAX_GEOM 32
+#define B2H_MAX_PAIR 512
+#define B2H_MAX_TENDON 4
+#define B2H_MAX_ACT 32
+
+enum { B2H_OK = 0, B2H_EINVAL = -1, B2H_ECUDA = -2, B2H_EUNSUPPORTED = -3, B2H_ENOMEM = -4 };
+enum { B2H_F32 = 0, B2H_F64 = 1 };                        /* arithmetic type of the physics state    */
+enum { B2H_REWARD_STAND = 0, B2H_REWARD_KNEELING = 1, B2H_REWARD_WALK = 2 };
+enum { B2H_OBS_FULL352 = 0, B2H_OBS_QPOS_QVEL = 1 };      /* custom_env.py:242-256 / its 53-col prefix */
+enum { B2H_GEOM_PLANE = 0, B2H_GEOM_SPHERE = 2, B2H_GEOM_CAPSULE = 3 };
+enum { B2H_JNT_FREE = 0, B2H_JNT_HINGE = 3 };
+
+/* Compiled model constants (the mjModel fields the path reads).  Filled by mjcf.py on the host. */
+typedef struct B2HModel {
+  int32_t nq, nv, nu, nbody, njnt, ngeom, ntendon, npair;
+  double timestep;
+  double gravity[3];
+  double meaninertia;
+  /* bodies */
+  int32_t body_parentid[B2H_MAX_BODY];
+  int32_t body_jntadr[B2H_MAX_BODY];
+  int32_t body_jntnum[B2H_MAX_BODY];
+  int32_t body_dofadr[B2H_MAX_BODY];
+  int32_t body_dofnum[B2H_MAX_BODY];
+  int32_t body_lastdof[B2H_MAX_BODY];      /* last dof on the chain root->body, -1 for the world  */
+  double body_pos[B2H_MAX_BODY][3];
+  double body_quat[B2H_MAX_BODY][4];
+  double body_ipos[B2H_MAX_BODY][3];
+  double body_iquat[B2H_MAX_BODY][4];
+  double body_inertia[B2H_MAX_BODY][3];      /* principal moments (mjModel.body_inertia)           */
+  double body_inertia_full[B2H_MAX_BODY][6]; /* xx yy zz xy xz yz about the COM in body axes       */
+  double body_mass[B2H_MAX_BODY];
+  double body_subtreemass[B2H_MAX_BODY];
+  double body_invweight0[B2H_MAX_BODY][2];
+  /* joints */
+  int32_t jnt_type[B2H_MAX_JNT];
+  int32_t jnt_bodyid[B2H_MAX_JNT];
+  int32_t jnt_qposadr[B2H_MAX_JNT];
+  int32_t jnt_dofadr[B2H_MAX_JNT];
+  int32_t jnt_limited[B2H_MAX_JNT];
+  double jnt_pos[B2H_MAX_JNT][3];
+  double jnt_axis[B2H_MAX_JNT][3];
+  double jnt_range[B2H_MAX_JNT][2];
+  double jnt_stiffness[B2H_MAX_JNT];
+  double jnt_margin[B2H_MAX_JNT];
+  double jnt_solref[B2H_MAX_JNT][2];
+  double jnt_solimp[B2H_MAX_JNT][5];
+  /* dofs */
+  int32_t dof_bodyid[B2H_MAX_DOF];
+  int32_t dof_jntid[B2H_MAX_DOF];
+  int32_t dof_parentid[B2H_MAX_DOF];
+  double dof_armature[B2H_MAX_DOF];
+  double dof_damping[B2H_MAX_DOF];
+  double dof_invweight0[B2H_MAX_DOF];
+  double qpos0[B2H_MAX_QPOS];
+  double qpos_spring[B2H_MAX_QPOS];
+  /* geoms */
+  int32_t geom_type[B2H_MAX_GEOM];
+  int32_t geom_bodyid[B2H_MAX_GEOM];
+  double geom_size[B2H_MAX_GEOM][3];
+  double geom_pos[B2H_MAX_GEOM][3];
+  double geom_quat[B2H_MAX_GEOM][4];
+  /* static collision candidates with mixed contact parameters */
+  int32_t pair_geom1[B2H_MAX_PAIR];
+  int32_t pair_geom2[B2H_MAX_PAIR];
+  int32_t pair_condim[B2H_MAX_PAIR];
+  double pair_friction[B2H_MAX_PAIR][3];
+  double pair_solref[B2H_MAX_PAIR][2];
+  double pair_solimp[B2H_MAX_PAIR][5];
+  double pair_margin[B2H_MAX_PAIR];
+  double pair_gap[B2H_MAX_PAIR];
+  /* fixed tendons */
+  int32_t ten_limited[B2H_MAX_TENDON];
+  double ten_J[B2H_MAX_TENDON][B2H_MAX_DOF];
+  double ten_qcoef[B2H_MAX_TENDON][B2H_MAX_QPOS];
+  double ten_range[B2H_MAX_TENDON][2];
+  double ten_solref[B2H_MAX_TENDON][2];
+  double ten_solimp[B2H_MAX_TENDON][5];
+  double ten_margin[B2H_MAX_TENDON];
+  double ten_invweight0[B2H_MAX_TENDON];
+  /* motors */
+  int32_t actuator_dofid[B2H_MAX_ACT];
+  int32_t actuator_ctrllimited[B2H_MAX_ACT];
+  double actuator_gear[B2H_MAX_ACT];
+  double actuator_ctrlrange[B2H_MAX_ACT][2];
+} B2HModel;
+
+/* Environment configuration: the env_config dict of custom_env.py:21-32 plus batch parameters. */
+typedef struct B2HConfig {
+  int32_t n_envs;          /* environments on this GPU                                             */
+  int32_t env_id_offset;   /* global id of local env 0 (keys the reset-noise stream; multi-GPU)     */
+  int32_t frame_skip;      /* custom_env.py:28 (default 5; train_sb3.py:199 passes 3)               */
+  int32_t reward_type;     /* B2H_REWARD_*                                                         */
+  int32_t obs_mode;        /* B2H_OBS_*                                                            */
+  int32_t dtype;           /* B2H_F32 / B2H_F64                                                    */
+  int32_t max_steps;       /* truncation threshold, custom_env.py:203 (750)                        */
+  int32_t device;          /* CUDA device ordinal                                                  */
+  double duration;         /* custom_env.py:22 (terminated = time >= duration, :213)               */
+  uint64_t seed;           /* reset-noise Philox key                                               */
+  double kneeling_params[9]; /* target_height,min_height,max_roll_pitch,com_radius,energy_w,posture_w,com_w,foot_w,alive_w */
+} B2HConfig;
+
+typedef struct B2HHandle B2HHandle;
+
+int b2h_abi_version(void);
+size_t b2h_sizeof_model(void);
+size_t b2h_sizeof_config(void);
+const char* b2h_last_error(void);
+
+int b2h_create(const B2HModel* model, const B2HConfig* cfg, B2HHandle** out);
+void b2h_destroy(B2HHandle* h);
+int b2h_obs_dim(const B2HHandle* h);
+
+/* Reset every env whose mask_dev[i] != 0 (mask_dev == NULL: all).  Writes the first observation of the
+ * new episode into obs_dev ([n_envs, obs_dim], float for B2H_F32, double for B2H_F64). */
+int b2h_reset(B2HHandle* h, const uint8_t* mask_dev, void* obs_dev, void* stream);
+
+/* Parity hook: explicit reset noise [n_envs, nq+nv] (double, device) consumed by the next reset of each
+ * env instead of the Philox stream (custom_env.py:109-117 draws it from the global numpy RNG). */
+int b2h_set_reset_noise(B2HHandle* h, const double* noise_dev, void* stream);
+/* The noise vector the most recent reset of each env used, [n_envs, nq+nv] double (device -> device). */
+int b2h_get_last_reset_noise(B2HHandle* h, double* noise_dev, void* stream);
+
+/* One control step for all envs (custom_env.py:152-230) followed by SubprocVecEnv auto-reset semantics:
+ * for done envs obs_dev holds the first observation of the next episode and terminal_obs_dev (may be
+ * NULL) the last observation of the finished one.  actions_dev: float [n_envs, nu] (already clipped by
+ * the caller as SB3 does; the motor ctrlrange clamp of mj_fwdActuation is applied regardless).
+ * reward_dev: float/double [n_envs]; terminated_dev / truncated_dev: uint8 [n_envs]. */
+int b2h_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward_dev,
+             uint8_t* terminated_dev, uint8_t* truncated_dev, void* terminal_obs_dev, void* stream);
+
+/* Host-buffer form of b2h_step: copies actions H2D, steps, copies results D2H, synchronises.  obs_host is
+ * float [n_envs, obs_dim] for B2H_F32 (double for B2H_F64); reward_host likewise; flags uint8. */
+int b2h_step_host(B2HHandle* h, const float* actions_host, void* obs_host, void* reward_host,
+                  uint8_t* terminated_host, uint8_t* truncated_host, void* terminal_obs_host, void* stream);
+int b2h_reset_host(B2HHandle* h, const uint8_t* mask_host, void* obs_host, void* stream);
+
+/* Physics state access, all double on the host side regardless of dtype (tests, checkpoints):
+ * qpos [n_envs,nq], qvel [n_envs,nv], warmstart [n_envs,nv], nstep int32 [n_envs] (physics steps since
+ * mj_resetData: time = nstep*timestep), step_count int32 [n_envs], total_reward [n_envs].  NULL = skip. */
+int b2h_get_state(B2HHandle* h, double* qpos_host, double* qvel_host, double* warmstart_host,
+                  int32_t* nstep_host, int32_t* step_count_host, double* total_reward_host);
+int b2h_set_state(B2HHandle* h, const double* qpos_host, const double* qvel_host, const double* warmstart_host,
+                  const int32_t* nstep_host, const int32_t* step_count_host, const double* total_reward_host);
+
+/* Debug / parity: run mj_forward-equivalent stages on the current state with ctrl = actions_dev (may be
+ * NULL) and dump intermediates of env `env` as doubles into out_host; `what` selects the array by name
+ * ("xpos","xquat","cinert","cvel","cdof","qM","qfrc_bias","qfrc_passive","qfrc_actuator",
+ * "qacc_smooth","qacc","contact_dist","contact_pos","contact_frame","efc_aref","efc_D","efc_force",...).
+ * Returns the number of doubles written (>= 0) or a negative error. */
+int b2h_debug_forward(B2HHandle* h, const float* actions_dev, int env, const char* what, double* out_host, int max_out);
+
+/* Counters since creation: [0] physics steps, [1] contact overflows (more than the kernel's contact
+ * capacity were active; extras dropped), [2] solver iteration cap hits, [3] bad-state resets
+ * (mj_checkPos/Vel/Acc equivalents), [4] total Newton iterations, [5] kernels launched. */
+int b2h_get_counters(B2HHandle* h, uint64_t counters_host[8]);
+
+/* GAE reverse scan (SB3 2.3.2 RolloutBuffer.compute_returns_and_advantage).  All [T, E] float arrays,
+ * E fastest; last_values [E]; last_dones uint8 [E]. */
+int b2h_gae(const float* rewards_dev, const float* values_dev, const float* episode_starts_dev,
+            const float* last_values_dev, const uint8_t* last_dones_dev, float gamma, float gae_lambda,
+            int T, int E, float* advantages_dev, float* returns_dev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2H_H_ */

@@ -1,0 +1,1252 @@
+// b2h_physics.cuh — one warp simulates one humanoid environment (warp-cooperative mj_step + env epilogue).
+//
+// Replaces, for the MJCF subset of the reference model, what `mujoco.mj_step` does at custom_env.py:121,160
+// (MuJoCo 3.2.5 pipeline: kinematics, comPos, crb, collision, makeConstraint, comVel, passive, rne, actuation,
+// Newton constraint solver, implicit-damping Euler) and what HumanoidEnv.step/reset/_get_state and the
+// reward functions do around it (custom_env.py:97-261, reward_functions.py:66-261).  This is not a port of the
+// C engine: the recursion over the kinematic tree is re-expressed as lane-parallel sums over ancestor chains
+// and depth-first subtree ranges, lanes are bodies / joints / dofs / geom pairs / constraint rows depending on
+// the stage, per-env matrices live in shared memory with 128-bit row access, and cross-lane traffic is warp
+// shuffles.  Joint-limit rows are never materialised (their Jacobian is +-e_dof, kept lane-resident).
+//
+// The same source compiles for sm_100a and, with -DB2H_HOST_EMU, for a 32-host-thread lane emulation used only
+// by the CPU test-suite (tests/emu): every shuffle / ballot / sync below is executed by all 32 lanes.
+#pragma once
+#include "b2h_model.h"
+
+#ifdef B2H_HOST_EMU
+#define B2H_DEV inline
+#define B2H_DEV_NOINLINE
+#define B2H_LDG(x) (x)
+namespace b2h { namespace emu {
+int lane();
+uint64_t xchg(uint64_t v, int src);
+unsigned ballot(int p);
+void sync();
+} }
+#else
+#define B2H_DEV __device__ __forceinline__
+#define B2H_DEV_NOINLINE __device__ __noinline__
+#define B2H_LDG(x) __ldg(&(x))
+#endif
+
+namespace b2h {
+
+// ------------------------------------------------------------------------------------------------ warp layer
+#ifdef B2H_HOST_EMU
+B2H_DEV int lane_id() { return emu::lane(); }
+B2H_DEV void wsync() { emu::sync(); }
+B2H_DEV unsigned ballot(bool p) { return emu::ballot(p); }
+template <typename V> B2H_DEV V shfl(V v, int src) {
+  uint64_t bits = 0;
+  memcpy(&bits, &v, sizeof(V));
+  bits = emu::xchg(bits, src & 31);
+  V r;
+  memcpy(&r, &bits, sizeof(V));
+  return r;
+}
+#else
+B2H_DEV int lane_id() { return threadIdx.x & 31; }
+B2H_DEV void wsync() { __syncwarp(); }
+B2H_DEV unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
+template <typename V> B2H_DEV V shfl(V v, int src) { return __shfl_sync(0xffffffffu, v, src); }
+#endif
+template <typename V> B2H_DEV V shfl_xor(V v, int m) { return shfl(v, lane_id() ^ m); }
+template <typename V> B2H_DEV V wsum(V v) {  // butterfly all-reduce: every lane ends with the same bits
+  v += shfl_xor(v, 16); v += shfl_xor(v, 8); v += shfl_xor(v, 4); v += shfl_xor(v, 2); v += shfl_xor(v, 1);
+  return v;
+}
+B2H_DEV int wscan_excl(int v, int lane) {  // exclusive prefix sum over lanes
+  int x = v;
+  for (int o = 1; o < 32; o <<= 1) { int y = shfl(x, lane - o); if (lane >= o) x += y; }
+  return x - v;
+}
+B2H_DEV int popc(unsigned x) {
+#ifdef B2H_HOST_EMU
+  return __builtin_popcount(x);
+#else
+  return __popc(x);
+#endif
+}
+B2H_DEV int ffs32(unsigned x) {  // 1-based index of the lowest set bit
+#ifdef B2H_HOST_EMU
+  return __builtin_ffs((int)x);
+#else
+  return __ffs((int)x);
+#endif
+}
+
+// ------------------------------------------------------------------------------------------------ scalar math
+B2H_DEV float m_sqrt(float x) { return sqrtf(x); }
+B2H_DEV double m_sqrt(double x) { return sqrt(x); }
+B2H_DEV float m_abs(float x) { return fabsf(x); }
+B2H_DEV double m_abs(double x) { return fabs(x); }
+B2H_DEV float m_min(float a, float b) { return fminf(a, b); }
+B2H_DEV double m_min(double a, double b) { return fmin(a, b); }
+B2H_DEV float m_max(float a, float b) { return fmaxf(a, b); }
+B2H_DEV double m_max(double a, double b) { return fmax(a, b); }
+B2H_DEV float m_exp(float x) { return expf(x); }
+B2H_DEV double m_exp(double x) { return exp(x); }
+B2H_DEV float m_pow(float a, float b) { return powf(a, b); }
+B2H_DEV double m_pow(double a, double b) { return pow(a, b); }
+B2H_DEV float m_atan2(float a, float b) { return atan2f(a, b); }
+B2H_DEV double m_atan2(double a, double b) { return atan2(a, b); }
+B2H_DEV float m_asin(float a) { return asinf(a); }
+B2H_DEV double m_asin(double a) { return asin(a); }
+B2H_DEV void m_sincos(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
+B2H_DEV void m_sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
+template <typename T> B2H_DEV T clampT(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+template <typename T> B2H_DEV bool is_bad(T x) { return !(x == x) || x > T(1e10) || x < T(-1e10); }
+
+template <typename T> struct Tol;  // arithmetic-type dependent solver slack (0 in double = MuJoCo's tests verbatim)
+template <> struct Tol<double> { static constexpr double ls_rel = 0.0, cost_rel = 0.0; static constexpr int maxiter = 100; };
+template <> struct Tol<float> { static constexpr float ls_rel = 2e-5f, cost_rel = 1e-6f; static constexpr int maxiter = 30; };
+
+#define B2H_MINVAL T(1e-15)
+// the (at most two) dense-row slots a lane owns, fully unrolled so per-slot registers stay registers
+#define B2H_SLOTS(s) _Pragma("unroll") for (int s = 0; s < 2; s++) if (s < nslot)
+
+template <typename T> struct V4 { T x, y, z, w; };
+#ifdef B2H_HOST_EMU
+template <typename T> B2H_DEV V4<T> ld4(const T* p) { return V4<T>{p[0], p[1], p[2], p[3]}; }
+#else
+B2H_DEV V4<float> ld4(const float* p) { float4 v = *reinterpret_cast<const float4*>(p); return V4<float>{v.x, v.y, v.z, v.w}; }
+B2H_DEV V4<double> ld4(const double* p) {
+  double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+  return V4<double>{a.x, a.y, b.x, b.y};
+}
+#endif
+
+template <typename T> B2H_DEV T dot3(const T* a, const T* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <typename T> B2H_DEV void cross3(T* r, const T* a, const T* b) {
+  T x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+template <typename T> B2H_DEV T normalize3(T* v) {  // mju_normalize3
+  T n = m_sqrt(dot3(v, v));
+  if (n < B2H_MINVAL) { v[0] = 1; v[1] = 0; v[2] = 0; }
+  else { T s = T(1) / n; v[0] *= s; v[1] *= s; v[2] *= s; }
+  return n;
+}
+template <typename T> B2H_DEV void normalize4(T* q) {  // mju_normalize4
+  T n = m_sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < B2H_MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; }
+  else { T s = T(1) / n; q[0] *= s; q[1] *= s; q[2] *= s; q[3] *= s; }
+}
+template <typename T> B2H_DEV void mul_quat(T* r, const T* a, const T* b) {
+  T t0 = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  T t1 = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  T t2 = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  T t3 = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = t0; r[1] = t1; r[2] = t2; r[3] = t3;
+}
+template <typename T> B2H_DEV void quat2mat(T* R, const T* q) {
+  T q00 = q[0] * q[0], q01 = q[0] * q[1], q02 = q[0] * q[2], q03 = q[0] * q[3];
+  T q11 = q[1] * q[1], q12 = q[1] * q[2], q13 = q[1] * q[3], q22 = q[2] * q[2], q23 = q[2] * q[3], q33 = q[3] * q[3];
+  R[0] = q00 + q11 - q22 - q33; R[4] = q00 - q11 + q22 - q33; R[8] = q00 - q11 - q22 + q33;
+  R[1] = 2 * (q12 - q03); R[2] = 2 * (q13 + q02); R[3] = 2 * (q12 + q03);
+  R[5] = 2 * (q23 - q01); R[6] = 2 * (q13 - q02); R[7] = 2 * (q23 + q01);
+}
+template <typename T> B2H_DEV void rot_quat(T* r, const T* v, const T* q) {  // r = R(q) v via q v q*
+  T t[3], u[3] = {q[1], q[2], q[3]};
+  cross3(t, u, v);
+  t[0] *= 2; t[1] *= 2; t[2] *= 2;
+  T c[3];
+  cross3(c, u, t);
+  r[0] = v[0] + q[0] * t[0] + c[0]; r[1] = v[1] + q[0] * t[1] + c[1]; r[2] = v[2] + q[0] * t[2] + c[2];
+}
+template <typename T> B2H_DEV void mat_vec3(T* r, const T* R, const T* v) {
+  T x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2], y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2],
+    z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+// spatial 6-vectors are [angular; linear]; inertia is the 10-number cinert format
+template <typename T> B2H_DEV void mul_inert_vec(T* r, const T* i, const T* v) {
+  r[0] = i[0] * v[0] + i[3] * v[1] + i[4] * v[2] - i[8] * v[4] + i[7] * v[5];
+  r[1] = i[3] * v[0] + i[1] * v[1] + i[5] * v[2] + i[8] * v[3] - i[6] * v[5];
+  r[2] = i[4] * v[0] + i[5] * v[1] + i[2] * v[2] - i[7] * v[3] + i[6] * v[4];
+  r[3] = i[8] * v[1] - i[7] * v[2] + i[9] * v[3];
+  r[4] = i[6] * v[2] - i[8] * v[0] + i[9] * v[4];
+  r[5] = i[7] * v[0] - i[6] * v[1] + i[9] * v[5];
+}
+template <typename T> B2H_DEV void cross_motion(T* r, const T* vel, const T* v) {
+  r[0] = -vel[2] * v[1] + vel[1] * v[2];
+  r[1] = vel[2] * v[0] - vel[0] * v[2];
+  r[2] = -vel[1] * v[0] + vel[0] * v[1];
+  r[3] = -vel[2] * v[4] + vel[1] * v[5] - vel[5] * v[1] + vel[4] * v[2];
+  r[4] = vel[2] * v[3] - vel[0] * v[5] + vel[5] * v[0] - vel[3] * v[2];
+  r[5] = -vel[1] * v[3] + vel[0] * v[4] - vel[4] * v[0] + vel[3] * v[1];
+}
+template <typename T> B2H_DEV void cross_force(T* r, const T* vel, const T* f) {
+  r[0] = -vel[2] * f[1] + vel[1] * f[2] - vel[5] * f[4] + vel[4] * f[5];
+  r[1] = vel[2] * f[0] - vel[0] * f[2] + vel[5] * f[3] - vel[3] * f[5];
+  r[2] = -vel[1] * f[0] + vel[0] * f[1] - vel[4] * f[3] + vel[3] * f[4];
+  r[3] = -vel[2] * f[4] + vel[1] * f[5];
+  r[4] = vel[2] * f[3] - vel[0] * f[5];
+  r[5] = -vel[1] * f[3] + vel[0] * f[4];
+}
+
+// ------------------------------------------------------------------------------------------------ per-warp scratch
+template <typename T>
+struct alignas(16) Scratch {
+  T J[NROW * LD];   // dense constraint rows (tendon limits, contact rows); column 27 is a zero pad
+  T A[LD * LD];     // factorisation workspace; before the solve stages it is stage-local scratch (TMP_*)
+  T M[LD * LD];     // joint-space inertia, dense symmetric
+  T vec[4][32];     // lane vectors that other lanes index (qpos, search direction, ...)
+  T xpos[KB * 3], xmat[KB * 9], xipos[KB * 3];
+  T cinert[KB * 10], cvel[KB * 6];
+  T cdof[KV * 6], cdofdot[KV * 6];
+  T xanchor[KJ * 3], xaxis[KJ * 3];
+  T gpos[KG * 3], gaxis[KG * 3];
+  T con_dist[NCON], con_pos[NCON * 3], con_frame[NCON * 9];
+  uint32_t con_info[NCON];  // body1 | body2 << 8 | class << 16
+  int con_row[NCON];        // first dense row of the contact, -1 if dropped
+  int row_con[NROW];        // dense row -> contact id (or -1 - tendon id)
+  T com[4];
+};
+// stage-local aliases inside Scratch::A (all dead before the factorisations start)
+constexpr int TMP_QLOC = 0, TMP_ANCL = TMP_QLOC + KJ * 4, TMP_AXL = TMP_ANCL + KJ * 3, TMP_XQUAT = TMP_AXL + KJ * 3,
+              TMP_CRB = TMP_XQUAT + KB * 4;                       // position stage
+constexpr int TMP_DOFW = 0, TMP_DOFA = TMP_DOFW + KV * 6, TMP_CFRC = TMP_DOFA + KV * 6;  // velocity stage
+static_assert(TMP_CRB + KB * 10 <= LD * LD, "position-stage scratch must fit in A");
+static_assert(TMP_CFRC + KB * 6 <= LD * LD, "velocity-stage scratch must fit in A");
+
+struct Counters {  // per-warp tallies, flushed with atomics at the end of the launch
+  unsigned long long physics_steps, contact_overflow, iter_cap, bad_state, newton_iter, ls_eval;
+};
+
+// per-row soft-constraint parameters (mj_makeImpedance + mj_referenceConstraint)
+template <typename T>
+B2H_DEV void row_params(const T* solref, const T* solimp, T pos, T margin, T diag_approx, T vel, T rscale, T* D, T* aref) {
+  T imp;
+  if (solimp[0] == solimp[1] || solimp[2] <= B2H_MINVAL) imp = T(0.5) * (solimp[0] + solimp[1]);
+  else {
+    T x = m_abs((pos - margin) / solimp[2]);
+    if (x >= T(1)) imp = solimp[1];
+    else if (x <= T(0)) imp = solimp[0];
+    else {
+      T y, p = solimp[4], mid = solimp[3];
+      if (p == T(1)) y = x;
+      else if (p == T(2)) y = x <= mid ? x * x / mid : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - mid);
+      else y = x <= mid ? m_pow(x, p) / m_pow(mid, p - 1) : T(1) - m_pow(T(1) - x, p) / m_pow(T(1) - mid, p - 1);
+      imp = solimp[0] + y * (solimp[1] - solimp[0]);
+    }
+  }
+  T dmax = solimp[1], K, B;
+  if (solref[0] <= T(0)) { K = -solref[0] / m_max(B2H_MINVAL, dmax * dmax); B = -solref[1] / m_max(B2H_MINVAL, dmax); }
+  else {
+    K = T(1) / m_max(B2H_MINVAL, dmax * dmax * solref[0] * solref[0] * solref[1] * solref[1]);
+    B = T(2) / m_max(B2H_MINVAL, dmax * solref[0]);
+  }
+  T R = m_max(B2H_MINVAL, (T(1) - imp) * diag_approx / imp) * rscale;
+  *D = T(1) / R;
+  *aref = -B * vel - K * imp * (pos - margin);
+}
+
+// ------------------------------------------------------------------------------------------------ dense 27x27 algebra
+// In-place Cholesky of the lower triangle of A (stride LD); lane i owns row i (left-looking, 128-bit row loads).
+template <typename T>
+B2H_DEV void chol_factor(T* A, int n, int lane) {
+  for (int j = 0; j < n; j++) {
+    T s = 0;
+    if (lane >= j && lane < n) {
+      const T* ri = A + lane * LD;
+      const T* rj = A + j * LD;
+      s = ri[j];
+      int k4 = j & ~3;
+      for (int k = 0; k < k4; k += 4) {
+        V4<T> a = ld4(ri + k), b = ld4(rj + k);
+        s -= a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+      }
+      for (int k = k4; k < j; k++) s -= ri[k] * rj[k];
+    }
+    T piv = m_max(shfl(s, j), B2H_MINVAL);  // mju_cholFactor floors the pivot
+    T root = m_sqrt(piv);
+    if (lane >= j && lane < n) A[lane * LD + j] = lane == j ? root : s / root;
+    wsync();
+  }
+}
+// x = (L L^T)^-1 b, b and x one entry per lane
+template <typename T>
+B2H_DEV T chol_solve(const T* A, int n, int lane, T b) {
+  T dinv = lane < n ? T(1) / A[lane * LD + lane] : T(0);
+  T row[LD];
+#pragma unroll
+  for (int c = 0; c < LD; c += 4) {
+    V4<T> v = ld4(A + (lane < n ? lane : 0) * LD + c);
+    row[c] = v.x; row[c + 1] = v.y; row[c + 2] = v.z; row[c + 3] = v.w;
+  }
+  T acc = 0, y = 0;
+#pragma unroll
+  for (int k = 0; k < KV - 1; k++) {
+    if (k < n) {
+      T yk = shfl((b - acc) * dinv, k);
+      if (lane == k) y = yk;
+      if (lane > k) acc += row[k] * yk;
+    }
+  }
+  acc = 0;
+  T x = 0;
+  for (int k = n - 1; k >= 0; k--) {
+    T xk = shfl((y - acc) * dinv, k);
+    if (lane == k) x = xk;
+    if (lane < k) acc += A[k * LD + lane] * xk;
+  }
+  return x;
+}
+// r[lane] = sum_k Mat[lane][k] * v[k], v taken from a 32-entry shared vector (entries >= n are zero)
+template <typename T>
+B2H_DEV T mat_vec(const T* Mat, const T* v, int n, int lane) {
+  T s = 0;
+  const T* r = Mat + (lane < n ? lane : 0) * LD;
+#pragma unroll
+  for (int c = 0; c < LD; c += 4) {
+    V4<T> a = ld4(r + c), b = ld4(v + c);
+    s += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+  }
+  return lane < n ? s : T(0);
+}
+
+// ------------------------------------------------------------------------------------------------ env state
+template <typename T>
+struct EnvState {      // registers of one lane
+  T qp, qv, warm;      // qpos[lane], qvel[lane], qacc_warmstart[lane]
+  T ctrl;              // control of the motor on dof `lane` (as written to data.ctrl), 0 without motor
+  T qfrc_act;          // qfrc_actuator[lane] of the last forward pass
+  int nstep;           // physics steps since mj_resetData (time = nstep * timestep)
+};
+
+struct StepStats { int ncon, nrow, nlimit, niter; };
+
+// One mj_step.  On return st holds the integrated state; S.cinert / S.cvel / S.com keep the pre-integration
+// values of this step, which is what the reference's observation and rewards read.
+// If `integrate` is false this is mj_forward: state untouched, qacc returned in *qacc_out.
+// Returns true when mj_checkAcc tripped: the state was reset and the caller must run the step once more.
+template <typename T>
+B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState<T>& st, Counters& cnt, bool integrate,
+                                   StepStats* stats, T* qacc_out, T* dbg_lane /* [8] optional per-lane dump */) {
+  const int lane = lane_id();
+  const int nv = B2H_LDG(m.nv), nq = B2H_LDG(m.nq), nbody = B2H_LDG(m.nbody), njnt = B2H_LDG(m.njnt);
+  const T h = B2H_LDG(m.timestep);
+  T* tmp = S.A;
+
+  // ---- mj_checkPos / mj_checkVel: NaN or |x| > 1e10 resets mjData (qpos0, zero velocity, time 0)
+  {
+    bool bad = (lane < nq && is_bad(st.qp)) || (lane < nv && is_bad(st.qv));
+    if (ballot(bad)) {
+      st.qp = lane < nq ? B2H_LDG(m.qpos0[lane]) : T(0);
+      st.qv = 0; st.warm = 0; st.ctrl = 0; st.nstep = 0;
+      cnt.bad_state++;
+    }
+  }
+
+  // =============================================================== position stage
+  // ---- mj_kinematics: joint-local rotations (lane = joint), per-body local chain (lane = body), tree levels
+  S.vec[0][lane] = st.qp;
+  if (lane == 0) {
+    S.xpos[0] = S.xpos[1] = S.xpos[2] = 0;
+    for (int k = 0; k < 9; k++) S.xmat[k] = (k % 4 == 0) ? T(1) : T(0);
+    tmp[TMP_XQUAT] = 1; tmp[TMP_XQUAT + 1] = tmp[TMP_XQUAT + 2] = tmp[TMP_XQUAT + 3] = 0;
+    S.xipos[0] = S.xipos[1] = S.xipos[2] = 0;
+    for (int k = 0; k < 10; k++) S.cinert[k] = 0;
+    for (int k = 0; k < 6; k++) S.cvel[k] = 0;
+  }
+  wsync();
+  if (lane < njnt && B2H_LDG(m.jnt_type[lane]) == B2H_JNT_HINGE) {
+    T ang = S.vec[0][B2H_LDG(m.jnt_qadr[lane])] - B2H_LDG(m.jnt_q0[lane]);
+    T s, c;
+    m_sincos(ang * T(0.5), &s, &c);
+    if (ang == T(0)) { s = 0; c = 1; }
+    tmp[TMP_QLOC + 4 * lane] = c;
+    for (int k = 0; k < 3; k++) tmp[TMP_QLOC + 4 * lane + 1 + k] = B2H_LDG(m.jnt_axis[lane][k]) * s;
+  }
+  wsync();
+  T rq[4] = {1, 0, 0, 0}, rp[3] = {0, 0, 0};  // body frame relative to its parent body
+  const int my_level = lane < nbody ? B2H_LDG(m.body_level[lane]) : -1;
+  const int my_parent = lane < nbody ? B2H_LDG(m.body_parent[lane]) : 0;
+  if (lane > 0 && lane < nbody) {
+    if (B2H_LDG(m.body_isfree[lane])) {
+      for (int k = 0; k < 3; k++) rp[k] = S.vec[0][k];
+      for (int k = 0; k < 4; k++) rq[k] = S.vec[0][3 + k];
+      normalize4(rq);
+      int j = B2H_LDG(m.body_jntadr[lane]);
+      for (int k = 0; k < 3; k++) { tmp[TMP_ANCL + 3 * j + k] = rp[k]; tmp[TMP_AXL + 3 * j + k] = B2H_LDG(m.jnt_axis[j][k]); }
+    } else {
+      for (int k = 0; k < 3; k++) rp[k] = B2H_LDG(m.body_pos[lane][k]);
+      for (int k = 0; k < 4; k++) rq[k] = B2H_LDG(m.body_quat[lane][k]);
+      int ja = B2H_LDG(m.body_jntadr[lane]), jn = B2H_LDG(m.body_jntnum[lane]);
+      for (int j = ja; j < ja + jn; j++) {
+        T jp[3], jax[3], anc[3], ax[3], v[3];
+        for (int k = 0; k < 3; k++) { jp[k] = B2H_LDG(m.jnt_pos[j][k]); jax[k] = B2H_LDG(m.jnt_axis[j][k]); }
+        rot_quat(ax, jax, rq);
+        rot_quat(anc, jp, rq);
+        for (int k = 0; k < 3; k++) anc[k] += rp[k];
+        mul_quat(rq, rq, tmp + TMP_QLOC + 4 * j);
+        rot_quat(v, jp, rq);
+        for (int k = 0; k < 3; k++) { rp[k] = anc[k] - v[k]; tmp[TMP_ANCL + 3 * j + k] = anc[k]; tmp[TMP_AXL + 3 * j + k] = ax[k]; }
+      }
+    }
+  }
+  const int nlevel = B2H_LDG(m.nlevel);
+  for (int L = 1; L <= nlevel; L++) {
+    if (my_level == L) {
+      T pq[4], xq[4], v[3];
+      for (int k = 0; k < 4; k++) pq[k] = tmp[TMP_XQUAT + 4 * my_parent + k];
+      mul_quat(xq, pq, rq);
+      normalize4(xq);
+      rot_quat(v, rp, pq);
+      for (int k = 0; k < 3; k++) S.xpos[3 * lane + k] = S.xpos[3 * my_parent + k] + v[k];
+      for (int k = 0; k < 4; k++) tmp[TMP_XQUAT + 4 * lane + k] = xq[k];
+      T R[9];
+      quat2mat(R, xq);
+      for (int k = 0; k < 9; k++) S.xmat[9 * lane + k] = R[k];
+    }
+    wsync();
+  }
+  // inertial frames (lane = body), joint anchors/axes in the world (lane = joint), geoms (lane = geom)
+  T my_mass = 0;
+  if (lane > 0 && lane < nbody) {
+    T ip[3], v[3];
+    for (int k = 0; k < 3; k++) ip[k] = B2H_LDG(m.body_ipos[lane][k]);
+    mat_vec3(v, S.xmat + 9 * lane, ip);
+    for (int k = 0; k < 3; k++) S.xipos[3 * lane + k] = S.xpos[3 * lane + k] + v[k];
+    my_mass = B2H_LDG(m.body_mass[lane]);
+  }
+  if (lane < njnt) {
+    int p = B2H_LDG(m.body_parent[B2H_LDG(m.jnt_body[lane])]);
+    T v[3];
+    mat_vec3(v, S.xmat + 9 * p, tmp + TMP_ANCL + 3 * lane);
+    for (int k = 0; k < 3; k++) S.xanchor[3 * lane + k] = S.xpos[3 * p + k] + v[k];
+    mat_vec3(v, S.xmat + 9 * p, tmp + TMP_AXL + 3 * lane);
+    for (int k = 0; k < 3; k++) S.xaxis[3 * lane + k] = v[k];
+  }
+  if (lane < B2H_LDG(m.ngeom)) {
+    int b = B2H_LDG(m.geom_body[lane]);
+    T gp[3], gz[3], v[3];
+    for (int k = 0; k < 3; k++) { gp[k] = B2H_LDG(m.geom_pos[lane][k]); gz[k] = B2H_LDG(m.geom_zaxis[lane][k]); }
+    mat_vec3(v, S.xmat + 9 * b, gp);
+    for (int k = 0; k < 3; k++) S.gpos[3 * lane + k] = S.xpos[3 * b + k] + v[k];
+    mat_vec3(v, S.xmat + 9 * b, gz);
+    for (int k = 0; k < 3; k++) S.gaxis[3 * lane + k] = v[k];
+  }
+  wsync();
+  // ---- mj_comPos: centre of mass (single tree), cinert, cdof
+  T com[3];
+  {
+    T inv = B2H_LDG(m.inv_total_mass);
+    for (int k = 0; k < 3; k++) com[k] = wsum(lane > 0 && lane < nbody ? my_mass * S.xipos[3 * lane + k] : T(0)) * inv;
+    if (lane < 3) S.com[lane] = com[lane];
+  }
+  if (lane > 0 && lane < nbody) {  // mju_inertCom with the full body-frame tensor: R I R^T + m (|d|^2 1 - d d^T)
+    const T* R = S.xmat + 9 * lane;
+    T I6[6], dif[3];
+    for (int k = 0; k < 6; k++) I6[k] = B2H_LDG(m.body_inertia[lane][k]);
+    for (int k = 0; k < 3; k++) dif[k] = S.xipos[3 * lane + k] - com[k];
+    T Ib[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]}, RI[9];
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++) RI[3 * r + c] = R[3 * r] * Ib[c] + R[3 * r + 1] * Ib[3 + c] + R[3 * r + 2] * Ib[6 + c];
+    T W[6];  // xx yy zz xy xz yz
+    W[0] = RI[0] * R[0] + RI[1] * R[1] + RI[2] * R[2];
+    W[1] = RI[3] * R[3] + RI[4] * R[4] + RI[5] * R[5];
+    W[2] = RI[6] * R[6] + RI[7] * R[7] + RI[8] * R[8];
+    W[3] = RI[0] * R[3] + RI[1] * R[4] + RI[2] * R[5];
+    W[4] = RI[0] * R[6] + RI[1] * R[7] + RI[2] * R[8];
+    W[5] = RI[3] * R[6] + RI[4] * R[7] + RI[5] * R[8];
+    T* ci = S.cinert + 10 * lane;
+    ci[0] = W[0] + my_mass * (dif[1] * dif[1] + dif[2] * dif[2]);
+    ci[1] = W[1] + my_mass * (dif[0] * dif[0] + dif[2] * dif[2]);
+    ci[2] = W[2] + my_mass * (dif[0] * dif[0] + dif[1] * dif[1]);
+    ci[3] = W[3] - my_mass * dif[0] * dif[1];
+    ci[4] = W[4] - my_mass * dif[0] * dif[2];
+    ci[5] = W[5] - my_mass * dif[1] * dif[2];
+    ci[6] = my_mass * dif[0]; ci[7] = my_mass * dif[1]; ci[8] = my_mass * dif[2]; ci[9] = my_mass;
+  }
+  T cd[6] = {0, 0, 0, 0, 0, 0};  // cdof of dof `lane`
+  const int my_dbody = lane < nv ? B2H_LDG(m.dof_body[lane]) : 0;
+  const int my_dparent = lane < nv ? B2H_LDG(m.dof_parent[lane]) : -1;
+  if (lane < nv) {
+    int j = B2H_LDG(m.dof_jnt[lane]);
+    T off[3], ax[3];
+    for (int k = 0; k < 3; k++) off[k] = com[k] - S.xanchor[3 * j + k];
+    if (B2H_LDG(m.jnt_type[j]) == B2H_JNT_FREE) {
+      int k = lane - B2H_LDG(m.jnt_dadr[j]);
+      if (k < 3) cd[3 + k] = 1;
+      else {
+        const T* R = S.xmat + 9 * my_dbody;
+        ax[0] = R[k - 3]; ax[1] = R[k]; ax[2] = R[k + 3];
+        cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+        cross3(cd + 3, ax, off);
+      }
+    } else {
+      for (int k = 0; k < 3; k++) ax[k] = S.xaxis[3 * j + k];
+      cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
+      cross3(cd + 3, ax, off);
+    }
+  }
+  if (lane < KV) for (int k = 0; k < 6; k++) S.cdof[6 * lane + k] = cd[k];
+  wsync();
+  // ---- mj_crb: composite inertia = sum over the depth-first subtree range; M over ancestor chains
+  if (lane > 0 && lane < nbody) {
+    T c[10];
+    for (int k = 0; k < 10; k++) c[k] = S.cinert[10 * lane + k];
+    int end = B2H_LDG(m.body_subend[lane]);
+    for (int b = lane + 1; b < end; b++)
+      for (int k = 0; k < 10; k++) c[k] += S.cinert[10 * b + k];
+    for (int k = 0; k < 10; k++) tmp[TMP_CRB + 10 * lane + k] = c[k];
+  }
+  for (int i = lane; i < LD * LD; i += 32) S.M[i] = 0;
+  wsync();
+  if (lane < nv) {
+    T buf[6];
+    mul_inert_vec(buf, tmp + TMP_CRB + 10 * my_dbody, cd);
+    for (int j = lane; j >= 0; j = B2H_LDG(m.dof_parent[j])) {
+      const T* cj = S.cdof + 6 * j;
+      T s = cj[0] * buf[0] + cj[1] * buf[1] + cj[2] * buf[2] + cj[3] * buf[3] + cj[4] * buf[4] + cj[5] * buf[5];
+      if (j == lane) s += B2H_LDG(m.dof_armature[lane]);
+      S.M[lane * LD + j] = s;
+      S.M[j * LD + lane] = s;
+    }
+  }
+  wsync();
+
+  // =============================================================== collision (lane = candidate pair)
+  int ncon = 0;
+  {
+    const int npair = B2H_LDG(m.npair);
+    for (int base = 0; base < npair; base += 32) {
+      int p = base + lane;
+      int n = 0;
+      T cdist[2], cpos[2][3], cnrm[2][3], chint[3] = {0, 0, 0};
+      uint32_t info = 0;
+      if (p < npair) {
+        uint32_t pw = B2H_LDG(m.pair[p]);
+        int g1 = pw & 255, g2 = (pw >> 8) & 255, cls = pw >> 16;
+        T margin = B2H_LDG(m.cls_margin[cls]);
+        info = (uint32_t)B2H_LDG(m.geom_body[g1]) | ((uint32_t)B2H_LDG(m.geom_body[g2]) << 8) | ((uint32_t)cls << 16);
+        int t1 = B2H_LDG(m.geom_type[g1]);
+        T r2 = B2H_LDG(m.geom_size[g2][0]), h2 = B2H_LDG(m.geom_size[g2][1]);
+        const T* p2 = S.gpos + 3 * g2;
+        const T* a2 = S.gaxis + 3 * g2;
+        if (t1 == B2H_GEOM_PLANE) {  // mjc_PlaneSphere / mjc_PlaneCapsule (two end spheres, frame aligned with the axis)
+          const T* pn = S.gaxis + 3 * g1;
+          const T* pp = S.gpos + 3 * g1;
+          int nend = h2 > T(0) ? 2 : 1;
+          for (int e = 0; e < nend; e++) {
+            T sgn = e == 0 ? T(1) : T(-1), c[3], d[3];
+            for (int k = 0; k < 3; k++) { c[k] = p2[k] + a2[k] * h2 * sgn; d[k] = c[k] - pp[k]; }
+            T cd_ = dot3(d, pn);
+            if (cd_ <= margin + r2) {
+              T dist = cd_ - r2;
+              if (dist < margin) {
+                cdist[n] = dist;
+                for (int k = 0; k < 3; k++) { cnrm[n][k] = pn[k]; cpos[n][k] = c[k] - pn[k] * (dist * T(0.5) + r2); }
+                n++;
+              }
+            }
+          }
+          if (nend == 2) for (int k = 0; k < 3; k++) chint[k] = a2[k];
+        } else {  // sphere / capsule pairs: closest points of two segments, then sphere-sphere
+          T r1 = B2H_LDG(m.geom_size[g1][0]), h1 = B2H_LDG(m.geom_size[g1][1]);
+          const T* p1 = S.gpos + 3 * g1;
+          const T* a1 = S.gaxis + 3 * g1;
+          T v1[2][3], v2[2][3];
+          int ncand = 1;
+          if (h1 == T(0)) {  // mjc_SphereSphere / mjc_SphereCapsule
+            T d[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
+            T x = clampT(dot3(a2, d), -h2, h2);
+            for (int k = 0; k < 3; k++) { v1[0][k] = p1[k]; v2[0][k] = p2[k] + a2[k] * x; }
+          } else {           // mjc_CapsuleCapsule
+            T dif[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]}, cr[3];
+            T ma = dot3(a1, a1), mb = -dot3(a1, a2), mc = dot3(a2, a2), u = -dot3(a1, dif), v = dot3(a2, dif);
+            cross3(cr, a1, a2);
+            T det = dot3(cr, cr);  // = ma*mc - mb*mb without the cancellation
+            if (det >= B2H_MINVAL) {
+              T x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
+              if (x1 > h1) { x1 = h1; x2 = (v - mb * h1) / mc; }
+              else if (x1 < -h1) { x1 = -h1; x2 = (v + mb * h1) / mc; }
+              if (x2 > h2) { x2 = h2; x1 = clampT((u - mb * h2) / ma, -h1, h1); }
+              else if (x2 < -h2) { x2 = -h2; x1 = clampT((u + mb * h2) / ma, -h1, h1); }
+              for (int k = 0; k < 3; k++) { v1[0][k] = p1[k] + a1[k] * x1; v2[0][k] = p2[k] + a2[k] * x2; }
+            } else {  // parallel axes: end points of 1 projected on 2, then of 2 on 1; at most two contacts
+              ncand = 0;
+              T mind = margin + r1 + r2;
+              for (int e = 0; e < 4 && ncand < 2; e++) {
+                T sgn = (e & 1) ? T(-1) : T(1), a[3], b[3], t[3];
+                if (e < 2) {
+                  for (int k = 0; k < 3; k++) { a[k] = p1[k] + a1[k] * h1 * sgn; t[k] = a[k] - p2[k]; }
+                  T x2 = clampT(dot3(t, a2), -h2, h2);
+                  for (int k = 0; k < 3; k++) b[k] = p2[k] + a2[k] * x2;
+                } else {
+                  for (int k = 0; k < 3; k++) { b[k] = p2[k] + a2[k] * h2 * sgn; t[k] = b[k] - p1[k]; }
+                  T x1 = clampT(dot3(t, a1), -h1, h1);
+                  for (int k = 0; k < 3; k++) a[k] = p1[k] + a1[k] * x1;
+                }
+                T d[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
+                if (dot3(d, d) <= mind * mind) {
+                  for (int k = 0; k < 3; k++) { v1[ncand][k] = a[k]; v2[ncand][k] = b[k]; }
+                  ncand++;
+                }
+              }
+            }
+          }
+          T mind = margin + r1 + r2;
+          for (int e = 0; e < ncand; e++) {
+            T d[3] = {v2[e][0] - v1[e][0], v2[e][1] - v1[e][1], v2[e][2] - v1[e][2]};
+            if (dot3(d, d) <= mind * mind) {
+              T dist = normalize3(d) - r1 - r2;
+              if (dist < margin) {
+                cdist[n] = dist;
+                for (int k = 0; k < 3; k++) { cnrm[n][k] = d[k]; cpos[n][k] = v1[e][k] + d[k] * (r1 + dist * T(0.5)); }
+                n++;
+              }
+            }
+          }
+        }
+      }
+      int slot = ncon + wscan_excl(n, lane);
+      int total = shfl(slot + n, 31) - ncon;
+      for (int e = 0; e < n; e++) {
+        int c = slot + e;
+        if (c < NCON) {
+          T f[9];  // mju_makeFrame
+          for (int k = 0; k < 3; k++) { f[k] = cnrm[e][k]; f[3 + k] = chint[k]; }
+          normalize3(f);
+          if (m_sqrt(dot3(f + 3, f + 3)) < T(0.5)) {
+            f[3] = f[4] = f[5] = 0;
+            if (f[1] < T(0.5) && f[1] > T(-0.5)) f[4] = 1; else f[5] = 1;
+          }
+          T dp = dot3(f, f + 3);
+          for (int k = 0; k < 3; k++) f[3 + k] -= f[k] * dp;
+          normalize3(f + 3);
+          cross3(f + 6, f, f + 3);
+          S.con_dist[c] = cdist[e];
+          for (int k = 0; k < 3; k++) S.con_pos[3 * c + k] = cpos[e][k];
+          for (int k = 0; k < 9; k++) S.con_frame[9 * c + k] = f[k];
+          S.con_info[c] = info;
+        }
+      }
+      ncon += total;
+    }
+    if (ncon > NCON) { cnt.contact_overflow += ncon - NCON; ncon = NCON; }
+  }
+  wsync();
+
+  // =============================================================== constraint rows
+  // dense rows: tendon limits first, then contacts (1 row frictionless, 4 rows pyramidal condim 3)
+  int nrow = 0;
+  T ten_pos[KT];   // signed distance of an active tendon limit (uniform)
+  int ten_row[KT], ten_side[KT];
+  for (int t = 0; t < B2H_LDG(m.ntendon); t++) {
+    ten_row[t] = -1; ten_side[t] = 0; ten_pos[t] = 0;
+    T len = wsum(lane < nq ? B2H_LDG(m.ten_qcoef[t][lane]) * st.qp : T(0));
+    if (B2H_LDG(m.ten_limited[t])) {
+      T lo = B2H_LDG(m.ten_range[t][0]), hi = B2H_LDG(m.ten_range[t][1]), mg = B2H_LDG(m.ten_margin[t]);
+      if (len - lo < mg) { ten_side[t] = 1; ten_pos[t] = len - lo; }
+      else if (hi - len < mg) { ten_side[t] = -1; ten_pos[t] = hi - len; }
+      if (ten_side[t]) {
+        ten_row[t] = nrow;
+        if (lane < LD) S.J[nrow * LD + lane] = lane < nv ? T(ten_side[t]) * B2H_LDG(m.ten_J[t][lane]) : T(0);
+        if (lane == 0) S.row_con[nrow] = -1 - t;
+        nrow++;
+      }
+    }
+  }
+  {
+    int nr = 0;
+    if (lane < ncon) nr = B2H_LDG(m.cls_condim[S.con_info[lane] >> 16]) == 1 ? 1 : 4;
+    int r0 = nrow + wscan_excl(nr, lane);
+    bool drop = lane < ncon && r0 + nr > NROW;
+    if (lane < ncon) S.con_row[lane] = drop ? -1 : r0;
+    unsigned dm = ballot(drop);
+    if (dm) cnt.contact_overflow += popc(dm);
+    int keep_rows = drop ? 0 : nr;
+    nrow += wsum(keep_rows);
+  }
+  wsync();
+  // contact Jacobians (lane = dof): J_k[d] = frame_k . (jacp_body2[d] - jacp_body1[d]), mj_jac about the com
+  for (int c = 0; c < ncon; c++) {
+    int r0 = S.con_row[c];
+    if (r0 < 0) continue;
+    uint32_t info = S.con_info[c];
+    int b1 = info & 255, b2 = (info >> 8) & 255, cls = info >> 16;
+    int sg = (int)((B2H_LDG(m.body_dofmask[b2]) >> lane) & 1u) - (int)((B2H_LDG(m.body_dofmask[b1]) >> lane) & 1u);
+    T off[3], jp[3];
+    for (int k = 0; k < 3; k++) off[k] = S.con_pos[3 * c + k] - com[k];
+    cross3(jp, cd, off);
+    for (int k = 0; k < 3; k++) jp[k] = (jp[k] + cd[3 + k]) * T(sg);
+    const T* f = S.con_frame + 9 * c;
+    T jn = dot3(f, jp);
+    if (B2H_LDG(m.cls_condim[cls]) == 1) {
+      if (lane < LD) S.J[r0 * LD + lane] = jn;
+      if (lane == 0) S.row_con[r0] = c;
+    } else {
+      T mu = B2H_LDG(m.cls_mu[cls]);
+      T j1 = dot3(f + 3, jp) * mu, j2 = dot3(f + 6, jp) * mu;
+      if (lane < LD) {
+        S.J[(r0 + 0) * LD + lane] = jn + j1;
+        S.J[(r0 + 1) * LD + lane] = jn - j1;
+        S.J[(r0 + 2) * LD + lane] = jn + j2;
+        S.J[(r0 + 3) * LD + lane] = jn - j2;
+      }
+      if (lane < 4) S.row_con[r0 + lane] = c;
+    }
+  }
+  S.vec[1][lane] = lane < nv ? st.qv : T(0);
+  wsync();
+
+  // per-row parameters; lane owns dense rows lane and lane+32 (slot 0/1) and the joint limit of dof `lane`
+  const int nslot = nrow > 32 ? 2 : 1;
+  T rD[2] = {0, 0}, raref[2] = {0, 0};
+  B2H_SLOTS(s) {
+    int r = lane + 32 * s;
+    if (r < nrow) {
+      T vel = 0;
+      const T* jr = S.J + r * LD;
+#pragma unroll
+      for (int c4 = 0; c4 < LD; c4 += 4) {
+        V4<T> a = ld4(jr + c4), b = ld4(S.vec[1] + c4);
+        vel += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
+      }
+      int rc = S.row_con[r];
+      if (rc < 0) {
+        int t = -1 - rc;
+        T sr[2] = {B2H_LDG(m.ten_solref[t][0]), B2H_LDG(m.ten_solref[t][1])}, si[5];
+        for (int k = 0; k < 5; k++) si[k] = B2H_LDG(m.ten_solimp[t][k]);
+        row_params(sr, si, ten_pos[t], B2H_LDG(m.ten_margin[t]), B2H_LDG(m.ten_invw[t]), vel, T(1), &rD[s], &raref[s]);
+      } else {
+        uint32_t info = S.con_info[rc];
+        int cls = info >> 16;
+        T sr[2] = {B2H_LDG(m.cls_solref[cls][0]), B2H_LDG(m.cls_solref[cls][1])}, si[5];
+        for (int k = 0; k < 5; k++) si[k] = B2H_LDG(m.cls_solimp[cls][k]);
+        T tran = B2H_LDG(m.body_invw[info & 255]) + B2H_LDG(m.body_invw[(info >> 8) & 255]);
+        T mu = B2H_LDG(m.cls_mu[cls]);
+        bool pyr = B2H_LDG(m.cls_condim[cls]) != 1;
+        // mj_diagApprox: tran (frictionless) or tran + mu^2 tran; pyramidal rows share Rpy = 2 mu^2 R
+        row_params(sr, si, S.con_dist[rc], B2H_LDG(m.cls_incmargin[cls]), pyr ? tran + mu * mu * tran : tran, vel,
+                   pyr ? T(2) * mu * mu : T(1), &rD[s], &raref[s]);
+      }
+    }
+  }
+  T lsign = 0, lD = 0, laref = 0;  // joint limit of this lane's dof: row = lsign * e_dof
+  {
+    int qa = lane < nv ? B2H_LDG(m.dof_qadr[lane]) : 0;
+    T q = shfl(st.qp, qa);
+    if (lane < nv && B2H_LDG(m.dof_limited[lane])) {
+      T lo = B2H_LDG(m.dof_lo[lane]), hi = B2H_LDG(m.dof_hi[lane]), mg = B2H_LDG(m.dof_margin[lane]), pos = 0;
+      if (q - lo < mg) { lsign = 1; pos = q - lo; }
+      else if (hi - q < mg) { lsign = -1; pos = hi - q; }
+      if (lsign != T(0)) {
+        T sr[2] = {B2H_LDG(m.dof_solref[lane][0]), B2H_LDG(m.dof_solref[lane][1])}, si[5];
+        for (int k = 0; k < 5; k++) si[k] = B2H_LDG(m.dof_solimp[lane][k]);
+        row_params(sr, si, pos, mg, B2H_LDG(m.dof_invw[lane]), lsign * st.qv, T(1), &lD, &laref);
+      }
+    }
+  }
+  const unsigned limit_mask = ballot(lsign != T(0));
+  const int nefc = nrow + popc(limit_mask);
+
+  // =============================================================== velocity stage
+  // ---- mj_comVel as sums over ancestor chains: vprev[d] = sum of cdof*qvel over the dofs before d
+  if (lane < KV) for (int k = 0; k < 6; k++) tmp[TMP_DOFW + 6 * lane + k] = cd[k] * (lane < nv ? st.qv : T(0));
+  wsync();
+  T cdd[6] = {0, 0, 0, 0, 0, 0};
+  T vprev[6] = {0, 0, 0, 0, 0, 0};
+  if (lane < nv) {
+    for (int j = B2H_LDG(m.dof_vparent[lane]); j >= 0; j = B2H_LDG(m.dof_parent[j]))
+      for (int k = 0; k < 6; k++) vprev[k] += tmp[TMP_DOFW + 6 * j + k];
+    if (!B2H_LDG(m.dof_cdotzero[lane])) cross_motion(cdd, vprev, cd);
+  }
+  if (lane < KV) for (int k = 0; k < 6; k++) { S.cdofdot[6 * lane + k] = cdd[k]; tmp[TMP_DOFA + 6 * lane + k] = cdd[k] * (lane < nv ? st.qv : T(0)); }
+  wsync();
+  // ---- cvel, cacc (lane = body) as chain sums; cfrc_body = I cacc + cvel x* (I cvel)   (mj_rne, flg_acc = 0)
+  if (lane > 0 && lane < nbody) {
+    T cv[6] = {0, 0, 0, 0, 0, 0}, ca[6] = {0, 0, 0, 0, 0, 0};
+    uint32_t mask = B2H_LDG(m.body_dofmask[lane]);
+    for (int j = 0; j < nv; j++)
+      if ((mask >> j) & 1u)
+        for (int k = 0; k < 6; k++) { cv[k] += tmp[TMP_DOFW + 6 * j + k]; ca[k] += tmp[TMP_DOFA + 6 * j + k]; }
+    for (int k = 0; k < 3; k++) ca[3 + k] -= B2H_LDG(m.gravity[k]);
+    for (int k = 0; k < 6; k++) S.cvel[6 * lane + k] = cv[k];
+    T f[6], t1[6], t2[6];
+    mul_inert_vec(f, S.cinert + 10 * lane, ca);
+    mul_inert_vec(t1, S.cinert + 10 * lane, cv);
+    cross_force(t2, cv, t1);
+    for (int k = 0; k < 6; k++) tmp[TMP_CFRC + 6 * lane + k] = f[k] + t2[k];
+  }
+  wsync();
+  // ---- qfrc_bias[d] = cdof[d] . sum of cfrc over the subtree of the dof's body
+  T qfrc_bias = 0;
+  if (lane < nv) {
+    int end = B2H_LDG(m.body_subend[my_dbody]);
+    T f[6] = {0, 0, 0, 0, 0, 0};
+    for (int b = my_dbody; b < end; b++)
+      for (int k = 0; k < 6; k++) f[k] += tmp[TMP_CFRC + 6 * b + k];
+    qfrc_bias = cd[0] * f[0] + cd[1] * f[1] + cd[2] * f[2] + cd[3] * f[3] + cd[4] * f[4] + cd[5] * f[5];
+  }
+  // ---- mj_passive (joint springs, dampers), mj_fwdActuation (motors: gain 1, ctrl clamp, gear)
+  T qfrc_smooth = 0;
+  {
+    int qa = lane < nv ? B2H_LDG(m.dof_qadr[lane]) : 0;
+    T q = shfl(st.qp, qa);
+    if (lane < nv) {
+      T passive = -B2H_LDG(m.dof_damping[lane]) * st.qv - B2H_LDG(m.dof_stiff[lane]) * (q - B2H_LDG(m.dof_qspring[lane]));
+      T act = 0;
+      if (B2H_LDG(m.dof_act[lane]) >= 0) {
+        T c = st.ctrl;
+        if (B2H_LDG(m.act_limited[lane])) c = clampT(c, B2H_LDG(m.act_lo[lane]), B2H_LDG(m.act_hi[lane]));
+        act = B2H_LDG(m.act_gear[lane]) * c;
+      }
+      st.qfrc_act = act;
+      qfrc_smooth = passive - qfrc_bias + act;
+    } else st.qfrc_act = 0;
+  }
+  wsync();  // stage scratch in A is dead from here
+
+  // =============================================================== acceleration: qacc_smooth = M^-1 qfrc_smooth
+  for (int i = lane; i < LD * LD; i += 32) S.A[i] = S.M[i];
+  wsync();
+  chol_factor(S.A, nv, lane);
+  T qacc_smooth = chol_solve(S.A, nv, lane, qfrc_smooth);
+  wsync();
+
+  // =============================================================== mj_fwdConstraint: Newton solver (primal)
+  T qacc = qacc_smooth, qfrc_con = 0;
+  int niter = 0;
+  if (nefc > 0) {
+    // J*x - aref for the dense rows of this lane and its limit row; x is read from S.vec[2]
+    auto jar_of = [&](T x_lane, T* jar, T* ljar) {
+      wsync();
+      S.vec[2][lane] = lane < nv ? x_lane : T(0);
+      wsync();
+      B2H_SLOTS(s) {
+        int r = lane + 32 * s;
+        T a = 0;
+        if (r < nrow) {
+          const T* jr = S.J + r * LD;
+#pragma unroll
+          for (int c4 = 0; c4 < LD; c4 += 4) {
+            V4<T> u = ld4(jr + c4), w = ld4(S.vec[2] + c4);
+            a += u.x * w.x + u.y * w.y + u.z * w.z + u.w * w.w;
+          }
+        }
+        jar[s] = a;
+      }
+      *ljar = lsign * x_lane;
+    };
+    auto row_cost = [&](const T* jar, T ljar) {  // sum of 0.5 D r^2 over rows with r < 0
+      T c = 0;
+      B2H_SLOTS(s) { T r = jar[s] - raref[s]; if (lane + 32 * s < nrow && r < T(0)) c += T(0.5) * rD[s] * r * r; }
+      T r = ljar - laref;
+      if (lsign != T(0) && r < T(0)) c += T(0.5) * lD * r * r;
+      return wsum(c);
+    };
+    // ---- warmstart(): the cheaper of qacc_warmstart and qacc_smooth
+    T jar[2], ljar;
+    jar_of(st.warm, jar, &ljar);
+    T cost_warm = row_cost(jar, ljar);
+    T Ma = mat_vec(S.M, S.vec[2], nv, lane);
+    cost_warm += wsum(lane < nv ? T(0.5) * (Ma - qfrc_smooth) * (st.warm - qacc_smooth) : T(0));
+    jar_of(qacc_smooth, jar, &ljar);
+    T cost_smooth = row_cost(jar, ljar);
+    if (cost_warm > cost_smooth) qacc = qacc_smooth;
+    else { qacc = st.warm; }
+    // ---- mj_solPrimal (Newton): state at the starting point
+    T Jaref[2], lJaref;
+    jar_of(qacc, jar, &ljar);
+    for (int s = 0; s < 2; s++) Jaref[s] = jar[s] - raref[s];
+    lJaref = ljar - laref;
+    Ma = mat_vec(S.M, S.vec[2], nv, lane);
+    const T scale = T(1) / (B2H_LDG(m.meaninertia) * T(nv > 1 ? nv : 1));
+    const T tolerance = T(1e-8), ls_tolerance = T(0.01);
+    const int ls_iterations = 50;
+    T cost = 0, gauss = 0, grad = 0, search = 0;
+    bool first = true;
+    for (;;) {
+      // -- PrimalUpdateConstraint: active rows, forces, cost
+      unsigned act0, act1 = 0, actl;
+      T f[2] = {0, 0}, lf = 0, c = 0;
+      B2H_SLOTS(s) {
+        bool on = lane + 32 * s < nrow && Jaref[s] < T(0);
+        if (on) { f[s] = -rD[s] * Jaref[s]; c += T(0.5) * rD[s] * Jaref[s] * Jaref[s]; }
+        if (s == 0) act0 = ballot(on); else act1 = ballot(on);
+      }
+      {
+        bool on = lsign != T(0) && lJaref < T(0);
+        if (on) { lf = -lD * lJaref; c += T(0.5) * lD * lJaref * lJaref; }
+        actl = ballot(on);
+      }
+      T oldcost = cost;
+      gauss = wsum(lane < nv ? T(0.5) * (Ma - qfrc_smooth) * (qacc - qacc_smooth) : T(0));
+      cost = wsum(c) + gauss;
+      // qfrc_constraint = J^T f (dense active rows) + limit force
+      qfrc_con = lsign * lf;
+      B2H_SLOTS(s) {
+        unsigned am = s == 0 ? act0 : act1;
+        while (am) {
+          int b = ffs32(am) - 1;
+          am &= am - 1;
+          T fr = shfl(f[s], b);
+          if (lane < nv) qfrc_con += S.J[(b + 32 * s) * LD + lane] * fr;
+        }
+      }
+      if (!first) {
+        T improvement = scale * (oldcost - cost);
+        T gn = m_sqrt(wsum(lane < nv ? (Ma - qfrc_smooth - qfrc_con) * (Ma - qfrc_smooth - qfrc_con) : T(0)));
+        niter++;
+        if (improvement < m_max(tolerance, Tol<T>::cost_rel * scale * m_abs(cost)) || scale * gn < tolerance) break;
+        if (niter >= Tol<T>::maxiter) { cnt.iter_cap++; break; }
+      }
+      first = false;
+      // -- Hessian H = M + J^T diag(D active) J, built per column (lane j owns column j), then factored
+      {
+        T acc[LD];
+#pragma unroll
+        for (int i = 0; i < LD; i++) acc[i] = S.M[i * LD + (lane < LD ? lane : 0)];
+        B2H_SLOTS(s) {
+          unsigned am = s == 0 ? act0 : act1;
+          while (am) {
+            int b = ffs32(am) - 1;
+            am &= am - 1;
+            const T* jr = S.J + (b + 32 * s) * LD;
+            T t = shfl(rD[s], b) * jr[lane < LD ? lane : 0];
+#pragma unroll
+            for (int c4 = 0; c4 < LD; c4 += 4) {
+              V4<T> u = ld4(jr + c4);
+              acc[c4] += u.x * t; acc[c4 + 1] += u.y * t; acc[c4 + 2] += u.z * t; acc[c4 + 3] += u.w * t;
+            }
+          }
+        }
+        wsync();
+        if (lane < LD) {
+#pragma unroll
+          for (int i = 0; i < LD; i++) S.A[i * LD + lane] = acc[i];
+        }
+        wsync();
+        if ((actl >> lane) & 1u) S.A[lane * LD + lane] += lD;
+        wsync();
+        chol_factor(S.A, nv, lane);
+      }
+      // -- PrimalUpdateGradient + Newton direction
+      grad = lane < nv ? Ma - qfrc_smooth - qfrc_con : T(0);
+      search = -chol_solve(S.A, nv, lane, grad);
+      // -- PrimalSearch: exact line search on the piecewise-quadratic cost along `search`
+      T snorm = m_sqrt(wsum(lane < nv ? search * search : T(0)));
+      T alpha = 0;
+      T Jv[2] = {0, 0}, lJv = 0, Mv = 0;
+      if (snorm >= B2H_MINVAL) {
+        T gtol = tolerance * ls_tolerance * snorm / scale;
+        jar_of(search, Jv, &lJv);
+        Mv = mat_vec(S.M, S.vec[2], nv, lane);
+        T qg1 = wsum(lane < nv ? search * (Ma - qfrc_smooth) : T(0));
+        T qg2 = wsum(lane < nv ? T(0.5) * search * Mv : T(0));
+        T q0r[3] = {0, 0, 0}, q1r[3] = {0, 0, 0}, q2r[3] = {0, 0, 0};  // per-row quadratics (slots 0,1 + limit)
+        B2H_SLOTS(s) {
+          if (lane + 32 * s < nrow) {
+            q0r[s] = T(0.5) * rD[s] * Jaref[s] * Jaref[s]; q1r[s] = rD[s] * Jaref[s] * Jv[s]; q2r[s] = T(0.5) * rD[s] * Jv[s] * Jv[s];
+          }
+        }
+        if (lsign != T(0)) { q0r[2] = T(0.5) * lD * lJaref * lJaref; q1r[2] = lD * lJaref * lJv; q2r[2] = T(0.5) * lD * lJv * lJv; }
+        int lsiter = 0;
+        struct Pnt { T alpha, cost, d0, d1; };
+        auto eval = [&](T a) {
+          T s0 = 0, s1 = 0, s2 = 0;
+          B2H_SLOTS(s)
+            if (lane + 32 * s < nrow && Jaref[s] + a * Jv[s] < T(0)) { s0 += q0r[s]; s1 += q1r[s]; s2 += q2r[s]; }
+          if (lsign != T(0) && lJaref + a * lJv < T(0)) { s0 += q0r[2]; s1 += q1r[2]; s2 += q2r[2]; }
+          s0 = wsum(s0) + gauss; s1 = wsum(s1) + qg1; s2 = wsum(s2) + qg2;
+          Pnt p;
+          p.alpha = a; p.cost = a * a * s2 + a * s1 + s0; p.d0 = T(2) * a * s2 + s1; p.d1 = T(2) * s2;
+          if (p.d1 <= T(0)) p.d1 = B2H_MINVAL;
+          lsiter++;
+          return p;
+        };
+        Pnt p0 = eval(T(0));
+        gtol = m_max(gtol, Tol<T>::ls_rel * m_abs(p0.d0));
+        Pnt p1 = eval(p0.alpha - p0.d0 / p0.d1);
+        if (p0.cost < p1.cost) p1 = p0;
+        bool done = false;
+        if (m_abs(p1.d0) < gtol) { alpha = p1.alpha; done = true; }
+        if (!done) {
+          int dir = p1.d0 < T(0) ? 1 : -1;
+          bool p2update = false;
+          Pnt p2 = p1;
+          while (p1.d0 * T(dir) <= -gtol && lsiter < ls_iterations) {
+            p2 = p1; p2update = true;
+            p1 = eval(p1.alpha - p1.d0 / p1.d1);
+            if (m_abs(p1.d0) < gtol) { alpha = p1.alpha; done = true; break; }
+          }
+          if (!done && (lsiter >= ls_iterations || !p2update)) { alpha = p1.alpha; done = true; }
+          if (!done) {
+            Pnt p2next = p1;
+            Pnt p1next = eval(p1.alpha - p1.d0 / p1.d1);
+            while (lsiter < ls_iterations && !done) {
+              Pnt pmid = eval(T(0.5) * (p1.alpha + p2.alpha));
+              Pnt cand[3] = {p1next, p2next, pmid};
+              T bestcost = 0; int best = -1;
+              for (int i = 0; i < 3; i++)
+                if (m_abs(cand[i].d0) < gtol && (best == -1 || cand[i].cost < bestcost)) { bestcost = cand[i].cost; best = i; }
+              if (best >= 0) { alpha = cand[best].alpha; done = true; break; }
+              int b1 = 0, b2 = 0;
+              for (int i = 0; i < 3; i++) {
+                if (p1.d0 < T(0) && cand[i].d0 < T(0) && p1.d0 < cand[i].d0) { p1 = cand[i]; b1 = 1; }
+                else if (p1.d0 > T(0) && cand[i].d0 > T(0) && p1.d0 > cand[i].d0) { p1 = cand[i]; b1 = 1; }
+              }
+              if (b1) p1next = eval(p1.alpha - p1.d0 / p1.d1);
+              for (int i = 0; i < 3; i++) {
+                if (p2.d0 < T(0) && cand[i].d0 < T(0) && p2.d0 < cand[i].d0) { p2 = cand[i]; b2 = 1; }
+                else if (p2.d0 > T(0) && cand[i].d0 > T(0) && p2.d0 > cand[i].d0) { p2 = cand[i]; b2 = 1; }
+              }
+              if (b2) p2next = eval(p2.alpha - p2.d0 / p2.d1);
+              if (!b1 && !b2) { alpha = pmid.cost < p0.cost ? pmid.alpha : T(0); done = true; }
+            }
+            if (!done) {
+              if (p1.cost <= p2.cost && p1.cost < p0.cost) alpha = p1.alpha;
+              else if (p2.cost <= p1.cost && p2.cost < p0.cost) alpha = p2.alpha;
+              else alpha = 0;
+            }
+          }
+        }
+        cnt.ls_eval += lsiter;
+      }
+      if (alpha == T(0)) break;
+      qacc += alpha * search; Ma += alpha * Mv;
+      for (int s = 0; s < 2; s++) Jaref[s] += alpha * Jv[s];
+      lJaref += alpha * lJv;
+    }
+    cnt.newton_iter += niter;
+    st.warm = qacc;
+  } else {
+    st.warm = qacc_smooth;
+  }
+  if (stats) { stats->ncon = ncon; stats->nrow = nrow; stats->nlimit = popc(limit_mask); stats->niter = niter; }
+  if (dbg_lane) {
+    dbg_lane[0] = qfrc_bias; dbg_lane[1] = qfrc_smooth; dbg_lane[2] = qacc_smooth; dbg_lane[3] = qacc;
+    dbg_lane[4] = qfrc_con; dbg_lane[5] = st.qfrc_act; dbg_lane[6] = lsign * lD; dbg_lane[7] = laref;
+  }
+  if (qacc_out) *qacc_out = qacc;
+  if (!integrate) return false;
+
+  // ---- mj_checkAcc: MuJoCo resets mjData and re-runs mj_forward before integrating
+  if (ballot(lane < nv && is_bad(qacc))) {
+    st.qp = lane < nq ? B2H_LDG(m.qpos0[lane]) : T(0);
+    st.qv = 0; st.warm = 0; st.ctrl = 0; st.nstep = 0;
+    cnt.bad_state++;
+    return true;
+  }
+
+  // =============================================================== mj_Euler (implicit joint damping) + mj_advance
+  wsync();
+  for (int i = lane; i < LD * LD; i += 32) S.A[i] = S.M[i];
+  wsync();
+  if (lane < nv) S.A[lane * LD + lane] += h * B2H_LDG(m.dof_damping[lane]);
+  wsync();
+  chol_factor(S.A, nv, lane);
+  T qacc_e = chol_solve(S.A, nv, lane, qfrc_smooth + qfrc_con);
+  if (lane < nv) st.qv += h * qacc_e;
+  {  // mj_integratePos: hinges and root position by lanes, root quaternion (lanes 3..6) via mju_quatIntegrate
+    int dsrc = lane < nq ? B2H_LDG(m.qpos_dof[lane]) : -1;
+    bool has_free = B2H_LDG(m.jnt_type[0]) == B2H_JNT_FREE;
+    T v = shfl(st.qv, dsrc >= 0 ? dsrc : (lane < 3 ? lane : 0));
+    T w[3], q[4];
+    for (int k = 0; k < 3; k++) w[k] = shfl(st.qv, 3 + k);
+    for (int k = 0; k < 4; k++) q[k] = shfl(st.qp, 3 + k);
+    if (dsrc >= 0) st.qp += h * v;
+    else if (has_free && lane < 3) st.qp += h * v;
+    else if (has_free && lane < 7) {
+      T ang = h * normalize3(w), qr[4], s, c;
+      m_sincos(ang * T(0.5), &s, &c);
+      if (ang == T(0)) { s = 0; c = 1; }
+      qr[0] = c; qr[1] = w[0] * s; qr[2] = w[1] * s; qr[3] = w[2] * s;
+      normalize4(q);
+      T out[4];
+      mul_quat(out, q, qr);
+      st.qp = out[lane - 3];
+    }
+  }
+  st.nstep++;
+  cnt.physics_steps++;
+  wsync();
+  return false;
+}
+template <typename T>
+B2H_DEV void mj_step(const DevModel<T>& m, Scratch<T>& S, EnvState<T>& st, Counters& cnt) {
+  for (int tries = 0; tries < 2; tries++)
+    if (!physics_step<T>(m, S, st, cnt, true, nullptr, nullptr, nullptr)) break;
+}
+
+// ------------------------------------------------------------------------------------------------ env layer
+// counter-based reset noise: Philox4x32-10 keyed by the seed, counter = (global env id, episode, lane)
+B2H_DEV void philox4x32(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+B2H_DEV double u53(uint32_t hi, uint32_t lo) {  // uniform double in [0,1) from 53 random bits
+  return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct EnvParams {
+  int frame_skip, reward_type, obs_mode, max_steps;
+  double duration, timestep;
+  double kneel[9];
+  uint64_t seed;
+  int env_id_offset;
+};
+
+template <typename T> B2H_DEV void quat_to_euler(const T* q, T* roll, T* pitch) {  // utils.py:3-20 (pitch unclamped)
+  T w = q[0], x = q[1], y = q[2], z = q[3];
+  *roll = m_atan2(T(2) * (w * x + y * z), T(1) - T(2) * (x * x + y * y));
+  *pitch = m_asin(T(2) * (w * y - z * x));
+}
+
+// reward_functions.py: stand (:156-211), kneeling (:66-154), walk (:213-261); cfrc_ext and subtree_linvel are
+// identically zero in the reference (no sensors), so the foot / com-velocity terms are the constants below.
+template <typename T>
+B2H_DEV T compute_reward(const DevModel<T>& m, const Scratch<T>& S, const EnvState<T>& st, const EnvParams& P, int lane) {
+  const int nv = B2H_LDG(m.nv);
+  T hgt = shfl(st.qp, 2), vx = shfl(st.qv, 0), q[4], roll, pitch;
+  for (int k = 0; k < 4; k++) q[k] = shfl(st.qp, 3 + k);
+  T ctrl2 = wsum(lane < nv ? st.ctrl * st.ctrl : T(0));
+  T power = wsum(lane >= 6 && lane < nv ? (st.qfrc_act * st.qv) * (st.qfrc_act * st.qv) : T(0));
+  quat_to_euler(q, &roll, &pitch);
+  if (P.reward_type == B2H_REWARD_STAND) {
+    if (hgt < T(0.8)) return T(0);
+    T vr = m_exp(T(-2) * (vx - T(1)) * (vx - T(1)));
+    T hr = m_exp(T(-2) * (hgt - T(1.282)) * (hgt - T(1.282)));
+    T orr = m_exp(T(-3) * (roll * roll + pitch * pitch));
+    T foot = T(1) - m_min(T(0), T(0)) / (T(0) + T(0) + T(1e-8));
+    return T(0.4) * vr + T(0.3) * (T(0.5) * hr + T(0.5) * orr) + T(0.2) * foot + T(0.1) * m_exp(T(-0.05) * ctrl2);
+  }
+  if (P.reward_type == B2H_REWARD_WALK) {
+    if (hgt < T(0.8)) return T(0.1) * hgt / T(0.8);
+    T vr = m_exp(T(-0.5) * (vx - T(10)) * (vx - T(10)));
+    T hr = m_exp(T(-2) * (hgt - T(1.282)) * (hgt - T(1.282)));
+    T orr = m_exp(T(-3) * (roll * roll + pitch * pitch));
+    return vr + (T(0.5) * hr + T(0.5) * orr) * m_exp(T(-0.05) * ctrl2);
+  }
+  const T th = T(P.kneel[0]), minh = T(P.kneel[1]), mrp = T(P.kneel[2]), crad = T(P.kneel[3]);
+  if (hgt < minh) return hgt * hgt;
+  T oerr = (roll * roll + pitch * pitch) / (mrp * mrp);
+  T posture = T(0.7) * m_exp(T(-5) * oerr) + T(0.3) * m_exp(T(-5) * (hgt - th) * (hgt - th));
+  T dist = m_sqrt(S.com[0] * S.com[0] + S.com[1] * S.com[1]);
+  T com_score = T(0.7) * m_exp(T(-10) * (dist / crad)) + T(0.3) * m_exp(T(-0.1) * T(0));
+  T foot_balance = m_min(T(0), T(0)) / (T(0) + T(0) + T(1e-8));
+  T energy = m_exp(T(-0.01) * power);
+  T alive = T(1) - m_exp(T(-0.5) * T((double)st.nstep * P.timestep));
+  return T(P.kneel[5]) * posture + T(P.kneel[6]) * com_score + T(P.kneel[7]) * foot_balance + T(P.kneel[4]) * energy +
+         T(P.kneel[8]) * alive;
+}
+
+// custom_env.py:242-256: qpos[2:] | qvel | cinert | cvel | qfrc_actuator  (B2H_OBS_QPOS_QVEL = first two blocks)
+template <typename T>
+B2H_DEV void write_obs(const DevModel<T>& m, const Scratch<T>& S, const EnvState<T>& st, int obs_mode, T* obs, int lane) {
+  const int nq = B2H_LDG(m.nq), nv = B2H_LDG(m.nv), nbody = B2H_LDG(m.nbody);
+  if (lane >= 2 && lane < nq) obs[lane - 2] = st.qp;
+  if (lane < nv) obs[nq - 2 + lane] = st.qv;
+  if (obs_mode == B2H_OBS_QPOS_QVEL) return;
+  int o = nq - 2 + nv;
+  for (int i = lane; i < 10 * nbody; i += 32) obs[o + i] = S.cinert[i];
+  o += 10 * nbody;
+  for (int i = lane; i < 6 * nbody; i += 32) obs[o + i] = S.cvel[i];
+  o += 6 * nbody;
+  if (lane < nv) obs[o + lane] = st.qfrc_act;
+}
+
+template <typename T>
+struct EnvIO {  // device arrays, all [n_envs, dim] row-major
+  T *qpos, *qvel, *warm;
+  int *nstep, *step_count, *episode;
+  T* total_reward;
+  double* reset_noise;      // [n_envs, nq+nv] noise of the most recent reset (and injected noise for the next one)
+  uint8_t* noise_injected;  // 1: take reset_noise[e] as is for the next reset (parity hook)
+  const float* actions;     // [n_envs, nu]
+  T *obs, *reward, *terminal_obs;
+  uint8_t *terminated, *truncated;
+  int obs_dim;
+};
+
+// HumanoidEnv.reset (custom_env.py:97-150): qpos0 + masked U(-0.01,0.01) noise, one settle step with ctrl = 0
+template <typename T>
+B2H_DEV void env_reset(const DevModel<T>& m, Scratch<T>& S, EnvState<T>& st, Counters& cnt, const EnvParams& P,
+                       const EnvIO<T>& io, int env, int lane) {
+  const int nq = B2H_LDG(m.nq), nv = B2H_LDG(m.nv);
+  const int nqv = nq + nv;
+  double npos = 0, nvel = 0;
+  if (io.noise_injected[env]) {
+    if (lane < nq) npos = io.reset_noise[(size_t)env * nqv + lane];
+    if (lane < nv) nvel = io.reset_noise[(size_t)env * nqv + nq + lane];
+  } else {
+    uint32_t c[4] = {(uint32_t)(env + P.env_id_offset), (uint32_t)io.episode[env], (uint32_t)lane, 0x6232683Fu};
+    philox4x32(c, (uint32_t)P.seed, (uint32_t)(P.seed >> 32));
+    npos = -0.01 + 0.02 * u53(c[0], c[1]);
+    nvel = -0.01 + 0.02 * u53(c[2], c[3]);
+    if (lane < nq) io.reset_noise[(size_t)env * nqv + lane] = npos;
+    if (lane < nv) io.reset_noise[(size_t)env * nqv + nq + lane] = nvel;
+  }
+  wsync();
+  if (lane == 0) { io.noise_injected[env] = 0; io.episode[env] += 1; }
+  if (lane == 2) npos *= 0.1;
+  if (lane >= 3 && lane < 7) npos = 0;
+  double q0 = lane < nq ? (double)B2H_LDG(m.qpos0[lane]) : 0.0;
+  if (lane == 2) q0 = 1.282;                       // init_qpos, custom_env.py:58-61
+  if (lane >= 3 && lane < 7) q0 = lane == 3 ? 1.0 : 0.0;
+  st.qp = lane < nq ? T(q0 + npos) : T(0);
+  st.qv = lane < nv ? T(nvel) : T(0);
+  st.warm = 0; st.ctrl = 0; st.qfrc_act = 0; st.nstep = 0;
+  mj_step<T>(m, S, st, cnt);
+}
+
+// HumanoidEnv.step + SubprocVecEnv auto-reset for one env (custom_env.py:152-230; SB3 subproc_vec_env._worker)
+template <typename T>
+B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, Counters& cnt, const EnvParams& P, const EnvIO<T>& io, int env) {
+  const int lane = lane_id();
+  const int nq = B2H_LDG(m.nq), nv = B2H_LDG(m.nv), nu = B2H_LDG(m.nu);
+  EnvState<T> st;
+  st.qp = lane < nq ? io.qpos[(size_t)env * nq + lane] : T(0);
+  st.qv = lane < nv ? io.qvel[(size_t)env * nv + lane] : T(0);
+  st.warm = lane < nv ? io.warm[(size_t)env * nv + lane] : T(0);
+  st.nstep = io.nstep[env];
+  st.qfrc_act = 0;
+  int a = lane < nv ? B2H_LDG(m.dof_act[lane]) : -1;
+  st.ctrl = a >= 0 ? T(io.actions[(size_t)env * nu + a]) : T(0);
+  int step_count = io.step_count[env] + 1;
+  for (int s = 0; s < P.frame_skip; s++) {
+    // data.ctrl[:] = action before every mj_step (a bad-state reset inside the previous sub-step zeroed it)
+    st.ctrl = a >= 0 ? T(io.actions[(size_t)env * nu + a]) : T(0);
+    mj_step<T>(m, S, st, cnt);
+  }
+  T* obs = io.obs + (size_t)env * io.obs_dim;
+  bool truncated = step_count >= P.max_steps;
+  T reward = truncated ? T(0) : compute_reward<T>(m, S, st, P, lane);
+  // terminated = data.time >= duration, with time = nstep * timestep evaluated in double
+  bool terminated = (double)st.nstep * P.timestep >= P.duration;
+  T total = io.total_reward[env] + reward;
+  if (lane == 0) { io.reward[env] = reward; io.terminated[env] = terminated; io.truncated[env] = truncated; }
+  if (terminated || truncated) {
+    if (io.terminal_obs) write_obs<T>(m, S, st, P.obs_mode, io.terminal_obs + (size_t)env * io.obs_dim, lane);
+    env_reset<T>(m, S, st, cnt, P, io, env, lane);
+    step_count = 0; total = 0;
+  }
+  write_obs<T>(m, S, st, P.obs_mode, obs, lane);
+  if (lane < nq) io.qpos[(size_t)env * nq + lane] = st.qp;
+  if (lane < nv) { io.qvel[(size_t)env * nv + lane] = st.qv; io.warm[(size_t)env * nv + lane] = st.warm; }
+  if (lane == 0) { io.nstep[env] = st.nstep; io.step_count[env] = step_count; io.total_reward[env] = total; }
+}
+
+// reset path on its own (b2h_reset): reset env, write the first observation
+template <typename T>
+B2H_DEV void env_reset_only(const DevModel<T>& m, Scratch<T>& S, Counters& cnt, const EnvParams& P, const EnvIO<T>& io, int env) {
+  const int lane = lane_id();
+  const int nq = B2H_LDG(m.nq), nv = B2H_LDG(m.nv);
+  EnvState<T> st;
+  env_reset<T>(m, S, st, cnt, P, io, env, lane);
+  if (io.obs) write_obs<T>(m, S, st, P.obs_mode, io.obs + (size_t)env * io.obs_dim, lane);
+  if (lane < nq) io.qpos[(size_t)env * nq + lane] = st.qp;
+  if (lane < nv) { io.qvel[(size_t)env * nv + lane] = st.qv; io.warm[(size_t)env * nv + lane] = st.warm; }
+  if (lane == 0) { io.nstep[env] = st.nstep; io.step_count[env] = 0; io.total_reward[env] = 0; }
+}
+
+}  // namespace b2h

@@ -1,0 +1,90 @@
+"""ctypes driver of the TEST-ONLY lane emulation (tests/emu/b2h_emu.cpp): runs the kernel source on the CPU.
+
+Not importable from the package; used by the `not gpu` tests to check the warp-level kernel logic against
+the fp64 oracle without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+SRC = HERE / "emu" / "b2h_emu.cpp"
+LIB = HERE / "emu" / "_build" / "libb2h_emu.so"
+CSRC = HERE.parent / "mujocoposelearning_b200" / "csrc"
+_lib = None
+
+
+def build(force=False):
+    deps = [SRC] + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "b2h.h"]
+    if force or not LIB.exists() or LIB.stat().st_mtime < max(p.stat().st_mtime for p in deps):
+        LIB.parent.mkdir(exist_ok=True)
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", str(LIB), str(SRC),
+                        "-lpthread"], check=True, capture_output=True)
+    return LIB
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(str(LIB))
+        _lib.emu_run_any.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class EmuBatch:
+    """State of n envs advanced by the emulated kernels (host arrays in double, like b2h_get_state)."""
+
+    def __init__(self, model_struct, cfg, nq, nv, nu):
+        self.model, self.cfg = model_struct, cfg
+        self.n, self.nq, self.nv, self.nu = cfg.n_envs, nq, nv, nu
+        self.f64 = int(cfg.dtype == 1)
+        n = self.n
+        self.qpos, self.qvel, self.warm = np.zeros((n, nq)), np.zeros((n, nv)), np.zeros((n, nv))
+        self.nstep, self.step_count, self.episode = (np.zeros(n, np.int32) for _ in range(3))
+        self.total_reward = np.zeros(n)
+        self.reset_noise = np.zeros((n, nq + nv))
+        self.noise_injected = np.zeros(n, np.uint8)
+        self.counters = np.zeros(8, np.uint64)
+        self.obs_dim = (nq - 2 + nv) if cfg.obs_mode == 1 else (nq - 2 + nv + 16 * model_struct.nbody + nv)
+
+    def _run(self, mode, actions=None, dump_env=0, what=b"", dump=None):
+        n = self.n
+        obs, tobs = np.zeros((n, self.obs_dim)), np.zeros((n, self.obs_dim))
+        rew = np.zeros(n)
+        term, trunc = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
+        a = None if actions is None else np.ascontiguousarray(actions, np.float32).reshape(n, self.nu)
+        rc = lib().emu_run_any(self.f64, mode, C.byref(self.model), C.byref(self.cfg), _p(self.qpos), _p(self.qvel),
+                               _p(self.warm), _p(self.nstep), _p(self.step_count), _p(self.episode), _p(self.total_reward),
+                               _p(self.reset_noise), _p(self.noise_injected), _p(a), _p(obs), _p(rew), _p(tobs), _p(term),
+                               _p(trunc), _p(self.counters), dump_env, what, _p(dump), 0 if dump is None else dump.size)
+        return rc, obs, rew, term.astype(bool), trunc.astype(bool), tobs
+
+    def set_reset_noise(self, noise):
+        self.reset_noise[:] = np.asarray(noise).reshape(self.n, -1)
+        self.noise_injected[:] = 1
+
+    def reset(self):
+        rc, obs, *_ = self._run(1)
+        assert rc == 0
+        return obs
+
+    def step(self, actions):
+        rc, obs, rew, term, trunc, tobs = self._run(0, actions)
+        assert rc == 0
+        return obs, rew, term, trunc, tobs
+
+    def forward(self, what, env=0, actions=None, max_out=4096):
+        out = np.zeros(max_out)
+        rc, *_ = self._run(2, actions, env, what.encode(), out)
+        if rc < 0:
+            raise KeyError(f"{what}: {rc}")
+        return out[:rc].copy()

@@ -1,0 +1,293 @@
+#!/usr/bin/env python
+"""bench.py — humanoid physics env-steps/sec (BASELINE.json metric) on N B200s of one node.
+
+Workload (config.workload): BASELINE config 3 — random-action rollout, `stand` reward, frame_skip 3,
+duration 10 s, 4096 envs per GPU (weak scaling: every rank owns its own env range, no data-path collective).
+One "step" = one control step of all envs = frame_skip physics steps per env, through b2h_step.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--n-envs E] [--dtype f32|f64] [--impl reference]
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes through the
+public VecEnv.step (host numpy actions in, host numpy obs/reward/done out, pinned staging, copies inside the
+timed region); `cpu_baseline` times the CPU oracle port on the box's host cores on a bounded sample;
+`--impl reference` times that CPU path on all host threads as the reference arm.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "humanoid_physics_env_steps_per_sec"
+UNIT = "physics env-steps/s"
+FRAME_SKIP, DURATION, REWARD = 3, 10.0, "stand"
+# algorithmic HBM bytes and FP32 flops per physics step (obs 352, fused 3 sub-steps)
+BYTES_PER_PHYSICS_STEP = 724.0
+FLOP_PER_PHYSICS_STEP = 1.0e5
+FP32_NOMINAL_TFLOPS = 74.5
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--n-envs", type=int, default=4096, help="environments per GPU")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {"workload": f"random-action rollout, humanoid `stand`, {args.n_envs} envs/GPU, frame_skip {FRAME_SKIP}, duration {DURATION}s "
+                        f"(BASELINE config 3)", "n_envs_per_gpu": args.n_envs, "frame_skip": FRAME_SKIP, "obs_dim": 352,
+            "parallelism": f"env-sharded x{world} (no data-path collective)", "l2": "256 MiB device memset between timed steps (outside the event pairs)"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU (oracle) legs
+def cpu_rollout(n_envs, nthreads, budget_s, seed=0, min_steps=2):
+    """Times the CPU oracle port (SubprocVecEnv semantics, one pthread per core, no Python in the loop)."""
+    from mujocoposelearning_b200.abi import pack_model
+    from mujocoposelearning_b200.mjcf import compile_mjcf
+    from oracle.oracle import OracleVecEnv
+    cm = compile_mjcf()
+    env = OracleVecEnv(pack_model(cm), cm.nq, cm.nv, cm.nu, n_envs, frame_skip=FRAME_SKIP, duration=DURATION, reward_type=0,
+                       nthreads=nthreads)
+    rng = np.random.default_rng(seed)
+    env.reset(rng.uniform(-0.01, 0.01, (n_envs, cm.nq + cm.nv)))
+    noise = rng.uniform(-0.01, 0.01, (n_envs, cm.nq + cm.nv))
+    acts = rng.uniform(-1, 1, (8, n_envs, cm.nu)).astype(np.float32)
+    env.step(acts[0], noise)  # warm-up
+    steps, t0 = 0, time.perf_counter()
+    per_step = []
+    while True:
+        t1 = time.perf_counter()
+        env.step(acts[steps % 8], noise)
+        per_step.append(time.perf_counter() - t1)
+        steps += 1
+        if steps >= min_steps and time.perf_counter() - t0 >= budget_s:
+            break
+    dt = sum(per_step)
+    return n_envs * FRAME_SKIP * steps / dt, steps, dt
+
+
+def run_reference(args):
+    """Reference arm: the reference's CPU path (MuJoCo mj_step x frame_skip under SubprocVecEnv semantics).
+    mujoco / stable-baselines3 are not installable in this image, so this is the oracle port (kind: port)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_envs = args.n_envs
+    # bounded sample: time warm-up + K steps of the full env count if one step stays under ~2 s, else fewer envs
+    v, steps, dt = cpu_rollout(min(n_envs, 8 * cores), cores, 1.0)
+    est_step = n_envs * FRAME_SKIP / v
+    if est_step * (args.steps + args.warmup) > 150.0:
+        n_envs = max(cores, int(150.0 * v / (FRAME_SKIP * (args.steps + args.warmup))))
+    from mujocoposelearning_b200.abi import pack_model
+    from mujocoposelearning_b200.mjcf import compile_mjcf
+    from oracle.oracle import OracleVecEnv
+    cm = compile_mjcf()
+    env = OracleVecEnv(pack_model(cm), cm.nq, cm.nv, cm.nu, n_envs, frame_skip=FRAME_SKIP, duration=DURATION, reward_type=0, nthreads=cores)
+    rng = np.random.default_rng(0)
+    env.reset(rng.uniform(-0.01, 0.01, (n_envs, cm.nq + cm.nv)))
+    noise = rng.uniform(-0.01, 0.01, (n_envs, cm.nq + cm.nv))
+    acts = rng.uniform(-1, 1, (8, n_envs, cm.nu)).astype(np.float32)
+    for i in range(args.warmup):
+        env.step(acts[i % 8], noise)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        env.step(acts[i % 8], noise)
+    dt = time.perf_counter() - t0
+    value = n_envs * FRAME_SKIP * args.steps / dt
+    sample = f"{n_envs} envs x {args.steps} control steps x frame_skip {FRAME_SKIP} on {cores} host threads (oracle port of mj_step; mujoco wheel not installable)"
+    out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, 1),
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+            t = time.perf_counter()
+            while not self.rows and time.perf_counter() - t < 10.0:   # nvidia-smi takes a moment to start sampling
+                time.sleep(0.05)
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7 or not (t0 <= t <= t1 + 0.2):
+                continue
+            try:
+                sm.append(float(f[0])); smax = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------ B200 arm
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from mujocoposelearning_b200.vec_env import B200HumanoidVecEnv
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the CPU path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E, K, W = args.n_envs, args.steps, args.warmup
+    if W < 3:
+        W = 3
+    env_cfg = {"model_path": None, "duration": DURATION, "frame_skip": FRAME_SKIP, "reward_config": {"type": REWARD}}
+    batch = HumanoidBatch(E, frame_skip=FRAME_SKIP, duration=DURATION, reward_type=REWARD, dtype=args.dtype, device=local,
+                          seed=1234, env_id_offset=rank * E)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    pool = torch.rand(16, E, batch.nu, device=dev, generator=gen) * 2 - 1   # U(-1,1) actions resident in HBM
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    batch.reset()
+    for i in range(W):
+        batch.step(pool[i % 16])
+    torch.cuda.synchronize()
+    c0 = batch.counters()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()                      # evict L2 between timed steps (not inside the event pair)
+        starts[i].record()
+        batch.step(pool[(W + i) % 16])
+        stops[i].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t1 = time.perf_counter()
+    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
+    total_ms = float(step_ms.sum())
+    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    c1 = batch.counters()
+    # ---- e2e: the public VecEnv.step with host numpy actions / results (pinned staging, copies timed)
+    venv = B200HumanoidVecEnv(env_cfg, n_envs=E, device=local, dtype=args.dtype, seed=99, env_id_offset=rank * E, info_mode="lazy")
+    venv.reset()
+    host_actions = np.random.default_rng(rank).uniform(-1, 1, (8, E, batch.nu)).astype(np.float32)
+    for i in range(W):
+        venv.step(host_actions[i % 8])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    Ke = max(10, K // 2)
+    te0 = time.perf_counter()
+    for i in range(Ke):
+        obs, rew, dones, infos = venv.step(host_actions[i % 8])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - te0
+    esz = 8 if args.dtype == "f64" else 4
+    h2d = E * batch.nu * 4
+    d2h = E * (batch.obs_dim * esz + esz + 2)
+    # ---- reduce over ranks: max time
+    tt = torch.tensor([total_ms, e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    total_ms, e2e_s = float(tt[0]), float(tt[1])
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = world * E * FRAME_SKIP * K / (total_ms * 1e-3)
+    e2e_value = world * E * FRAME_SKIP * Ke / e2e_s
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    kernel_ms = total_ms / K                       # one kernel launch per step (max over ranks)
+    achieved_gbs = BYTES_PER_PHYSICS_STEP * E * FRAME_SKIP / (kernel_ms * 1e-3) / 1e9
+    fp32_tflops = FLOP_PER_PHYSICS_STEP * E * FRAME_SKIP / (kernel_ms * 1e-3) / 1e12
+    psteps = c1["physics_steps"] - c0["physics_steps"]
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": kernel_ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+        "config": workload_config(args, world),
+        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                     "traffic": None, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
+                     "note": "latency/issue-bound irregular FP32 work, not HBM-bound (SURVEY 8d); see fp32 block",
+                     "fp32": {"achieved_tflops": fp32_tflops, "nominal_peak_tflops": FP32_NOMINAL_TFLOPS,
+                              "frac": fp32_tflops / FP32_NOMINAL_TFLOPS, "flop_per_physics_step": FLOP_PER_PHYSICS_STEP}},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
+                "api": "B200HumanoidVecEnv.step (numpy in/out, lazy infos)"},
+        "gpu_launches": K, "clocks": clocks,
+        "solver": {"newton_iter_per_physics_step": (c1["newton_iter"] - c0["newton_iter"]) / max(1, psteps),
+                   "ls_eval_per_physics_step": (c1["ls_eval"] - c0["ls_eval"]) / max(1, psteps),
+                   "contact_overflow": c1["contact_overflow"], "iter_cap": c1["iter_cap"], "bad_state": c1["bad_state"]},
+        "launch": batch.launch_info(), "step_ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
+    }
+    if not args.no_cpu_baseline and world == 1:
+        cores = os.cpu_count() or 1
+        nenv = min(E, 8 * cores)
+        v, steps, dt = cpu_rollout(nenv, cores, args.cpu_seconds)
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                               "sample": f"{nenv} envs x {steps} control steps x frame_skip {FRAME_SKIP} in {dt:.1f}s, oracle port on {cores} threads"}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

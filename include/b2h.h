@@ -151,6 +151,12 @@ const char* b2h_last_error(void);
 int b2h_create(const B2HModel* model, const B2HConfig* cfg, B2HHandle** out);
 void b2h_destroy(B2HHandle* h);
 int b2h_obs_dim(const B2HHandle* h);
+/* Launch shape the step kernel uses on this device: CTAs, warps (= envs in flight) per CTA, dynamic smem. */
+int b2h_launch_info(const B2HHandle* h, int* grid, int* warps_per_cta, size_t* smem_bytes);
+
+/* Re-key the reset-noise stream (VecEnv.seed / Env.reset(seed=...), custom_env.py:99-100) and restart the
+ * per-env episode counters, so the following resets replay the same noise for the same seed. */
+int b2h_set_seed(B2HHandle* h, uint64_t seed);
 
 /* Reset every env whose mask_dev[i] != 0 (mask_dev == NULL: all).  Writes the first observation of the
  * new episode into obs_dev ([n_envs, obs_dim], float for B2H_F32, double for B2H_F64). */
@@ -193,13 +199,15 @@ int b2h_debug_forward(B2HHandle* h, const float* actions_dev, int env, const cha
 
 /* Counters since creation: [0] physics steps, [1] contact overflows (more than the kernel's contact
  * capacity were active; extras dropped), [2] solver iteration cap hits, [3] bad-state resets
- * (mj_checkPos/Vel/Acc equivalents), [4] total Newton iterations, [5] kernels launched. */
+ * (mj_checkPos/Vel/Acc equivalents), [4] total Newton iterations, [5] kernels launched, [6] line-search
+ * cost evaluations. */
 int b2h_get_counters(B2HHandle* h, uint64_t counters_host[8]);
 
 /* GAE reverse scan (SB3 2.3.2 RolloutBuffer.compute_returns_and_advantage).  All [T, E] float arrays,
- * E fastest; last_values [E]; last_dones uint8 [E]. */
+ * E fastest; last_values [E]; last_dones uint8 [E].  gamma / gae_lambda are Python floats in SB3: they are
+ * rounded to float32 the way numpy does (gamma, and the double product gamma*gae_lambda, once each). */
 int b2h_gae(const float* rewards_dev, const float* values_dev, const float* episode_starts_dev,
-            const float* last_values_dev, const uint8_t* last_dones_dev, float gamma, float gae_lambda,
+            const float* last_values_dev, const uint8_t* last_dones_dev, double gamma, double gae_lambda,
             int T, int E, float* advantages_dev, float* returns_dev, void* stream);
 
 #ifdef __cplusplus

@@ -1,0 +1,438 @@
+// b2h_api.cu — kernels + C-ABI (include/b2h.h) of the batched humanoid rollout library, sm_100a.
+//
+// Launch shape: persistent grid, one CTA per SM, one warp per environment in flight; every warp owns a
+// Scratch<T> slice of dynamic shared memory and pulls environment ids from a global work counter (per-env cost
+// varies with contact count and Newton iterations).  Per-env state is [n_envs, dim] row-major so a warp reads
+// and writes one contiguous record per field.
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "b2h_debug.h"
+
+using namespace b2h;
+
+// ------------------------------------------------------------------------------------------------ kernels
+// at most 10 env-warps fit the shared-memory budget (fp32), so each thread may use up to ~200 registers
+#define B2H_MAX_THREADS 320
+extern __shared__ __align__(16) unsigned char b2h_smem[];
+
+__device__ __forceinline__ void flush_counters(const Counters& c, unsigned long long* g) {
+  if (lane_id() == 0) {
+    if (c.physics_steps) atomicAdd(g + 0, c.physics_steps);
+    if (c.contact_overflow) atomicAdd(g + 1, c.contact_overflow);
+    if (c.iter_cap) atomicAdd(g + 2, c.iter_cap);
+    if (c.bad_state) atomicAdd(g + 3, c.bad_state);
+    if (c.newton_iter) atomicAdd(g + 4, c.newton_iter);
+    if (c.ls_eval) atomicAdd(g + 6, c.ls_eval);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(B2H_MAX_THREADS, 1)
+step_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, int n_envs, unsigned long long* counters,
+            int* work) {
+  Scratch<T>& S = reinterpret_cast<Scratch<T>*>(b2h_smem)[threadIdx.x >> 5];
+  Counters cnt = {0, 0, 0, 0, 0, 0};
+  for (;;) {
+    int env = 0;
+    if (lane_id() == 0) env = atomicAdd(work, 1);
+    env = __shfl_sync(0xffffffffu, env, 0);
+    if (env >= n_envs) break;
+    env_step<T>(*model, S, cnt, P, io, env);
+  }
+  flush_counters(cnt, counters);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(B2H_MAX_THREADS, 1)
+reset_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, int n_envs, const uint8_t* mask,
+             unsigned long long* counters, int* work) {
+  Scratch<T>& S = reinterpret_cast<Scratch<T>*>(b2h_smem)[threadIdx.x >> 5];
+  Counters cnt = {0, 0, 0, 0, 0, 0};
+  for (;;) {
+    int env = 0;
+    if (lane_id() == 0) env = atomicAdd(work, 1);
+    env = __shfl_sync(0xffffffffu, env, 0);
+    if (env >= n_envs) break;
+    if (mask && !mask[env]) continue;
+    env_reset_only<T>(*model, S, cnt, P, io, env);
+  }
+  flush_counters(cnt, counters);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32, 1)
+debug_kernel(const DevModel<T>* __restrict__ model, EnvIO<T> io, int env, DebugDump<T>* out) {
+  Scratch<T>& S = reinterpret_cast<Scratch<T>*>(b2h_smem)[0];
+  const int lane = lane_id(), nq = model->nq, nv = model->nv, nu = model->nu;
+  Counters cnt = {0, 0, 0, 0, 0, 0};
+  EnvState<T> st;
+  st.qp = lane < nq ? io.qpos[(size_t)env * nq + lane] : T(0);
+  st.qv = lane < nv ? io.qvel[(size_t)env * nv + lane] : T(0);
+  st.warm = lane < nv ? io.warm[(size_t)env * nv + lane] : T(0);
+  st.nstep = io.nstep[env];
+  st.qfrc_act = 0;
+  int a = lane < nv ? model->dof_act[lane] : -1;
+  st.ctrl = (a >= 0 && io.actions) ? T(io.actions[(size_t)env * nu + a]) : T(0);
+  T qacc, dl[8];
+  StepStats stats;
+  physics_step<T>(*model, S, st, cnt, false, &stats, &qacc, dl);
+  __syncwarp();
+  for (int k = 0; k < 8; k++) out->lane[lane][k] = dl[k];
+  if (lane == 0) out->stats = stats;
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&S);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(&out->S);
+  for (size_t i = lane; i < sizeof(Scratch<T>) / 4; i += 32) dst[i] = src[i];
+}
+
+// SB3 RolloutBuffer.compute_returns_and_advantage: one thread per env, reverse scan over T; [T, E] arrays, E fastest.
+// Explicit _rn intrinsics keep the rounding sequence of the numpy float32 expression (no FMA contraction).
+__global__ void gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
+                           const float* __restrict__ episode_starts, const float* __restrict__ last_values,
+                           const uint8_t* __restrict__ dones, float gamma, float gl, int T, int E,
+                           float* __restrict__ adv, float* __restrict__ ret) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  float last_gae = 0.0f;
+  float nnt = 1.0f - (float)dones[e], nv = last_values[e];
+  for (int t = T - 1; t >= 0; t--) {
+    size_t i = (size_t)t * E + e;
+    float v = values[i];
+    float delta = __fsub_rn(__fadd_rn(rewards[i], __fmul_rn(__fmul_rn(gamma, nv), nnt)), v);
+    last_gae = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, nnt), last_gae));
+    adv[i] = last_gae;
+    ret[i] = __fadd_rn(last_gae, v);
+    nnt = 1.0f - episode_starts[i];
+    nv = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(B2H_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_)); } while (0)
+
+struct B2HHandle {
+  B2HConfig cfg;
+  B2HModel model;
+  int nq, nv, nu, nbody, obs_dim, esz;  // esz = sizeof(T)
+  void* dmodel = nullptr;               // DevModel<T> on the device
+  void *qpos = nullptr, *qvel = nullptr, *warm = nullptr, *total_reward = nullptr;
+  int *nstep = nullptr, *step_count = nullptr, *episode = nullptr;
+  double* reset_noise = nullptr;
+  uint8_t* noise_injected = nullptr;
+  unsigned long long* counters = nullptr;
+  int* work = nullptr;
+  void* dump = nullptr;
+  // staging for the *_host entry points
+  float* actions_stage = nullptr;
+  void *obs_stage = nullptr, *tobs_stage = nullptr, *rew_stage = nullptr;
+  uint8_t *term_stage = nullptr, *trunc_stage = nullptr, *mask_stage = nullptr;
+  int grid = 0, warps = 0;
+  size_t smem = 0;
+  unsigned long long launches = 0;
+  EnvParams P;
+};
+
+template <typename T>
+static EnvIO<T> make_io(B2HHandle* h, const float* actions, void* obs, void* reward, uint8_t* term, uint8_t* trunc, void* tobs) {
+  EnvIO<T> io;
+  io.qpos = (T*)h->qpos; io.qvel = (T*)h->qvel; io.warm = (T*)h->warm; io.nstep = h->nstep; io.step_count = h->step_count;
+  io.episode = h->episode; io.total_reward = (T*)h->total_reward; io.reset_noise = h->reset_noise;
+  io.noise_injected = h->noise_injected; io.actions = actions; io.obs = (T*)obs; io.reward = (T*)reward;
+  io.terminal_obs = (T*)tobs; io.terminated = term; io.truncated = trunc; io.obs_dim = h->obs_dim;
+  return io;
+}
+
+template <typename T>
+static int create_typed(B2HHandle* h) {
+  std::vector<unsigned char> buf(sizeof(DevModel<T>));
+  DevModel<T>* dm = reinterpret_cast<DevModel<T>*>(buf.data());
+  std::string err = build_dev_model<T>(h->model, *dm);
+  if (!err.empty()) return fail(B2H_EUNSUPPORTED, err);
+  CU(cudaMalloc(&h->dmodel, sizeof(DevModel<T>)));
+  CU(cudaMemcpy(h->dmodel, dm, sizeof(DevModel<T>), cudaMemcpyHostToDevice));
+  CU(cudaMalloc(&h->dump, sizeof(DebugDump<T>)));
+  int dev = h->cfg.device, nsm = 0, max_smem = 0;
+  CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
+  CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  // leave L1 room for the model tables (read through the read-only path): cap the carve-out below the maximum
+  size_t budget = (size_t)max_smem > 200 * 1024 ? 195 * 1024 : (size_t)max_smem;
+  int warps = (int)(budget / sizeof(Scratch<T>));
+  if (warps > B2H_MAX_THREADS / 32) warps = B2H_MAX_THREADS / 32;
+  if (warps < 1) return fail(B2H_EUNSUPPORTED, "per-env scratch does not fit in shared memory");
+  h->warps = warps;
+  h->smem = (size_t)warps * sizeof(Scratch<T>);
+  h->grid = nsm;
+  CU(cudaFuncSetAttribute(step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  CU(cudaFuncSetAttribute(reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  CU(cudaFuncSetAttribute(debug_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Scratch<T>)));
+  return B2H_OK;
+}
+
+extern "C" {
+
+int b2h_abi_version(void) { return B2H_ABI_VERSION; }
+size_t b2h_sizeof_model(void) { return sizeof(B2HModel); }
+size_t b2h_sizeof_config(void) { return sizeof(B2HConfig); }
+const char* b2h_last_error(void) { return g_err.c_str(); }
+
+void b2h_destroy(B2HHandle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  void* ptrs[] = {h->dmodel, h->qpos, h->qvel, h->warm, h->total_reward, h->nstep, h->step_count, h->episode,
+                  h->reset_noise, h->noise_injected, h->counters, h->work, h->dump, h->actions_stage, h->obs_stage,
+                  h->tobs_stage, h->rew_stage, h->term_stage, h->trunc_stage, h->mask_stage};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete h;
+}
+
+int b2h_create(const B2HModel* model, const B2HConfig* cfg, B2HHandle** out) {
+  if (!model || !cfg || !out) return fail(B2H_EINVAL, "null argument");
+  if (cfg->n_envs <= 0 || cfg->frame_skip <= 0) return fail(B2H_EINVAL, "n_envs and frame_skip must be positive");
+  if (cfg->reward_type < 0 || cfg->reward_type > B2H_REWARD_WALK) return fail(B2H_EINVAL, "Unknown reward type");
+  if (cfg->obs_mode != B2H_OBS_FULL352 && cfg->obs_mode != B2H_OBS_QPOS_QVEL) return fail(B2H_EINVAL, "unknown obs_mode");
+  if (cfg->dtype != B2H_F32 && cfg->dtype != B2H_F64) return fail(B2H_EINVAL, "unknown dtype");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(B2H_ECUDA, "no CUDA device: this library has no CPU path");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(B2H_EINVAL, "bad device ordinal");
+  CU(cudaSetDevice(cfg->device));
+  B2HHandle* h = new B2HHandle();
+  h->cfg = *cfg; h->model = *model;
+  h->nq = model->nq; h->nv = model->nv; h->nu = model->nu; h->nbody = model->nbody;
+  h->obs_dim = cfg->obs_mode == B2H_OBS_QPOS_QVEL ? model->nq - 2 + model->nv : model->nq - 2 + model->nv + 16 * model->nbody + model->nv;
+  h->esz = cfg->dtype == B2H_F64 ? 8 : 4;
+  h->P.frame_skip = cfg->frame_skip; h->P.reward_type = cfg->reward_type; h->P.obs_mode = cfg->obs_mode;
+  h->P.max_steps = cfg->max_steps; h->P.duration = cfg->duration; h->P.timestep = model->timestep;
+  for (int k = 0; k < 9; k++) h->P.kneel[k] = cfg->kneeling_params[k];
+  h->P.seed = cfg->seed; h->P.env_id_offset = cfg->env_id_offset;
+  int rc = cfg->dtype == B2H_F64 ? create_typed<double>(h) : create_typed<float>(h);
+  if (rc != B2H_OK) { b2h_destroy(h); return rc; }
+  size_t E = (size_t)cfg->n_envs, esz = (size_t)h->esz;
+#define ALLOC(ptr, bytes) do { cudaError_t e_ = cudaMalloc((void**)&(ptr), (bytes)); if (e_ != cudaSuccess) { b2h_destroy(h); return fail(B2H_ENOMEM, cudaGetErrorString(e_)); } cudaMemset((ptr), 0, (bytes)); } while (0)
+  ALLOC(h->qpos, E * h->nq * esz); ALLOC(h->qvel, E * h->nv * esz); ALLOC(h->warm, E * h->nv * esz);
+  ALLOC(h->total_reward, E * esz); ALLOC(h->nstep, E * 4); ALLOC(h->step_count, E * 4); ALLOC(h->episode, E * 4);
+  ALLOC(h->reset_noise, E * (h->nq + h->nv) * 8); ALLOC(h->noise_injected, E);
+  ALLOC(h->counters, 8 * 8); ALLOC(h->work, 4);
+  ALLOC(h->actions_stage, E * h->nu * 4); ALLOC(h->obs_stage, E * h->obs_dim * esz); ALLOC(h->tobs_stage, E * h->obs_dim * esz);
+  ALLOC(h->rew_stage, E * esz); ALLOC(h->term_stage, E); ALLOC(h->trunc_stage, E); ALLOC(h->mask_stage, E);
+#undef ALLOC
+  CU(cudaDeviceSynchronize());
+  *out = h;
+  return B2H_OK;
+}
+
+int b2h_obs_dim(const B2HHandle* h) { return h ? h->obs_dim : B2H_EINVAL; }
+
+int b2h_set_seed(B2HHandle* h, uint64_t seed) {
+  if (!h) return fail(B2H_EINVAL, "null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaDeviceSynchronize());
+  h->cfg.seed = seed; h->P.seed = seed;
+  CU(cudaMemset(h->episode, 0, (size_t)h->cfg.n_envs * 4));
+  return B2H_OK;
+}
+
+int b2h_launch_info(const B2HHandle* h, int* grid, int* warps_per_cta, size_t* smem_bytes) {
+  if (!h) return fail(B2H_EINVAL, "null handle");
+  if (grid) *grid = h->grid;
+  if (warps_per_cta) *warps_per_cta = h->warps;
+  if (smem_bytes) *smem_bytes = h->smem;
+  return B2H_OK;
+}
+
+int b2h_reset(B2HHandle* h, const uint8_t* mask_dev, void* obs_dev, void* stream) {
+  if (!h) return fail(B2H_EINVAL, "null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaMemsetAsync(h->work, 0, 4, s));
+  if (h->cfg.dtype == B2H_F64)
+    reset_kernel<double><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<double>*)h->dmodel, h->P,
+        make_io<double>(h, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr), h->cfg.n_envs, mask_dev, h->counters, h->work);
+  else
+    reset_kernel<float><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<float>*)h->dmodel, h->P,
+        make_io<float>(h, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr), h->cfg.n_envs, mask_dev, h->counters, h->work);
+  CU(cudaGetLastError());
+  h->launches++;
+  return B2H_OK;
+}
+
+int b2h_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward_dev, uint8_t* terminated_dev,
+             uint8_t* truncated_dev, void* terminal_obs_dev, void* stream) {
+  if (!h || !actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail(B2H_EINVAL, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaMemsetAsync(h->work, 0, 4, s));
+  if (h->cfg.dtype == B2H_F64)
+    step_kernel<double><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<double>*)h->dmodel, h->P,
+        make_io<double>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev), h->cfg.n_envs,
+        h->counters, h->work);
+  else
+    step_kernel<float><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<float>*)h->dmodel, h->P,
+        make_io<float>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev), h->cfg.n_envs,
+        h->counters, h->work);
+  CU(cudaGetLastError());
+  h->launches++;
+  return B2H_OK;
+}
+
+int b2h_step_host(B2HHandle* h, const float* actions_host, void* obs_host, void* reward_host, uint8_t* terminated_host,
+                  uint8_t* truncated_host, void* terminal_obs_host, void* stream) {
+  if (!h || !actions_host || !obs_host || !reward_host || !terminated_host || !truncated_host) return fail(B2H_EINVAL, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t E = (size_t)h->cfg.n_envs, esz = (size_t)h->esz;
+  CU(cudaMemcpyAsync(h->actions_stage, actions_host, E * h->nu * 4, cudaMemcpyHostToDevice, s));
+  int rc = b2h_step(h, h->actions_stage, h->obs_stage, h->rew_stage, h->term_stage, h->trunc_stage,
+                    terminal_obs_host ? h->tobs_stage : nullptr, stream);
+  if (rc != B2H_OK) return rc;
+  CU(cudaMemcpyAsync(obs_host, h->obs_stage, E * h->obs_dim * esz, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(reward_host, h->rew_stage, E * esz, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(terminated_host, h->term_stage, E, cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(truncated_host, h->trunc_stage, E, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  if (terminal_obs_host) {  // terminal observations only travel on the steps where an episode ended
+    bool any = false;
+    for (size_t i = 0; i < E && !any; i++) any = terminated_host[i] || truncated_host[i];
+    if (any) {
+      CU(cudaMemcpyAsync(terminal_obs_host, h->tobs_stage, E * h->obs_dim * esz, cudaMemcpyDeviceToHost, s));
+      CU(cudaStreamSynchronize(s));
+    }
+  }
+  return B2H_OK;
+}
+
+int b2h_reset_host(B2HHandle* h, const uint8_t* mask_host, void* obs_host, void* stream) {
+  if (!h) return fail(B2H_EINVAL, "null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t E = (size_t)h->cfg.n_envs, esz = (size_t)h->esz;
+  if (mask_host) CU(cudaMemcpyAsync(h->mask_stage, mask_host, E, cudaMemcpyHostToDevice, s));
+  int rc = b2h_reset(h, mask_host ? h->mask_stage : nullptr, h->obs_stage, stream);
+  if (rc != B2H_OK) return rc;
+  if (obs_host) CU(cudaMemcpyAsync(obs_host, h->obs_stage, E * h->obs_dim * esz, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return B2H_OK;
+}
+
+int b2h_set_reset_noise(B2HHandle* h, const double* noise_dev, void* stream) {
+  if (!h || !noise_dev) return fail(B2H_EINVAL, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  size_t E = (size_t)h->cfg.n_envs;
+  CU(cudaMemcpyAsync(h->reset_noise, noise_dev, E * (h->nq + h->nv) * 8, cudaMemcpyDeviceToDevice, s));
+  CU(cudaMemsetAsync(h->noise_injected, 1, E, s));
+  return B2H_OK;
+}
+
+int b2h_get_last_reset_noise(B2HHandle* h, double* noise_dev, void* stream) {
+  if (!h || !noise_dev) return fail(B2H_EINVAL, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaMemcpyAsync(noise_dev, h->reset_noise, (size_t)h->cfg.n_envs * (h->nq + h->nv) * 8, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return B2H_OK;
+}
+
+}  // extern "C"
+// double host arrays <-> T device arrays
+template <typename T>
+static int copy_state(B2HHandle* h, double* host, void* dev, size_t n, bool to_host) {
+  std::vector<T> tmp(n);
+  if (to_host) {
+    CU(cudaMemcpy(tmp.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) host[i] = (double)tmp[i];
+  } else {
+    for (size_t i = 0; i < n; i++) tmp[i] = (T)host[i];
+    CU(cudaMemcpy(dev, tmp.data(), n * sizeof(T), cudaMemcpyHostToDevice));
+  }
+  return B2H_OK;
+}
+static int copy_any(B2HHandle* h, double* host, void* dev, size_t n, bool to_host) {
+  return h->cfg.dtype == B2H_F64 ? copy_state<double>(h, host, dev, n, to_host) : copy_state<float>(h, host, dev, n, to_host);
+}
+extern "C" {
+
+int b2h_get_state(B2HHandle* h, double* qpos, double* qvel, double* warm, int32_t* nstep, int32_t* step_count, double* total_reward) {
+  if (!h) return fail(B2H_EINVAL, "null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaDeviceSynchronize());
+  size_t E = (size_t)h->cfg.n_envs;
+  int rc = B2H_OK;
+  if (qpos && (rc = copy_any(h, qpos, h->qpos, E * h->nq, true))) return rc;
+  if (qvel && (rc = copy_any(h, qvel, h->qvel, E * h->nv, true))) return rc;
+  if (warm && (rc = copy_any(h, warm, h->warm, E * h->nv, true))) return rc;
+  if (total_reward && (rc = copy_any(h, total_reward, h->total_reward, E, true))) return rc;
+  if (nstep) CU(cudaMemcpy(nstep, h->nstep, E * 4, cudaMemcpyDeviceToHost));
+  if (step_count) CU(cudaMemcpy(step_count, h->step_count, E * 4, cudaMemcpyDeviceToHost));
+  return B2H_OK;
+}
+
+int b2h_set_state(B2HHandle* h, const double* qpos, const double* qvel, const double* warm, const int32_t* nstep,
+                  const int32_t* step_count, const double* total_reward) {
+  if (!h) return fail(B2H_EINVAL, "null handle");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaDeviceSynchronize());
+  size_t E = (size_t)h->cfg.n_envs;
+  int rc = B2H_OK;
+  if (qpos && (rc = copy_any(h, (double*)qpos, h->qpos, E * h->nq, false))) return rc;
+  if (qvel && (rc = copy_any(h, (double*)qvel, h->qvel, E * h->nv, false))) return rc;
+  if (warm && (rc = copy_any(h, (double*)warm, h->warm, E * h->nv, false))) return rc;
+  if (total_reward && (rc = copy_any(h, (double*)total_reward, h->total_reward, E, false))) return rc;
+  if (nstep) CU(cudaMemcpy(h->nstep, nstep, E * 4, cudaMemcpyHostToDevice));
+  if (step_count) CU(cudaMemcpy(h->step_count, step_count, E * 4, cudaMemcpyHostToDevice));
+  return B2H_OK;
+}
+
+}  // extern "C"
+template <typename T>
+static int debug_typed(B2HHandle* h, const float* actions_dev, int env, const char* what, double* out, int max_out) {
+  debug_kernel<T><<<1, 32, sizeof(Scratch<T>)>>>((const DevModel<T>*)h->dmodel,
+      make_io<T>(h, actions_dev, nullptr, nullptr, nullptr, nullptr, nullptr), env, (DebugDump<T>*)h->dump);
+  CU(cudaGetLastError());
+  CU(cudaDeviceSynchronize());
+  h->launches++;
+  std::vector<unsigned char> hb(sizeof(DebugDump<T>)), mb(sizeof(DevModel<T>));
+  CU(cudaMemcpy(hb.data(), h->dump, sizeof(DebugDump<T>), cudaMemcpyDeviceToHost));
+  CU(cudaMemcpy(mb.data(), h->dmodel, sizeof(DevModel<T>), cudaMemcpyDeviceToHost));
+  int n = extract_named<T>(*reinterpret_cast<DevModel<T>*>(mb.data()), *reinterpret_cast<DebugDump<T>*>(hb.data()), what, out, max_out);
+  if (n == -2) return fail(B2H_EINVAL, std::string("unknown array name: ") + what);
+  if (n < 0) return fail(B2H_EINVAL, "output buffer too small");
+  return n;
+}
+
+extern "C" {
+int b2h_debug_forward(B2HHandle* h, const float* actions_dev, int env, const char* what, double* out_host, int max_out) {
+  if (!h || !what || !out_host) return fail(B2H_EINVAL, "null argument");
+  if (env < 0 || env >= h->cfg.n_envs) return fail(B2H_EINVAL, "env out of range");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaDeviceSynchronize());
+  return h->cfg.dtype == B2H_F64 ? debug_typed<double>(h, actions_dev, env, what, out_host, max_out)
+                                 : debug_typed<float>(h, actions_dev, env, what, out_host, max_out);
+}
+
+int b2h_get_counters(B2HHandle* h, uint64_t counters_host[8]) {
+  if (!h || !counters_host) return fail(B2H_EINVAL, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpy(counters_host, h->counters, 64, cudaMemcpyDeviceToHost));
+  counters_host[5] = h->launches;
+  return B2H_OK;
+}
+
+int b2h_gae(const float* rewards_dev, const float* values_dev, const float* episode_starts_dev, const float* last_values_dev,
+            const uint8_t* last_dones_dev, double gamma, double gae_lambda, int T, int E, float* advantages_dev,
+            float* returns_dev, void* stream) {
+  if (!rewards_dev || !values_dev || !episode_starts_dev || !last_values_dev || !last_dones_dev || !advantages_dev || !returns_dev)
+    return fail(B2H_EINVAL, "null argument");
+  if (T <= 0 || E <= 0) return fail(B2H_EINVAL, "T and E must be positive");
+  // numpy float32 semantics: python-float scalars round to float32 once (gamma, and the double product gamma*lambda)
+  gae_kernel<<<(E + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rewards_dev, values_dev, episode_starts_dev, last_values_dev,
+      last_dones_dev, (float)gamma, (float)(gamma * gae_lambda), T, E, advantages_dev, returns_dev);
+  CU(cudaGetLastError());
+  return B2H_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,69 @@
+"""ctypes binding of libb2h.so — exactly the entry points declared in include/b2h.h.
+
+The library is the product: if it is missing (not built) or there is no CUDA device, calls fail loudly.
+There is no CPU path behind this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import abi
+from .build import LIB
+
+_lib = None
+vp, i32p, u8p, f64p = C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.POINTER(C.c_double)
+
+# name -> (restype, argtypes); mirrors include/b2h.h
+SIGNATURES = {
+    "b2h_abi_version": (C.c_int, []),
+    "b2h_sizeof_model": (C.c_size_t, []),
+    "b2h_sizeof_config": (C.c_size_t, []),
+    "b2h_last_error": (C.c_char_p, []),
+    "b2h_create": (C.c_int, [C.POINTER(abi.B2HModel), C.POINTER(abi.B2HConfig), C.POINTER(vp)]),
+    "b2h_destroy": (None, [vp]),
+    "b2h_obs_dim": (C.c_int, [vp]),
+    "b2h_set_seed": (C.c_int, [vp, C.c_uint64]),
+    "b2h_launch_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "b2h_reset": (C.c_int, [vp, vp, vp, vp]),
+    "b2h_set_reset_noise": (C.c_int, [vp, vp, vp]),
+    "b2h_get_last_reset_noise": (C.c_int, [vp, vp, vp]),
+    "b2h_step": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b2h_step_host": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
+    "b2h_reset_host": (C.c_int, [vp, vp, vp, vp]),
+    "b2h_get_state": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "b2h_set_state": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "b2h_debug_forward": (C.c_int, [vp, vp, C.c_int, C.c_char_p, vp, C.c_int]),
+    "b2h_get_counters": (C.c_int, [vp, vp]),
+    "b2h_gae": (C.c_int, [vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp]),
+    "b2h_mlp_forward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+}
+
+
+class B2HError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libb2h.so (must have been built: `python -c 'import __graft_entry__ as g; g.build()'`)."""
+    global _lib
+    if _lib is None:
+        if not LIB.exists():
+            raise B2HError(f"{LIB} is not built; run __graft_entry__.build() (nvcc, sm_100a). There is no CPU fallback.")
+        L = C.CDLL(str(LIB))
+        for name, (res, args) in SIGNATURES.items():
+            if not hasattr(L, name):
+                if name == "b2h_mlp_forward":
+                    continue
+                raise B2HError(f"libb2h.so does not export {name}")
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        if L.b2h_sizeof_model() != C.sizeof(abi.B2HModel) or L.b2h_sizeof_config() != C.sizeof(abi.B2HConfig):
+            raise B2HError("struct layout mismatch between abi.py and libb2h.so")
+        _lib = L
+    return _lib
+
+
+def check(rc):
+    if rc < 0:
+        raise B2HError(f"b2h error {rc}: {load().b2h_last_error().decode()}")
+    return rc

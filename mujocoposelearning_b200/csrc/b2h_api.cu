@@ -16,8 +16,9 @@
 using namespace b2h;
 
 // ------------------------------------------------------------------------------------------------ kernels
-// at most 10 env-warps fit the shared-memory budget (fp32), so each thread may use up to ~200 registers
-#define B2H_MAX_THREADS 320
+// 14 env-warps of fp32 scratch fit 227 KB of shared memory; 448 threads leave 146 registers per thread
+#define B2H_MAX_THREADS 448
+template <typename T> constexpr int max_threads() { return sizeof(T) == 8 ? B2H_MAX_THREADS / 2 : B2H_MAX_THREADS; }
 extern __shared__ __align__(16) unsigned char b2h_smem[];
 
 __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long long* g) {
@@ -32,26 +33,32 @@ __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long 
 }
 
 template <typename T>
-__global__ void __launch_bounds__(B2H_MAX_THREADS, 1)
+__global__ void __launch_bounds__(max_threads<T>(), 1)
 step_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, int n_envs, unsigned long long* counters,
-            int* work) {
+            int* work, T* spill) {
   Scratch<T>& S = reinterpret_cast<Scratch<T>*>(b2h_smem)[threadIdx.x >> 5];
+  T* Jspill = spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ((NROW - NROW_S) * LD);
   Counters cnt = {0, 0, 0, 0, 0, 0};
-  for (;;) {
-    int env = 0;
-    if (lane_id() == 0) env = atomicAdd(work, 1);
-    env = __shfl_sync(0xffffffffu, env, 0);
-    if (env >= n_envs) break;
-    env_step<T>(*model, S, cnt, P, io, env);
+  __shared__ int s_base;
+  const int nwarps = blockDim.x >> 5;
+  for (;;) {  // the CTA claims one env per warp at a time and steps them in lockstep (see env_step)
+    __syncthreads();
+    if (threadIdx.x == 0) s_base = atomicAdd(work, nwarps);
+    __syncthreads();
+    const int base = s_base;
+    if (base >= n_envs) break;
+    const int env = base + (threadIdx.x >> 5);
+    env_step<T>(*model, S, Jspill, cnt, P, io, env, env < n_envs);
   }
   flush_counters(cnt, counters);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(B2H_MAX_THREADS, 1)
+__global__ void __launch_bounds__(max_threads<T>(), 1)
 reset_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, int n_envs, const uint8_t* mask,
-             unsigned long long* counters, int* work) {
+             unsigned long long* counters, int* work, T* spill) {
   Scratch<T>& S = reinterpret_cast<Scratch<T>*>(b2h_smem)[threadIdx.x >> 5];
+  T* Jspill = spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ((NROW - NROW_S) * LD);
   Counters cnt = {0, 0, 0, 0, 0, 0};
   for (;;) {
     int env = 0;
@@ -59,14 +66,14 @@ reset_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, in
     env = __shfl_sync(0xffffffffu, env, 0);
     if (env >= n_envs) break;
     if (mask && !mask[env]) continue;
-    env_reset_only<T>(*model, S, cnt, P, io, env);
+    env_reset_only<T>(*model, S, Jspill, cnt, P, io, env);
   }
   flush_counters(cnt, counters);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(32, 1)
-debug_kernel(const DevModel<T>* __restrict__ model, EnvIO<T> io, int env, DebugDump<T>* out) {
+debug_kernel(const DevModel<T>* __restrict__ model, EnvIO<T> io, int env, DebugDump<T>* out, T* Jspill) {
   Scratch<T>& S = reinterpret_cast<Scratch<T>*>(b2h_smem)[0];
   const int lane = lane_id(), nq = model->nq, nv = model->nv, nu = model->nu;
   Counters cnt = {0, 0, 0, 0, 0, 0};
@@ -78,15 +85,11 @@ debug_kernel(const DevModel<T>* __restrict__ model, EnvIO<T> io, int env, DebugD
   st.qfrc_act = 0;
   int a = lane < nv ? model->dof_act[lane] : -1;
   st.ctrl = (a >= 0 && io.actions) ? T(io.actions[(size_t)env * nu + a]) : T(0);
-  T qacc, dl[8];
+  T qacc;
   StepStats stats;
-  physics_step<T>(*model, S, st, cnt, false, &stats, &qacc, dl);
+  physics_step<T>(*model, S, Jspill, st, cnt, false, &stats, &qacc, out);
   __syncwarp();
-  for (int k = 0; k < 8; k++) out->lane[lane][k] = dl[k];
   if (lane == 0) out->stats = stats;
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(&S);
-  uint32_t* dst = reinterpret_cast<uint32_t*>(&out->S);
-  for (size_t i = lane; i < sizeof(Scratch<T>) / 4; i += 32) dst[i] = src[i];
 }
 
 // SB3 RolloutBuffer.compute_returns_and_advantage: one thread per env, reverse scan over T; [T, E] arrays, E fastest.
@@ -128,6 +131,7 @@ struct B2HHandle {
   unsigned long long* counters = nullptr;
   int* work = nullptr;
   void* dump = nullptr;
+  void* spill = nullptr;  // per-warp dense rows beyond NROW_S
   // staging for the *_host entry points
   float* actions_stage = nullptr;
   void *obs_stage = nullptr, *tobs_stage = nullptr, *rew_stage = nullptr;
@@ -160,14 +164,14 @@ static int create_typed(B2HHandle* h) {
   int dev = h->cfg.device, nsm = 0, max_smem = 0;
   CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  // leave L1 room for the model tables (read through the read-only path): cap the carve-out below the maximum
-  size_t budget = (size_t)max_smem > 200 * 1024 ? 195 * 1024 : (size_t)max_smem;
-  int warps = (int)(budget / sizeof(Scratch<T>));
-  if (warps > B2H_MAX_THREADS / 32) warps = B2H_MAX_THREADS / 32;
+  // the unified L1/shared array keeps >= 28 KB of L1 at the maximum carve-out: enough for the model tables
+  int warps = (int)((size_t)max_smem / sizeof(Scratch<T>));
+  if (warps > max_threads<T>() / 32) warps = max_threads<T>() / 32;
   if (warps < 1) return fail(B2H_EUNSUPPORTED, "per-env scratch does not fit in shared memory");
   h->warps = warps;
   h->smem = (size_t)warps * sizeof(Scratch<T>);
   h->grid = nsm;
+  CU(cudaMalloc(&h->spill, (size_t)h->grid * warps * (NROW - NROW_S) * LD * sizeof(T)));
   CU(cudaFuncSetAttribute(step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   CU(cudaFuncSetAttribute(reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   CU(cudaFuncSetAttribute(debug_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Scratch<T>)));
@@ -185,7 +189,7 @@ void b2h_destroy(B2HHandle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   void* ptrs[] = {h->dmodel, h->qpos, h->qvel, h->warm, h->total_reward, h->nstep, h->step_count, h->episode,
-                  h->reset_noise, h->noise_injected, h->counters, h->work, h->dump, h->actions_stage, h->obs_stage,
+                  h->reset_noise, h->noise_injected, h->counters, h->work, h->dump, h->spill, h->actions_stage, h->obs_stage,
                   h->tobs_stage, h->rew_stage, h->term_stage, h->trunc_stage, h->mask_stage};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
@@ -252,10 +256,10 @@ int b2h_reset(B2HHandle* h, const uint8_t* mask_dev, void* obs_dev, void* stream
   CU(cudaMemsetAsync(h->work, 0, 4, s));
   if (h->cfg.dtype == B2H_F64)
     reset_kernel<double><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<double>*)h->dmodel, h->P,
-        make_io<double>(h, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr), h->cfg.n_envs, mask_dev, h->counters, h->work);
+        make_io<double>(h, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr), h->cfg.n_envs, mask_dev, h->counters, h->work, (double*)h->spill);
   else
     reset_kernel<float><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<float>*)h->dmodel, h->P,
-        make_io<float>(h, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr), h->cfg.n_envs, mask_dev, h->counters, h->work);
+        make_io<float>(h, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr), h->cfg.n_envs, mask_dev, h->counters, h->work, (float*)h->spill);
   CU(cudaGetLastError());
   h->launches++;
   return B2H_OK;
@@ -270,11 +274,11 @@ int b2h_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward
   if (h->cfg.dtype == B2H_F64)
     step_kernel<double><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<double>*)h->dmodel, h->P,
         make_io<double>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev), h->cfg.n_envs,
-        h->counters, h->work);
+        h->counters, h->work, (double*)h->spill);
   else
     step_kernel<float><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<float>*)h->dmodel, h->P,
         make_io<float>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev), h->cfg.n_envs,
-        h->counters, h->work);
+        h->counters, h->work, (float*)h->spill);
   CU(cudaGetLastError());
   h->launches++;
   return B2H_OK;
@@ -390,7 +394,7 @@ int b2h_set_state(B2HHandle* h, const double* qpos, const double* qvel, const do
 template <typename T>
 static int debug_typed(B2HHandle* h, const float* actions_dev, int env, const char* what, double* out, int max_out) {
   debug_kernel<T><<<1, 32, sizeof(Scratch<T>)>>>((const DevModel<T>*)h->dmodel,
-      make_io<T>(h, actions_dev, nullptr, nullptr, nullptr, nullptr, nullptr), env, (DebugDump<T>*)h->dump);
+      make_io<T>(h, actions_dev, nullptr, nullptr, nullptr, nullptr, nullptr), env, (DebugDump<T>*)h->dump, (T*)h->spill);
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
   h->launches++;

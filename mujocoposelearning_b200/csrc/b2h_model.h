@@ -24,15 +24,20 @@ constexpr int KT = 2;     // fixed tendons
 constexpr int KCLS = 8;   // contact parameter classes
 constexpr int KPAIR = 512;
 constexpr int LD = 28;    // leading dimension of J / M / A rows (multiple of 4 for 128-bit shared loads)
-constexpr int NROW = 64;  // dense constraint rows per env (tendon limits + contact rows)
-constexpr int NCON = 32;  // contacts per env
+constexpr int NSLOT = 3;          // dense rows per lane
+constexpr int NROW = 32 * NSLOT;  // dense constraint rows per env (tendon limits + contact rows)
+#ifndef B2H_NROW_S
+#define B2H_NROW_S 48
+#endif
+constexpr int NROW_S = B2H_NROW_S;       // rows kept in shared memory; rows beyond live in a per-warp global spill area
+constexpr int NCON = 32;          // contacts per env
 
 template <typename T>
 struct DevModel {
   int nq, nv, nu, nbody, njnt, ngeom, ntendon, npair, nlevel, ncls, maxsub;
   T timestep, gravity[3], meaninertia, inv_total_mass;
   // bodies
-  int body_parent[KB], body_level[KB], body_jntadr[KB], body_jntnum[KB], body_subend[KB], body_isfree[KB];
+  int body_parent[KB], body_level[KB], body_jntadr[KB], body_jntnum[KB], body_subend[KB], body_isfree[KB], body_lastdof[KB];
   uint32_t body_dofmask[KB];  // bit d set iff dof d moves body b
   T body_pos[KB][3], body_quat[KB][4], body_ipos[KB][3], body_inertia[KB][6], body_mass[KB], body_invw[KB];
   // joints
@@ -104,7 +109,7 @@ std::string build_dev_model(const B2HModel& m, DevModel<T>& d) {
     d.body_parent[b] = m.body_parentid[b];
     d.body_level[b] = b == 0 ? 0 : d.body_level[m.body_parentid[b]] + 1;
     if (d.body_level[b] > d.nlevel) d.nlevel = d.body_level[b];
-    d.body_jntadr[b] = m.body_jntadr[b]; d.body_jntnum[b] = m.body_jntnum[b];
+    d.body_jntadr[b] = m.body_jntadr[b]; d.body_jntnum[b] = m.body_jntnum[b]; d.body_lastdof[b] = m.body_lastdof[b];
     d.body_isfree[b] = m.body_jntnum[b] == 1 && m.jnt_type[m.body_jntadr[b]] == B2H_JNT_FREE;
     if (d.body_isfree[b] && (m.body_parentid[b] != 0 || m.jnt_qposadr[m.body_jntadr[b]] != 0))
       return "a free joint must belong to the root body and come first in qpos";

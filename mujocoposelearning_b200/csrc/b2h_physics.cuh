@@ -36,6 +36,7 @@ namespace b2h {
 #ifdef B2H_HOST_EMU
 B2H_DEV int lane_id() { return emu::lane(); }
 B2H_DEV void wsync() { emu::sync(); }
+B2H_DEV void cta_sync() {}
 B2H_DEV unsigned ballot(bool p) { return emu::ballot(p); }
 template <typename V> B2H_DEV V shfl(V v, int src) {
   uint64_t bits = 0;
@@ -48,6 +49,7 @@ template <typename V> B2H_DEV V shfl(V v, int src) {
 #else
 B2H_DEV int lane_id() { return threadIdx.x & 31; }
 B2H_DEV void wsync() { __syncwarp(); }
+B2H_DEV void cta_sync() { __syncthreads(); }
 B2H_DEV unsigned ballot(bool p) { return __ballot_sync(0xffffffffu, p); }
 template <typename V> B2H_DEV V shfl(V v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 #endif
@@ -99,12 +101,15 @@ template <typename T> B2H_DEV T clampT(T x, T lo, T hi) { return x < lo ? lo : (
 template <typename T> B2H_DEV bool is_bad(T x) { return !(x == x) || x > T(1e10) || x < T(-1e10); }
 
 template <typename T> struct Tol;  // arithmetic-type dependent solver slack (0 in double = MuJoCo's tests verbatim)
-template <> struct Tol<double> { static constexpr double ls_rel = 0.0, cost_rel = 0.0; static constexpr int maxiter = 100; };
-template <> struct Tol<float> { static constexpr float ls_rel = 2e-5f, cost_rel = 1e-6f; static constexpr int maxiter = 30; };
+template <> struct Tol<double> { static constexpr double ls_rel = 0.0, cost_rel = 0.0, step_rel = 0.0; static constexpr bool exact_stop = false; static constexpr int maxiter = 100; };
+// float: MuJoCo's absolute 1e-8 tests sit below fp32 round-off.  The cost is piecewise quadratic, so a full Newton
+// step that leaves the active set unchanged lands on the minimiser exactly (exact_stop); otherwise stop when the
+// step is below the resolution of qacc (step_rel) or the cost stops resolving (cost_rel).
+template <> struct Tol<float> { static constexpr float ls_rel = 2e-5f, cost_rel = 1e-6f, step_rel = 2e-7f; static constexpr bool exact_stop = true; static constexpr int maxiter = 30; };
 
 #define B2H_MINVAL T(1e-15)
-// the (at most two) dense-row slots a lane owns, fully unrolled so per-slot registers stay registers
-#define B2H_SLOTS(s) _Pragma("unroll") for (int s = 0; s < 2; s++) if (s < nslot)
+// the (at most NSLOT) dense-row slots a lane owns, fully unrolled so per-slot registers stay registers
+#define B2H_SLOTS(s) _Pragma("unroll") for (int s = 0; s < NSLOT; s++) if (s < nslot)
 
 template <typename T> struct V4 { T x, y, z, w; };
 #ifdef B2H_HOST_EMU
@@ -189,35 +194,41 @@ template <typename T> B2H_DEV void cross_force(T* r, const T* vel, const T* f) {
 // ------------------------------------------------------------------------------------------------ per-warp scratch
 template <typename T>
 struct alignas(16) Scratch {
-  T J[NROW * LD];   // dense constraint rows (tendon limits, contact rows); column 27 is a zero pad
-  T A[LD * LD];     // factorisation workspace; before the solve stages it is stage-local scratch (TMP_*)
-  T M[LD * LD];     // joint-space inertia, dense symmetric
-  T vec[4][32];     // lane vectors that other lanes index (qpos, search direction, ...)
-  T xpos[KB * 3], xmat[KB * 9], xipos[KB * 3];
-  T cinert[KB * 10], cvel[KB * 6];
-  T cdof[KV * 6], cdofdot[KV * 6];
-  T xanchor[KJ * 3], xaxis[KJ * 3];
-  T gpos[KG * 3], gaxis[KG * 3];
+  T J[NROW_S * LD];  // first NROW_S dense constraint rows (tendon limits, contact rows); column 27 is a zero pad.
+                     // Until the rows are written (after collision) it holds the kinematics scratch POS_*.
+  T A[LD * LD];      // factor transposition buffer of chol_solve_fused; stage-local scratch TMP_* otherwise
+  T M[LD * LD];      // joint-space inertia, dense symmetric
+  T vec[3][32];      // lane vectors that other lanes index (qpos, qvel, matvec operand)
+  T cinert[KB * 10], cvel[KB * 6];   // live until the observation is written (custom_env.py:242-256)
+  T cdof[KV * 6];
   T con_dist[NCON], con_pos[NCON * 3], con_frame[NCON * 9];
   uint32_t con_info[NCON];  // body1 | body2 << 8 | class << 16
   int con_row[NCON];        // first dense row of the contact, -1 if dropped
   int row_con[NROW];        // dense row -> contact id (or -1 - tendon id)
   T com[4];
 };
+// kinematics / collision scratch inside Scratch::J (dead before the first constraint row is written)
+constexpr int POS_XPOS = 0, POS_XMAT = POS_XPOS + KB * 3, POS_XIPOS = POS_XMAT + KB * 9, POS_XANCHOR = POS_XIPOS + KB * 3,
+              POS_XAXIS = POS_XANCHOR + KJ * 3, POS_GPOS = POS_XAXIS + KJ * 3, POS_GAXIS = POS_GPOS + KG * 3,
+              POS_END = POS_GAXIS + KG * 3;
+static_assert(POS_END <= NROW_S * LD, "kinematics scratch must fit in the row storage");
 // stage-local aliases inside Scratch::A (all dead before the factorisations start)
 constexpr int TMP_QLOC = 0, TMP_ANCL = TMP_QLOC + KJ * 4, TMP_AXL = TMP_ANCL + KJ * 3, TMP_XQUAT = TMP_AXL + KJ * 3,
               TMP_CRB = TMP_XQUAT + KB * 4;                       // position stage
-constexpr int TMP_DOFW = 0, TMP_DOFA = TMP_DOFW + KV * 6, TMP_CFRC = TMP_DOFA + KV * 6;  // velocity stage
+constexpr int TMP_DOFW = 0, TMP_DOFA = TMP_DOFW + KV * 6, TMP_CFRC = TMP_DOFA + KV * 6, TMP_CDD = TMP_CFRC + KB * 6;  // velocity stage
 static_assert(TMP_CRB + KB * 10 <= LD * LD, "position-stage scratch must fit in A");
-static_assert(TMP_CFRC + KB * 6 <= LD * LD, "velocity-stage scratch must fit in A");
+static_assert(TMP_CDD + KV * 6 <= LD * LD, "velocity-stage scratch must fit in A");
 
 struct Counters {  // per-warp tallies, flushed with atomics at the end of the launch
   unsigned long long physics_steps, contact_overflow, iter_cap, bad_state, newton_iter, ls_eval;
 };
 
 // per-row soft-constraint parameters (mj_makeImpedance + mj_referenceConstraint)
+template <typename T> struct RowParam { T D, aref; };
 template <typename T>
-B2H_DEV void row_params(const T* solref, const T* solimp, T pos, T margin, T diag_approx, T vel, T rscale, T* D, T* aref) {
+B2H_DEV_NOINLINE RowParam<T> row_params(T solref0, T solref1, T solimp0, T solimp1, T solimp2, T solimp3, T solimp4, T pos,
+                                        T margin, T diag_approx, T vel, T rscale) {
+  const T solref[2] = {solref0, solref1}, solimp[5] = {solimp0, solimp1, solimp2, solimp3, solimp4};
   T imp;
   if (solimp[0] == solimp[1] || solimp[2] <= B2H_MINVAL) imp = T(0.5) * (solimp[0] + solimp[1]);
   else {
@@ -239,60 +250,71 @@ B2H_DEV void row_params(const T* solref, const T* solimp, T pos, T margin, T dia
     B = T(2) / m_max(B2H_MINVAL, dmax * solref[0]);
   }
   T R = m_max(B2H_MINVAL, (T(1) - imp) * diag_approx / imp) * rscale;
-  *D = T(1) / R;
-  *aref = -B * vel - K * imp * (pos - margin);
+  RowParam<T> out;
+  out.D = T(1) / R;
+  out.aref = -B * vel - K * imp * (pos - margin);
+  return out;
 }
 
 // ------------------------------------------------------------------------------------------------ dense 27x27 algebra
-// In-place Cholesky of the lower triangle of A (stride LD); lane i owns row i (left-looking, 128-bit row loads).
-template <typename T>
-B2H_DEV void chol_factor(T* A, int n, int lane) {
-  for (int j = 0; j < n; j++) {
-    T s = 0;
-    if (lane >= j && lane < n) {
-      const T* ri = A + lane * LD;
-      const T* rj = A + j * LD;
-      s = ri[j];
-      int k4 = j & ~3;
-      for (int k = 0; k < k4; k += 4) {
-        V4<T> a = ld4(ri + k), b = ld4(rj + k);
-        s -= a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
-      }
-      for (int k = k4; k < j; k++) s -= ri[k] * rj[k];
-    }
-    T piv = m_max(shfl(s, j), B2H_MINVAL);  // mju_cholFactor floors the pivot
-    T root = m_sqrt(piv);
-    if (lane >= j && lane < n) A[lane * LD + j] = lane == j ? root : s / root;
-    wsync();
-  }
+B2H_DEV float m_rsqrt(float x) {
+#ifdef B2H_HOST_EMU
+  return 1.0f / sqrtf(x);
+#else
+  return rsqrtf(x);
+#endif
 }
-// x = (L L^T)^-1 b, b and x one entry per lane
+B2H_DEV double m_rsqrt(double x) { return 1.0 / sqrt(x); }
+
+// x = A^-1 b for the SPD matrix in shared memory A (stride LD, lower triangle read, contents destroyed).
+// Lane i keeps row i of the factor in registers; the right-hand side rides along as row 27 of the augmented
+// matrix (lane 27), so the forward substitution is the same 27 column steps as the factorisation:
+//   step j: broadcast the pivot, scale column j, then a[k] -= L[i][j] * L[k][j] with L[k][j] shuffled from lane k.
+// The factor is then transposed through shared memory for the backward substitution.  mju_cholFactor's pivot
+// floor (mjMINVAL) is kept.
 template <typename T>
-B2H_DEV T chol_solve(const T* A, int n, int lane, T b) {
-  T dinv = lane < n ? T(1) / A[lane * LD + lane] : T(0);
-  T row[LD];
+B2H_DEV_NOINLINE T chol_solve_fused(T* A, int n, int lane, T b) {
+  constexpr int N = KV - 1;
+  if (lane < LD) A[N * LD + lane] = lane < n ? b : T(0);
+  if (lane >= n && lane < N) A[lane * LD + lane] = 1;  // unused dof slots factor as identity
+  wsync();
+  T a[LD];
+  {
+    const T* r = A + (lane < LD ? lane : 0) * LD;
 #pragma unroll
-  for (int c = 0; c < LD; c += 4) {
-    V4<T> v = ld4(A + (lane < n ? lane : 0) * LD + c);
-    row[c] = v.x; row[c + 1] = v.y; row[c + 2] = v.z; row[c + 3] = v.w;
-  }
-  T acc = 0, y = 0;
-#pragma unroll
-  for (int k = 0; k < KV - 1; k++) {
-    if (k < n) {
-      T yk = shfl((b - acc) * dinv, k);
-      if (lane == k) y = yk;
-      if (lane > k) acc += row[k] * yk;
+    for (int c = 0; c < LD; c += 4) {
+      V4<T> v = ld4(r + c);
+      a[c] = v.x; a[c + 1] = v.y; a[c + 2] = v.z; a[c + 3] = v.w;
     }
   }
-  acc = 0;
-  T x = 0;
-  for (int k = n - 1; k >= 0; k--) {
-    T xk = shfl((y - acc) * dinv, k);
+  T dinv = 0;  // 1 / L[lane][lane]
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    T piv = m_max(shfl(a[j], j), B2H_MINVAL);
+    T r = m_rsqrt(piv);
+    T l = a[j] * r;
+    a[j] = l;
+    if (lane == j) dinv = r;
+#pragma unroll
+    for (int k = j + 1; k < N; k++) a[k] -= l * shfl(l, k);
+  }
+  wsync();
+  if (lane < N) {  // rows of L to shared memory, read back by columns below
+    T* r = A + lane * LD;
+#pragma unroll
+    for (int c = 0; c < LD; c++) r[c] = a[c];
+  }
+  wsync();
+  T acc = 0, x = 0;
+#pragma unroll
+  for (int k = N - 1; k >= 0; k--) {
+    T yk = shfl(a[k], N);               // y[k] sits in the augmented row
+    T xk = shfl((yk - acc) * dinv, k);
     if (lane == k) x = xk;
     if (lane < k) acc += A[k * LD + lane] * xk;
   }
-  return x;
+  wsync();
+  return lane < n ? x : T(0);
 }
 // r[lane] = sum_k Mat[lane][k] * v[k], v taken from a 32-entry shared vector (entries >= n are zero)
 template <typename T>
@@ -318,17 +340,32 @@ struct EnvState {      // registers of one lane
 
 struct StepStats { int ncon, nrow, nlimit, niter; };
 
+template <typename T>
+struct DebugDump {  // named views of one mj_forward (parity / debug only)
+  T pos[POS_END];      // xpos xmat xipos xanchor xaxis geom_xpos geom_zaxis
+  T M[LD * LD], J[NROW * LD];
+  T cinert[KB * 10], cvel[KB * 6], cdof[KV * 6], cdofdot[KV * 6];
+  T con_dist[NCON], con_pos[NCON * 3], con_frame[NCON * 9], com[4];
+  T lane[32][8];       // per-lane: qfrc_bias, qfrc_smooth, qacc_smooth, qacc, qfrc_constraint, qfrc_actuator, limit D, limit aref
+  StepStats stats;
+};
+
 // One mj_step.  On return st holds the integrated state; S.cinert / S.cvel / S.com keep the pre-integration
 // values of this step, which is what the reference's observation and rewards read.
 // If `integrate` is false this is mj_forward: state untouched, qacc returned in *qacc_out.
 // Returns true when mj_checkAcc tripped: the state was reset and the caller must run the step once more.
 template <typename T>
-B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState<T>& st, Counters& cnt, bool integrate,
-                                   StepStats* stats, T* qacc_out, T* dbg_lane /* [8] optional per-lane dump */) {
+B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, bool integrate,
+                                   StepStats* stats, T* qacc_out, DebugDump<T>* dbg /* optional named dump */) {
   const int lane = lane_id();
   const int nv = B2H_LDG(m.nv), nq = B2H_LDG(m.nq), nbody = B2H_LDG(m.nbody), njnt = B2H_LDG(m.njnt);
   const T h = B2H_LDG(m.timestep);
   T* tmp = S.A;
+  T* const xpos = S.J + POS_XPOS; T* const xmat = S.J + POS_XMAT; T* const xipos = S.J + POS_XIPOS;
+  T* const xanchor = S.J + POS_XANCHOR; T* const xaxis = S.J + POS_XAXIS;
+  T* const gpos = S.J + POS_GPOS; T* const gaxis = S.J + POS_GAXIS;
+  // dense row r lives in shared memory below NROW_S and in this warp's global spill area above it
+  auto jrow = [&](int r) -> T* { return r < NROW_S ? S.J + r * LD : Jspill + (size_t)(r - NROW_S) * LD; };
 
   // ---- mj_checkPos / mj_checkVel: NaN or |x| > 1e10 resets mjData (qpos0, zero velocity, time 0)
   {
@@ -344,10 +381,10 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
   // ---- mj_kinematics: joint-local rotations (lane = joint), per-body local chain (lane = body), tree levels
   S.vec[0][lane] = st.qp;
   if (lane == 0) {
-    S.xpos[0] = S.xpos[1] = S.xpos[2] = 0;
-    for (int k = 0; k < 9; k++) S.xmat[k] = (k % 4 == 0) ? T(1) : T(0);
+    xpos[0] = xpos[1] = xpos[2] = 0;
+    for (int k = 0; k < 9; k++) xmat[k] = (k % 4 == 0) ? T(1) : T(0);
     tmp[TMP_XQUAT] = 1; tmp[TMP_XQUAT + 1] = tmp[TMP_XQUAT + 2] = tmp[TMP_XQUAT + 3] = 0;
-    S.xipos[0] = S.xipos[1] = S.xipos[2] = 0;
+    xipos[0] = xipos[1] = xipos[2] = 0;
     for (int k = 0; k < 10; k++) S.cinert[k] = 0;
     for (int k = 0; k < 6; k++) S.cvel[k] = 0;
   }
@@ -395,11 +432,11 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
       mul_quat(xq, pq, rq);
       normalize4(xq);
       rot_quat(v, rp, pq);
-      for (int k = 0; k < 3; k++) S.xpos[3 * lane + k] = S.xpos[3 * my_parent + k] + v[k];
+      for (int k = 0; k < 3; k++) xpos[3 * lane + k] = xpos[3 * my_parent + k] + v[k];
       for (int k = 0; k < 4; k++) tmp[TMP_XQUAT + 4 * lane + k] = xq[k];
       T R[9];
       quat2mat(R, xq);
-      for (int k = 0; k < 9; k++) S.xmat[9 * lane + k] = R[k];
+      for (int k = 0; k < 9; k++) xmat[9 * lane + k] = R[k];
     }
     wsync();
   }
@@ -408,40 +445,40 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
   if (lane > 0 && lane < nbody) {
     T ip[3], v[3];
     for (int k = 0; k < 3; k++) ip[k] = B2H_LDG(m.body_ipos[lane][k]);
-    mat_vec3(v, S.xmat + 9 * lane, ip);
-    for (int k = 0; k < 3; k++) S.xipos[3 * lane + k] = S.xpos[3 * lane + k] + v[k];
+    mat_vec3(v, xmat + 9 * lane, ip);
+    for (int k = 0; k < 3; k++) xipos[3 * lane + k] = xpos[3 * lane + k] + v[k];
     my_mass = B2H_LDG(m.body_mass[lane]);
   }
   if (lane < njnt) {
     int p = B2H_LDG(m.body_parent[B2H_LDG(m.jnt_body[lane])]);
     T v[3];
-    mat_vec3(v, S.xmat + 9 * p, tmp + TMP_ANCL + 3 * lane);
-    for (int k = 0; k < 3; k++) S.xanchor[3 * lane + k] = S.xpos[3 * p + k] + v[k];
-    mat_vec3(v, S.xmat + 9 * p, tmp + TMP_AXL + 3 * lane);
-    for (int k = 0; k < 3; k++) S.xaxis[3 * lane + k] = v[k];
+    mat_vec3(v, xmat + 9 * p, tmp + TMP_ANCL + 3 * lane);
+    for (int k = 0; k < 3; k++) xanchor[3 * lane + k] = xpos[3 * p + k] + v[k];
+    mat_vec3(v, xmat + 9 * p, tmp + TMP_AXL + 3 * lane);
+    for (int k = 0; k < 3; k++) xaxis[3 * lane + k] = v[k];
   }
   if (lane < B2H_LDG(m.ngeom)) {
     int b = B2H_LDG(m.geom_body[lane]);
     T gp[3], gz[3], v[3];
     for (int k = 0; k < 3; k++) { gp[k] = B2H_LDG(m.geom_pos[lane][k]); gz[k] = B2H_LDG(m.geom_zaxis[lane][k]); }
-    mat_vec3(v, S.xmat + 9 * b, gp);
-    for (int k = 0; k < 3; k++) S.gpos[3 * lane + k] = S.xpos[3 * b + k] + v[k];
-    mat_vec3(v, S.xmat + 9 * b, gz);
-    for (int k = 0; k < 3; k++) S.gaxis[3 * lane + k] = v[k];
+    mat_vec3(v, xmat + 9 * b, gp);
+    for (int k = 0; k < 3; k++) gpos[3 * lane + k] = xpos[3 * b + k] + v[k];
+    mat_vec3(v, xmat + 9 * b, gz);
+    for (int k = 0; k < 3; k++) gaxis[3 * lane + k] = v[k];
   }
   wsync();
   // ---- mj_comPos: centre of mass (single tree), cinert, cdof
   T com[3];
   {
     T inv = B2H_LDG(m.inv_total_mass);
-    for (int k = 0; k < 3; k++) com[k] = wsum(lane > 0 && lane < nbody ? my_mass * S.xipos[3 * lane + k] : T(0)) * inv;
+    for (int k = 0; k < 3; k++) com[k] = wsum(lane > 0 && lane < nbody ? my_mass * xipos[3 * lane + k] : T(0)) * inv;
     if (lane < 3) S.com[lane] = com[lane];
   }
   if (lane > 0 && lane < nbody) {  // mju_inertCom with the full body-frame tensor: R I R^T + m (|d|^2 1 - d d^T)
-    const T* R = S.xmat + 9 * lane;
+    const T* R = xmat + 9 * lane;
     T I6[6], dif[3];
     for (int k = 0; k < 6; k++) I6[k] = B2H_LDG(m.body_inertia[lane][k]);
-    for (int k = 0; k < 3; k++) dif[k] = S.xipos[3 * lane + k] - com[k];
+    for (int k = 0; k < 3; k++) dif[k] = xipos[3 * lane + k] - com[k];
     T Ib[9] = {I6[0], I6[3], I6[4], I6[3], I6[1], I6[5], I6[4], I6[5], I6[2]}, RI[9];
     for (int r = 0; r < 3; r++)
       for (int c = 0; c < 3; c++) RI[3 * r + c] = R[3 * r] * Ib[c] + R[3 * r + 1] * Ib[3 + c] + R[3 * r + 2] * Ib[6 + c];
@@ -467,18 +504,18 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
   if (lane < nv) {
     int j = B2H_LDG(m.dof_jnt[lane]);
     T off[3], ax[3];
-    for (int k = 0; k < 3; k++) off[k] = com[k] - S.xanchor[3 * j + k];
+    for (int k = 0; k < 3; k++) off[k] = com[k] - xanchor[3 * j + k];
     if (B2H_LDG(m.jnt_type[j]) == B2H_JNT_FREE) {
       int k = lane - B2H_LDG(m.jnt_dadr[j]);
       if (k < 3) cd[3 + k] = 1;
       else {
-        const T* R = S.xmat + 9 * my_dbody;
+        const T* R = xmat + 9 * my_dbody;
         ax[0] = R[k - 3]; ax[1] = R[k]; ax[2] = R[k + 3];
         cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
         cross3(cd + 3, ax, off);
       }
     } else {
-      for (int k = 0; k < 3; k++) ax[k] = S.xaxis[3 * j + k];
+      for (int k = 0; k < 3; k++) ax[k] = xaxis[3 * j + k];
       cd[0] = ax[0]; cd[1] = ax[1]; cd[2] = ax[2];
       cross3(cd + 3, ax, off);
     }
@@ -525,11 +562,11 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
         info = (uint32_t)B2H_LDG(m.geom_body[g1]) | ((uint32_t)B2H_LDG(m.geom_body[g2]) << 8) | ((uint32_t)cls << 16);
         int t1 = B2H_LDG(m.geom_type[g1]);
         T r2 = B2H_LDG(m.geom_size[g2][0]), h2 = B2H_LDG(m.geom_size[g2][1]);
-        const T* p2 = S.gpos + 3 * g2;
-        const T* a2 = S.gaxis + 3 * g2;
+        const T* p2 = gpos + 3 * g2;
+        const T* a2 = gaxis + 3 * g2;
         if (t1 == B2H_GEOM_PLANE) {  // mjc_PlaneSphere / mjc_PlaneCapsule (two end spheres, frame aligned with the axis)
-          const T* pn = S.gaxis + 3 * g1;
-          const T* pp = S.gpos + 3 * g1;
+          const T* pn = gaxis + 3 * g1;
+          const T* pp = gpos + 3 * g1;
           int nend = h2 > T(0) ? 2 : 1;
           for (int e = 0; e < nend; e++) {
             T sgn = e == 0 ? T(1) : T(-1), c[3], d[3];
@@ -547,8 +584,8 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
           if (nend == 2) for (int k = 0; k < 3; k++) chint[k] = a2[k];
         } else {  // sphere / capsule pairs: closest points of two segments, then sphere-sphere
           T r1 = B2H_LDG(m.geom_size[g1][0]), h1 = B2H_LDG(m.geom_size[g1][1]);
-          const T* p1 = S.gpos + 3 * g1;
-          const T* a1 = S.gaxis + 3 * g1;
+          const T* p1 = gpos + 3 * g1;
+          const T* a1 = gaxis + 3 * g1;
           T v1[2][3], v2[2][3];
           int ncand = 1;
           if (h1 == T(0)) {  // mjc_SphereSphere / mjc_SphereCapsule
@@ -631,6 +668,10 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
   }
   wsync();
 
+  if (dbg) {  // kinematics scratch is about to be overwritten by the constraint rows
+    for (int i = lane; i < POS_END; i += 32) dbg->pos[i] = S.J[i];
+    wsync();
+  }
   // =============================================================== constraint rows
   // dense rows: tendon limits first, then contacts (1 row frictionless, 4 rows pyramidal condim 3)
   int nrow = 0;
@@ -645,7 +686,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
       else if (hi - len < mg) { ten_side[t] = -1; ten_pos[t] = hi - len; }
       if (ten_side[t]) {
         ten_row[t] = nrow;
-        if (lane < LD) S.J[nrow * LD + lane] = lane < nv ? T(ten_side[t]) * B2H_LDG(m.ten_J[t][lane]) : T(0);
+        if (lane < LD) jrow(nrow)[lane] = lane < nv ? T(ten_side[t]) * B2H_LDG(m.ten_J[t][lane]) : T(0);
         if (lane == 0) S.row_con[nrow] = -1 - t;
         nrow++;
       }
@@ -677,16 +718,16 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
     const T* f = S.con_frame + 9 * c;
     T jn = dot3(f, jp);
     if (B2H_LDG(m.cls_condim[cls]) == 1) {
-      if (lane < LD) S.J[r0 * LD + lane] = jn;
+      if (lane < LD) jrow(r0)[lane] = jn;
       if (lane == 0) S.row_con[r0] = c;
     } else {
       T mu = B2H_LDG(m.cls_mu[cls]);
       T j1 = dot3(f + 3, jp) * mu, j2 = dot3(f + 6, jp) * mu;
       if (lane < LD) {
-        S.J[(r0 + 0) * LD + lane] = jn + j1;
-        S.J[(r0 + 1) * LD + lane] = jn - j1;
-        S.J[(r0 + 2) * LD + lane] = jn + j2;
-        S.J[(r0 + 3) * LD + lane] = jn - j2;
+        jrow(r0 + 0)[lane] = jn + j1;
+        jrow(r0 + 1)[lane] = jn - j1;
+        jrow(r0 + 2)[lane] = jn + j2;
+        jrow(r0 + 3)[lane] = jn - j2;
       }
       if (lane < 4) S.row_con[r0 + lane] = c;
     }
@@ -694,37 +735,41 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
   S.vec[1][lane] = lane < nv ? st.qv : T(0);
   wsync();
 
-  // per-row parameters; lane owns dense rows lane and lane+32 (slot 0/1) and the joint limit of dof `lane`
-  const int nslot = nrow > 32 ? 2 : 1;
-  T rD[2] = {0, 0}, raref[2] = {0, 0};
+  // per-row parameters; lane owns dense rows lane, lane+32, lane+64 (slots) and the joint limit of dof `lane`
+  const int nslot = (nrow + 31) >> 5;
+  T rD[NSLOT] = {0, 0, 0}, raref[NSLOT] = {0, 0, 0};
   B2H_SLOTS(s) {
     int r = lane + 32 * s;
     if (r < nrow) {
       T vel = 0;
-      const T* jr = S.J + r * LD;
+      const T* jr = jrow(r);
 #pragma unroll
       for (int c4 = 0; c4 < LD; c4 += 4) {
         V4<T> a = ld4(jr + c4), b = ld4(S.vec[1] + c4);
         vel += a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w;
       }
       int rc = S.row_con[r];
+      T sr0, sr1, si[5], pos, mg, dA, rs = 1;
       if (rc < 0) {
         int t = -1 - rc;
-        T sr[2] = {B2H_LDG(m.ten_solref[t][0]), B2H_LDG(m.ten_solref[t][1])}, si[5];
+        sr0 = B2H_LDG(m.ten_solref[t][0]); sr1 = B2H_LDG(m.ten_solref[t][1]);
         for (int k = 0; k < 5; k++) si[k] = B2H_LDG(m.ten_solimp[t][k]);
-        row_params(sr, si, ten_pos[t], B2H_LDG(m.ten_margin[t]), B2H_LDG(m.ten_invw[t]), vel, T(1), &rD[s], &raref[s]);
+        pos = ten_pos[t]; mg = B2H_LDG(m.ten_margin[t]); dA = B2H_LDG(m.ten_invw[t]);
       } else {
         uint32_t info = S.con_info[rc];
         int cls = info >> 16;
-        T sr[2] = {B2H_LDG(m.cls_solref[cls][0]), B2H_LDG(m.cls_solref[cls][1])}, si[5];
+        sr0 = B2H_LDG(m.cls_solref[cls][0]); sr1 = B2H_LDG(m.cls_solref[cls][1]);
         for (int k = 0; k < 5; k++) si[k] = B2H_LDG(m.cls_solimp[cls][k]);
         T tran = B2H_LDG(m.body_invw[info & 255]) + B2H_LDG(m.body_invw[(info >> 8) & 255]);
         T mu = B2H_LDG(m.cls_mu[cls]);
         bool pyr = B2H_LDG(m.cls_condim[cls]) != 1;
         // mj_diagApprox: tran (frictionless) or tran + mu^2 tran; pyramidal rows share Rpy = 2 mu^2 R
-        row_params(sr, si, S.con_dist[rc], B2H_LDG(m.cls_incmargin[cls]), pyr ? tran + mu * mu * tran : tran, vel,
-                   pyr ? T(2) * mu * mu : T(1), &rD[s], &raref[s]);
+        pos = S.con_dist[rc]; mg = B2H_LDG(m.cls_incmargin[cls]);
+        dA = pyr ? tran + mu * mu * tran : tran;
+        rs = pyr ? T(2) * mu * mu : T(1);
       }
+      RowParam<T> rp_ = row_params<T>(sr0, sr1, si[0], si[1], si[2], si[3], si[4], pos, mg, dA, vel, rs);
+      rD[s] = rp_.D; raref[s] = rp_.aref;
     }
   }
   T lsign = 0, lD = 0, laref = 0;  // joint limit of this lane's dof: row = lsign * e_dof
@@ -736,9 +781,11 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
       if (q - lo < mg) { lsign = 1; pos = q - lo; }
       else if (hi - q < mg) { lsign = -1; pos = hi - q; }
       if (lsign != T(0)) {
-        T sr[2] = {B2H_LDG(m.dof_solref[lane][0]), B2H_LDG(m.dof_solref[lane][1])}, si[5];
+        T si[5];
         for (int k = 0; k < 5; k++) si[k] = B2H_LDG(m.dof_solimp[lane][k]);
-        row_params(sr, si, pos, mg, B2H_LDG(m.dof_invw[lane]), lsign * st.qv, T(1), &lD, &laref);
+        RowParam<T> rp_ = row_params<T>(B2H_LDG(m.dof_solref[lane][0]), B2H_LDG(m.dof_solref[lane][1]), si[0], si[1], si[2], si[3],
+                                        si[4], pos, mg, B2H_LDG(m.dof_invw[lane]), lsign * st.qv, T(1));
+        lD = rp_.D; laref = rp_.aref;
       }
     }
   }
@@ -756,15 +803,13 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
       for (int k = 0; k < 6; k++) vprev[k] += tmp[TMP_DOFW + 6 * j + k];
     if (!B2H_LDG(m.dof_cdotzero[lane])) cross_motion(cdd, vprev, cd);
   }
-  if (lane < KV) for (int k = 0; k < 6; k++) { S.cdofdot[6 * lane + k] = cdd[k]; tmp[TMP_DOFA + 6 * lane + k] = cdd[k] * (lane < nv ? st.qv : T(0)); }
+  if (lane < KV) for (int k = 0; k < 6; k++) { tmp[TMP_CDD + 6 * lane + k] = cdd[k]; tmp[TMP_DOFA + 6 * lane + k] = cdd[k] * (lane < nv ? st.qv : T(0)); }
   wsync();
   // ---- cvel, cacc (lane = body) as chain sums; cfrc_body = I cacc + cvel x* (I cvel)   (mj_rne, flg_acc = 0)
   if (lane > 0 && lane < nbody) {
     T cv[6] = {0, 0, 0, 0, 0, 0}, ca[6] = {0, 0, 0, 0, 0, 0};
-    uint32_t mask = B2H_LDG(m.body_dofmask[lane]);
-    for (int j = 0; j < nv; j++)
-      if ((mask >> j) & 1u)
-        for (int k = 0; k < 6; k++) { cv[k] += tmp[TMP_DOFW + 6 * j + k]; ca[k] += tmp[TMP_DOFA + 6 * j + k]; }
+    for (int j = B2H_LDG(m.body_lastdof[lane]); j >= 0; j = B2H_LDG(m.dof_parent[j]))
+      for (int k = 0; k < 6; k++) { cv[k] += tmp[TMP_DOFW + 6 * j + k]; ca[k] += tmp[TMP_DOFA + 6 * j + k]; }
     for (int k = 0; k < 3; k++) ca[3 + k] -= B2H_LDG(m.gravity[k]);
     for (int k = 0; k < 6; k++) S.cvel[6 * lane + k] = cv[k];
     T f[6], t1[6], t2[6];
@@ -800,14 +845,13 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
       qfrc_smooth = passive - qfrc_bias + act;
     } else st.qfrc_act = 0;
   }
+  if (dbg) for (int i = lane; i < KV * 6; i += 32) dbg->cdofdot[i] = tmp[TMP_CDD + i];
   wsync();  // stage scratch in A is dead from here
 
   // =============================================================== acceleration: qacc_smooth = M^-1 qfrc_smooth
   for (int i = lane; i < LD * LD; i += 32) S.A[i] = S.M[i];
   wsync();
-  chol_factor(S.A, nv, lane);
-  T qacc_smooth = chol_solve(S.A, nv, lane, qfrc_smooth);
-  wsync();
+  T qacc_smooth = chol_solve_fused(S.A, nv, lane, qfrc_smooth);
 
   // =============================================================== mj_fwdConstraint: Newton solver (primal)
   T qacc = qacc_smooth, qfrc_con = 0;
@@ -822,7 +866,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
         int r = lane + 32 * s;
         T a = 0;
         if (r < nrow) {
-          const T* jr = S.J + r * LD;
+          const T* jr = jrow(r);
 #pragma unroll
           for (int c4 = 0; c4 < LD; c4 += 4) {
             V4<T> u = ld4(jr + c4), w = ld4(S.vec[2] + c4);
@@ -841,7 +885,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
       return wsum(c);
     };
     // ---- warmstart(): the cheaper of qacc_warmstart and qacc_smooth
-    T jar[2], ljar;
+    T jar[NSLOT] = {0, 0, 0}, ljar;
     jar_of(st.warm, jar, &ljar);
     T cost_warm = row_cost(jar, ljar);
     T Ma = mat_vec(S.M, S.vec[2], nv, lane);
@@ -851,24 +895,26 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
     if (cost_warm > cost_smooth) qacc = qacc_smooth;
     else { qacc = st.warm; }
     // ---- mj_solPrimal (Newton): state at the starting point
-    T Jaref[2], lJaref;
+    T Jaref[NSLOT], lJaref;
     jar_of(qacc, jar, &ljar);
-    for (int s = 0; s < 2; s++) Jaref[s] = jar[s] - raref[s];
+#pragma unroll
+    for (int s = 0; s < NSLOT; s++) Jaref[s] = jar[s] - raref[s];
     lJaref = ljar - laref;
     Ma = mat_vec(S.M, S.vec[2], nv, lane);
     const T scale = T(1) / (B2H_LDG(m.meaninertia) * T(nv > 1 ? nv : 1));
     const T tolerance = T(1e-8), ls_tolerance = T(0.01);
     const int ls_iterations = 50;
     T cost = 0, gauss = 0, grad = 0, search = 0;
-    bool first = true;
+    bool first = true, full_step = false, tiny_step = false;
+    unsigned pact[NSLOT] = {0, 0, 0}, pactl = 0;  // active sets the current Hessian was built from
     for (;;) {
       // -- PrimalUpdateConstraint: active rows, forces, cost
-      unsigned act0, act1 = 0, actl;
-      T f[2] = {0, 0}, lf = 0, c = 0;
+      unsigned act[NSLOT] = {0, 0, 0}, actl;
+      T f[NSLOT] = {0, 0, 0}, lf = 0, c = 0;
       B2H_SLOTS(s) {
         bool on = lane + 32 * s < nrow && Jaref[s] < T(0);
         if (on) { f[s] = -rD[s] * Jaref[s]; c += T(0.5) * rD[s] * Jaref[s] * Jaref[s]; }
-        if (s == 0) act0 = ballot(on); else act1 = ballot(on);
+        act[s] = ballot(on);
       }
       {
         bool on = lsign != T(0) && lJaref < T(0);
@@ -881,12 +927,12 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
       // qfrc_constraint = J^T f (dense active rows) + limit force
       qfrc_con = lsign * lf;
       B2H_SLOTS(s) {
-        unsigned am = s == 0 ? act0 : act1;
+        unsigned am = act[s];
         while (am) {
           int b = ffs32(am) - 1;
           am &= am - 1;
           T fr = shfl(f[s], b);
-          if (lane < nv) qfrc_con += S.J[(b + 32 * s) * LD + lane] * fr;
+          if (lane < nv) qfrc_con += jrow(b + 32 * s)[lane] * fr;
         }
       }
       if (!first) {
@@ -894,20 +940,24 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
         T gn = m_sqrt(wsum(lane < nv ? (Ma - qfrc_smooth - qfrc_con) * (Ma - qfrc_smooth - qfrc_con) : T(0)));
         niter++;
         if (improvement < m_max(tolerance, Tol<T>::cost_rel * scale * m_abs(cost)) || scale * gn < tolerance) break;
+        if (Tol<T>::exact_stop && (full_step || tiny_step) && act[0] == pact[0] && act[1] == pact[1] && act[2] == pact[2] && actl == pactl) break;
         if (niter >= Tol<T>::maxiter) { cnt.iter_cap++; break; }
       }
       first = false;
+#pragma unroll
+      for (int s = 0; s < NSLOT; s++) pact[s] = act[s];
+      pactl = actl;
       // -- Hessian H = M + J^T diag(D active) J, built per column (lane j owns column j), then factored
       {
         T acc[LD];
 #pragma unroll
         for (int i = 0; i < LD; i++) acc[i] = S.M[i * LD + (lane < LD ? lane : 0)];
         B2H_SLOTS(s) {
-          unsigned am = s == 0 ? act0 : act1;
+          unsigned am = act[s];
           while (am) {
             int b = ffs32(am) - 1;
             am &= am - 1;
-            const T* jr = S.J + (b + 32 * s) * LD;
+            const T* jr = jrow(b + 32 * s);
             T t = shfl(rD[s], b) * jr[lane < LD ? lane : 0];
 #pragma unroll
             for (int c4 = 0; c4 < LD; c4 += 4) {
@@ -924,35 +974,34 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
         wsync();
         if ((actl >> lane) & 1u) S.A[lane * LD + lane] += lD;
         wsync();
-        chol_factor(S.A, nv, lane);
       }
-      // -- PrimalUpdateGradient + Newton direction
+      // -- PrimalUpdateGradient + Newton direction: search = -H^-1 grad
       grad = lane < nv ? Ma - qfrc_smooth - qfrc_con : T(0);
-      search = -chol_solve(S.A, nv, lane, grad);
+      search = -chol_solve_fused(S.A, nv, lane, grad);
       // -- PrimalSearch: exact line search on the piecewise-quadratic cost along `search`
       T snorm = m_sqrt(wsum(lane < nv ? search * search : T(0)));
       T alpha = 0;
-      T Jv[2] = {0, 0}, lJv = 0, Mv = 0;
+      T Jv[NSLOT] = {0, 0, 0}, lJv = 0, Mv = 0;
       if (snorm >= B2H_MINVAL) {
         T gtol = tolerance * ls_tolerance * snorm / scale;
         jar_of(search, Jv, &lJv);
         Mv = mat_vec(S.M, S.vec[2], nv, lane);
         T qg1 = wsum(lane < nv ? search * (Ma - qfrc_smooth) : T(0));
         T qg2 = wsum(lane < nv ? T(0.5) * search * Mv : T(0));
-        T q0r[3] = {0, 0, 0}, q1r[3] = {0, 0, 0}, q2r[3] = {0, 0, 0};  // per-row quadratics (slots 0,1 + limit)
+        T q0r[NSLOT + 1] = {0, 0, 0, 0}, q1r[NSLOT + 1] = {0, 0, 0, 0}, q2r[NSLOT + 1] = {0, 0, 0, 0};  // per-row quadratics (slots + limit)
         B2H_SLOTS(s) {
           if (lane + 32 * s < nrow) {
             q0r[s] = T(0.5) * rD[s] * Jaref[s] * Jaref[s]; q1r[s] = rD[s] * Jaref[s] * Jv[s]; q2r[s] = T(0.5) * rD[s] * Jv[s] * Jv[s];
           }
         }
-        if (lsign != T(0)) { q0r[2] = T(0.5) * lD * lJaref * lJaref; q1r[2] = lD * lJaref * lJv; q2r[2] = T(0.5) * lD * lJv * lJv; }
+        if (lsign != T(0)) { q0r[NSLOT] = T(0.5) * lD * lJaref * lJaref; q1r[NSLOT] = lD * lJaref * lJv; q2r[NSLOT] = T(0.5) * lD * lJv * lJv; }
         int lsiter = 0;
         struct Pnt { T alpha, cost, d0, d1; };
         auto eval = [&](T a) {
           T s0 = 0, s1 = 0, s2 = 0;
           B2H_SLOTS(s)
             if (lane + 32 * s < nrow && Jaref[s] + a * Jv[s] < T(0)) { s0 += q0r[s]; s1 += q1r[s]; s2 += q2r[s]; }
-          if (lsign != T(0) && lJaref + a * lJv < T(0)) { s0 += q0r[2]; s1 += q1r[2]; s2 += q2r[2]; }
+          if (lsign != T(0) && lJaref + a * lJv < T(0)) { s0 += q0r[NSLOT]; s1 += q1r[NSLOT]; s2 += q2r[NSLOT]; }
           s0 = wsum(s0) + gauss; s1 = wsum(s1) + qg1; s2 = wsum(s2) + qg2;
           Pnt p;
           p.alpha = a; p.cost = a * a * s2 + a * s1 + s0; p.d0 = T(2) * a * s2 + s1; p.d1 = T(2) * s2;
@@ -963,9 +1012,11 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
         Pnt p0 = eval(T(0));
         gtol = m_max(gtol, Tol<T>::ls_rel * m_abs(p0.d0));
         Pnt p1 = eval(p0.alpha - p0.d0 / p0.d1);
+        full_step = !(p0.cost < p1.cost);
         if (p0.cost < p1.cost) p1 = p0;
         bool done = false;
         if (m_abs(p1.d0) < gtol) { alpha = p1.alpha; done = true; }
+        else full_step = false;
         if (!done) {
           int dir = p1.d0 < T(0) ? 1 : -1;
           bool p2update = false;
@@ -1009,8 +1060,14 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
         cnt.ls_eval += lsiter;
       }
       if (alpha == T(0)) break;
+      if (Tol<T>::step_rel > T(0)) {  // step below the resolution of qacc
+        T amax = m_abs(qacc), smax = m_abs(alpha * search);
+        for (int o = 16; o > 0; o >>= 1) { amax = m_max(amax, shfl_xor(amax, o)); smax = m_max(smax, shfl_xor(smax, o)); }
+        tiny_step = smax < Tol<T>::step_rel * m_max(amax, T(1));
+      }
       qacc += alpha * search; Ma += alpha * Mv;
-      for (int s = 0; s < 2; s++) Jaref[s] += alpha * Jv[s];
+#pragma unroll
+      for (int s = 0; s < NSLOT; s++) Jaref[s] += alpha * Jv[s];
       lJaref += alpha * lJv;
     }
     cnt.newton_iter += niter;
@@ -1019,9 +1076,19 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
     st.warm = qacc_smooth;
   }
   if (stats) { stats->ncon = ncon; stats->nrow = nrow; stats->nlimit = popc(limit_mask); stats->niter = niter; }
-  if (dbg_lane) {
-    dbg_lane[0] = qfrc_bias; dbg_lane[1] = qfrc_smooth; dbg_lane[2] = qacc_smooth; dbg_lane[3] = qacc;
-    dbg_lane[4] = qfrc_con; dbg_lane[5] = st.qfrc_act; dbg_lane[6] = lsign * lD; dbg_lane[7] = laref;
+  if (dbg) {
+    T* dl = dbg->lane[lane];
+    dl[0] = qfrc_bias; dl[1] = qfrc_smooth; dl[2] = qacc_smooth; dl[3] = qacc;
+    dl[4] = qfrc_con; dl[5] = st.qfrc_act; dl[6] = lsign * lD; dl[7] = laref;
+    for (int i = lane; i < LD * LD; i += 32) dbg->M[i] = S.M[i];
+    for (int r = 0; r < nrow; r++) if (lane < LD) dbg->J[r * LD + lane] = jrow(r)[lane];
+    for (int i = lane; i < KB * 10; i += 32) dbg->cinert[i] = S.cinert[i];
+    for (int i = lane; i < KB * 6; i += 32) dbg->cvel[i] = S.cvel[i];
+    for (int i = lane; i < KV * 6; i += 32) dbg->cdof[i] = S.cdof[i];
+    for (int i = lane; i < NCON; i += 32) dbg->con_dist[i] = S.con_dist[i];
+    for (int i = lane; i < NCON * 3; i += 32) dbg->con_pos[i] = S.con_pos[i];
+    for (int i = lane; i < NCON * 9; i += 32) dbg->con_frame[i] = S.con_frame[i];
+    if (lane < 3) dbg->com[lane] = S.com[lane];
   }
   if (qacc_out) *qacc_out = qacc;
   if (!integrate) return false;
@@ -1040,8 +1107,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
   wsync();
   if (lane < nv) S.A[lane * LD + lane] += h * B2H_LDG(m.dof_damping[lane]);
   wsync();
-  chol_factor(S.A, nv, lane);
-  T qacc_e = chol_solve(S.A, nv, lane, qfrc_smooth + qfrc_con);
+  T qacc_e = chol_solve_fused(S.A, nv, lane, qfrc_smooth + qfrc_con);
   if (lane < nv) st.qv += h * qacc_e;
   {  // mj_integratePos: hinges and root position by lanes, root quaternion (lanes 3..6) via mju_quatIntegrate
     int dsrc = lane < nq ? B2H_LDG(m.qpos_dof[lane]) : -1;
@@ -1069,9 +1135,9 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, EnvState
   return false;
 }
 template <typename T>
-B2H_DEV void mj_step(const DevModel<T>& m, Scratch<T>& S, EnvState<T>& st, Counters& cnt) {
+B2H_DEV void mj_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt) {
   for (int tries = 0; tries < 2; tries++)
-    if (!physics_step<T>(m, S, st, cnt, true, nullptr, nullptr, nullptr)) break;
+    if (!physics_step<T>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr)) break;
 }
 
 // ------------------------------------------------------------------------------------------------ env layer
@@ -1170,7 +1236,7 @@ struct EnvIO {  // device arrays, all [n_envs, dim] row-major
 
 // HumanoidEnv.reset (custom_env.py:97-150): qpos0 + masked U(-0.01,0.01) noise, one settle step with ctrl = 0
 template <typename T>
-B2H_DEV void env_reset(const DevModel<T>& m, Scratch<T>& S, EnvState<T>& st, Counters& cnt, const EnvParams& P,
+B2H_DEV void env_reset(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, const EnvParams& P,
                        const EnvIO<T>& io, int env, int lane) {
   const int nq = B2H_LDG(m.nq), nv = B2H_LDG(m.nv);
   const int nqv = nq + nv;
@@ -1196,53 +1262,69 @@ B2H_DEV void env_reset(const DevModel<T>& m, Scratch<T>& S, EnvState<T>& st, Cou
   st.qp = lane < nq ? T(q0 + npos) : T(0);
   st.qv = lane < nv ? T(nvel) : T(0);
   st.warm = 0; st.ctrl = 0; st.qfrc_act = 0; st.nstep = 0;
-  mj_step<T>(m, S, st, cnt);
+  mj_step<T>(m, S, Jspill, st, cnt);
 }
 
 // HumanoidEnv.step + SubprocVecEnv auto-reset for one env (custom_env.py:152-230; SB3 subproc_vec_env._worker)
 template <typename T>
-B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, Counters& cnt, const EnvParams& P, const EnvIO<T>& io, int env) {
+B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& cnt, const EnvParams& P, const EnvIO<T>& io, int env,
+                      bool active) {
+  // All warps of a CTA enter every sub-step together (cta_sync): they then walk the same instructions at about
+  // the same time, which keeps the (large, mostly straight-line) step code resident in the instruction cache.
+  // `active` is warp-uniform; inactive warps (tail of the env list) only take part in the barriers.
   const int lane = lane_id();
   const int nq = B2H_LDG(m.nq), nv = B2H_LDG(m.nv), nu = B2H_LDG(m.nu);
   EnvState<T> st;
-  st.qp = lane < nq ? io.qpos[(size_t)env * nq + lane] : T(0);
-  st.qv = lane < nv ? io.qvel[(size_t)env * nv + lane] : T(0);
-  st.warm = lane < nv ? io.warm[(size_t)env * nv + lane] : T(0);
-  st.nstep = io.nstep[env];
-  st.qfrc_act = 0;
-  int a = lane < nv ? B2H_LDG(m.dof_act[lane]) : -1;
-  st.ctrl = a >= 0 ? T(io.actions[(size_t)env * nu + a]) : T(0);
-  int step_count = io.step_count[env] + 1;
-  for (int s = 0; s < P.frame_skip; s++) {
-    // data.ctrl[:] = action before every mj_step (a bad-state reset inside the previous sub-step zeroed it)
-    st.ctrl = a >= 0 ? T(io.actions[(size_t)env * nu + a]) : T(0);
-    mj_step<T>(m, S, st, cnt);
+  st.qp = 0; st.qv = 0; st.warm = 0; st.ctrl = 0; st.qfrc_act = 0; st.nstep = 0;
+  int a = -1, step_count = 0;
+  if (active) {
+    st.qp = lane < nq ? io.qpos[(size_t)env * nq + lane] : T(0);
+    st.qv = lane < nv ? io.qvel[(size_t)env * nv + lane] : T(0);
+    st.warm = lane < nv ? io.warm[(size_t)env * nv + lane] : T(0);
+    st.nstep = io.nstep[env];
+    a = lane < nv ? B2H_LDG(m.dof_act[lane]) : -1;
+    step_count = io.step_count[env] + 1;
   }
-  T* obs = io.obs + (size_t)env * io.obs_dim;
-  bool truncated = step_count >= P.max_steps;
-  T reward = truncated ? T(0) : compute_reward<T>(m, S, st, P, lane);
-  // terminated = data.time >= duration, with time = nstep * timestep evaluated in double
-  bool terminated = (double)st.nstep * P.timestep >= P.duration;
-  T total = io.total_reward[env] + reward;
-  if (lane == 0) { io.reward[env] = reward; io.terminated[env] = terminated; io.truncated[env] = truncated; }
-  if (terminated || truncated) {
-    if (io.terminal_obs) write_obs<T>(m, S, st, P.obs_mode, io.terminal_obs + (size_t)env * io.obs_dim, lane);
-    env_reset<T>(m, S, st, cnt, P, io, env, lane);
+  for (int s = 0; s < P.frame_skip; s++) {
+    cta_sync();
+    if (active) {
+      // data.ctrl[:] = action before every mj_step (a bad-state reset inside the previous sub-step zeroed it)
+      st.ctrl = a >= 0 ? T(io.actions[(size_t)env * nu + a]) : T(0);
+      mj_step<T>(m, S, Jspill, st, cnt);
+    }
+  }
+  bool done = false;
+  T total = 0;
+  if (active) {
+    bool truncated = step_count >= P.max_steps;
+    T reward = truncated ? T(0) : compute_reward<T>(m, S, st, P, lane);
+    // terminated = data.time >= duration, with time = nstep * timestep evaluated in double
+    bool terminated = (double)st.nstep * P.timestep >= P.duration;
+    total = io.total_reward[env] + reward;
+    if (lane == 0) { io.reward[env] = reward; io.terminated[env] = terminated; io.truncated[env] = truncated; }
+    done = terminated || truncated;
+    if (done && io.terminal_obs) write_obs<T>(m, S, st, P.obs_mode, io.terminal_obs + (size_t)env * io.obs_dim, lane);
+  }
+  cta_sync();
+  if (active && done) {
+    env_reset<T>(m, S, Jspill, st, cnt, P, io, env, lane);
     step_count = 0; total = 0;
   }
-  write_obs<T>(m, S, st, P.obs_mode, obs, lane);
-  if (lane < nq) io.qpos[(size_t)env * nq + lane] = st.qp;
-  if (lane < nv) { io.qvel[(size_t)env * nv + lane] = st.qv; io.warm[(size_t)env * nv + lane] = st.warm; }
-  if (lane == 0) { io.nstep[env] = st.nstep; io.step_count[env] = step_count; io.total_reward[env] = total; }
+  if (active) {
+    write_obs<T>(m, S, st, P.obs_mode, io.obs + (size_t)env * io.obs_dim, lane);
+    if (lane < nq) io.qpos[(size_t)env * nq + lane] = st.qp;
+    if (lane < nv) { io.qvel[(size_t)env * nv + lane] = st.qv; io.warm[(size_t)env * nv + lane] = st.warm; }
+    if (lane == 0) { io.nstep[env] = st.nstep; io.step_count[env] = step_count; io.total_reward[env] = total; }
+  }
 }
 
 // reset path on its own (b2h_reset): reset env, write the first observation
 template <typename T>
-B2H_DEV void env_reset_only(const DevModel<T>& m, Scratch<T>& S, Counters& cnt, const EnvParams& P, const EnvIO<T>& io, int env) {
+B2H_DEV void env_reset_only(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& cnt, const EnvParams& P, const EnvIO<T>& io, int env) {
   const int lane = lane_id();
   const int nq = B2H_LDG(m.nq), nv = B2H_LDG(m.nv);
   EnvState<T> st;
-  env_reset<T>(m, S, st, cnt, P, io, env, lane);
+  env_reset<T>(m, S, Jspill, st, cnt, P, io, env, lane);
   if (io.obs) write_obs<T>(m, S, st, P.obs_mode, io.obs + (size_t)env * io.obs_dim, lane);
   if (lane < nq) io.qpos[(size_t)env * nq + lane] = st.qp;
   if (lane < nv) { io.qvel[(size_t)env * nv + lane] = st.qv; io.warm[(size_t)env * nv + lane] = st.warm; }

@@ -44,6 +44,7 @@ struct Job {
   int mode;  // 0 step, 1 reset, 2 forward-dump
   const DevModel<T>* m;
   Scratch<T>* S;
+  T* Jspill;
   EnvParams P;
   EnvIO<T> io;
   int n_envs;
@@ -59,8 +60,8 @@ static void* lane_main(void* arg) {
   emu::tl_lane = pr->second;
   Counters& cnt = j->cnt[pr->second];
   for (int e = 0; e < j->n_envs; e++) {
-    if (j->mode == 0) env_step<T>(*j->m, *j->S, cnt, j->P, j->io, e);
-    else if (j->mode == 1) env_reset_only<T>(*j->m, *j->S, cnt, j->P, j->io, e);
+    if (j->mode == 0) env_step<T>(*j->m, *j->S, j->Jspill, cnt, j->P, j->io, e, true);
+    else if (j->mode == 1) env_reset_only<T>(*j->m, *j->S, j->Jspill, cnt, j->P, j->io, e);
     else if (e == j->dump_env) {
       const int lane = emu::tl_lane, nq = j->m->nq, nv = j->m->nv, nu = j->m->nu;
       EnvState<T> st;
@@ -72,7 +73,7 @@ static void* lane_main(void* arg) {
       int a = lane < nv ? j->m->dof_act[lane] : -1;
       st.ctrl = (a >= 0 && j->io.actions) ? T(j->io.actions[(size_t)e * nu + a]) : T(0);
       T qacc;
-      physics_step<T>(*j->m, *j->S, st, cnt, false, &j->dump->stats, &qacc, j->dump->lane[lane]);
+      physics_step<T>(*j->m, *j->S, j->Jspill, st, cnt, false, &j->dump->stats, &qacc, j->dump);
       emu::sync();
     }
   }
@@ -108,7 +109,9 @@ static int emu_run(int mode, const B2HModel* model, const B2HConfig* cfg, double
   for (int i = 0; i < E; i++) tr[i] = (T)total_reward[i];
   static Scratch<T> S;
   static DebugDump<T> dump;
+  static T spill[(NROW - NROW_S) * LD];
   Job<T> job;
+  job.Jspill = spill;
   job.mode = mode; job.m = &dm; job.S = &S; job.n_envs = E; job.dump_env = dump_env; job.dump = &dump;
   job.P.frame_skip = cfg->frame_skip; job.P.reward_type = cfg->reward_type; job.P.obs_mode = cfg->obs_mode;
   job.P.max_steps = cfg->max_steps; job.P.duration = cfg->duration; job.P.timestep = model->timestep;
@@ -119,10 +122,7 @@ static int emu_run(int mode, const B2HModel* model, const B2HConfig* cfg, double
   job.io.actions = actions; job.io.obs = ob.data(); job.io.reward = rw.data(); job.io.terminal_obs = tob.data();
   job.io.terminated = terminated; job.io.truncated = truncated; job.io.obs_dim = obs_dim;
   run_lanes<T>(job);
-  if (mode == 2) {
-    dump.S = S;
-    return extract_named<T>(dm, dump, what, dump_out, dump_max);
-  }
+  if (mode == 2) return extract_named<T>(dm, dump, what, dump_out, dump_max);
   for (int i = 0; i < E * nq; i++) qpos[i] = (double)q[i];
   for (int i = 0; i < E * nv; i++) { qvel[i] = (double)v[i]; warm[i] = (double)w[i]; }
   for (int i = 0; i < E; i++) { total_reward[i] = (double)tr[i]; if (reward) reward[i] = (double)rw[i]; }

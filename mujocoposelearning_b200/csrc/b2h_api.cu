@@ -6,6 +6,7 @@
 // and writes one contiguous record per field.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include <mutex>
 #include <string>
@@ -168,9 +169,14 @@ static int create_typed(B2HHandle* h) {
   int warps = (int)((size_t)max_smem / sizeof(Scratch<T>));
   if (warps > max_threads<T>() / 32) warps = max_threads<T>() / 32;
   if (warps < 1) return fail(B2H_EUNSUPPORTED, "per-env scratch does not fit in shared memory");
+  int ctas_per_sm = 1;
+  if (const char* w = getenv("B2H_WARPS_PER_CTA")) {  // tuning knob: smaller lockstep groups, several CTAs per SM
+    int req = atoi(w);
+    if (req >= 1 && req <= warps) { ctas_per_sm = warps / req; warps = req; }
+  }
   h->warps = warps;
   h->smem = (size_t)warps * sizeof(Scratch<T>);
-  h->grid = nsm;
+  h->grid = nsm * ctas_per_sm;
   CU(cudaMalloc(&h->spill, (size_t)h->grid * warps * (NROW - NROW_S) * LD * sizeof(T)));
   CU(cudaFuncSetAttribute(step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   CU(cudaFuncSetAttribute(reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
@@ -214,6 +220,8 @@ int b2h_create(const B2HModel* model, const B2HConfig* cfg, B2HHandle** out) {
   h->P.max_steps = cfg->max_steps; h->P.duration = cfg->duration; h->P.timestep = model->timestep;
   for (int k = 0; k < 9; k++) h->P.kneel[k] = cfg->kneeling_params[k];
   h->P.seed = cfg->seed; h->P.env_id_offset = cfg->env_id_offset;
+  h->P.sync_mode = 2;
+  if (const char* sm = getenv("B2H_SYNC_MODE")) h->P.sync_mode = atoi(sm);  // tuning knob, see env_step
   int rc = cfg->dtype == B2H_F64 ? create_typed<double>(h) : create_typed<float>(h);
   if (rc != B2H_OK) { b2h_destroy(h); return rc; }
   size_t E = (size_t)cfg->n_envs, esz = (size_t)h->esz;

@@ -1160,6 +1160,7 @@ struct EnvParams {
   double kneel[9];
   uint64_t seed;
   int env_id_offset;
+  int sync_mode;  // CTA lockstep: 0 none, 1 once per control step, 2 before every physics sub-step
 };
 
 template <typename T> B2H_DEV void quat_to_euler(const T* q, T* roll, T* pitch) {  // utils.py:3-20 (pitch unclamped)
@@ -1285,8 +1286,9 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     a = lane < nv ? B2H_LDG(m.dof_act[lane]) : -1;
     step_count = io.step_count[env] + 1;
   }
+  if (P.sync_mode == 1) cta_sync();
   for (int s = 0; s < P.frame_skip; s++) {
-    cta_sync();
+    if (P.sync_mode == 2) cta_sync();
     if (active) {
       // data.ctrl[:] = action before every mj_step (a bad-state reset inside the previous sub-step zeroed it)
       st.ctrl = a >= 0 ? T(io.actions[(size_t)env * nu + a]) : T(0);
@@ -1305,7 +1307,7 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     done = terminated || truncated;
     if (done && io.terminal_obs) write_obs<T>(m, S, st, P.obs_mode, io.terminal_obs + (size_t)env * io.obs_dim, lane);
   }
-  cta_sync();
+  if (P.sync_mode == 2) cta_sync();
   if (active && done) {
     env_reset<T>(m, S, Jspill, st, cnt, P, io, env, lane);
     step_count = 0; total = 0;

@@ -1,0 +1,46 @@
+"""Multi-GPU plumbing: environments shard across ranks with no data-path collective.
+
+One process per GPU (torchrun); rank r owns the global env ids [r * E, (r + 1) * E).  Reset noise is keyed by the
+*global* env id, so a trajectory does not depend on how many GPUs the batch is spread over.  Collectives (NCCL on
+GPUs, gloo in the CPU tests) carry only rollout statistics and timing.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.distributed as dist
+
+
+def rank_info():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def env_shard(envs_per_gpu, rank=None, world=None):
+    """(env_id_offset, global env count) of this rank's shard."""
+    r, w, _ = rank_info()
+    rank = r if rank is None else rank
+    world = w if world is None else world
+    return rank * envs_per_gpu, world * envs_per_gpu
+
+
+def max_over_ranks(values):
+    """Element-wise max over ranks of a list of floats (timing: a step is as slow as the slowest rank)."""
+    t = torch.tensor(list(values), dtype=torch.float64)
+    if dist.is_available() and dist.is_initialized():
+        dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+        t = t.to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.cpu().tolist()
+
+
+def reduce_rollout_stats(episode_return_sum, episode_len_sum, episode_count, device=None):
+    """Sum episode statistics over ranks -> (mean return, mean length, episodes).  The only rollout-time collective."""
+    t = torch.tensor([float(episode_return_sum), float(episode_len_sum), float(episode_count)], dtype=torch.float64)
+    if dist.is_available() and dist.is_initialized():
+        if device is not None:
+            t = t.to(device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    s = t.cpu().tolist()
+    n = max(s[2], 1.0)
+    return s[0] / n, s[1] / n, int(s[2])

@@ -1027,6 +1027,20 @@ static double reward_kneeling(const OrcEnv* d, const double* p) { /* reward_func
   return p[5] * posture + p[6] * com_score + p[7] * foot_balance + p[4] * energy + p[8] * alive;
 }
 
+/* reward of `reward_type` on an explicit mjData-like record (golden-vector checks against reward_functions.py) */
+double orc_reward_eval(OrcEnv* d, int reward_type, const double* kneel, const double* qpos, const double* qvel,
+                       const double* ctrl, const double* qfrc_actuator, const double* com0, double time) {
+  memcpy(d->qpos, qpos, sizeof(double) * d->m.nq);
+  memcpy(d->qvel, qvel, sizeof(double) * d->m.nv);
+  memcpy(d->ctrl, ctrl, sizeof(double) * d->m.nu);
+  memcpy(d->qfrc_actuator, qfrc_actuator, sizeof(double) * d->m.nv);
+  memcpy(d->subtree_com[0], com0, sizeof(double) * 3);
+  d->time = time;
+  if (reward_type == B2H_REWARD_STAND) return reward_stand(d);
+  if (reward_type == B2H_REWARD_KNEELING) return reward_kneeling(d, kneel);
+  return reward_walk(d);
+}
+
 /* HumanoidEnv.reset (custom_env.py:97-150) with explicit noise [nq+nv] (the reference draws it from the
  * global numpy RNG: U(-0.01,0.01), pos first then vel); the z/quaternion masking is applied here. */
 void orc_env_reset(OrcEnv* d, const double* noise, double* obs) {

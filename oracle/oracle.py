@@ -52,6 +52,8 @@ def lib():
         L.orc_vec_step.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_int, C.c_int]
+        L.orc_reward_eval.restype = C.c_double
+        L.orc_reward_eval.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 6 + [C.c_double]
         L.orc_gae.argtypes = [C.c_void_p] * 5 + [C.c_double, C.c_double, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -116,6 +118,14 @@ class OracleEnv:
         o = np.zeros(self.obs_dim)
         lib().orc_obs(self.h, _p(o))
         return o
+
+    def reward_eval(self, reward_type, qpos, qvel, ctrl, qfrc_actuator, com0, time, kneel_params=None):
+        from mujocoposelearning_b200.abi import KNEELING_DEFAULTS
+        kp = _d(KNEELING_DEFAULTS if kneel_params is None else kneel_params)
+        c = np.zeros(32)
+        c[:self.nu] = ctrl
+        a = [_d(x) for x in (qpos, qvel, c, qfrc_actuator, com0)]
+        return lib().orc_reward_eval(self.h, reward_type, _p(kp), *[_p(x) for x in a], float(time))
 
     # --- HumanoidEnv
     def env_reset(self, noise):

@@ -13,27 +13,28 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 SRC = HERE / "emu" / "b2h_emu.cpp"
-LIB = HERE / "emu" / "_build" / "libb2h_emu.so"
 CSRC = HERE.parent / "mujocoposelearning_b200" / "csrc"
-_lib = None
+_libs = {}
 
 
-def build(force=False):
+def build(nrow_s=None, force=False):
+    """nrow_s overrides the number of constraint rows kept in shared memory (exercises the global spill path)."""
+    out = HERE / "emu" / "_build" / (f"libb2h_emu_s{nrow_s}.so" if nrow_s else "libb2h_emu.so")
     deps = [SRC] + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "b2h.h"]
-    if force or not LIB.exists() or LIB.stat().st_mtime < max(p.stat().st_mtime for p in deps):
-        LIB.parent.mkdir(exist_ok=True)
-        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", str(LIB), str(SRC),
-                        "-lpthread"], check=True, capture_output=True)
-    return LIB
+    if force or not out.exists() or out.stat().st_mtime < max(p.stat().st_mtime for p in deps):
+        out.parent.mkdir(exist_ok=True)
+        extra = [f"-DB2H_NROW_S={nrow_s}"] if nrow_s else []
+        subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas"] + extra +
+                       ["-o", str(out), str(SRC), "-lpthread"], check=True, capture_output=True)
+    return out
 
 
-def lib():
-    global _lib
-    if _lib is None:
-        build()
-        _lib = C.CDLL(str(LIB))
-        _lib.emu_run_any.restype = C.c_int
-    return _lib
+def lib(nrow_s=None):
+    if nrow_s not in _libs:
+        L = C.CDLL(str(build(nrow_s)))
+        L.emu_run_any.restype = C.c_int
+        _libs[nrow_s] = L
+    return _libs[nrow_s]
 
 
 def _p(a):
@@ -43,8 +44,8 @@ def _p(a):
 class EmuBatch:
     """State of n envs advanced by the emulated kernels (host arrays in double, like b2h_get_state)."""
 
-    def __init__(self, model_struct, cfg, nq, nv, nu):
-        self.model, self.cfg = model_struct, cfg
+    def __init__(self, model_struct, cfg, nq, nv, nu, nrow_s=None):
+        self.model, self.cfg, self.nrow_s = model_struct, cfg, nrow_s
         self.n, self.nq, self.nv, self.nu = cfg.n_envs, nq, nv, nu
         self.f64 = int(cfg.dtype == 1)
         n = self.n
@@ -62,7 +63,7 @@ class EmuBatch:
         rew = np.zeros(n)
         term, trunc = np.zeros(n, np.uint8), np.zeros(n, np.uint8)
         a = None if actions is None else np.ascontiguousarray(actions, np.float32).reshape(n, self.nu)
-        rc = lib().emu_run_any(self.f64, mode, C.byref(self.model), C.byref(self.cfg), _p(self.qpos), _p(self.qvel),
+        rc = lib(self.nrow_s).emu_run_any(self.f64, mode, C.byref(self.model), C.byref(self.cfg), _p(self.qpos), _p(self.qvel),
                                _p(self.warm), _p(self.nstep), _p(self.step_count), _p(self.episode), _p(self.total_reward),
                                _p(self.reset_noise), _p(self.noise_injected), _p(a), _p(obs), _p(rew), _p(tobs), _p(term),
                                _p(trunc), _p(self.counters), dump_env, what, _p(dump), 0 if dump is None else dump.size)

@@ -1,0 +1,56 @@
+"""The C-ABI boundary: libb2h.so builds for sm_100a, loads, and exports every symbol include/b2h.h declares.
+No compute calls here (no GPU in this suite): b2h_create must refuse loudly instead of falling back to the CPU."""
+import ctypes as C
+import re
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parents[1]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mujocoposelearning_b200.build import build
+    build()
+    from mujocoposelearning_b200.lib import load
+    return load()
+
+
+def test_exports_every_declared_symbol(lib):
+    header = (ROOT / "include" / "b2h.h").read_text()
+    declared = set(re.findall(r"\b(b2h_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 18
+    raw = C.CDLL(str(ROOT / "mujocoposelearning_b200" / "libb2h.so"))
+    missing = [n for n in sorted(declared) if not hasattr(raw, n)]
+    assert not missing, missing
+
+
+def test_struct_layouts_match(lib):
+    from mujocoposelearning_b200 import abi
+    assert lib.b2h_abi_version() == 1
+    assert lib.b2h_sizeof_model() == C.sizeof(abi.B2HModel) and lib.b2h_sizeof_config() == C.sizeof(abi.B2HConfig)
+
+
+def test_create_fails_loudly_without_gpu(lib, model_struct):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from mujocoposelearning_b200 import abi
+    cfg = abi.make_config(4, frame_skip=3, duration=10.0)
+    h = C.c_void_p()
+    rc = lib.b2h_create(C.byref(model_struct), C.byref(cfg), C.byref(h))
+    assert rc == abi.ECUDA and b"no CPU path" in lib.b2h_last_error()
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from mujocoposelearning_b200.lib import B2HError
+    with pytest.raises(B2HError):
+        HumanoidBatch(4)
+
+
+def test_bad_arguments(lib, model_struct):
+    from mujocoposelearning_b200 import abi
+    cfg = abi.make_config(4)
+    cfg.reward_type = 9
+    h = C.c_void_p()
+    assert lib.b2h_create(C.byref(model_struct), C.byref(cfg), C.byref(h)) == abi.EINVAL
+    assert lib.b2h_gae(None, None, None, None, None, 0.99, 0.95, 4, 4, None, None, None) == abi.EINVAL

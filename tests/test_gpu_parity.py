@@ -133,3 +133,64 @@ def test_vec_env_auto_reset_and_determinism(cm):
         outs.append(np.stack(rows))
         env.close()
     assert np.array_equal(outs[0], outs[1])  # same seed -> same reset noise -> identical trajectories
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-9), ("f32", 2e-4)])
+@pytest.mark.parametrize("name", ["env_stand_fs3", "env_kneeling_fs3", "env_walk_default", "env_short_episode"])
+def test_golden_fixture_rollouts(dtype, tol, name):
+    """Whole multi-step trajectories recorded through the reference's own HumanoidEnv class (tests/golden):
+    observation layout, reward dispatch, counters and flags on the CUDA path.  fp32 drifts along a chaotic
+    trajectory, so its tolerance is per-trajectory (single-step fp32 parity is test_single_step_parity)."""
+    from pathlib import Path
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    g = np.load(Path(__file__).parent / "golden" / f"{name}.npz")
+    b = HumanoidBatch(2, frame_skip=int(g["frame_skip"]), duration=float(g["duration"]), reward_type=str(g["reward_type"]), dtype=dtype)
+    noise = np.stack([g["reset_noise"]] * 2)
+    b.set_reset_noise(noise)
+    obs = b.reset().cpu().numpy().astype(np.float64)
+    assert _rel(obs[0], g["reset_obs"]) < tol and np.array_equal(obs[0], obs[1])
+    nsteps = len(g["reward"]) if dtype == "f64" else min(len(g["reward"]), 5)
+    for k in range(nsteps):
+        b.set_reset_noise(noise)
+        a = torch.as_tensor(np.stack([g["actions"][k]] * 2)).cuda()
+        obs, rew, term, trunc = b.step(a)
+        done = bool(g["terminated"][k] or g["truncated"][k])
+        o = (b.terminal_obs if done else obs).cpu().numpy().astype(np.float64)
+        lim = tol * (10 if dtype == "f64" else 1 + k)
+        assert _rel(o[0], g["obs"][k]) < lim, (k, _rel(o[0], g["obs"][k]))
+        assert abs(float(rew[0]) - g["reward"][k]) < lim
+        assert bool(term[0]) == bool(g["terminated"][k]) and bool(trunc[0]) == bool(g["truncated"][k])
+        if done:
+            assert _rel(obs.cpu().numpy()[0].astype(np.float64), g["reset_obs"]) < lim   # auto-reset replays the noise
+    b.close()
+
+
+def test_many_contacts_spill_rows(cm, model_struct):
+    """Prone on the floor (48 dense rows) and a deeper pile-up: contact capacity and the global row spill."""
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from oracle.oracle import OracleEnv
+    n = 4
+    b = HumanoidBatch(n, frame_skip=3, duration=10.0, reward_type="stand", dtype="f64")
+    rng = np.random.default_rng(0)
+    qs, vs = [], []
+    for i in range(n):
+        q = cm.qpos0.copy()
+        q[2] = [0.12, 0.10, 0.07, 0.2][i]
+        ang = [np.pi / 2, np.pi / 2, np.pi / 2, -np.pi / 2][i]
+        q[3:7] = [np.cos(ang / 2), 0, np.sin(ang / 2), 0]
+        q[7:] = rng.uniform(-0.3, 0.3, 21) * (i > 1)
+        qs.append(q); vs.append(rng.normal(0, 0.2, 27))
+    b.set_state(qpos=np.stack(qs), qvel=np.stack(vs), warmstart=np.zeros((n, 27)), nstep=np.zeros(n, np.int32))
+    act = rng.uniform(-1, 1, (n, cm.nu)).astype(np.float32)
+    nrows = [int(b.debug_forward("nrow", i, act)[0]) for i in range(n)]
+    assert max(nrows) >= 48
+    obs, rew, term, trunc = b.step(torch.as_tensor(act).cuda())
+    got = b.get_state()
+    for i in range(n):
+        e = OracleEnv(model_struct, cm.nq, cm.nv, cm.nu)
+        e.set_state(qs[i], vs[i], np.zeros(27), 0, 0)
+        e.env_step(act[i])
+        s = e.get_state()
+        assert _rel(got["qpos"][i], s["qpos"]) < 1e-9 and _rel(got["qvel"][i], s["qvel"]) < 1e-8, (i, nrows[i])
+    assert b.counters()["contact_overflow"] == 0
+    b.close()

@@ -1,0 +1,34 @@
+#!/usr/bin/env python
+"""Text summary of an .ncu-rep (raw page) for profiles/: python tools/ncu_summary.py gpurun_out/prof.ncu-rep > profiles/x.txt"""
+import csv
+import io
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max", "smsp__inst_executed.sum",
+        "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "smsp__warps_eligible.avg.per_cycle_active", "sm__warps_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+
+
+def main(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        print("kernel:", r[hdr.index("Kernel Name")][:110])
+        for k in KEYS:
+            if k in hdr:
+                print(f"  {k:72s} {r[hdr.index(k)]:>16s} {units[hdr.index(k)]}")
+        for i, k in enumerate(hdr):
+            if "issue_stalled" in k and "per_issue_active" in k and float(r[i] or 0) >= 0.05:
+                print(f"  {k:72s} {r[i]:>16s}")
+        print()
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])

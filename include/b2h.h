@@ -210,6 +210,22 @@ int b2h_gae(const float* rewards_dev, const float* values_dev, const float* epis
             const float* last_values_dev, const uint8_t* last_dones_dev, double gamma, double gae_lambda,
             int T, int E, float* advantages_dev, float* returns_dev, void* stream);
 
+/* Policy / value MLP forward of collect_rollouts (SB3 2.3.2 MlpPolicy selected at train_sb3.py:209; separate
+ * pi / vf trunks of two hidden layers + a linear head, ReLU: main.py:99-105, README.md:45-50) on the tcgen05 tensor
+ * cores: y = W3 relu(W2 relu(W1 x + b1) + b2) + b3 for one trunk+head.  x [n_rows, in_dim]; W in nn.Linear layout
+ * [out_features, in_features]; in_dim, hidden multiples of 16, hidden <= 256, out_dim <= 32.  precise = 1: tf32 hi/lo
+ * split (fp32-faithful), 0: single tf32 pass.  error_flag_dev (int, device) is set to 1 if the tensor pipeline timed out. */
+int b2h_mlp_forward(const float* x_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
+                    const float* w3_dev, const float* b3_dev, float* y_dev, int n_rows, int in_dim, int hidden, int out_dim,
+                    int precise, int* error_flag_dev, void* stream);
+const char* b2h_mlp_last_error(void);
+
+/* DiagGaussian sampling of collect_rollouts (SB3 distributions.py): actions = mean + exp(log_std) * eps (stored
+ * unclipped), clipped = clip(actions, -1, 1) for the env (custom_env.py:88-93 bounds), log_prob summed over dims.
+ * eps is Philox4x32-10 keyed by (seed, row_offset + row, step); deterministic != 0 gives actions = mean. */
+int b2h_policy_sample(const float* mean_dev, const float* log_std_dev, int n_rows, int act_dim, uint64_t seed, uint64_t step,
+                      int row_offset, int deterministic, float* actions_dev, float* clipped_dev, float* log_prob_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

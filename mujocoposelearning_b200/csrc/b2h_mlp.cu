@@ -1,0 +1,266 @@
+// b2h_mlp.cu — policy / value MLP forward of the rollout (SB3 MlpPolicy, train_sb3.py:208-214; main.py:99-105:
+// separate pi / vf trunks, in -> 256 -> 256 -> out, ReLU) on the 5th-generation tensor cores, sm_100a.
+//
+// One CTA pushes a 128-row tile of the batch through all three layers of one network without leaving the SM:
+//   * operands are staged into shared memory in the canonical no-swizzle K-major UMMA layout (8x16-byte core
+//     matrices) by all 256 threads; weights come from global memory (L2-resident, 0.6 MB per network), the
+//     activations of layers 2 and 3 from the previous layer's epilogue in shared memory;
+//   * one elected thread issues tcgen05.mma kind::tf32 (M=128, N=256 / 32, K=8) with the accumulator in TMEM;
+//     completion is signalled through tcgen05.commit -> mbarrier;
+//   * the epilogue reads the accumulator with tcgen05.ld (each warp its 32-lane quadrant), adds the bias, applies
+//     ReLU and writes the next layer's input (or the network output).
+// precise = 1 splits every operand into tf32 hi + lo parts and issues hi*hi + hi*lo + lo*hi, which recovers
+// fp32-level accuracy (the reference policy runs in fp32 on the CPU); precise = 0 is a single tf32 pass.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/b2h.h"
+
+namespace {
+
+constexpr int TILE_M = 128;   // batch rows per CTA (UMMA M)
+constexpr int KC = 16;        // K columns staged per round (two K=8 MMAs)
+constexpr int MAXH = 256;     // hidden width (UMMA N) supported
+constexpr int HSTRIDE = MAXH + 4;  // fp32 row stride of the activation buffer (16-byte shift per row: conflict-free float4)
+constexpr int NTHREADS = 256;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor, no swizzle, K-major: start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | version 1 <<46
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46);
+}
+// instruction descriptor kind::tf32: D fp32 (bit 4), A/B tf32 (2 at bits 7 and 10), both K-major, N>>3 at 17, M>>4 at 24
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
+  for (int spin = 0; spin < (1 << 22); spin++) {   // bounded: a lost arrive must not hang the GPU
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
+struct MlpArgs {
+  const float *x, *w[3], *b[3];
+  float* y;
+  int n_rows, in_dim, hidden, out_dim, precise;
+  int* error;
+};
+
+// stage `rows` x KC columns (k0..k0+KC) of a row-major fp32 matrix into the UMMA core-matrix layout, hi and lo parts.
+// src row r is at src + r * ld (global or shared); rows >= valid_rows are zero.  dst_lo may be nullptr.
+__device__ __forceinline__ void stage_chunk(float* dst_hi, float* dst_lo, const float* src, int ld, int rows, int valid_rows,
+                                            int k0, int row_base) {
+  const int nvec = rows * (KC / 4);
+  const int groups = rows >> 3;
+  for (int f = threadIdx.x; f < nvec; f += NTHREADS) {
+    int r = f / (KC / 4), k4 = f % (KC / 4);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < valid_rows) v = *reinterpret_cast<const float4*>(src + (size_t)(row_base + r) * ld + k0 + 4 * k4);
+    float4 hi, lo;
+    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
+    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+    int off = ((k4 * groups + (r >> 3)) * 32) + (r & 7) * 4;   // in floats: core matrix = 32 floats (128 B)
+    *reinterpret_cast<float4*>(dst_hi + off) = hi;
+    if (dst_lo) *reinterpret_cast<float4*>(dst_lo + off) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(MlpArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* A_hi = reinterpret_cast<float*>(smem);                 // TILE_M x KC
+  float* A_lo = A_hi + TILE_M * KC;
+  float* W_hi = A_lo + TILE_M * KC;                             // MAXH x KC
+  float* W_lo = W_hi + MAXH * KC;
+  float* H = W_lo + MAXH * KC;                                  // TILE_M x HSTRIDE activations
+  __shared__ __align__(8) unsigned long long mbar_storage;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * TILE_M;
+  const int valid = min(TILE_M, a.n_rows - row0);
+  const uint32_t mbar = smem_u32(&mbar_storage);
+
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {  // TMEM: 256 fp32 accumulator columns, allocated and freed by warp 0
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  uint32_t parity = 0;
+  bool ok = true;
+
+  for (int layer = 0; layer < 3; layer++) {
+    const int K = layer == 0 ? a.in_dim : a.hidden;
+    const int nout = layer == 2 ? a.out_dim : a.hidden;      // real output features
+    const int N = layer == 2 ? 32 : a.hidden;                // UMMA N (last layer padded to 32)
+    const float* W = a.w[layer];
+    const uint32_t idesc = umma_idesc_tf32(TILE_M, N);
+    const uint32_t lboA = (TILE_M / 8) * 128, lboW = (N / 8) * 128;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+      if (layer == 0) stage_chunk(A_hi, a.precise ? A_lo : nullptr, a.x, a.in_dim, TILE_M, valid, k0, row0);
+      else stage_chunk(A_hi, a.precise ? A_lo : nullptr, H, HSTRIDE, TILE_M, TILE_M, k0, 0);
+      stage_chunk(W_hi, a.precise ? W_lo : nullptr, W, K, N, nout, k0, 0);
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to the MMA
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+        for (int ks = 0; ks < KC / 8; ks++) {
+          uint64_t ah = umma_desc(smem_u32(A_hi) + ks * 2 * lboA, lboA, 128), wh = umma_desc(smem_u32(W_hi) + ks * 2 * lboW, lboW, 128);
+          umma_tf32(tmem, ah, wh, idesc, (k0 | ks) != 0);
+          if (a.precise) {
+            uint64_t al = umma_desc(smem_u32(A_lo) + ks * 2 * lboA, lboA, 128), wl = umma_desc(smem_u32(W_lo) + ks * 2 * lboW, lboW, 128);
+            umma_tf32(tmem, ah, wl, idesc, 1);
+            umma_tf32(tmem, al, wh, idesc, 1);
+          }
+        }
+        // commit: the mbarrier fires when every MMA issued so far has finished reading shared memory / writing TMEM
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mbar) : "memory");
+      }
+      ok = mbar_wait(mbar, parity) && ok;
+      parity ^= 1;
+      if (!ok) break;
+    }
+    if (!ok) break;
+    // ---- epilogue: TMEM -> registers -> bias (+ReLU) -> shared activations / global output
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;
+    const int ncols = N / 2;                                  // each half of the warps takes half of the columns
+    for (int c0 = half * ncols; c0 < (half + 1) * ncols; c0 += 16) {
+      uint32_t v[16];
+      uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+            "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      if (layer < 2) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          float4 o;
+          o.x = fmaxf(__uint_as_float(v[4 * q + 0]) + __ldg(a.b[layer] + c0 + 4 * q + 0), 0.f);
+          o.y = fmaxf(__uint_as_float(v[4 * q + 1]) + __ldg(a.b[layer] + c0 + 4 * q + 1), 0.f);
+          o.z = fmaxf(__uint_as_float(v[4 * q + 2]) + __ldg(a.b[layer] + c0 + 4 * q + 2), 0.f);
+          o.w = fmaxf(__uint_as_float(v[4 * q + 3]) + __ldg(a.b[layer] + c0 + 4 * q + 3), 0.f);
+          *reinterpret_cast<float4*>(H + r * HSTRIDE + c0 + 4 * q) = o;
+        }
+      } else if (r < valid) {
+#pragma unroll
+        for (int q = 0; q < 16; q++)
+          if (c0 + q < nout) a.y[(size_t)(row0 + r) * nout + c0 + q] = __uint_as_float(v[q]) + __ldg(a.b[2] + c0 + q);
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();   // accumulator drained and H complete before the next layer overwrites TMEM / reads H
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  }
+  if (!ok && threadIdx.x == 0) atomicExch(a.error, 1);
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem) : "memory");
+}
+
+// ---- DiagGaussian sampling of SB3 (common/distributions.py): a = mean + exp(log_std) * eps, log_prob summed over
+// action dims, clipped copy for the env (collect_rollouts clips to the Box bounds, the buffer keeps the raw action).
+__device__ __forceinline__ void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__global__ void policy_sample_kernel(const float* __restrict__ mean, const float* __restrict__ log_std, int n_rows, int act_dim,
+                                     unsigned long long seed, unsigned long long step, int row_offset, int deterministic,
+                                     float* __restrict__ actions, float* __restrict__ clipped, float* __restrict__ log_prob) {
+  int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= n_rows) return;
+  float lp = 0.f;
+  for (int j0 = 0; j0 < act_dim; j0 += 4) {
+    uint32_t c[4] = {(uint32_t)(row + row_offset), (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(j0 >> 2) ^ 0x504F4C49u};
+    philox(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+    float eps[4];
+    for (int h = 0; h < 2; h++) {  // Box-Muller, two normals per pair of words
+      float u1 = ((c[2 * h] >> 8) + 1) * (1.0f / 16777216.0f), u2 = (c[2 * h + 1] >> 8) * (1.0f / 16777216.0f);
+      float rad = sqrtf(-2.0f * logf(u1)), s, co;
+      sincospif(2.0f * u2, &s, &co);
+      eps[2 * h] = rad * co; eps[2 * h + 1] = rad * s;
+    }
+    for (int q = 0; q < 4 && j0 + q < act_dim; q++) {
+      int j = j0 + q;
+      float ls = log_std[j], m = mean[(size_t)row * act_dim + j];
+      float e = deterministic ? 0.f : eps[q];
+      float av = m + expf(ls) * e;
+      actions[(size_t)row * act_dim + j] = av;
+      clipped[(size_t)row * act_dim + j] = fminf(fmaxf(av, -1.f), 1.f);
+      lp += -0.5f * e * e - ls - 0.91893853320467274f;   // -(a-mu)^2/(2 sigma^2) - log sigma - 0.5 log(2 pi)
+    }
+  }
+  log_prob[row] = lp;
+}
+
+thread_local std::string g_err_mlp;
+
+}  // namespace
+
+extern "C" {
+
+const char* b2h_mlp_last_error(void) { return g_err_mlp.c_str(); }
+
+int b2h_mlp_forward(const float* x_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
+                    const float* w3_dev, const float* b3_dev, float* y_dev, int n_rows, int in_dim, int hidden, int out_dim,
+                    int precise, int* error_flag_dev, void* stream) {
+  if (!x_dev || !w1_dev || !b1_dev || !w2_dev || !b2_dev || !w3_dev || !b3_dev || !y_dev || !error_flag_dev) { g_err_mlp = "null argument"; return B2H_EINVAL; }
+  if (n_rows <= 0 || in_dim <= 0 || in_dim % KC || hidden % KC || hidden < 16 || hidden > MAXH || out_dim < 1 || out_dim > 32) {
+    g_err_mlp = "unsupported MLP shape (in_dim and hidden must be multiples of 16, hidden <= 256, out_dim <= 32)";
+    return B2H_EUNSUPPORTED;
+  }
+  MlpArgs a;
+  a.x = x_dev; a.w[0] = w1_dev; a.w[1] = w2_dev; a.w[2] = w3_dev; a.b[0] = b1_dev; a.b[1] = b2_dev; a.b[2] = b3_dev;
+  a.y = y_dev; a.n_rows = n_rows; a.in_dim = in_dim; a.hidden = hidden; a.out_dim = out_dim; a.precise = precise; a.error = error_flag_dev;
+  size_t smem = (size_t)(2 * TILE_M * KC + 2 * MAXH * KC + TILE_M * HSTRIDE) * sizeof(float);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { g_err_mlp = cudaGetErrorString(e); return B2H_ECUDA; }
+    attr_set = true;
+  }
+  mlp_forward_kernel<<<(n_rows + TILE_M - 1) / TILE_M, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_err_mlp = cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
+}
+
+int b2h_policy_sample(const float* mean_dev, const float* log_std_dev, int n_rows, int act_dim, uint64_t seed, uint64_t step,
+                      int row_offset, int deterministic, float* actions_dev, float* clipped_dev, float* log_prob_dev, void* stream) {
+  if (!mean_dev || !log_std_dev || !actions_dev || !clipped_dev || !log_prob_dev || n_rows <= 0 || act_dim <= 0) { g_err_mlp = "bad argument"; return B2H_EINVAL; }
+  policy_sample_kernel<<<(n_rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean_dev, log_std_dev, n_rows, act_dim, seed, step,
+                                                                                row_offset, deterministic, actions_dev, clipped_dev, log_prob_dev);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_err_mlp = cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
+}
+
+}  // extern "C"

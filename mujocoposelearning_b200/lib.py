@@ -36,6 +36,8 @@ SIGNATURES = {
     "b2h_get_counters": (C.c_int, [vp, vp]),
     "b2h_gae": (C.c_int, [vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp]),
     "b2h_mlp_forward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "b2h_mlp_last_error": (C.c_char_p, []),
+    "b2h_policy_sample": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, vp, vp, vp, vp]),
 }
 
 
@@ -52,8 +54,6 @@ def load():
         L = C.CDLL(str(LIB))
         for name, (res, args) in SIGNATURES.items():
             if not hasattr(L, name):
-                if name == "b2h_mlp_forward":
-                    continue
                 raise B2HError(f"libb2h.so does not export {name}")
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args

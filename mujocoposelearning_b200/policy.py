@@ -1,0 +1,171 @@
+"""Policy / value MLP forward + device-resident rollout collection (SB3 2.3.2 semantics, train_sb3.py:208-231).
+
+* ``MlpPolicyParams`` — the parameters of SB3's ``MlpPolicy`` with ``net_arch=dict(pi=[256,256], vf=[256,256])`` and ReLU
+  (main.py:99-105): two separate trunks, ``action_net`` (256->21), ``value_net`` (256->1), state-independent ``log_std``;
+  SB3's orthogonal init (gains sqrt 2 / 0.01 / 1, zero biases, log_std 0).  ``from_sb3_state_dict`` loads a trained policy.
+* ``forward`` runs both networks through ``b2h_mlp_forward`` (tcgen05 tensor cores); ``sample`` is ``b2h_policy_sample``.
+* ``RolloutCollector.collect`` is ``OnPolicyAlgorithm.collect_rollouts`` + ``RolloutBuffer.compute_returns_and_advantage``
+  with everything resident on the GPU: policy forward -> sample -> clip -> ``b2h_step`` -> buffer write -> GAE, no host sync.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from .lib import check, load
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class MlpPolicyParams:
+    def __init__(self, obs_dim=352, act_dim=21, hidden=256, device="cuda", seed=0):
+        g = torch.Generator().manual_seed(seed)
+
+        def ortho(out_f, in_f, gain):
+            w = torch.empty(out_f, in_f)
+            torch.nn.init.orthogonal_(w, gain=gain, generator=g)
+            return w.to(device).contiguous()
+        z = lambda n: torch.zeros(n, device=device)
+        s2 = math.sqrt(2.0)
+        self.obs_dim, self.act_dim, self.hidden, self.device = obs_dim, act_dim, hidden, torch.device(device)
+        self.pi = [ortho(hidden, obs_dim, s2), z(hidden), ortho(hidden, hidden, s2), z(hidden), ortho(act_dim, hidden, 0.01), z(act_dim)]
+        self.vf = [ortho(hidden, obs_dim, s2), z(hidden), ortho(hidden, hidden, s2), z(hidden), ortho(1, hidden, 1.0), z(1)]
+        self.log_std = torch.zeros(act_dim, device=device)
+
+    @classmethod
+    def from_sb3_state_dict(cls, sd, device="cuda"):
+        """``sd = PPO.load(...).policy.state_dict()`` (keys of SB3 ActorCriticPolicy)."""
+        w = lambda k: sd[k].detach().to(device, torch.float32).contiguous()
+        self = cls.__new__(cls)
+        self.pi = [w("mlp_extractor.policy_net.0.weight"), w("mlp_extractor.policy_net.0.bias"), w("mlp_extractor.policy_net.2.weight"),
+                   w("mlp_extractor.policy_net.2.bias"), w("action_net.weight"), w("action_net.bias")]
+        self.vf = [w("mlp_extractor.value_net.0.weight"), w("mlp_extractor.value_net.0.bias"), w("mlp_extractor.value_net.2.weight"),
+                   w("mlp_extractor.value_net.2.bias"), w("value_net.weight"), w("value_net.bias")]
+        self.log_std = w("log_std")
+        self.hidden, self.obs_dim = self.pi[0].shape
+        self.act_dim = self.pi[4].shape[0]
+        self.device = torch.device(device)
+        return self
+
+    def n_params(self):
+        return sum(t.numel() for t in self.pi + self.vf) + self.log_std.numel()
+
+
+class MlpPolicy:
+    """Forward-only policy used during rollout."""
+
+    def __init__(self, params: MlpPolicyParams, precise=True, seed=0, row_offset=0):
+        self.p, self.precise, self.seed, self.row_offset = params, int(precise), int(seed), int(row_offset)
+        self.lib = load()
+        self.err = torch.zeros(1, dtype=torch.int32, device=params.device)
+
+    def _net(self, net, x, out_dim):
+        p = self.p
+        y = torch.empty(x.shape[0], out_dim, device=p.device, dtype=torch.float32)
+        s = C.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)
+        rc = self.lib.b2h_mlp_forward(_p(x), _p(net[0]), _p(net[1]), _p(net[2]), _p(net[3]), _p(net[4]), _p(net[5]), _p(y), x.shape[0],
+                                      p.obs_dim, p.hidden, out_dim, self.precise, _p(self.err), s)
+        if rc < 0:
+            raise RuntimeError(f"b2h_mlp_forward: {self.lib.b2h_mlp_last_error().decode()}")
+        return y
+
+    def forward(self, obs):
+        """obs float32 CUDA [E, obs_dim] -> (action mean [E, act_dim], value [E])."""
+        if obs.dtype != torch.float32 or not obs.is_contiguous():
+            obs = obs.to(torch.float32).contiguous()     # SB3 casts the float64 observation to float32 for the net
+        return self._net(self.p.pi, obs, self.p.act_dim), self._net(self.p.vf, obs, 1).squeeze(1)
+
+    def values(self, obs):
+        if obs.dtype != torch.float32 or not obs.is_contiguous():
+            obs = obs.to(torch.float32).contiguous()
+        return self._net(self.p.vf, obs, 1).squeeze(1)
+
+    def sample(self, mean, step, deterministic=False):
+        E, A = mean.shape
+        actions, clipped = torch.empty_like(mean), torch.empty_like(mean)
+        logp = torch.empty(E, device=mean.device, dtype=torch.float32)
+        s = C.c_void_p(torch.cuda.current_stream(mean.device).cuda_stream)
+        check(self.lib.b2h_policy_sample(_p(mean), _p(self.p.log_std), E, A, C.c_uint64(self.seed), C.c_uint64(int(step)),
+                                         self.row_offset, int(deterministic), _p(actions), _p(clipped), _p(logp), s))
+        return actions, clipped, logp
+
+    def check_error(self):
+        if int(self.err.item()):
+            raise RuntimeError("tcgen05 MLP pipeline timed out (mbarrier wait exceeded its bound)")
+
+    # plain PyTorch fp32 reference of the same op (numerics tests only)
+    def forward_torch(self, obs):
+        def net(n, x):
+            h = torch.relu(torch.nn.functional.linear(x, n[0], n[1]))
+            h = torch.relu(torch.nn.functional.linear(h, n[2], n[3]))
+            return torch.nn.functional.linear(h, n[4], n[5])
+        tf = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            x = obs.to(torch.float32)
+            return net(self.p.pi, x), net(self.p.vf, x).squeeze(1)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = tf
+
+
+class RolloutCollector:
+    """collect_rollouts + GAE with the SB3 buffer layout ([T, E, ...] float32), all on the device."""
+
+    def __init__(self, batch, policy: MlpPolicy, n_steps=64, gamma=0.99, gae_lambda=0.95, deterministic=False):
+        from .batch import gae
+        self.b, self.pol, self.T, self.gamma, self.lam, self.det = batch, policy, n_steps, gamma, gae_lambda, deterministic
+        self._gae = gae
+        E, dev, f32 = batch.n_envs, batch.device, torch.float32
+        self.obs = torch.zeros(n_steps, E, batch.obs_dim, device=dev, dtype=f32)
+        self.actions = torch.zeros(n_steps, E, batch.nu, device=dev, dtype=f32)
+        self.rewards, self.values, self.log_probs, self.episode_starts = (torch.zeros(n_steps, E, device=dev, dtype=f32) for _ in range(4))
+        self.last_obs = None
+        self.last_episode_starts = torch.ones(E, device=dev, dtype=f32)      # _setup_learn: ones
+        self.num_timesteps = 0
+        h = float(batch.cm.timestep)
+        # TimeLimit.truncated (step_count >= 750 while not terminated) can only happen when the duration outlasts 750 steps
+        self.can_truncate = batch.cfg.duration > (1 + batch.cfg.frame_skip * batch.cfg.max_steps) * h
+        # on-device episode statistics ("rollout statistics" of the north star)
+        self.ep_return = torch.zeros(E, device=dev, dtype=f32)
+        self.ep_len = torch.zeros(E, device=dev, dtype=f32)
+        self.stats = torch.zeros(3, device=dev, dtype=torch.float64)        # sum of returns, sum of lengths, episodes
+
+    def reset(self):
+        self.last_obs = self.b.reset().to(torch.float32).clone()
+        self.last_episode_starts.fill_(1.0)
+
+    def collect(self):
+        if self.last_obs is None:
+            self.reset()
+        b, pol = self.b, self.pol
+        for t in range(self.T):
+            mean, value = pol.forward(self.last_obs)
+            actions, clipped, logp = pol.sample(mean, self.num_timesteps // b.n_envs, self.det)
+            obs, rew, term, trunc = b.step(clipped)
+            rew = rew.to(torch.float32).clone()
+            done = (term | trunc).to(torch.float32)
+            if self.can_truncate:   # bootstrap with V(terminal_obs) where the episode was cut by the step limit only
+                tl = (trunc.bool() & ~term.bool()).to(torch.float32)
+                rew += self.gamma * pol.values(b.terminal_obs.to(torch.float32)) * tl
+            self.obs[t].copy_(self.last_obs)
+            self.actions[t].copy_(actions)
+            self.rewards[t].copy_(rew)
+            self.values[t].copy_(value)
+            self.log_probs[t].copy_(logp)
+            self.episode_starts[t].copy_(self.last_episode_starts)
+            self.ep_return += rew
+            self.ep_len += 1
+            self.stats += torch.stack([(self.ep_return * done).sum(), (self.ep_len * done).sum(), done.sum()]).to(torch.float64)
+            self.ep_return *= 1 - done
+            self.ep_len *= 1 - done
+            self.last_obs = obs.to(torch.float32).clone()
+            self.last_episode_starts = done
+            self.num_timesteps += b.n_envs
+        last_values = pol.values(self.last_obs)
+        self.advantages, self.returns = self._gae(self.rewards, self.values, self.episode_starts, last_values,
+                                                  self.last_episode_starts.to(torch.uint8), self.gamma, self.lam)
+        return self.advantages, self.returns

@@ -1,0 +1,64 @@
+"""tcgen05 MLP forward / Gaussian sampling / device-resident rollout collection on the GPU.
+Numerics are compared with a plain PyTorch fp32 reference of the same op (this is the one floating-point
+tensor-core kernel): precise (tf32 hi/lo split) within 2e-5, single-pass tf32 within 5e-3."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.mark.parametrize("n_rows", [1, 127, 128, 1000, 4096])
+@pytest.mark.parametrize("precise,tol", [(True, 2e-5), (False, 5e-3)])
+def test_mlp_forward_matches_torch_fp32(n_rows, precise, tol):
+    from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams
+    p = MlpPolicyParams(seed=3)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    for t in p.pi[1::2] + p.vf[1::2]:                        # non-zero biases so the epilogue is exercised
+        t.copy_(torch.randn(t.shape, device="cuda", generator=g) * 0.1)
+    pol = MlpPolicy(p, precise=precise)
+    obs = torch.randn(n_rows, 352, device="cuda", generator=g) * 2.0
+    mean, value = pol.forward(obs)
+    torch.cuda.synchronize()
+    pol.check_error()
+    mref, vref = pol.forward_torch(obs)
+    scale_m, scale_v = float(mref.abs().max()), float(vref.abs().max())
+    assert float((mean - mref).abs().max()) < tol * max(1.0, scale_m) and float((value - vref).abs().max()) < tol * max(1.0, scale_v)
+
+
+def test_policy_sample_statistics_and_logprob():
+    from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams
+    p = MlpPolicyParams(seed=0)
+    p.log_std.copy_(torch.linspace(-1.0, 0.5, 21, device="cuda"))
+    pol = MlpPolicy(p, seed=5)
+    mean = torch.randn(8192, 21, device="cuda") * 0.3
+    a, c, lp = pol.sample(mean, step=7)
+    a2, _, _ = pol.sample(mean, step=7)
+    a3, _, _ = pol.sample(mean, step=8)
+    assert torch.equal(a, a2) and not torch.equal(a, a3)                    # counter-based: same (seed, step) -> same noise
+    eps = (a - mean) / p.log_std.exp()
+    assert abs(float(eps.mean())) < 0.01 and abs(float(eps.std()) - 1.0) < 0.01
+    assert torch.equal(c, a.clamp(-1, 1))
+    ref = torch.distributions.Normal(mean, p.log_std.exp().expand_as(mean)).log_prob(a).sum(1)
+    assert float((lp - ref).abs().max()) < 2e-4
+    d, _, lpd = pol.sample(mean, step=7, deterministic=True)
+    assert torch.equal(d, mean)
+
+
+def test_rollout_collector_buffers_and_gae():
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams, RolloutCollector
+    from oracle import oracle as orc
+    b = HumanoidBatch(256, frame_skip=3, duration=0.2, reward_type="stand", seed=2)     # time = (1 + 3n) h >= 0.2 at n = 13
+    col = RolloutCollector(b, MlpPolicy(MlpPolicyParams(seed=1), seed=9), n_steps=32)
+    adv, ret = col.collect()
+    torch.cuda.synchronize()
+    col.pol.check_error()
+    es = col.episode_starts.cpu().numpy()
+    assert es[0].all() and es[13].all() and es[26].all() and es.sum() == 3 * 256       # every env restarts every 13 steps
+    a_ref, r_ref = orc.gae(col.rewards.cpu().numpy(), col.values.cpu().numpy(), es, col.pol.values(col.last_obs).cpu().numpy(),
+                           col.last_episode_starts.cpu().numpy().astype(np.uint8), 0.99, 0.95)
+    assert np.array_equal(adv.cpu().numpy(), a_ref) and np.array_equal(ret.cpu().numpy(), r_ref)
+    assert float(col.actions.abs().max()) > 1.0 and col.num_timesteps == 32 * 256         # raw (unclipped) actions are stored
+    ep = col.stats.cpu().numpy()
+    assert ep[2] == 2 * 256 and abs(ep[1] / ep[2] - 13) < 1e-9

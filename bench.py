@@ -232,6 +232,27 @@ def run_b200(args):
     esz = 8 if args.dtype == "f64" else 4
     h2d = E * batch.nu * 4
     d2h = E * (batch.obs_dim * esz + esz + 2)
+    # ---- random-init-policy rollout (north star): tcgen05 MLP forward + Gaussian sampling + step, all on device
+    from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams
+    pol = MlpPolicy(MlpPolicyParams(seed=7), precise=True, seed=11, row_offset=rank * E)
+    obs_t = batch.obs
+    for i in range(W):
+        mean, _ = pol.forward(obs_t); _, clipped, _ = pol.sample(mean, i); batch.step(clipped)
+    torch.cuda.synchronize()
+    Kp = max(10, K // 2)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * Kp)]
+    for i in range(Kp):
+        flush.zero_()
+        ev[3 * i].record()
+        mean, value = pol.forward(obs_t)
+        _, clipped, _ = pol.sample(mean, W + i)
+        ev[3 * i + 1].record()
+        batch.step(clipped)
+        ev[3 * i + 2].record()
+    torch.cuda.synchronize()
+    pol.check_error()
+    mlp_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(Kp))
+    pol_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 2]) for i in range(Kp))
     # ---- reduce over ranks: max time
     tt = torch.tensor([total_ms, e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
@@ -268,6 +289,9 @@ def run_b200(args):
         "solver": {"newton_iter_per_physics_step": (c1["newton_iter"] - c0["newton_iter"]) / max(1, psteps),
                    "ls_eval_per_physics_step": (c1["ls_eval"] - c0["ls_eval"]) / max(1, psteps),
                    "contact_overflow": c1["contact_overflow"], "iter_cap": c1["iter_cap"], "bad_state": c1["bad_state"]},
+        "policy_rollout": {"value": world * E * FRAME_SKIP * Kp / (pol_ms * 1e-3), "unit": UNIT, "ms_per_step": pol_ms / Kp,
+                           "mlp_and_sampling_ms_per_step": mlp_ms / Kp, "steps": Kp,
+                           "what": "random-init 2x256 ReLU pi/vf MLP forward (tcgen05, tf32 hi/lo split) + Gaussian sampling + b2h_step; rank-0 time"},
         "launch": batch.launch_info(), "step_ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
     }
     if not args.no_cpu_baseline and world == 1:

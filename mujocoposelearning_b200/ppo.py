@@ -1,0 +1,104 @@
+"""PPO update on the device — the "next" row after the rollout path (BASELINE config 4).
+
+Semantics are SB3 2.3.2 ``PPO.train`` with the reference's kwargs (train_sb3.py:208-214, config.py:17-32): per epoch a
+random permutation of the T*E samples, minibatches, per-minibatch advantage normalisation, clipped surrogate
+(clip 0.2), value MSE x vf_coef 0.5, entropy bonus, grad-norm clip 0.5, Adam(eps 1e-5).  With several GPUs every rank
+holds a replica of the 318 k parameters and gradients are averaged with one NCCL all-reduce (1.27 MB) per minibatch.
+
+The rollout (policy forward, sampling, physics, GAE) runs on the hand-written kernels; this update step is plain
+PyTorch autograd + library GEMMs for now — it is outside the round-1 hot path and is stated as such in DESIGN.md.
+The kernels read the very tensors Adam updates in place (shared storage), so no weight copies are needed.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+from .policy import MlpPolicy, MlpPolicyParams, RolloutCollector
+
+
+class PPOTrainer:
+    def __init__(self, batch, params: MlpPolicyParams | None = None, n_steps=64, batch_size=16384, n_epochs=4, lr=3e-4, gamma=0.99,
+                 gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, seed=0, precise=True):
+        self.b = batch
+        self.params = params or MlpPolicyParams(batch.obs_dim, batch.nu, 256, batch.device, seed)
+        rank = dist.get_rank() if dist.is_initialized() else 0
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.policy = MlpPolicy(self.params, precise=precise, seed=seed + 1, row_offset=rank * batch.n_envs)
+        self.col = RolloutCollector(batch, self.policy, n_steps, gamma, gae_lambda)
+        self.tensors = self.params.pi + self.params.vf + [self.params.log_std]
+        for t in self.tensors:
+            t.requires_grad_(True)
+        if self.world > 1:                       # identical replicas: broadcast rank 0's initialisation
+            for t in self.tensors:
+                dist.broadcast(t.data, 0)
+        self.opt = torch.optim.Adam(self.tensors, lr=lr, eps=1e-5)
+        self.batch_size, self.n_epochs, self.clip, self.ent_coef, self.vf_coef, self.max_grad_norm = batch_size, n_epochs, clip_range, ent_coef, vf_coef, max_grad_norm
+        self.gen = torch.Generator(device=batch.device).manual_seed(seed + 17 + rank)
+        self.iterations = 0
+
+    def _evaluate(self, obs, actions):
+        p = self.params
+
+        def net(n, x):
+            h = F.relu(F.linear(x, n[0], n[1]))
+            h = F.relu(F.linear(h, n[2], n[3]))
+            return F.linear(h, n[4], n[5])
+        mean, value = net(p.pi, obs), net(p.vf, obs).squeeze(1)
+        std = p.log_std.exp()
+        logp = (-0.5 * ((actions - mean) / std) ** 2 - p.log_std - 0.5 * math.log(2 * math.pi)).sum(1)
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + p.log_std).sum()
+        return value, logp, entropy
+
+    def update(self):
+        """One PPO.train() over the current rollout buffer; returns the last minibatch's loss terms."""
+        c = self.col
+        n = c.T * self.b.n_envs
+        obs, actions = c.obs.reshape(n, -1), c.actions.reshape(n, -1)
+        old_logp, adv, ret = c.log_probs.reshape(n), c.advantages.reshape(n), c.returns.reshape(n)
+        stats = {}
+        for _ in range(self.n_epochs):
+            perm = torch.randperm(n, device=obs.device, generator=self.gen)
+            for i in range(0, n, self.batch_size):
+                idx = perm[i:i + self.batch_size]
+                a = adv[idx]
+                if a.numel() > 1:
+                    a = (a - a.mean()) / (a.std() + 1e-8)
+                value, logp, entropy = self._evaluate(obs[idx], actions[idx])
+                ratio = torch.exp(logp - old_logp[idx])
+                pl = -torch.min(a * ratio, a * torch.clamp(ratio, 1 - self.clip, 1 + self.clip)).mean()
+                vl = F.mse_loss(ret[idx], value)
+                loss = pl - self.ent_coef * entropy + self.vf_coef * vl
+                self.opt.zero_grad(set_to_none=True)
+                loss.backward()
+                if self.world > 1:               # average gradients: one flat NCCL all-reduce over NVLink
+                    flat = torch.cat([t.grad.reshape(-1) for t in self.tensors])
+                    dist.all_reduce(flat)
+                    flat /= self.world
+                    o = 0
+                    for t in self.tensors:
+                        t.grad.copy_(flat[o:o + t.numel()].view_as(t))
+                        o += t.numel()
+                torch.nn.utils.clip_grad_norm_(self.tensors, self.max_grad_norm)
+                self.opt.step()
+                stats = dict(policy_loss=pl.detach(), value_loss=vl.detach(), clip_fraction=((ratio - 1).abs() > self.clip).float().mean())
+        return stats
+
+    def iterate(self):
+        """collect_rollouts + train, as one iteration of ``model.learn`` (train_sb3.py:228)."""
+        with torch.no_grad():
+            before = self.col.stats.clone()
+            self.col.collect()
+            d = self.col.stats - before
+        stats = self.update()
+        self.iterations += 1
+        ep = d.clone()
+        if self.world > 1:                       # rollout statistics: the only other collective
+            dist.all_reduce(ep)
+        ep = ep.tolist()
+        stats.update(ep_rew_mean=ep[0] / max(ep[2], 1.0), ep_len_mean=ep[1] / max(ep[2], 1.0), episodes=int(ep[2]),
+                     timesteps=self.col.num_timesteps * self.world)
+        return stats

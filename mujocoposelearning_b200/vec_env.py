@@ -97,6 +97,11 @@ class B200HumanoidVecEnv(_VecEnvBase):
         self._step_count = np.zeros(n_envs, np.int64)
         self._total_reward = np.zeros(n_envs)
         self.info_mode = ("full" if n_envs <= 256 else "lazy") if info_mode == "auto" else info_mode
+        # returned arrays alternate between two preallocated sets: SB3 keeps `_last_obs` (and the callbacks the
+        # rewards/dones) of the previous step while the next one is produced, never older ones
+        self._out = [dict(obs=np.zeros((n_envs, self.batch.obs_dim), np.float64), rew=np.zeros(n_envs, np.float64),
+                          term=np.zeros(n_envs, bool), trunc=np.zeros(n_envs, bool)) for _ in range(2)]
+        self._flip = 0
         self._lazy_info = {"TimeLimit.truncated": False}
         self.closed = False
 
@@ -123,10 +128,13 @@ class B200HumanoidVecEnv(_VecEnvBase):
     def step_wait(self):
         hb = self.hb
         self.batch.step_host(hb)
-        obs = hb["obs"].numpy().astype(np.float64)            # fresh arrays: SB3 keeps references across steps
-        rewards = hb["reward"].numpy().astype(np.float64)
-        term = hb["terminated"].numpy().astype(bool)
-        trunc = hb["truncated"].numpy().astype(bool)
+        out = self._out[self._flip]
+        self._flip ^= 1
+        obs, rewards, term, trunc = out["obs"], out["rew"], out["term"], out["trunc"]
+        np.copyto(obs, hb["obs"].numpy())                     # float32 -> float64 (observation_space dtype)
+        np.copyto(rewards, hb["reward"].numpy())
+        np.copyto(term, hb["terminated"].numpy(), casting="unsafe")
+        np.copyto(trunc, hb["truncated"].numpy(), casting="unsafe")
         dones = term | trunc
         self._step_count += 1
         self._total_reward += rewards

@@ -62,3 +62,24 @@ def test_rollout_collector_buffers_and_gae():
     assert float(col.actions.abs().max()) > 1.0 and col.num_timesteps == 32 * 256         # raw (unclipped) actions are stored
     ep = col.stats.cpu().numpy()
     assert ep[2] == 2 * 256 and abs(ep[1] / ep[2] - 13) < 1e-9
+
+
+def test_ppo_iteration_updates_policy_and_stats():
+    """collect_rollouts + PPO.train mechanics (the update itself is PyTorch autograd; 'next' row 8f-1)."""
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from mujocoposelearning_b200.ppo import PPOTrainer
+    b = HumanoidBatch(512, frame_skip=3, duration=0.2, reward_type="stand", seed=4)       # 13-step episodes
+    tr = PPOTrainer(b, n_steps=26, batch_size=4096, n_epochs=2, lr=3e-4, seed=3)
+    w0 = [t.detach().clone() for t in tr.tensors]
+    s = tr.iterate()
+    tr.policy.check_error()
+    assert s["episodes"] == 2 * 512 and abs(s["ep_len_mean"] - 13) < 1e-9 and 0 < s["ep_rew_mean"] < 13
+    assert all(torch.isfinite(t).all() for t in tr.tensors)
+    assert sum(float((a - b_).abs().sum()) for a, b_ in zip(w0, tr.tensors)) > 0
+    # the rollout kernels see the updated weights (shared storage): the next forward differs from the old one
+    obs = tr.col.last_obs
+    m1, _ = tr.policy.forward(obs)
+    mref, _ = tr.policy.forward_torch(obs)
+    assert float((m1 - mref.detach()).abs().max()) < 1e-4
+    s2 = tr.iterate()
+    assert s2["timesteps"] == 2 * 26 * 512 and float(s2["value_loss"]) == float(s2["value_loss"])

@@ -231,7 +231,7 @@ def run_b200(args):
     e2e_s = time.perf_counter() - te0
     esz = 8 if args.dtype == "f64" else 4
     h2d = E * batch.nu * 4
-    d2h = E * (batch.obs_dim * esz + esz + 2)
+    d2h = E * (batch.obs_dim * 8 + 8 + 2)   # float64 observation + reward (observation_space dtype), two flag bytes
     # ---- random-init-policy rollout (north star): tcgen05 MLP forward + Gaussian sampling + step, all on device
     from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams
     pol = MlpPolicy(MlpPolicyParams(seed=7), precise=True, seed=11, row_offset=rank * E)
@@ -274,12 +274,19 @@ def run_b200(args):
     achieved_gbs = BYTES_PER_PHYSICS_STEP * E * FRAME_SKIP / (kernel_ms * 1e-3) / 1e9
     fp32_tflops = FLOP_PER_PHYSICS_STEP * E * FRAME_SKIP / (kernel_ms * 1e-3) / 1e12
     psteps = c1["physics_steps"] - c0["physics_steps"]
+    traffic = None
+    try:   # dram bytes of one step-kernel launch from the committed ncu capture (same env count only)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tj["n_envs"] == E and args.dtype == "f32":
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+    except Exception:
+        pass
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": kernel_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": workload_config(args, world),
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                     "traffic": None, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
+                     "traffic": traffic, "algorithmic_bytes_per_launch": BYTES_PER_PHYSICS_STEP * E * FRAME_SKIP, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
                      "note": "latency/issue-bound irregular FP32 work, not HBM-bound (SURVEY 8d); see fp32 block",
                      "fp32": {"achieved_tflops": fp32_tflops, "nominal_peak_tflops": FP32_NOMINAL_TFLOPS,
                               "frac": fp32_tflops / FP32_NOMINAL_TFLOPS, "flop_per_physics_step": FLOP_PER_PHYSICS_STEP}},

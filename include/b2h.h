@@ -218,6 +218,11 @@ int b2h_gae(const float* rewards_dev, const float* values_dev, const float* epis
 int b2h_mlp_forward(const float* x_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
                     const float* w3_dev, const float* b3_dev, float* y_dev, int n_rows, int in_dim, int hidden, int out_dim,
                     int precise, int* error_flag_dev, void* stream);
+/* Both trunks of MlpPolicy in one launch (what `policy(obs_tensor)` computes in collect_rollouts): pi_dev / vf_dev
+ * are {W1, b1, W2, b2, W3, b3} device pointers; mean_dev [n_rows, act_dim], value_dev [n_rows]. */
+int b2h_policy_forward(const float* x_dev, const float* const pi_dev[6], const float* const vf_dev[6], float* mean_dev,
+                       float* value_dev, int n_rows, int in_dim, int hidden, int act_dim, int precise, int* error_flag_dev,
+                       void* stream);
 const char* b2h_mlp_last_error(void);
 
 /* DiagGaussian sampling of collect_rollouts (SB3 distributions.py): actions = mean + exp(log_std) * eps (stored

@@ -53,24 +53,40 @@ __device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
   return false;
 }
 
-struct MlpArgs {
-  const float *x, *w[3], *b[3];
-  float* y;
-  int n_rows, in_dim, hidden, out_dim, precise;
+struct MlpArgs {     // up to two networks (blockIdx.y) over the same input: policy and value trunks of MlpPolicy
+  const float* x;
+  const float *w[2][3], *b[2][3];
+  float* y[2];
+  int out_dim[2];
+  int n_rows, in_dim, hidden, precise;
   int* error;
 };
 
-// stage `rows` x KC columns (k0..k0+KC) of a row-major fp32 matrix into the UMMA core-matrix layout, hi and lo parts.
-// src row r is at src + r * ld (global or shared); rows >= valid_rows are zero.  dst_lo may be nullptr.
-__device__ __forceinline__ void stage_chunk(float* dst_hi, float* dst_lo, const float* src, int ld, int rows, int valid_rows,
-                                            int k0, int row_base) {
+// One K-chunk (KC columns) of an operand travels global/shared -> registers -> shared (UMMA core-matrix layout,
+// split into tf32 hi and lo parts).  The loads of chunk k+1 are issued before the wait on the MMAs of chunk k.
+template <int NV>
+struct ChunkRegs { float4 v[NV]; };
+
+template <int NV>
+__device__ __forceinline__ void load_chunk(ChunkRegs<NV>& c, const float* src, int ld, int rows, int valid_rows, int k0, int row_base) {
   const int nvec = rows * (KC / 4);
-  const int groups = rows >> 3;
-  for (int f = threadIdx.x; f < nvec; f += NTHREADS) {
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    int f = threadIdx.x + i * NTHREADS;
     int r = f / (KC / 4), k4 = f % (KC / 4);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r < valid_rows) v = *reinterpret_cast<const float4*>(src + (size_t)(row_base + r) * ld + k0 + 4 * k4);
-    float4 hi, lo;
+    c.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f < nvec && r < valid_rows) c.v[i] = *reinterpret_cast<const float4*>(src + (size_t)(row_base + r) * ld + k0 + 4 * k4);
+  }
+}
+template <int NV>
+__device__ __forceinline__ void store_chunk(const ChunkRegs<NV>& c, float* dst_hi, float* dst_lo, int rows) {
+  const int nvec = rows * (KC / 4), groups = rows >> 3;
+#pragma unroll
+  for (int i = 0; i < NV; i++) {
+    int f = threadIdx.x + i * NTHREADS;
+    if (f >= nvec) continue;
+    int r = f / (KC / 4), k4 = f % (KC / 4);
+    float4 v = c.v[i], hi, lo;
     hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
     hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
     hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
@@ -91,6 +107,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(MlpArgs a) {
   __shared__ __align__(8) unsigned long long mbar_storage;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int net = blockIdx.y;
   const int row0 = blockIdx.x * TILE_M;
   const int valid = min(TILE_M, a.n_rows - row0);
   const uint32_t mbar = smem_u32(&mbar_storage);
@@ -110,17 +127,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(MlpArgs a) {
   uint32_t parity = 0;
   bool ok = true;
 
-  for (int layer = 0; layer < 3; layer++) {
+  for (int layer = 0; layer < 3 && ok; layer++) {
     const int K = layer == 0 ? a.in_dim : a.hidden;
-    const int nout = layer == 2 ? a.out_dim : a.hidden;      // real output features
+    const int nout = layer == 2 ? a.out_dim[net] : a.hidden;  // real output features
     const int N = layer == 2 ? 32 : a.hidden;                // UMMA N (last layer padded to 32)
-    const float* W = a.w[layer];
+    const float* W = a.w[net][layer];
+    const float* Asrc = layer == 0 ? a.x : H;
+    const int Ald = layer == 0 ? a.in_dim : HSTRIDE, Avalid = layer == 0 ? valid : TILE_M, Abase = layer == 0 ? row0 : 0;
     const uint32_t idesc = umma_idesc_tf32(TILE_M, N);
     const uint32_t lboA = (TILE_M / 8) * 128, lboW = (N / 8) * 128;
+    ChunkRegs<TILE_M * (KC / 4) / NTHREADS> ra;
+    ChunkRegs<MAXH * (KC / 4) / NTHREADS> rw;
+    load_chunk(ra, Asrc, Ald, TILE_M, Avalid, 0, Abase);
+    load_chunk(rw, W, K, N, nout, 0, 0);
     for (int k0 = 0; k0 < K; k0 += KC) {
-      if (layer == 0) stage_chunk(A_hi, a.precise ? A_lo : nullptr, a.x, a.in_dim, TILE_M, valid, k0, row0);
-      else stage_chunk(A_hi, a.precise ? A_lo : nullptr, H, HSTRIDE, TILE_M, TILE_M, k0, 0);
-      stage_chunk(W_hi, a.precise ? W_lo : nullptr, W, K, N, nout, k0, 0);
+      store_chunk(ra, A_hi, a.precise ? A_lo : nullptr, TILE_M);
+      store_chunk(rw, W_hi, a.precise ? W_lo : nullptr, N);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to the MMA
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -138,6 +160,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(MlpArgs a) {
         // commit: the mbarrier fires when every MMA issued so far has finished reading shared memory / writing TMEM
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mbar) : "memory");
       }
+      if (k0 + KC < K) {  // next chunk's loads fly while the tensor core works on this one
+        load_chunk(ra, Asrc, Ald, TILE_M, Avalid, k0 + KC, Abase);
+        load_chunk(rw, W, K, N, nout, k0 + KC, 0);
+      }
       ok = mbar_wait(mbar, parity) && ok;
       parity ^= 1;
       if (!ok) break;
@@ -148,6 +174,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(MlpArgs a) {
     const int quad = warp & 3, half = warp >> 2;
     const int r = quad * 32 + lane;
     const int ncols = N / 2;                                  // each half of the warps takes half of the columns
+    const float* bias = a.b[net][layer];
     for (int c0 = half * ncols; c0 < (half + 1) * ncols; c0 += 16) {
       uint32_t v[16];
       uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
@@ -161,16 +188,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(MlpArgs a) {
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           float4 o;
-          o.x = fmaxf(__uint_as_float(v[4 * q + 0]) + __ldg(a.b[layer] + c0 + 4 * q + 0), 0.f);
-          o.y = fmaxf(__uint_as_float(v[4 * q + 1]) + __ldg(a.b[layer] + c0 + 4 * q + 1), 0.f);
-          o.z = fmaxf(__uint_as_float(v[4 * q + 2]) + __ldg(a.b[layer] + c0 + 4 * q + 2), 0.f);
-          o.w = fmaxf(__uint_as_float(v[4 * q + 3]) + __ldg(a.b[layer] + c0 + 4 * q + 3), 0.f);
+          o.x = fmaxf(__uint_as_float(v[4 * q + 0]) + __ldg(bias + c0 + 4 * q + 0), 0.f);
+          o.y = fmaxf(__uint_as_float(v[4 * q + 1]) + __ldg(bias + c0 + 4 * q + 1), 0.f);
+          o.z = fmaxf(__uint_as_float(v[4 * q + 2]) + __ldg(bias + c0 + 4 * q + 2), 0.f);
+          o.w = fmaxf(__uint_as_float(v[4 * q + 3]) + __ldg(bias + c0 + 4 * q + 3), 0.f);
           *reinterpret_cast<float4*>(H + r * HSTRIDE + c0 + 4 * q) = o;
         }
       } else if (r < valid) {
 #pragma unroll
         for (int q = 0; q < 16; q++)
-          if (c0 + q < nout) a.y[(size_t)(row0 + r) * nout + c0 + q] = __uint_as_float(v[q]) + __ldg(a.b[2] + c0 + q);
+          if (c0 + q < nout) a.y[net][(size_t)(row0 + r) * nout + c0 + q] = __uint_as_float(v[q]) + __ldg(bias + c0 + q);
       }
     }
     asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
@@ -229,17 +256,13 @@ extern "C" {
 
 const char* b2h_mlp_last_error(void) { return g_err_mlp.c_str(); }
 
-int b2h_mlp_forward(const float* x_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
-                    const float* w3_dev, const float* b3_dev, float* y_dev, int n_rows, int in_dim, int hidden, int out_dim,
-                    int precise, int* error_flag_dev, void* stream) {
-  if (!x_dev || !w1_dev || !b1_dev || !w2_dev || !b2_dev || !w3_dev || !b3_dev || !y_dev || !error_flag_dev) { g_err_mlp = "null argument"; return B2H_EINVAL; }
-  if (n_rows <= 0 || in_dim <= 0 || in_dim % KC || hidden % KC || hidden < 16 || hidden > MAXH || out_dim < 1 || out_dim > 32) {
-    g_err_mlp = "unsupported MLP shape (in_dim and hidden must be multiples of 16, hidden <= 256, out_dim <= 32)";
+static int launch_mlp(MlpArgs& a, int nnets, void* stream) {
+  if (a.n_rows <= 0 || a.in_dim <= 0 || a.in_dim % KC || a.hidden % KC || a.hidden < 16 || a.hidden > MAXH) {
+    g_err_mlp = "unsupported MLP shape (in_dim and hidden must be multiples of 16, hidden <= 256)";
     return B2H_EUNSUPPORTED;
   }
-  MlpArgs a;
-  a.x = x_dev; a.w[0] = w1_dev; a.w[1] = w2_dev; a.w[2] = w3_dev; a.b[0] = b1_dev; a.b[1] = b2_dev; a.b[2] = b3_dev;
-  a.y = y_dev; a.n_rows = n_rows; a.in_dim = in_dim; a.hidden = hidden; a.out_dim = out_dim; a.precise = precise; a.error = error_flag_dev;
+  for (int n = 0; n < nnets; n++)
+    if (a.out_dim[n] < 1 || a.out_dim[n] > 32) { g_err_mlp = "out_dim must be in [1, 32]"; return B2H_EUNSUPPORTED; }
   size_t smem = (size_t)(2 * TILE_M * KC + 2 * MAXH * KC + TILE_M * HSTRIDE) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
@@ -247,10 +270,35 @@ int b2h_mlp_forward(const float* x_dev, const float* w1_dev, const float* b1_dev
     if (e != cudaSuccess) { g_err_mlp = cudaGetErrorString(e); return B2H_ECUDA; }
     attr_set = true;
   }
-  mlp_forward_kernel<<<(n_rows + TILE_M - 1) / TILE_M, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+  dim3 grid((a.n_rows + TILE_M - 1) / TILE_M, nnets);
+  mlp_forward_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_err_mlp = cudaGetErrorString(e); return B2H_ECUDA; }
   return B2H_OK;
+}
+
+int b2h_mlp_forward(const float* x_dev, const float* w1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
+                    const float* w3_dev, const float* b3_dev, float* y_dev, int n_rows, int in_dim, int hidden, int out_dim,
+                    int precise, int* error_flag_dev, void* stream) {
+  if (!x_dev || !w1_dev || !b1_dev || !w2_dev || !b2_dev || !w3_dev || !b3_dev || !y_dev || !error_flag_dev) { g_err_mlp = "null argument"; return B2H_EINVAL; }
+  MlpArgs a = {};
+  a.x = x_dev; a.w[0][0] = w1_dev; a.w[0][1] = w2_dev; a.w[0][2] = w3_dev; a.b[0][0] = b1_dev; a.b[0][1] = b2_dev; a.b[0][2] = b3_dev;
+  a.y[0] = y_dev; a.out_dim[0] = out_dim; a.n_rows = n_rows; a.in_dim = in_dim; a.hidden = hidden; a.precise = precise; a.error = error_flag_dev;
+  return launch_mlp(a, 1, stream);
+}
+
+int b2h_policy_forward(const float* x_dev, const float* const pi_dev[6], const float* const vf_dev[6], float* mean_dev, float* value_dev,
+                       int n_rows, int in_dim, int hidden, int act_dim, int precise, int* error_flag_dev, void* stream) {
+  if (!x_dev || !pi_dev || !vf_dev || !mean_dev || !value_dev || !error_flag_dev) { g_err_mlp = "null argument"; return B2H_EINVAL; }
+  MlpArgs a = {};
+  a.x = x_dev;
+  for (int l = 0; l < 3; l++) {
+    a.w[0][l] = pi_dev[2 * l]; a.b[0][l] = pi_dev[2 * l + 1]; a.w[1][l] = vf_dev[2 * l]; a.b[1][l] = vf_dev[2 * l + 1];
+    if (!a.w[0][l] || !a.b[0][l] || !a.w[1][l] || !a.b[1][l]) { g_err_mlp = "null argument"; return B2H_EINVAL; }
+  }
+  a.y[0] = mean_dev; a.y[1] = value_dev; a.out_dim[0] = act_dim; a.out_dim[1] = 1;
+  a.n_rows = n_rows; a.in_dim = in_dim; a.hidden = hidden; a.precise = precise; a.error = error_flag_dev;
+  return launch_mlp(a, 2, stream);
 }
 
 int b2h_policy_sample(const float* mean_dev, const float* log_std_dev, int n_rows, int act_dim, uint64_t seed, uint64_t step,

@@ -36,6 +36,7 @@ SIGNATURES = {
     "b2h_get_counters": (C.c_int, [vp, vp]),
     "b2h_gae": (C.c_int, [vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp]),
     "b2h_mlp_forward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
+    "b2h_policy_forward": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "b2h_mlp_last_error": (C.c_char_p, []),
     "b2h_policy_sample": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, vp, vp, vp, vp]),
 }

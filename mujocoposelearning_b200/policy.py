@@ -74,10 +74,21 @@ class MlpPolicy:
         return y
 
     def forward(self, obs):
-        """obs float32 CUDA [E, obs_dim] -> (action mean [E, act_dim], value [E])."""
+        """obs float32 CUDA [E, obs_dim] -> (action mean [E, act_dim], value [E]); both trunks in one launch."""
         if obs.dtype != torch.float32 or not obs.is_contiguous():
             obs = obs.to(torch.float32).contiguous()     # SB3 casts the float64 observation to float32 for the net
-        return self._net(self.p.pi, obs, self.p.act_dim), self._net(self.p.vf, obs, 1).squeeze(1)
+        p = self.p
+        E = obs.shape[0]
+        mean = torch.empty(E, p.act_dim, device=p.device, dtype=torch.float32)
+        value = torch.empty(E, device=p.device, dtype=torch.float32)
+        pi = (C.c_void_p * 6)(*[t.data_ptr() for t in p.pi])
+        vf = (C.c_void_p * 6)(*[t.data_ptr() for t in p.vf])
+        s = C.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)
+        rc = self.lib.b2h_policy_forward(_p(obs), pi, vf, _p(mean), _p(value), E, p.obs_dim, p.hidden, p.act_dim, self.precise,
+                                         _p(self.err), s)
+        if rc < 0:
+            raise RuntimeError(f"b2h_policy_forward: {self.lib.b2h_mlp_last_error().decode()}")
+        return mean, value
 
     def values(self, obs):
         if obs.dtype != torch.float32 or not obs.is_contiguous():

@@ -97,10 +97,17 @@ class B200HumanoidVecEnv(_VecEnvBase):
         self._step_count = np.zeros(n_envs, np.int64)
         self._total_reward = np.zeros(n_envs)
         self.info_mode = ("full" if n_envs <= 256 else "lazy") if info_mode == "auto" else info_mode
-        # returned arrays alternate between two preallocated sets: SB3 keeps `_last_obs` (and the callbacks the
-        # rewards/dones) of the previous step while the next one is produced, never older ones
-        self._out = [dict(obs=np.zeros((n_envs, self.batch.obs_dim), np.float64), rew=np.zeros(n_envs, np.float64),
-                          term=np.zeros(n_envs, bool), trunc=np.zeros(n_envs, bool)) for _ in range(2)]
+        # Host results live in two alternating sets of pinned buffers (SB3 keeps `_last_obs` and the callbacks the
+        # rewards/dones of the previous step while the next one is produced, never older ones).  The float32 ->
+        # float64 widening of the observation (observation_space dtype) happens on the device, so the host only
+        # receives bytes: no per-step numpy conversion or allocation.
+        b = self.batch
+        pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
+        self._host = [dict(obs=pin((n_envs, b.obs_dim), torch.float64), rew=pin((n_envs,), torch.float64),
+                           term=pin((n_envs,), torch.bool), trunc=pin((n_envs,), torch.bool)) for _ in range(2)]
+        self._tobs_host = pin((n_envs, b.obs_dim), torch.float64)
+        self._dev = dict(actions=torch.zeros(n_envs, b.nu, device=b.device), obs64=torch.zeros(n_envs, b.obs_dim, dtype=torch.float64, device=b.device),
+                         rew64=torch.zeros(n_envs, dtype=torch.float64, device=b.device))
         self._flip = 0
         self._lazy_info = {"TimeLimit.truncated": False}
         self.closed = False
@@ -126,21 +133,28 @@ class B200HumanoidVecEnv(_VecEnvBase):
         self._actions = a
 
     def step_wait(self):
-        hb = self.hb
-        self.batch.step_host(hb)
-        out = self._out[self._flip]
+        b, dev = self.batch, self._dev
+        out = self._host[self._flip]
         self._flip ^= 1
-        obs, rewards, term, trunc = out["obs"], out["rew"], out["term"], out["trunc"]
-        np.copyto(obs, hb["obs"].numpy())                     # float32 -> float64 (observation_space dtype)
-        np.copyto(rewards, hb["reward"].numpy())
-        np.copyto(term, hb["terminated"].numpy(), casting="unsafe")
-        np.copyto(trunc, hb["truncated"].numpy(), casting="unsafe")
+        dev["actions"].copy_(self.hb["actions"], non_blocking=True)          # H2D from pinned memory
+        o, r, te, tr = b.step(dev["actions"])                                 # b2h_step on the current stream
+        dev["obs64"].copy_(o)
+        dev["rew64"].copy_(r)
+        out["obs"].copy_(dev["obs64"], non_blocking=True)                    # D2H into pinned memory
+        out["rew"].copy_(dev["rew64"], non_blocking=True)
+        out["term"].copy_(te.bool(), non_blocking=True)
+        out["trunc"].copy_(tr.bool(), non_blocking=True)
+        torch.cuda.current_stream(b.device).synchronize()
+        obs, rewards, term, trunc = out["obs"].numpy(), out["rew"].numpy(), out["term"].numpy(), out["trunc"].numpy()
         dones = term | trunc
+        tobs = None
+        if dones.any():                                                       # terminal observations travel only when an episode ended
+            self._tobs_host.copy_(b.terminal_obs)
+            tobs = self._tobs_host.numpy()
         self._step_count += 1
         self._total_reward += rewards
         if self.info_mode == "full":
-            tobs = hb["terminal_obs"].numpy()
-            heights = np.where(dones, tobs[:, 0], obs[:, 0])
+            heights = np.where(dones, tobs[:, 0], obs[:, 0]) if tobs is not None else obs[:, 0]
             infos = []
             for i in range(self.num_envs):
                 info = {"reward_components": {}, "height": float(heights[i]), "step_count": int(self._step_count[i]),
@@ -148,16 +162,14 @@ class B200HumanoidVecEnv(_VecEnvBase):
                         "terminated": bool(term[i]), "total_reward": float(self._total_reward[i]),
                         "TimeLimit.truncated": bool(trunc[i] and not term[i])}
                 if dones[i]:
-                    info["terminal_observation"] = tobs[i].astype(np.float64)
+                    info["terminal_observation"] = tobs[i].copy()
                 infos.append(info)
         else:
             infos = [self._lazy_info] * self.num_envs
-            if dones.any():
-                tobs = hb["terminal_obs"].numpy()
-                for i in np.nonzero(dones)[0]:
-                    infos[i] = {"terminal_observation": tobs[i].astype(np.float64), "terminated": bool(term[i]),
-                                "truncated": bool(trunc[i]), "TimeLimit.truncated": bool(trunc[i] and not term[i]),
-                                "step_count": int(self._step_count[i]), "total_reward": float(self._total_reward[i])}
+            for i in np.nonzero(dones)[0]:
+                infos[i] = {"terminal_observation": tobs[i].copy(), "terminated": bool(term[i]),
+                            "truncated": bool(trunc[i]), "TimeLimit.truncated": bool(trunc[i] and not term[i]),
+                            "step_count": int(self._step_count[i]), "total_reward": float(self._total_reward[i])}
         if dones.any():
             self._step_count[dones] = 0
             self._total_reward[dones] = 0

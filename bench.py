@@ -39,8 +39,8 @@ FP32_NOMINAL_TFLOPS = 74.5
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
-    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=200)
     ap.add_argument("--n-envs", type=int, default=4096, help="environments per GPU")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])

@@ -194,3 +194,57 @@ def test_many_contacts_spill_rows(cm, model_struct):
         assert _rel(got["qpos"][i], s["qpos"]) < 1e-9 and _rel(got["qvel"][i], s["qvel"]) < 1e-8, (i, nrows[i])
     assert b.counters()["contact_overflow"] == 0
     b.close()
+
+
+def test_obs_mode_prefix_and_reward_params(cm):
+    """obs_mode='qpos_qvel' is the 53-column prefix of the 352-d observation; kneeling params reach the kernel."""
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    rng = np.random.default_rng(3)
+    noise = rng.uniform(-0.01, 0.01, (8, 55))
+    act = rng.uniform(-1, 1, (8, 21)).astype(np.float32)
+    outs = {}
+    for mode in ("full352", "qpos_qvel"):
+        b = HumanoidBatch(8, frame_skip=3, duration=10.0, reward_type="kneeling", obs_mode=mode,
+                          reward_params={"min_height": 2.0})            # every height is "low": reward = h^2 (quirk D4)
+        b.set_reset_noise(noise)
+        b.reset()
+        o, r, *_ = b.step(torch.as_tensor(act).cuda())
+        outs[mode] = (o.cpu().numpy().copy(), r.cpu().numpy().copy())
+        b.close()
+    assert outs["qpos_qvel"][0].shape == (8, 53)
+    assert np.array_equal(outs["full352"][0][:, :53], outs["qpos_qvel"][0])
+    np.testing.assert_allclose(outs["full352"][1], outs["full352"][0][:, 0] ** 2, rtol=1e-6)
+
+
+def test_long_rollout_statistics_match_oracle(cm, model_struct):
+    """700 control steps of 256 fp32 envs (crossing the synchronous auto-reset at step 667): no bad states, no
+    capacity overflow, and the ensemble statistics follow the fp64 oracle's (trajectories themselves are chaotic)."""
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from oracle.oracle import OracleVecEnv
+    n, T = 256, 700
+    b = HumanoidBatch(n, frame_skip=3, duration=10.0, reward_type="stand", seed=5)
+    b.reset()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    h_gpu, r_gpu, dones = [], [], []
+    for t in range(T):
+        a = torch.rand(n, 21, device="cuda", generator=g) * 2 - 1
+        o, r, te, tr = b.step(a)
+        h_gpu.append(o[:, 0].mean().item()); r_gpu.append(r.mean().item()); dones.append(int(te.sum().item()))
+    c = b.counters()
+    assert c["bad_state"] == 0 and c["contact_overflow"] == 0 and c["physics_steps"] == n * (3 * T + 1 + 1)
+    assert dones[666] == n and sum(dones) == n                    # every episode ends exactly at control step 667
+    assert np.isfinite(h_gpu).all() and np.isfinite(r_gpu).all()
+    m = 32
+    orc = OracleVecEnv(model_struct, cm.nq, cm.nv, cm.nu, m, frame_skip=3, duration=10.0, reward_type=0, nthreads=8)
+    rng = np.random.default_rng(1)
+    orc.reset(rng.uniform(-0.01, 0.01, (m, 55)))
+    h_ref, r_ref = [], []
+    for t in range(150):
+        o, r, *_ = orc.step(rng.uniform(-1, 1, (m, 21)).astype(np.float32), rng.uniform(-0.01, 0.01, (m, 55)))
+        h_ref.append(o[:, 0].mean()); r_ref.append(r.mean())
+    h_gpu, r_gpu, h_ref, r_ref = map(np.array, (h_gpu, r_gpu, h_ref, r_ref))
+    # falling under random torques: same mean height profile and the same time of collapse below the 0.8 m reward gate
+    assert np.abs(h_gpu[:150] - h_ref).max() < 0.08
+    assert abs(int(np.argmax(h_gpu < 0.8)) - int(np.argmax(h_ref < 0.8))) <= 4
+    assert abs(r_gpu[:20].mean() - r_ref[:20].mean()) < 0.03
+    b.close()

@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="tuning runs: only the device-timed leg (no e2e / policy / CPU legs)")
     return ap.parse_args()
 
 
@@ -214,6 +215,14 @@ def run_b200(args):
     total_ms = float(step_ms.sum())
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     c1 = batch.counters()
+    if args.quick:
+        if rank == 0:
+            v = world * E * FRAME_SKIP * K / (total_ms * 1e-3)
+            print(json.dumps({"quick": True, "value": v, "ms_per_step": total_ms / K, "n_envs": E, "launch": batch.launch_info(),
+                              "newton_iter": (c1["newton_iter"] - c0["newton_iter"]) / max(1, c1["physics_steps"] - c0["physics_steps"]),
+                              "step_ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
+                              "clocks": clocks}), flush=True)
+        return
     # ---- e2e: the public VecEnv.step with host numpy actions / results (pinned staging, copies timed)
     venv = B200HumanoidVecEnv(env_cfg, n_envs=E, device=local, dtype=args.dtype, seed=99, env_id_offset=rank * E, info_mode="lazy")
     venv.reset()
@@ -292,7 +301,7 @@ def run_b200(args):
                               "frac": fp32_tflops / FP32_NOMINAL_TFLOPS, "flop_per_physics_step": FLOP_PER_PHYSICS_STEP}},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "api": "B200HumanoidVecEnv.step (numpy in/out, lazy infos)"},
-        "gpu_launches": K, "clocks": clocks,
+        "gpu_launches": c1["launches"] - c0["launches"], "clocks": clocks,
         "solver": {"newton_iter_per_physics_step": (c1["newton_iter"] - c0["newton_iter"]) / max(1, psteps),
                    "ls_eval_per_physics_step": (c1["ls_eval"] - c0["ls_eval"]) / max(1, psteps),
                    "contact_overflow": c1["contact_overflow"], "iter_cap": c1["iter_cap"], "bad_state": c1["bad_state"]},

@@ -17,29 +17,33 @@
 using namespace b2h;
 
 // ------------------------------------------------------------------------------------------------ kernels
-// 14 env-warps of fp32 scratch fit 227 KB of shared memory; 448 threads leave 146 registers per thread
-#define B2H_MAX_THREADS 448
+// B2H_WARPS env-warps of fp32 scratch (half as many fp64) share the 227 KB of shared memory of one SM; the register
+// file then allows 65536 / (32 * B2H_WARPS) registers per thread
+#ifndef B2H_WARPS
+#define B2H_WARPS 14
+#endif
+#define B2H_MAX_THREADS (32 * B2H_WARPS)
 template <typename T> constexpr int max_threads() { return sizeof(T) == 8 ? B2H_MAX_THREADS / 2 : B2H_MAX_THREADS; }
 extern __shared__ __align__(16) unsigned char b2h_smem[];
 
 __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long long* g) {
   if (lane_id() == 0) {
-    if (c.physics_steps) atomicAdd(g + 0, c.physics_steps);
-    if (c.contact_overflow) atomicAdd(g + 1, c.contact_overflow);
-    if (c.iter_cap) atomicAdd(g + 2, c.iter_cap);
-    if (c.bad_state) atomicAdd(g + 3, c.bad_state);
-    if (c.newton_iter) atomicAdd(g + 4, c.newton_iter);
-    if (c.ls_eval) atomicAdd(g + 6, c.ls_eval);
+    if (c.physics_steps) atomicAdd(g + 0, (unsigned long long)c.physics_steps);
+    if (c.contact_overflow) atomicAdd(g + 1, (unsigned long long)c.contact_overflow);
+    if (c.iter_cap) atomicAdd(g + 2, (unsigned long long)c.iter_cap);
+    if (c.bad_state) atomicAdd(g + 3, (unsigned long long)c.bad_state);
+    if (c.newton_iter) atomicAdd(g + 4, (unsigned long long)c.newton_iter);
+    if (c.ls_eval) atomicAdd(g + 6, (unsigned long long)c.ls_eval);
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(max_threads<T>(), 1)
 step_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, int n_envs, unsigned long long* counters,
-            int* work, T* spill) {
+            int* work, T* spill, const int* __restrict__ perm) {
   Scratch<T>& S = reinterpret_cast<Scratch<T>*>(b2h_smem)[threadIdx.x >> 5];
   T* Jspill = spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ((NROW - NROW_S) * LD);
-  Counters cnt = {0, 0, 0, 0, 0, 0};
+  Counters cnt = {0, 0, 0, 0, 0, 0, 0};
   __shared__ int s_base;
   const int nwarps = blockDim.x >> 5;
   for (;;) {  // the CTA claims one env per warp at a time and steps them in lockstep (see env_step)
@@ -48,10 +52,31 @@ step_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, int
     __syncthreads();
     const int base = s_base;
     if (base >= n_envs) break;
-    const int env = base + (threadIdx.x >> 5);
-    env_step<T>(*model, S, Jspill, cnt, P, io, env, env < n_envs);
+    // lockstep groups are taken from the effort-sorted order (order_kernel): warps that wait for each other at the
+    // sub-step barriers then carry similar solver work, and the costliest groups start first
+    const int slot = base + (threadIdx.x >> 5);
+    const bool active = slot < n_envs;
+    const int env = active ? (perm ? perm[slot] : slot) : 0;
+    env_step<T>(*model, S, Jspill, cnt, P, io, env, active);
   }
   flush_counters(cnt, counters);
+}
+
+// Counting sort of the envs by the solver effort of their previous control step, costliest first (one CTA).
+// Which warp steps which env never changes a result; the order inside a bucket is left to the atomics.
+constexpr int ORDER_BUCKETS = 256;
+__global__ void __launch_bounds__(1024, 1) order_kernel(const int* __restrict__ effort, int n, int* __restrict__ perm) {
+  __shared__ int hist[ORDER_BUCKETS], start[ORDER_BUCKETS];
+  for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[min(effort[i] >> 2, ORDER_BUCKETS - 1)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int acc = 0;
+    for (int b = ORDER_BUCKETS - 1; b >= 0; b--) { start[b] = acc; acc += hist[b]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[atomicAdd(&start[min(effort[i] >> 2, ORDER_BUCKETS - 1)], 1)] = i;
 }
 
 template <typename T>
@@ -60,7 +85,7 @@ reset_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, in
              unsigned long long* counters, int* work, T* spill) {
   Scratch<T>& S = reinterpret_cast<Scratch<T>*>(b2h_smem)[threadIdx.x >> 5];
   T* Jspill = spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ((NROW - NROW_S) * LD);
-  Counters cnt = {0, 0, 0, 0, 0, 0};
+  Counters cnt = {0, 0, 0, 0, 0, 0, 0};
   for (;;) {
     int env = 0;
     if (lane_id() == 0) env = atomicAdd(work, 1);
@@ -77,7 +102,7 @@ __global__ void __launch_bounds__(32, 1)
 debug_kernel(const DevModel<T>* __restrict__ model, EnvIO<T> io, int env, DebugDump<T>* out, T* Jspill) {
   Scratch<T>& S = reinterpret_cast<Scratch<T>*>(b2h_smem)[0];
   const int lane = lane_id(), nq = model->nq, nv = model->nv, nu = model->nu;
-  Counters cnt = {0, 0, 0, 0, 0, 0};
+  Counters cnt = {0, 0, 0, 0, 0, 0, 0};
   EnvState<T> st;
   st.qp = lane < nq ? io.qpos[(size_t)env * nq + lane] : T(0);
   st.qv = lane < nv ? io.qvel[(size_t)env * nv + lane] : T(0);
@@ -131,6 +156,8 @@ struct B2HHandle {
   uint8_t* noise_injected = nullptr;
   unsigned long long* counters = nullptr;
   int* work = nullptr;
+  int *effort = nullptr, *perm = nullptr;  // per-env solver effort of the last control step, effort-sorted env order
+  int schedule = 1;                        // 1: lockstep groups follow the effort-sorted order
   void* dump = nullptr;
   void* spill = nullptr;  // per-warp dense rows beyond NROW_S
   // staging for the *_host entry points
@@ -150,6 +177,7 @@ static EnvIO<T> make_io(B2HHandle* h, const float* actions, void* obs, void* rew
   io.episode = h->episode; io.total_reward = (T*)h->total_reward; io.reset_noise = h->reset_noise;
   io.noise_injected = h->noise_injected; io.actions = actions; io.obs = (T*)obs; io.reward = (T*)reward;
   io.terminal_obs = (T*)tobs; io.terminated = term; io.truncated = trunc; io.obs_dim = h->obs_dim;
+  io.work = h->effort;
   return io;
 }
 
@@ -195,7 +223,7 @@ void b2h_destroy(B2HHandle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   void* ptrs[] = {h->dmodel, h->qpos, h->qvel, h->warm, h->total_reward, h->nstep, h->step_count, h->episode,
-                  h->reset_noise, h->noise_injected, h->counters, h->work, h->dump, h->spill, h->actions_stage, h->obs_stage,
+                  h->reset_noise, h->noise_injected, h->counters, h->work, h->effort, h->perm, h->dump, h->spill, h->actions_stage, h->obs_stage,
                   h->tobs_stage, h->rew_stage, h->term_stage, h->trunc_stage, h->mask_stage};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
@@ -229,7 +257,8 @@ int b2h_create(const B2HModel* model, const B2HConfig* cfg, B2HHandle** out) {
   ALLOC(h->qpos, E * h->nq * esz); ALLOC(h->qvel, E * h->nv * esz); ALLOC(h->warm, E * h->nv * esz);
   ALLOC(h->total_reward, E * esz); ALLOC(h->nstep, E * 4); ALLOC(h->step_count, E * 4); ALLOC(h->episode, E * 4);
   ALLOC(h->reset_noise, E * (h->nq + h->nv) * 8); ALLOC(h->noise_injected, E);
-  ALLOC(h->counters, 8 * 8); ALLOC(h->work, 4);
+  ALLOC(h->counters, 8 * 8); ALLOC(h->work, 4); ALLOC(h->effort, E * 4); ALLOC(h->perm, E * 4);
+  if (const char* sc = getenv("B2H_SCHEDULE")) h->schedule = atoi(sc);  // tuning knob: 0 = env-id order
   ALLOC(h->actions_stage, E * h->nu * 4); ALLOC(h->obs_stage, E * h->obs_dim * esz); ALLOC(h->tobs_stage, E * h->obs_dim * esz);
   ALLOC(h->rew_stage, E * esz); ALLOC(h->term_stage, E); ALLOC(h->trunc_stage, E); ALLOC(h->mask_stage, E);
 #undef ALLOC
@@ -279,14 +308,20 @@ int b2h_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward
   CU(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   CU(cudaMemsetAsync(h->work, 0, 4, s));
+  const int* perm = nullptr;
+  if (h->schedule && h->P.sync_mode == 2 && h->cfg.n_envs > h->warps) {
+    order_kernel<<<1, 1024, 0, s>>>(h->effort, h->cfg.n_envs, h->perm);
+    perm = h->perm;
+    h->launches++;
+  }
   if (h->cfg.dtype == B2H_F64)
     step_kernel<double><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<double>*)h->dmodel, h->P,
         make_io<double>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev), h->cfg.n_envs,
-        h->counters, h->work, (double*)h->spill);
+        h->counters, h->work, (double*)h->spill, perm);
   else
     step_kernel<float><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<float>*)h->dmodel, h->P,
         make_io<float>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev), h->cfg.n_envs,
-        h->counters, h->work, (float*)h->spill);
+        h->counters, h->work, (float*)h->spill, perm);
   CU(cudaGetLastError());
   h->launches++;
   return B2H_OK;

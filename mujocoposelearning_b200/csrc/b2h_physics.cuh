@@ -219,8 +219,9 @@ constexpr int TMP_DOFW = 0, TMP_DOFA = TMP_DOFW + KV * 6, TMP_CFRC = TMP_DOFA + 
 static_assert(TMP_CRB + KB * 10 <= LD * LD, "position-stage scratch must fit in A");
 static_assert(TMP_CDD + KV * 6 <= LD * LD, "velocity-stage scratch must fit in A");
 
-struct Counters {  // per-warp tallies, flushed with atomics at the end of the launch
-  unsigned long long physics_steps, contact_overflow, iter_cap, bad_state, newton_iter, ls_eval;
+struct Counters {  // per-warp tallies of one launch (32-bit: a warp sees a few thousand events), flushed with atomics
+  unsigned physics_steps, contact_overflow, iter_cap, bad_state, newton_iter, ls_eval;
+  unsigned work;  // solver effort of the env in flight (Newton iterations weighted by row slots): next launch's schedule key
 };
 
 // per-row soft-constraint parameters (mj_makeImpedance + mj_referenceConstraint)
@@ -257,21 +258,43 @@ B2H_DEV_NOINLINE RowParam<T> row_params(T solref0, T solref1, T solimp0, T solim
 }
 
 // ------------------------------------------------------------------------------------------------ dense 27x27 algebra
-B2H_DEV float m_rsqrt(float x) {
+B2H_DEV float m_rsqrt(float x) {  // callers keep x >= mjMINVAL, so the flush-to-zero approximation needs no range fix-up
 #ifdef B2H_HOST_EMU
   return 1.0f / sqrtf(x);
 #else
-  return rsqrtf(x);
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 #endif
 }
 B2H_DEV double m_rsqrt(double x) { return 1.0 / sqrt(x); }
+B2H_DEV float m_rcp(float x) {
+#ifdef B2H_HOST_EMU
+  return 1.0f / x;
+#else
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+#endif
+}
+B2H_DEV double m_rcp(double x) { return 1.0 / x; }
+template <typename T> B2H_DEV void st4(T* p, T x, T y, T z, T w) {
+#ifdef B2H_HOST_EMU
+  p[0] = x; p[1] = y; p[2] = z; p[3] = w;
+#else
+  if constexpr (sizeof(T) == 4) *reinterpret_cast<float4*>(p) = make_float4(x, y, z, w);
+  else { *reinterpret_cast<double2*>(p) = make_double2(x, y); *reinterpret_cast<double2*>(p + 2) = make_double2(z, w); }
+#endif
+}
 
 // x = A^-1 b for the SPD matrix in shared memory A (stride LD, lower triangle read, contents destroyed).
 // Lane i keeps row i of the factor in registers; the right-hand side rides along as row 27 of the augmented
-// matrix (lane 27), so the forward substitution is the same 27 column steps as the factorisation:
-//   step j: broadcast the pivot, scale column j, then a[k] -= L[i][j] * L[k][j] with L[k][j] shuffled from lane k.
-// The factor is then transposed through shared memory for the backward substitution.  mju_cholFactor's pivot
-// floor (mjMINVAL) is kept.
+// matrix (lane 27), so the forward substitution is the same 27 column steps as the factorisation.
+//   step j: every lane stores its (not yet scaled) entry of column j to shared memory; the pivot and the entries
+//   below it come back as 128-bit broadcast loads (one shared-memory wavefront per four entries, where a shuffle
+//   per entry would cost one each), then a[k] -= (a[j] / pivot) * column[k].
+// The factor (and y = L^-1 b in row 27) then goes back to shared memory by rows and is read by columns for the
+// backward substitution.  mju_cholFactor's pivot floor (mjMINVAL) is kept.
 template <typename T>
 B2H_DEV_NOINLINE T chol_solve_fused(T* A, int n, int lane, T b) {
   constexpr int N = KV - 1;
@@ -279,40 +302,47 @@ B2H_DEV_NOINLINE T chol_solve_fused(T* A, int n, int lane, T b) {
   if (lane >= n && lane < N) A[lane * LD + lane] = 1;  // unused dof slots factor as identity
   wsync();
   T a[LD];
-  {
-    const T* r = A + (lane < LD ? lane : 0) * LD;
+  T* const row = A + (lane < LD ? lane : 0) * LD;
 #pragma unroll
-    for (int c = 0; c < LD; c += 4) {
-      V4<T> v = ld4(r + c);
-      a[c] = v.x; a[c + 1] = v.y; a[c + 2] = v.z; a[c + 3] = v.w;
-    }
+  for (int c = 0; c < LD; c += 4) {
+    V4<T> v = ld4(row + c);
+    a[c] = v.x; a[c + 1] = v.y; a[c + 2] = v.z; a[c + 3] = v.w;
   }
-  T dinv = 0;  // 1 / L[lane][lane]
+  wsync();  // rows are in registers: A is free to stage the columns
 #pragma unroll
   for (int j = 0; j < N; j++) {
-    T piv = m_max(shfl(a[j], j), B2H_MINVAL);
+    T* const col = A + j * LD;
+    if (lane < LD) col[lane] = a[j];
+    wsync();
+    T c[LD];
+#pragma unroll
+    for (int k4 = (j / 4) * 4; k4 < LD; k4 += 4) {
+      V4<T> v = ld4(col + k4);
+      c[k4] = v.x; c[k4 + 1] = v.y; c[k4 + 2] = v.z; c[k4 + 3] = v.w;
+    }
+    T piv = m_max(c[j], B2H_MINVAL);
     T r = m_rsqrt(piv);
-    T l = a[j] * r;
-    a[j] = l;
-    if (lane == j) dinv = r;
+    T lr = a[j] * r * r;  // L[lane][j] / L[j][j]
+    a[j] = a[j] * r;
 #pragma unroll
-    for (int k = j + 1; k < N; k++) a[k] -= l * shfl(l, k);
+    for (int k = j + 1; k < N; k++) a[k] -= lr * c[k];
   }
   wsync();
-  if (lane < N) {  // rows of L to shared memory, read back by columns below
-    T* r = A + lane * LD;
+  if (lane < LD) {  // rows of L (lane 27: y = L^-1 b) to shared memory, read back by columns below
 #pragma unroll
-    for (int c = 0; c < LD; c++) r[c] = a[c];
+    for (int c = 0; c < LD; c += 4) st4(row + c, a[c], a[c + 1], a[c + 2], a[c + 3]);
   }
   wsync();
-  T acc = 0, x = 0;
+  const int me = lane < N ? lane : 0;
+  const T dinv = m_rcp(A[me * LD + me]);  // 1 / L[lane][lane]
+  const T y = A[N * LD + me];
+  T acc = 0;
 #pragma unroll
-  for (int k = N - 1; k >= 0; k--) {
-    T yk = shfl(a[k], N);               // y[k] sits in the augmented row
-    T xk = shfl((yk - acc) * dinv, k);
-    if (lane == k) x = xk;
+  for (int k = N - 1; k > 0; k--) {  // x[k] is final in lane k once the columns above it are folded into acc
+    T xk = shfl((y - acc) * dinv, k);
     if (lane < k) acc += A[k * LD + lane] * xk;
   }
+  T x = (y - acc) * dinv;
   wsync();
   return lane < n ? x : T(0);
 }
@@ -1071,6 +1101,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
       lJaref += alpha * lJv;
     }
     cnt.newton_iter += niter;
+    cnt.work += niter * (8 + (nrow >> 2));
     st.warm = qacc;
   } else {
     st.warm = qacc_smooth;
@@ -1233,6 +1264,7 @@ struct EnvIO {  // device arrays, all [n_envs, dim] row-major
   T *obs, *reward, *terminal_obs;
   uint8_t *terminated, *truncated;
   int obs_dim;
+  int* work;                // [n_envs] solver effort of the last control step (schedule key of the next launch), or null
 };
 
 // HumanoidEnv.reset (custom_env.py:97-150): qpos0 + masked U(-0.01,0.01) noise, one settle step with ctrl = 0
@@ -1286,6 +1318,7 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     a = lane < nv ? B2H_LDG(m.dof_act[lane]) : -1;
     step_count = io.step_count[env] + 1;
   }
+  cnt.work = 0;
   if (P.sync_mode == 1) cta_sync();
   for (int s = 0; s < P.frame_skip; s++) {
     if (P.sync_mode == 2) cta_sync();
@@ -1316,7 +1349,10 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     write_obs<T>(m, S, st, P.obs_mode, io.obs + (size_t)env * io.obs_dim, lane);
     if (lane < nq) io.qpos[(size_t)env * nq + lane] = st.qp;
     if (lane < nv) { io.qvel[(size_t)env * nv + lane] = st.qv; io.warm[(size_t)env * nv + lane] = st.warm; }
-    if (lane == 0) { io.nstep[env] = st.nstep; io.step_count[env] = step_count; io.total_reward[env] = total; }
+    if (lane == 0) {
+      io.nstep[env] = st.nstep; io.step_count[env] = step_count; io.total_reward[env] = total;
+      if (io.work) io.work[env] = (int)cnt.work;
+    }
   }
 }
 

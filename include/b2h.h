@@ -182,6 +182,15 @@ int b2h_step_host(B2HHandle* h, const float* actions_host, void* obs_host, void*
                   uint8_t* terminated_host, uint8_t* truncated_host, void* terminal_obs_host, void* stream);
 int b2h_reset_host(B2HHandle* h, const uint8_t* mask_host, void* obs_host, void* stream);
 
+/* VecEnv form of the step: what SubprocVecEnv.step_wait hands to SB3 (train_sb3.py:203) - observations and rewards
+ * as float64 (observation_space dtype, custom_env.py:80-85) whatever the arithmetic dtype, flags as uint8, terminal
+ * observations only for the rows of envs that finished (other rows untouched).  When the host buffers are page-locked
+ * (cudaHostAlloc / cudaHostRegister / torch pin_memory) the kernel writes them directly, so results cross PCIe
+ * while the remaining envs are still being stepped; pageable buffers go through float64 staging in HBM.  Returns
+ * after the stream is synchronised; *n_done (may be NULL) receives the number of envs whose episode ended. */
+int b2h_step_vecenv(B2HHandle* h, const float* actions_host, double* obs_host, double* reward_host,
+                    uint8_t* terminated_host, uint8_t* truncated_host, double* terminal_obs_host, int* n_done, void* stream);
+
 /* Physics state access, all double on the host side regardless of dtype (tests, checkpoints):
  * qpos [n_envs,nq], qvel [n_envs,nv], warmstart [n_envs,nv], nstep int32 [n_envs] (physics steps since
  * mj_resetData: time = nstep*timestep), step_count int32 [n_envs], total_reward [n_envs].  NULL = skip. */

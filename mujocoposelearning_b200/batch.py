@@ -91,6 +91,15 @@ class HumanoidBatch:
         check(self.lib.b2h_step_host(self.h, p(hb["actions"]), p(hb["obs"]), p(hb["reward"]), p(hb["terminated"]),
                                      p(hb["truncated"]), p(hb["terminal_obs"]) if want_terminal_obs else None, self._stream()))
 
+    def step_vecenv(self, actions, obs, reward, terminated, truncated, terminal_obs):
+        """b2h_step_vecenv: CPU tensors in/out (float32 actions; float64 obs / reward / terminal_obs; bool or uint8 flags).
+        Page-locked outputs are written by the kernel itself.  Returns the number of envs whose episode ended."""
+        p = lambda t: C.c_void_p(t.data_ptr())
+        nd = C.c_int(0)
+        check(self.lib.b2h_step_vecenv(self.h, p(actions), p(obs), p(reward), p(terminated), p(truncated),
+                                       p(terminal_obs) if terminal_obs is not None else None, C.byref(nd), self._stream()))
+        return nd.value
+
     def reset_host(self, hb, mask=None):
         mp = None
         if mask is not None:

@@ -163,6 +163,7 @@ struct B2HHandle {
   // staging for the *_host entry points
   float* actions_stage = nullptr;
   void *obs_stage = nullptr, *tobs_stage = nullptr, *rew_stage = nullptr;
+  double *obs64_stage = nullptr, *tobs64_stage = nullptr, *rew64_stage = nullptr;  // b2h_step_vecenv with pageable buffers
   uint8_t *term_stage = nullptr, *trunc_stage = nullptr, *mask_stage = nullptr;
   int grid = 0, warps = 0;
   size_t smem = 0;
@@ -170,14 +171,18 @@ struct B2HHandle {
   EnvParams P;
 };
 
+struct Out64 { double *obs = nullptr, *reward = nullptr, *tobs = nullptr; };
+
 template <typename T>
-static EnvIO<T> make_io(B2HHandle* h, const float* actions, void* obs, void* reward, uint8_t* term, uint8_t* trunc, void* tobs) {
+static EnvIO<T> make_io(B2HHandle* h, const float* actions, void* obs, void* reward, uint8_t* term, uint8_t* trunc, void* tobs,
+                        Out64 o64 = Out64()) {
   EnvIO<T> io;
   io.qpos = (T*)h->qpos; io.qvel = (T*)h->qvel; io.warm = (T*)h->warm; io.nstep = h->nstep; io.step_count = h->step_count;
   io.episode = h->episode; io.total_reward = (T*)h->total_reward; io.reset_noise = h->reset_noise;
   io.noise_injected = h->noise_injected; io.actions = actions; io.obs = (T*)obs; io.reward = (T*)reward;
   io.terminal_obs = (T*)tobs; io.terminated = term; io.truncated = trunc; io.obs_dim = h->obs_dim;
   io.work = h->effort;
+  io.obs64 = o64.obs; io.reward64 = o64.reward; io.terminal_obs64 = o64.tobs;
   return io;
 }
 
@@ -224,7 +229,8 @@ void b2h_destroy(B2HHandle* h) {
   cudaSetDevice(h->cfg.device);
   void* ptrs[] = {h->dmodel, h->qpos, h->qvel, h->warm, h->total_reward, h->nstep, h->step_count, h->episode,
                   h->reset_noise, h->noise_injected, h->counters, h->work, h->effort, h->perm, h->dump, h->spill, h->actions_stage, h->obs_stage,
-                  h->tobs_stage, h->rew_stage, h->term_stage, h->trunc_stage, h->mask_stage};
+                  h->tobs_stage, h->rew_stage, h->term_stage, h->trunc_stage, h->mask_stage, h->obs64_stage, h->tobs64_stage,
+                  h->rew64_stage};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete h;
 }
@@ -302,11 +308,8 @@ int b2h_reset(B2HHandle* h, const uint8_t* mask_dev, void* obs_dev, void* stream
   return B2H_OK;
 }
 
-int b2h_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward_dev, uint8_t* terminated_dev,
-             uint8_t* truncated_dev, void* terminal_obs_dev, void* stream) {
-  if (!h || !actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail(B2H_EINVAL, "null argument");
-  CU(cudaSetDevice(h->cfg.device));
-  cudaStream_t s = (cudaStream_t)stream;
+static int launch_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward_dev, uint8_t* terminated_dev,
+                       uint8_t* truncated_dev, void* terminal_obs_dev, Out64 o64, cudaStream_t s) {
   CU(cudaMemsetAsync(h->work, 0, 4, s));
   const int* perm = nullptr;
   if (h->schedule && h->P.sync_mode == 2 && h->cfg.n_envs > h->warps) {
@@ -316,14 +319,68 @@ int b2h_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward
   }
   if (h->cfg.dtype == B2H_F64)
     step_kernel<double><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<double>*)h->dmodel, h->P,
-        make_io<double>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev), h->cfg.n_envs,
+        make_io<double>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, o64), h->cfg.n_envs,
         h->counters, h->work, (double*)h->spill, perm);
   else
     step_kernel<float><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<float>*)h->dmodel, h->P,
-        make_io<float>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev), h->cfg.n_envs,
+        make_io<float>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, o64), h->cfg.n_envs,
         h->counters, h->work, (float*)h->spill, perm);
   CU(cudaGetLastError());
   h->launches++;
+  return B2H_OK;
+}
+
+int b2h_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward_dev, uint8_t* terminated_dev,
+             uint8_t* truncated_dev, void* terminal_obs_dev, void* stream) {
+  if (!h || !actions_dev || !obs_dev || !reward_dev || !terminated_dev || !truncated_dev) return fail(B2H_EINVAL, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  return launch_step(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, Out64(), (cudaStream_t)stream);
+}
+
+// Device-visible alias of a page-locked host buffer (cudaHostAlloc / cudaHostRegister / torch pin_memory), or null.
+static void* mapped_alias(const void* host) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
+int b2h_step_vecenv(B2HHandle* h, const float* actions_host, double* obs_host, double* reward_host, uint8_t* terminated_host,
+                    uint8_t* truncated_host, double* terminal_obs_host, int* n_done, void* stream) {
+  if (!h || !actions_host || !obs_host || !reward_host || !terminated_host || !truncated_host) return fail(B2H_EINVAL, "null argument");
+  CU(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t E = (size_t)h->cfg.n_envs, obs_bytes = E * h->obs_dim * 8;
+  CU(cudaMemcpyAsync(h->actions_stage, actions_host, E * h->nu * 4, cudaMemcpyHostToDevice, s));
+  Out64 o64;
+  o64.obs = (double*)mapped_alias(obs_host);
+  o64.reward = (double*)mapped_alias(reward_host);
+  uint8_t* term = (uint8_t*)mapped_alias(terminated_host);
+  uint8_t* trunc = (uint8_t*)mapped_alias(truncated_host);
+  o64.tobs = terminal_obs_host ? (double*)mapped_alias(terminal_obs_host) : nullptr;
+  const bool direct = o64.obs && o64.reward && term && trunc && (!terminal_obs_host || o64.tobs);
+  if (!direct) {  // pageable host buffers: float64 staging in HBM, copied out after the kernel
+    if (!h->obs64_stage) {
+      CU(cudaMalloc(&h->obs64_stage, obs_bytes)); CU(cudaMalloc(&h->tobs64_stage, obs_bytes)); CU(cudaMalloc(&h->rew64_stage, E * 8));
+    }
+    o64.obs = h->obs64_stage; o64.reward = h->rew64_stage; o64.tobs = terminal_obs_host ? h->tobs64_stage : nullptr;
+    term = h->term_stage; trunc = h->trunc_stage;
+  }
+  int rc = launch_step(h, h->actions_stage, nullptr, nullptr, term, trunc, nullptr, o64, s);
+  if (rc != B2H_OK) return rc;
+  if (!direct) {
+    CU(cudaMemcpyAsync(obs_host, o64.obs, obs_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(reward_host, o64.reward, E * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(terminated_host, term, E, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(truncated_host, trunc, E, cudaMemcpyDeviceToHost, s));
+  }
+  CU(cudaStreamSynchronize(s));
+  int nd = 0;
+  for (size_t i = 0; i < E; i++) nd += (terminated_host[i] | truncated_host[i]) != 0;
+  if (!direct && nd && terminal_obs_host) {
+    CU(cudaMemcpyAsync(terminal_obs_host, o64.tobs, obs_bytes, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  if (n_done) *n_done = nd;
   return B2H_OK;
 }
 

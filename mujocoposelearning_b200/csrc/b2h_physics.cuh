@@ -1239,18 +1239,18 @@ B2H_DEV T compute_reward(const DevModel<T>& m, const Scratch<T>& S, const EnvSta
 }
 
 // custom_env.py:242-256: qpos[2:] | qvel | cinert | cvel | qfrc_actuator  (B2H_OBS_QPOS_QVEL = first two blocks)
-template <typename T>
-B2H_DEV void write_obs(const DevModel<T>& m, const Scratch<T>& S, const EnvState<T>& st, int obs_mode, T* obs, int lane) {
+template <typename T, typename O>  // O = T (device-resident rollouts) or double (the VecEnv's float64 observation)
+B2H_DEV void write_obs(const DevModel<T>& m, const Scratch<T>& S, const EnvState<T>& st, int obs_mode, O* obs, int lane) {
   const int nq = B2H_LDG(m.nq), nv = B2H_LDG(m.nv), nbody = B2H_LDG(m.nbody);
-  if (lane >= 2 && lane < nq) obs[lane - 2] = st.qp;
-  if (lane < nv) obs[nq - 2 + lane] = st.qv;
+  if (lane >= 2 && lane < nq) obs[lane - 2] = O(st.qp);
+  if (lane < nv) obs[nq - 2 + lane] = O(st.qv);
   if (obs_mode == B2H_OBS_QPOS_QVEL) return;
   int o = nq - 2 + nv;
-  for (int i = lane; i < 10 * nbody; i += 32) obs[o + i] = S.cinert[i];
+  for (int i = lane; i < 10 * nbody; i += 32) obs[o + i] = O(S.cinert[i]);
   o += 10 * nbody;
-  for (int i = lane; i < 6 * nbody; i += 32) obs[o + i] = S.cvel[i];
+  for (int i = lane; i < 6 * nbody; i += 32) obs[o + i] = O(S.cvel[i]);
   o += 6 * nbody;
-  if (lane < nv) obs[o + lane] = st.qfrc_act;
+  if (lane < nv) obs[o + lane] = O(st.qfrc_act);
 }
 
 template <typename T>
@@ -1264,6 +1264,8 @@ struct EnvIO {  // device arrays, all [n_envs, dim] row-major
   T *obs, *reward, *terminal_obs;
   uint8_t *terminated, *truncated;
   int obs_dim;
+  // float64 outputs of the VecEnv boundary (may be page-locked host memory written straight over PCIe), or null
+  double *obs64, *reward64, *terminal_obs64;
   int* work;                // [n_envs] solver effort of the last control step (schedule key of the next launch), or null
 };
 
@@ -1336,9 +1338,14 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     // terminated = data.time >= duration, with time = nstep * timestep evaluated in double
     bool terminated = (double)st.nstep * P.timestep >= P.duration;
     total = io.total_reward[env] + reward;
-    if (lane == 0) { io.reward[env] = reward; io.terminated[env] = terminated; io.truncated[env] = truncated; }
+    if (lane == 0) {
+      if (io.reward) io.reward[env] = reward;
+      if (io.reward64) io.reward64[env] = (double)reward;
+      io.terminated[env] = terminated; io.truncated[env] = truncated;
+    }
     done = terminated || truncated;
-    if (done && io.terminal_obs) write_obs<T>(m, S, st, P.obs_mode, io.terminal_obs + (size_t)env * io.obs_dim, lane);
+    if (done && io.terminal_obs) write_obs(m, S, st, P.obs_mode, io.terminal_obs + (size_t)env * io.obs_dim, lane);
+    if (done && io.terminal_obs64) write_obs(m, S, st, P.obs_mode, io.terminal_obs64 + (size_t)env * io.obs_dim, lane);
   }
   if (P.sync_mode == 2) cta_sync();
   if (active && done) {
@@ -1346,7 +1353,8 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     step_count = 0; total = 0;
   }
   if (active) {
-    write_obs<T>(m, S, st, P.obs_mode, io.obs + (size_t)env * io.obs_dim, lane);
+    if (io.obs) write_obs(m, S, st, P.obs_mode, io.obs + (size_t)env * io.obs_dim, lane);
+    if (io.obs64) write_obs(m, S, st, P.obs_mode, io.obs64 + (size_t)env * io.obs_dim, lane);
     if (lane < nq) io.qpos[(size_t)env * nq + lane] = st.qp;
     if (lane < nv) { io.qvel[(size_t)env * nv + lane] = st.qv; io.warm[(size_t)env * nv + lane] = st.warm; }
     if (lane == 0) {
@@ -1363,7 +1371,8 @@ B2H_DEV void env_reset_only(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Coun
   const int nq = B2H_LDG(m.nq), nv = B2H_LDG(m.nv);
   EnvState<T> st;
   env_reset<T>(m, S, Jspill, st, cnt, P, io, env, lane);
-  if (io.obs) write_obs<T>(m, S, st, P.obs_mode, io.obs + (size_t)env * io.obs_dim, lane);
+  if (io.obs) write_obs(m, S, st, P.obs_mode, io.obs + (size_t)env * io.obs_dim, lane);
+  if (io.obs64) write_obs(m, S, st, P.obs_mode, io.obs64 + (size_t)env * io.obs_dim, lane);
   if (lane < nq) io.qpos[(size_t)env * nq + lane] = st.qp;
   if (lane < nv) { io.qvel[(size_t)env * nv + lane] = st.qv; io.warm[(size_t)env * nv + lane] = st.warm; }
   if (lane == 0) { io.nstep[env] = st.nstep; io.step_count[env] = 0; io.total_reward[env] = 0; }

@@ -30,6 +30,7 @@ SIGNATURES = {
     "b2h_step": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "b2h_step_host": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "b2h_reset_host": (C.c_int, [vp, vp, vp, vp]),
+    "b2h_step_vecenv": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.POINTER(C.c_int), vp]),
     "b2h_get_state": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "b2h_set_state": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "b2h_debug_forward": (C.c_int, [vp, vp, C.c_int, C.c_char_p, vp, C.c_int]),

@@ -97,17 +97,15 @@ class B200HumanoidVecEnv(_VecEnvBase):
         self._step_count = np.zeros(n_envs, np.int64)
         self._total_reward = np.zeros(n_envs)
         self.info_mode = ("full" if n_envs <= 256 else "lazy") if info_mode == "auto" else info_mode
-        # Host results live in two alternating sets of pinned buffers (SB3 keeps `_last_obs` and the callbacks the
-        # rewards/dones of the previous step while the next one is produced, never older ones).  The float32 ->
-        # float64 widening of the observation (observation_space dtype) happens on the device, so the host only
-        # receives bytes: no per-step numpy conversion or allocation.
+        # Host results live in two alternating sets of page-locked buffers (SB3 keeps `_last_obs` and the callbacks the
+        # rewards/dones of the previous step while the next one is produced, never older ones).  The step kernel
+        # writes them itself, already widened to float64 (observation_space dtype): results cross PCIe while the
+        # other envs are still being stepped, and the host does no per-step conversion or allocation.
         b = self.batch
         pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
         self._host = [dict(obs=pin((n_envs, b.obs_dim), torch.float64), rew=pin((n_envs,), torch.float64),
                            term=pin((n_envs,), torch.bool), trunc=pin((n_envs,), torch.bool)) for _ in range(2)]
         self._tobs_host = pin((n_envs, b.obs_dim), torch.float64)
-        self._dev = dict(actions=torch.zeros(n_envs, b.nu, device=b.device), obs64=torch.zeros(n_envs, b.obs_dim, dtype=torch.float64, device=b.device),
-                         rew64=torch.zeros(n_envs, dtype=torch.float64, device=b.device))
         self._flip = 0
         self._lazy_info = {"TimeLimit.truncated": False}
         self.closed = False
@@ -133,24 +131,12 @@ class B200HumanoidVecEnv(_VecEnvBase):
         self._actions = a
 
     def step_wait(self):
-        b, dev = self.batch, self._dev
         out = self._host[self._flip]
         self._flip ^= 1
-        dev["actions"].copy_(self.hb["actions"], non_blocking=True)          # H2D from pinned memory
-        o, r, te, tr = b.step(dev["actions"])                                 # b2h_step on the current stream
-        dev["obs64"].copy_(o)
-        dev["rew64"].copy_(r)
-        out["obs"].copy_(dev["obs64"], non_blocking=True)                    # D2H into pinned memory
-        out["rew"].copy_(dev["rew64"], non_blocking=True)
-        out["term"].copy_(te.bool(), non_blocking=True)
-        out["trunc"].copy_(tr.bool(), non_blocking=True)
-        torch.cuda.current_stream(b.device).synchronize()
+        n_done = self.batch.step_vecenv(self.hb["actions"], out["obs"], out["rew"], out["term"], out["trunc"], self._tobs_host)
         obs, rewards, term, trunc = out["obs"].numpy(), out["rew"].numpy(), out["term"].numpy(), out["trunc"].numpy()
         dones = term | trunc
-        tobs = None
-        if dones.any():                                                       # terminal observations travel only when an episode ended
-            self._tobs_host.copy_(b.terminal_obs)
-            tobs = self._tobs_host.numpy()
+        tobs = self._tobs_host.numpy() if n_done else None   # rows of the envs that finished (others are stale)
         self._step_count += 1
         self._total_reward += rewards
         if self.info_mode == "full":

@@ -120,7 +120,7 @@ static int emu_run(int mode, const B2HModel* model, const B2HConfig* cfg, double
   job.io.qpos = q.data(); job.io.qvel = v.data(); job.io.warm = w.data(); job.io.nstep = nstep; job.io.step_count = step_count;
   job.io.episode = episode; job.io.total_reward = tr.data(); job.io.reset_noise = reset_noise; job.io.noise_injected = noise_injected;
   job.io.actions = actions; job.io.obs = ob.data(); job.io.reward = rw.data(); job.io.terminal_obs = tob.data();
-  job.io.terminated = terminated; job.io.truncated = truncated; job.io.obs_dim = obs_dim; job.io.work = nullptr;
+  job.io.terminated = terminated; job.io.truncated = truncated; job.io.obs_dim = obs_dim; job.io.work = nullptr; job.io.obs64 = nullptr; job.io.reward64 = nullptr; job.io.terminal_obs64 = nullptr;
   run_lanes<T>(job);
   if (mode == 2) return extract_named<T>(dm, dump, what, dump_out, dump_max);
   for (int i = 0; i < E * nq; i++) qpos[i] = (double)q[i];

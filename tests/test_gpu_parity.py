@@ -248,3 +248,35 @@ def test_long_rollout_statistics_match_oracle(cm, model_struct):
     assert abs(int(np.argmax(h_gpu < 0.8)) - int(np.argmax(h_ref < 0.8))) <= 4
     assert abs(r_gpu[:20].mean() - r_ref[:20].mean()) < 0.03
     b.close()
+
+
+def test_step_vecenv_pinned_and_pageable_agree_with_device_step(cm):
+    """b2h_step_vecenv (float64 host results written by the kernel into page-locked memory, or staged for pageable
+    buffers) returns exactly the widened values of the device-resident b2h_step, auto-reset rows included."""
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    n = 64
+    mk = lambda: HumanoidBatch(n, frame_skip=3, duration=0.049, reward_type="kneeling", seed=9)
+    ref, pin, page = mk(), mk(), mk()
+    for b in (ref, pin, page):
+        b.reset()
+    bufs = {}
+    for name, pinned in (("pin", True), ("page", False)):
+        mkbuf = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory() if pinned else torch.zeros(shape, dtype=dt)
+        bufs[name] = dict(a=mkbuf((n, 21), torch.float32), obs=mkbuf((n, 352), torch.float64), rew=mkbuf((n,), torch.float64),
+                          te=mkbuf((n,), torch.uint8), tr=mkbuf((n,), torch.uint8), tobs=mkbuf((n, 352), torch.float64))
+    rng = np.random.default_rng(4)
+    for k in range(4):
+        act = torch.as_tensor(rng.uniform(-1, 1, (n, 21)).astype(np.float32))
+        o, r, te, tr = ref.step(act.cuda())
+        o, r, te, tr, to = (x.cpu().numpy().copy() for x in (o, r, te, tr, ref.terminal_obs))
+        for name, b in (("pin", pin), ("page", page)):
+            h = bufs[name]
+            h["a"].copy_(act)
+            nd = b.step_vecenv(h["a"], h["obs"], h["rew"], h["te"], h["tr"], h["tobs"])
+            assert nd == int((te | tr).sum()) and nd == (n if k == 2 else 0)
+            assert np.array_equal(h["obs"].numpy(), o.astype(np.float64)) and np.array_equal(h["rew"].numpy(), r.astype(np.float64))
+            assert np.array_equal(h["te"].numpy(), te) and np.array_equal(h["tr"].numpy(), tr)
+            if nd:
+                assert np.array_equal(h["tobs"].numpy(), to.astype(np.float64))
+    for b in (ref, pin, page):
+        b.close()

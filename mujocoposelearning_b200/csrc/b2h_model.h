@@ -29,12 +29,13 @@ constexpr int NROW = 32 * NSLOT;  // dense constraint rows per env (tendon limit
 #ifndef B2H_NROW_S
 #define B2H_NROW_S 48
 #endif
-constexpr int NROW_S = B2H_NROW_S;       // rows kept in shared memory; rows beyond live in a per-warp global spill area
+constexpr int NROW_S = B2H_NROW_S;       // most rows a warp keeps in shared memory (DevModel::nrow_s is the launch's choice); rows beyond live in a per-warp global spill area
 constexpr int NCON = 32;          // contacts per env
 
 template <typename T>
 struct DevModel {
   int nq, nv, nu, nbody, njnt, ngeom, ntendon, npair, nlevel, ncls, maxsub;
+  int nrow_s;  // dense constraint rows kept in shared memory by this launch configuration (<= NROW_S)
   T timestep, gravity[3], meaninertia, inv_total_mass;
   // bodies
   int body_parent[KB], body_level[KB], body_jntadr[KB], body_jntnum[KB], body_subend[KB], body_isfree[KB], body_lastdof[KB];
@@ -92,6 +93,7 @@ std::string build_dev_model(const B2HModel& m, DevModel<T>& d) {
   if (m.nbody > KB || m.njnt > KJ || m.nv >= KV || m.nq > KQ || m.ngeom > KG || m.ntendon > KT || m.npair > KPAIR ||
       m.nu > KV || m.nbody < 2)
     return "model exceeds kernel capacities (bodies/joints/dofs/geoms/tendons/pairs)";
+  d.nrow_s = NROW_S;
   d.nq = m.nq; d.nv = m.nv; d.nu = m.nu; d.nbody = m.nbody; d.njnt = m.njnt; d.ngeom = m.ngeom;
   d.ntendon = m.ntendon; d.npair = m.npair;
   d.timestep = (T)m.timestep; d.meaninertia = (T)m.meaninertia;

@@ -194,8 +194,6 @@ template <typename T> B2H_DEV void cross_force(T* r, const T* vel, const T* f) {
 // ------------------------------------------------------------------------------------------------ per-warp scratch
 template <typename T>
 struct alignas(16) Scratch {
-  T J[NROW_S * LD];  // first NROW_S dense constraint rows (tendon limits, contact rows); column 27 is a zero pad.
-                     // Until the rows are written (after collision) it holds the kinematics scratch POS_*.
   T A[LD * LD];      // factor transposition buffer of chol_solve_fused; stage-local scratch TMP_* otherwise
   T M[LD * LD];      // joint-space inertia, dense symmetric
   T vec[3][32];      // lane vectors that other lanes index (qpos, qvel, matvec operand)
@@ -206,12 +204,18 @@ struct alignas(16) Scratch {
   int con_row[NCON];        // first dense row of the contact, -1 if dropped
   int row_con[NROW];        // dense row -> contact id (or -1 - tendon id)
   T com[4];
+  // Last member: the first m.nrow_s (<= NROW_S) dense constraint rows (tendon limits, contact rows); column 27 is a
+  // zero pad.  Until the rows are written (after collision) it holds the kinematics scratch POS_*.  The launch sizes
+  // each warp's slice as scratch_bytes(nrow_s), so fewer shared rows buy more env-warps per SM.
+  alignas(16) T J[NROW_S * LD];
 };
+template <typename T> constexpr size_t scratch_bytes(int nrow_s) { return sizeof(Scratch<T>) - (size_t)(NROW_S - nrow_s) * LD * sizeof(T); }
+constexpr int NROW_S_MIN = 21;
 // kinematics / collision scratch inside Scratch::J (dead before the first constraint row is written)
 constexpr int POS_XPOS = 0, POS_XMAT = POS_XPOS + KB * 3, POS_XIPOS = POS_XMAT + KB * 9, POS_XANCHOR = POS_XIPOS + KB * 3,
               POS_XAXIS = POS_XANCHOR + KJ * 3, POS_GPOS = POS_XAXIS + KJ * 3, POS_GAXIS = POS_GPOS + KG * 3,
               POS_END = POS_GAXIS + KG * 3;
-static_assert(POS_END <= NROW_S * LD, "kinematics scratch must fit in the row storage");
+static_assert(POS_END <= NROW_S_MIN * LD, "kinematics scratch must fit in the row storage");
 // stage-local aliases inside Scratch::A (all dead before the factorisations start)
 constexpr int TMP_QLOC = 0, TMP_ANCL = TMP_QLOC + KJ * 4, TMP_AXL = TMP_ANCL + KJ * 3, TMP_XQUAT = TMP_AXL + KJ * 3,
               TMP_CRB = TMP_XQUAT + KB * 4;                       // position stage
@@ -394,8 +398,9 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
   T* const xpos = S.J + POS_XPOS; T* const xmat = S.J + POS_XMAT; T* const xipos = S.J + POS_XIPOS;
   T* const xanchor = S.J + POS_XANCHOR; T* const xaxis = S.J + POS_XAXIS;
   T* const gpos = S.J + POS_GPOS; T* const gaxis = S.J + POS_GAXIS;
-  // dense row r lives in shared memory below NROW_S and in this warp's global spill area above it
-  auto jrow = [&](int r) -> T* { return r < NROW_S ? S.J + r * LD : Jspill + (size_t)(r - NROW_S) * LD; };
+  // dense row r lives in shared memory below nrow_s and in this warp's global spill area above it
+  const int nrow_s = B2H_LDG(m.nrow_s);
+  auto jrow = [&](int r) -> T* { return r < nrow_s ? S.J + r * LD : Jspill + (size_t)(r - nrow_s) * LD; };
 
   // ---- mj_checkPos / mj_checkVel: NaN or |x| > 1e10 resets mjData (qpos0, zero velocity, time 0)
   {

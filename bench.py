@@ -283,11 +283,25 @@ def run_b200(args):
     achieved_gbs = BYTES_PER_PHYSICS_STEP * E * FRAME_SKIP / (kernel_ms * 1e-3) / 1e9
     fp32_tflops = FLOP_PER_PHYSICS_STEP * E * FRAME_SKIP / (kernel_ms * 1e-3) / 1e12
     psteps = c1["physics_steps"] - c0["physics_steps"]
-    traffic = None
-    try:   # dram bytes of one step-kernel launch from the committed ncu capture (same env count only)
+    traffic, issue = None, None
+    try:   # dram bytes / warp instructions of one step-kernel launch from the committed ncu capture (same env count only)
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
         if tj["n_envs"] == E and args.dtype == "f32":
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
+            peak_issue = 4 * torch.cuda.get_device_properties(dev).multi_processor_count * sm_hz   # 4 schedulers per SM, 1 warp-inst/clk
+            ach = tj["warp_inst_per_launch"] / (kernel_ms * 1e-3)
+            issue = {"achieved_warp_inst_per_s": ach, "peak_warp_inst_per_s": peak_issue, "frac": ach / peak_issue,
+                     "warp_inst_per_physics_step": tj["warp_inst_per_launch"] / (E * FRAME_SKIP), "source": tj["source"]}
+    except Exception:
+        pass
+    fp32_peak, fp32_src = FP32_NOMINAL_TFLOPS, "nominal (148 SM x 128 lanes x 2 x 1.965 GHz)"
+    try:   # measured FFMA peak of this GPU (register-resident FMA kernel in libb2h.so)
+        import ctypes as C
+        from mujocoposelearning_b200.lib import load
+        tf = C.c_double(0.0)
+        if load().b2h_measure_fp32_peak(local, C.byref(tf)) == 0 and tf.value > 0:
+            fp32_peak, fp32_src = tf.value, "measured: b2h_measure_fp32_peak (FFMA kernel, best of 4)"
     except Exception:
         pass
     out = {
@@ -297,8 +311,10 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
                      "traffic": traffic, "algorithmic_bytes_per_launch": BYTES_PER_PHYSICS_STEP * E * FRAME_SKIP, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
                      "note": "latency/issue-bound irregular FP32 work, not HBM-bound (SURVEY 8d); see fp32 block",
-                     "fp32": {"achieved_tflops": fp32_tflops, "nominal_peak_tflops": FP32_NOMINAL_TFLOPS,
-                              "frac": fp32_tflops / FP32_NOMINAL_TFLOPS, "flop_per_physics_step": FLOP_PER_PHYSICS_STEP}},
+                     "fp32": {"achieved_tflops": fp32_tflops, "peak_tflops": fp32_peak, "peak_source": fp32_src,
+                              "nominal_peak_tflops": FP32_NOMINAL_TFLOPS, "frac": fp32_tflops / fp32_peak,
+                              "flop_per_physics_step": FLOP_PER_PHYSICS_STEP},
+                     "issue": issue},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "api": "B200HumanoidVecEnv.step (numpy in/out, lazy infos)"},
         "gpu_launches": c1["launches"] - c0["launches"], "clocks": clocks,

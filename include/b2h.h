@@ -212,6 +212,10 @@ int b2h_debug_forward(B2HHandle* h, const float* actions_dev, int env, const cha
  * cost evaluations. */
 int b2h_get_counters(B2HHandle* h, uint64_t counters_host[8]);
 
+/* Measurement aid: FP32 FMA throughput of `device` in TFLOP/s, measured with a register-resident FFMA kernel
+ * (the roofline denominator of this FP32 / issue-bound path; SURVEY 8d asks for "of measured", not nominal). */
+int b2h_measure_fp32_peak(int device, double* tflops);
+
 /* GAE reverse scan (SB3 2.3.2 RolloutBuffer.compute_returns_and_advantage).  All [T, E] float arrays,
  * E fastest; last_values [E]; last_dones uint8 [E].  gamma / gae_lambda are Python floats in SB3: they are
  * rounded to float32 the way numpy does (gamma, and the double product gamma*gae_lambda, once each). */

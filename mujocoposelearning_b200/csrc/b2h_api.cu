@@ -141,6 +141,22 @@ __global__ void gae_kernel(const float* __restrict__ rewards, const float* __res
   }
 }
 
+// FP32 FMA peak of the device, measured: the roofline denominator bench.py quotes for this issue/FP32-bound path
+// (MEASURED_PEAKS.json only carries HBM and tensor figures).  16 independent FFMA chains per thread, 8 CTAs of 256 threads per SM.
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* out, int iters, float x, float y) {
+  float a[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = (float)(threadIdx.x + i);
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = fmaf(a[i], x, y);
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += a[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 static thread_local std::string g_err;
 static int fail(int code, const std::string& msg) { g_err = msg; return code; }
@@ -541,6 +557,33 @@ int b2h_debug_forward(B2HHandle* h, const float* actions_dev, int env, const cha
   CU(cudaDeviceSynchronize());
   return h->cfg.dtype == B2H_F64 ? debug_typed<double>(h, actions_dev, env, what, out_host, max_out)
                                  : debug_typed<float>(h, actions_dev, env, what, out_host, max_out);
+}
+
+int b2h_measure_fp32_peak(int device, double* tflops) {
+  if (!tflops) return fail(B2H_EINVAL, "null argument");
+  int ndev = 0, nsm = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(B2H_ECUDA, "no such CUDA device");
+  CU(cudaSetDevice(device));
+  CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device));
+  const int grid = nsm * 8, block = 256, iters = 1 << 15;
+  float* out = nullptr;
+  CU(cudaMalloc(&out, (size_t)grid * block * sizeof(float)));
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  double best = 0;
+  for (int rep = 0; rep < 5; rep++) {  // first repetition warms the clocks up
+    CU(cudaEventRecord(e0));
+    ffma_peak_kernel<<<grid, block>>>(out, iters, 0.999f, 0.001f);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    double tf = 2.0 * 16 * iters * (double)grid * block / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops = best;
+  return B2H_OK;
 }
 
 int b2h_get_counters(B2HHandle* h, uint64_t counters_host[8]) {

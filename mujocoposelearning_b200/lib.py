@@ -35,6 +35,7 @@ SIGNATURES = {
     "b2h_set_state": (C.c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "b2h_debug_forward": (C.c_int, [vp, vp, C.c_int, C.c_char_p, vp, C.c_int]),
     "b2h_get_counters": (C.c_int, [vp, vp]),
+    "b2h_measure_fp32_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
     "b2h_gae": (C.c_int, [vp, vp, vp, vp, vp, C.c_double, C.c_double, C.c_int, C.c_int, vp, vp, vp]),
     "b2h_mlp_forward": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "b2h_policy_forward": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),

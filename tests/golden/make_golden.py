@@ -135,6 +135,27 @@ def install_shims():
     sys.modules["gymnasium"] = gym
 
 
+def make_keyframe_fixture():
+    """The 155 keyframes of the reference's own trajectory fixture (trajectories/humanoid_trajectory.xml:212-218: four
+    named poses and 151 states written by generate_trajectories.py:33-57 from a MuJoCo rollout of a trained policy,
+    6 decimals) as start states for the CPU-vs-GPU single-step parity of BASELINE config 2.
+    Data only; consecutive frames are 25 physics steps apart with unrecorded actions, so they pin no transition."""
+    import re
+    xml = (REF / "trajectories" / "humanoid_trajectory.xml").read_text()
+    qpos, qvel, time = [], [], []
+    for attrs in re.findall(r"<key\s+([^>]*?)/?>", xml):
+        qp = re.search(r'qpos="([^"]*)"', attrs)
+        qv = re.search(r'qvel="([^"]*)"', attrs)
+        t = re.search(r'time="([^"]*)"', attrs)
+        qpos.append([float(x) for x in qp.group(1).split()])
+        qvel.append([float(x) for x in qv.group(1).split()] if qv else [0.0] * 27)
+        time.append(float(t.group(1)) if t else 0.0)
+    qpos, qvel, time = np.array(qpos), np.array(qvel), np.array(time)
+    assert qpos.shape == (155, 28) and qvel.shape == (155, 27)
+    np.savez_compressed(OUT / "reference_keyframes.npz", qpos=qpos, qvel=qvel, time=time)
+    print("reference_keyframes.npz", qpos.shape)
+
+
 def make_env_fixtures():
     install_shims()
     sys.path.insert(0, str(REF))
@@ -184,3 +205,4 @@ if __name__ == "__main__":
         raise SystemExit("needs /root/reference (the golden fixtures are committed; regenerate only in the build container)")
     make_reward_fixtures()
     make_env_fixtures()
+    make_keyframe_fixture()

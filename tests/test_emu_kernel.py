@@ -120,3 +120,20 @@ def test_constraint_row_spill_path(cm, model_struct):
     obs, rew, *_ = emu.step(act)
     o, r, *_ = e.env_step(act[0])
     assert np.abs(obs[0] - o).max() < 1e-9 * max(1.0, np.abs(o).max())
+
+
+@pytest.mark.parametrize("idx", [0, 2, 80])   # squat pose, prone pose (many floor contacts), mid-trajectory MuJoCo state
+def test_reference_keyframe_state_step_f64(cm, model_struct, idx):
+    """Start states taken from the reference's trajectory fixture (tests/golden/reference_keyframes.npz)."""
+    g = np.load(GOLD / "reference_keyframes.npz")
+    e = OracleEnv(model_struct, cm.nq, cm.nv, cm.nu)
+    nstep = int(round(g["time"][idx] / cm.timestep)) + 1
+    e.set_state(qpos=g["qpos"][idx], qvel=g["qvel"][idx], warmstart=np.zeros(cm.nv), nstep=nstep, step_count=0)
+    emu = EmuBatch(model_struct, make_config(1, frame_skip=5, reward_type="walk", dtype="f64", duration=30.0), cm.nq, cm.nv, cm.nu)
+    emu.qpos[0], emu.qvel[0], emu.nstep[0] = g["qpos"][idx], g["qvel"][idx], nstep
+    act = np.random.default_rng(idx).uniform(-1, 1, (1, 21)).astype(np.float32)
+    obs, rew, term, trunc, _ = emu.step(act)
+    o, r, t, tr = e.env_step(act[0], frame_skip=5, duration=30.0, reward_type=2)
+    assert np.abs(obs[0] - o).max() < 1e-9 * max(1.0, np.abs(o).max()) and abs(rew[0] - r) < 1e-10
+    s = e.get_state()
+    assert np.abs(emu.qpos[0] - s["qpos"]).max() < 1e-9 and np.abs(emu.qvel[0] - s["qvel"]).max() < 1e-8

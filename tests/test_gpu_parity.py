@@ -280,3 +280,38 @@ def test_step_vecenv_pinned_and_pageable_agree_with_device_step(cm):
                 assert np.array_equal(h["tobs"].numpy(), to.astype(np.float64))
     for b in (ref, pin, page):
         b.close()
+
+
+@pytest.mark.parametrize("dtype,tol", [("f64", 1e-9), ("f32", 1e-5)])
+def test_reference_keyframe_states_single_step(cm, model_struct, dtype, tol):
+    """BASELINE config 2 start states: the 155 keyframes of the reference's own trajectories/humanoid_trajectory.xml
+    (MuJoCo-visited states of a trained policy + the four named poses).  One control step (frame_skip 5, `walk`, the
+    settings generate_trajectories.py:12-17 used) from identical states on the GPU and in the fp64 oracle."""
+    from pathlib import Path
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from oracle.oracle import OracleEnv
+    g = np.load(Path(__file__).parent / "golden" / "reference_keyframes.npz")
+    n = g["qpos"].shape[0]
+    b = HumanoidBatch(n, frame_skip=5, duration=30.0, reward_type="walk", dtype=dtype)
+    nstep = np.round(g["time"] / cm.timestep).astype(np.int32) + 1
+    b.set_state(qpos=g["qpos"], qvel=g["qvel"], warmstart=np.zeros((n, cm.nv)), nstep=nstep, step_count=np.zeros(n, np.int32))
+    act = np.random.default_rng(8).uniform(-1, 1, (n, cm.nu)).astype(np.float32)
+    obs, rew, term, trunc = b.step(torch.as_tensor(act).cuda())
+    obs, rew = obs.cpu().numpy().astype(np.float64), rew.cpu().numpy().astype(np.float64)
+    got = b.get_state()
+    assert not term.any() and not trunc.any()
+    eq, ev, eo, er = [], [], [], []
+    for i in range(n):
+        e = OracleEnv(model_struct, cm.nq, cm.nv, cm.nu)
+        e.set_state(qpos=g["qpos"][i], qvel=g["qvel"][i], warmstart=np.zeros(cm.nv), nstep=int(nstep[i]), step_count=0)
+        o, r, t, tr = e.env_step(act[i], frame_skip=5, duration=30.0, reward_type=2)
+        s = e.get_state()
+        eq.append(_rel(got["qpos"][i], s["qpos"])); ev.append(_rel(got["qvel"][i], s["qvel"]))
+        eo.append(_rel(obs[i], o)); er.append(abs(r - rew[i]))
+    eq, ev, eo, er = map(np.array, (eq, ev, eo, er))
+    assert eq.max() < tol, ("qpos", int(eq.argmax()), eq.max())
+    assert ev.max() < tol * 10, ("qvel", int(ev.argmax()), ev.max())
+    assert eo.max() < tol * 20 and er.max() < max(tol, 1e-5), (eo.max(), er.max())
+    c = b.counters()
+    assert c["bad_state"] == 0 and c["contact_overflow"] == 0
+    b.close()

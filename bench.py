@@ -188,6 +188,9 @@ def run_b200(args):
     gen.manual_seed(1234 + rank)
     pool = torch.rand(16, E, batch.nu, device=dev, generator=gen) * 2 - 1   # U(-1,1) actions resident in HBM
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    if os.environ.get("B2H_BENCH_IDENTICAL"):   # tuning experiment: every env gets the same noise and actions (no work variance)
+        pool = pool[:, :1].expand(16, E, batch.nu).contiguous()
+        batch.set_reset_noise(np.tile(np.random.default_rng(0).uniform(-0.01, 0.01, (1, batch.nq + batch.nv)), (E, 1)))
     batch.reset()
     for i in range(W):
         batch.step(pool[i % 16])

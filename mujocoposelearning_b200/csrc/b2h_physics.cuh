@@ -919,23 +919,26 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
       if (lsign != T(0) && r < T(0)) c += T(0.5) * lD * r * r;
       return wsum(c);
     };
-    // ---- warmstart(): the cheaper of qacc_warmstart and qacc_smooth
-    T jar[NSLOT] = {0, 0, 0}, ljar;
+    // ---- warmstart(): the cheaper of qacc_warmstart and qacc_smooth; J*x and M*x of the chosen point are kept
+    T jar[NSLOT] = {0, 0, 0}, ljar, jar_s[NSLOT] = {0, 0, 0}, ljar_s;
     jar_of(st.warm, jar, &ljar);
     T cost_warm = row_cost(jar, ljar);
     T Ma = mat_vec(S.M, S.vec[2], nv, lane);
     cost_warm += wsum(lane < nv ? T(0.5) * (Ma - qfrc_smooth) * (st.warm - qacc_smooth) : T(0));
-    jar_of(qacc_smooth, jar, &ljar);
-    T cost_smooth = row_cost(jar, ljar);
-    if (cost_warm > cost_smooth) qacc = qacc_smooth;
-    else { qacc = st.warm; }
+    jar_of(qacc_smooth, jar_s, &ljar_s);
+    T cost_smooth = row_cost(jar_s, ljar_s);
+    if (cost_warm > cost_smooth) {  // warp-uniform
+      qacc = qacc_smooth;
+#pragma unroll
+      for (int s = 0; s < NSLOT; s++) jar[s] = jar_s[s];
+      ljar = ljar_s;
+      Ma = mat_vec(S.M, S.vec[2], nv, lane);  // S.vec[2] still holds qacc_smooth
+    } else { qacc = st.warm; }
     // ---- mj_solPrimal (Newton): state at the starting point
     T Jaref[NSLOT], lJaref;
-    jar_of(qacc, jar, &ljar);
 #pragma unroll
     for (int s = 0; s < NSLOT; s++) Jaref[s] = jar[s] - raref[s];
     lJaref = ljar - laref;
-    Ma = mat_vec(S.M, S.vec[2], nv, lane);
     const T scale = T(1) / (B2H_LDG(m.meaninertia) * T(nv > 1 ? nv : 1));
     const T tolerance = T(1e-8), ls_tolerance = T(0.01);
     const int ls_iterations = 50;

@@ -22,7 +22,7 @@ from .policy import MlpPolicy, MlpPolicyParams, RolloutCollector
 
 class PPOTrainer:
     def __init__(self, batch, params: MlpPolicyParams | None = None, n_steps=64, batch_size=16384, n_epochs=4, lr=3e-4, gamma=0.99,
-                 gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, seed=0, precise=True):
+                 gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, seed=0, precise=True, update_tf32=False):
         self.b = batch
         self.params = params or MlpPolicyParams(batch.obs_dim, batch.nu, 256, batch.device, seed)
         rank = dist.get_rank() if dist.is_initialized() else 0
@@ -35,10 +35,18 @@ class PPOTrainer:
         if self.world > 1:                       # identical replicas: broadcast rank 0's initialisation
             for t in self.tensors:
                 dist.broadcast(t.data, 0)
-        self.opt = torch.optim.Adam(self.tensors, lr=lr, eps=1e-5)
+        # one flat gradient buffer: every tensor's .grad is a view of it, so the all-reduce, the norm clip and the
+        # zeroing are single calls on 1.27 MB instead of 13 small ones; Adam runs as one fused multi-tensor kernel
+        self.flat_grad = torch.zeros(sum(t.numel() for t in self.tensors), device=batch.device, dtype=torch.float32)
+        o = 0
+        for t in self.tensors:
+            t.grad = self.flat_grad[o:o + t.numel()].view_as(t)
+            o += t.numel()
+        self.opt = torch.optim.Adam(self.tensors, lr=lr, eps=1e-5, fused=True)
         self.batch_size, self.n_epochs, self.clip, self.ent_coef, self.vf_coef, self.max_grad_norm = batch_size, n_epochs, clip_range, ent_coef, vf_coef, max_grad_norm
         self.gen = torch.Generator(device=batch.device).manual_seed(seed + 17 + rank)
         self.iterations = 0
+        self.update_tf32 = bool(update_tf32)   # library GEMMs of the update on the tf32 tensor cores (default: fp32 like the reference)
 
     def _evaluate(self, obs, actions):
         p = self.params
@@ -55,6 +63,14 @@ class PPOTrainer:
 
     def update(self):
         """One PPO.train() over the current rollout buffer; returns the last minibatch's loss terms."""
+        prev_tf32 = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = self.update_tf32
+        try:
+            return self._update()
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev_tf32
+
+    def _update(self):
         c = self.col
         n = c.T * self.b.n_envs
         obs, actions = c.obs.reshape(n, -1), c.actions.reshape(n, -1)
@@ -72,17 +88,13 @@ class PPOTrainer:
                 pl = -torch.min(a * ratio, a * torch.clamp(ratio, 1 - self.clip, 1 + self.clip)).mean()
                 vl = F.mse_loss(ret[idx], value)
                 loss = pl - self.ent_coef * entropy + self.vf_coef * vl
-                self.opt.zero_grad(set_to_none=True)
-                loss.backward()
+                self.flat_grad.zero_()
+                loss.backward()                  # accumulates into the views of flat_grad
                 if self.world > 1:               # average gradients: one flat NCCL all-reduce over NVLink
-                    flat = torch.cat([t.grad.reshape(-1) for t in self.tensors])
-                    dist.all_reduce(flat)
-                    flat /= self.world
-                    o = 0
-                    for t in self.tensors:
-                        t.grad.copy_(flat[o:o + t.numel()].view_as(t))
-                        o += t.numel()
-                torch.nn.utils.clip_grad_norm_(self.tensors, self.max_grad_norm)
+                    dist.all_reduce(self.flat_grad)
+                    self.flat_grad /= self.world
+                # clip_grad_norm_(max_norm): scale = max_norm / (norm + 1e-6), clamped to 1
+                self.flat_grad *= torch.clamp(self.max_grad_norm / (self.flat_grad.norm() + 1e-6), max=1.0)
                 self.opt.step()
                 stats = dict(policy_loss=pl.detach(), value_loss=vl.detach(), clip_fraction=((ratio - 1).abs() > self.clip).float().mean())
         return stats

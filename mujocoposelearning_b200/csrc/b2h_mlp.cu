@@ -6,7 +6,9 @@
 //     matrices) by all 256 threads; weights come from global memory (L2-resident, 0.6 MB per network), the
 //     activations of layers 2 and 3 from the previous layer's epilogue in shared memory;
 //   * one elected thread issues tcgen05.mma kind::tf32 (M=128, N=256 / 32, K=8) with the accumulator in TMEM;
-//     completion is signalled through tcgen05.commit -> mbarrier;
+//     completion is signalled through tcgen05.commit -> mbarrier; the operand stage is a two-deep ring, so the
+//     tensor core works on chunk k while the threads stage chunk k+1 (a stage is only reused after the MMAs that
+//     read it have committed);
 //   * the epilogue reads the accumulator with tcgen05.ld (each warp its 32-lane quadrant), adds the bias, applies
 //     ReLU and writes the next layer's input (or the network output).
 // precise = 1 splits every operand into tf32 hi + lo parts and issues hi*hi + hi*lo + lo*hi, which recovers
@@ -21,10 +23,25 @@
 namespace {
 
 constexpr int TILE_M = 128;   // batch rows per CTA (UMMA M)
-constexpr int KC = 16;        // K columns staged per round (two K=8 MMAs)
+#ifndef B2H_MLP_KC
+#define B2H_MLP_KC 16
+#endif
+#ifndef B2H_MLP_NSTAGE
+#define B2H_MLP_NSTAGE 1
+#endif
+#ifndef B2H_MLP_PF
+#define B2H_MLP_PF 1
+#endif
+constexpr int KC = B2H_MLP_KC;          // K columns staged per round (KC / 8 MMA K-steps)
+constexpr int PF = B2H_MLP_PF;          // chunks prefetched into registers ahead of the staging (multiple of NSTAGE)
+static_assert(B2H_MLP_PF % B2H_MLP_NSTAGE == 0, "the stage of an unrolled ring slot must be a compile-time constant");
+constexpr int NSTAGE = B2H_MLP_NSTAGE;  // operand stages (KC 32 x 1 stage or KC 16 x 2 stages fill the 227 KB next to H)
 constexpr int MAXH = 256;     // hidden width (UMMA N) supported
 constexpr int HSTRIDE = MAXH + 4;  // fp32 row stride of the activation buffer (16-byte shift per row: conflict-free float4)
-constexpr int NTHREADS = 256;
+#ifndef B2H_MLP_THREADS
+#define B2H_MLP_THREADS 256
+#endif
+constexpr int NTHREADS = B2H_MLP_THREADS;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -67,13 +84,21 @@ struct MlpArgs {     // up to two networks (blockIdx.y) over the same input: pol
 template <int NV>
 struct ChunkRegs { float4 v[NV]; };
 
+// Work item f -> (row r, 16-byte K group k4): eight consecutive threads take eight consecutive rows of the same K
+// group, i.e. one whole 128-byte core matrix per quarter-warp (conflict-free shared stores; the global side still
+// reads 64 contiguous bytes of each of 8 rows per warp), then the K groups, then the next 8 rows.
+__device__ __forceinline__ void chunk_item(int f, int& r, int& k4) {
+  constexpr int G = KC / 4;
+  r = (f & 7) | ((f / (8 * G)) << 3);
+  k4 = (f >> 3) % G;
+}
 template <int NV>
 __device__ __forceinline__ void load_chunk(ChunkRegs<NV>& c, const float* src, int ld, int rows, int valid_rows, int k0, int row_base) {
   const int nvec = rows * (KC / 4);
 #pragma unroll
   for (int i = 0; i < NV; i++) {
-    int f = threadIdx.x + i * NTHREADS;
-    int r = f / (KC / 4), k4 = f % (KC / 4);
+    int f = threadIdx.x + i * NTHREADS, r, k4;
+    chunk_item(f, r, k4);
     c.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (f < nvec && r < valid_rows) c.v[i] = *reinterpret_cast<const float4*>(src + (size_t)(row_base + r) * ld + k0 + 4 * k4);
   }
@@ -83,9 +108,9 @@ __device__ __forceinline__ void store_chunk(const ChunkRegs<NV>& c, float* dst_h
   const int nvec = rows * (KC / 4), groups = rows >> 3;
 #pragma unroll
   for (int i = 0; i < NV; i++) {
-    int f = threadIdx.x + i * NTHREADS;
+    int f = threadIdx.x + i * NTHREADS, r, k4;
     if (f >= nvec) continue;
-    int r = f / (KC / 4), k4 = f % (KC / 4);
+    chunk_item(f, r, k4);
     float4 v = c.v[i], hi, lo;
     hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
     hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
@@ -97,23 +122,23 @@ __device__ __forceinline__ void store_chunk(const ChunkRegs<NV>& c, float* dst_h
   }
 }
 
+constexpr int STAGE_FLOATS = 2 * TILE_M * KC + 2 * MAXH * KC;   // A hi/lo + W hi/lo of one K chunk
+
 __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(MlpArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  float* A_hi = reinterpret_cast<float*>(smem);                 // TILE_M x KC
-  float* A_lo = A_hi + TILE_M * KC;
-  float* W_hi = A_lo + TILE_M * KC;                             // MAXH x KC
-  float* W_lo = W_hi + MAXH * KC;
-  float* H = W_lo + MAXH * KC;                                  // TILE_M x HSTRIDE activations
-  __shared__ __align__(8) unsigned long long mbar_storage;
+  float* stage0 = reinterpret_cast<float*>(smem);               // two operand stages: [A_hi | A_lo | W_hi | W_lo] each
+  float* H = stage0 + NSTAGE * STAGE_FLOATS;                         // TILE_M x HSTRIDE activations
+  __shared__ __align__(8) unsigned long long mbar_storage[2];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int net = blockIdx.y;
   const int row0 = blockIdx.x * TILE_M;
   const int valid = min(TILE_M, a.n_rows - row0);
-  const uint32_t mbar = smem_u32(&mbar_storage);
+  const uint32_t mbar[2] = {smem_u32(&mbar_storage[0]), smem_u32(&mbar_storage[1])};
 
   if (threadIdx.x == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar[0]));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(mbar[1]));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   if (warp == 0) {  // TMEM: 256 fp32 accumulator columns, allocated and freed by warp 0
@@ -124,7 +149,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(MlpArgs a) {
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   const uint32_t tmem = tmem_base_s;
-  uint32_t parity = 0;
+  uint32_t parity = 0;    // bit st: phase stage st's mbarrier completes next
+  uint32_t pending = 0;   // bit st: a commit was issued on stage st and not yet waited for
   bool ok = true;
 
   for (int layer = 0; layer < 3 && ok; layer++) {
@@ -136,46 +162,68 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(MlpArgs a) {
     const int Ald = layer == 0 ? a.in_dim : HSTRIDE, Avalid = layer == 0 ? valid : TILE_M, Abase = layer == 0 ? row0 : 0;
     const uint32_t idesc = umma_idesc_tf32(TILE_M, N);
     const uint32_t lboA = (TILE_M / 8) * 128, lboW = (N / 8) * 128;
-    ChunkRegs<TILE_M * (KC / 4) / NTHREADS> ra;
-    ChunkRegs<MAXH * (KC / 4) / NTHREADS> rw;
-    load_chunk(ra, Asrc, Ald, TILE_M, Avalid, 0, Abase);
-    load_chunk(rw, W, K, N, nout, 0, 0);
-    for (int k0 = 0; k0 < K; k0 += KC) {
-      store_chunk(ra, A_hi, a.precise ? A_lo : nullptr, TILE_M);
-      store_chunk(rw, W_hi, a.precise ? W_lo : nullptr, N);
-      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to the MMA
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    // Register prefetch ring: the loads of chunk k + PF are issued as soon as chunk k's registers have been staged, so
+    // an L2 / HBM round trip is covered by PF rounds of staging + MMA (one CTA per SM: registers are plentiful).
+    ChunkRegs<TILE_M * (KC / 4) / NTHREADS> ra[PF];
+    ChunkRegs<MAXH * (KC / 4) / NTHREADS> rw[PF];
 #pragma unroll
-        for (int ks = 0; ks < KC / 8; ks++) {
-          uint64_t ah = umma_desc(smem_u32(A_hi) + ks * 2 * lboA, lboA, 128), wh = umma_desc(smem_u32(W_hi) + ks * 2 * lboW, lboW, 128);
-          umma_tf32(tmem, ah, wh, idesc, (k0 | ks) != 0);
-          if (a.precise) {
-            uint64_t al = umma_desc(smem_u32(A_lo) + ks * 2 * lboA, lboA, 128), wl = umma_desc(smem_u32(W_lo) + ks * 2 * lboW, lboW, 128);
-            umma_tf32(tmem, ah, wl, idesc, 1);
-            umma_tf32(tmem, al, wh, idesc, 1);
-          }
+    for (int p = 0; p < PF; p++)
+      if (p * KC < K) {
+        load_chunk(ra[p], Asrc, Ald, TILE_M, Avalid, p * KC, Abase);
+        load_chunk(rw[p], W, K, N, nout, p * KC, 0);
+      }
+    for (int kb = 0; kb < K && ok; kb += PF * KC) {
+#pragma unroll
+      for (int p = 0; p < PF; p++) {
+        const int k0 = kb + p * KC;
+        if (k0 >= K || !ok) break;
+        const int st = p % NSTAGE;   // compile-time after unrolling (PF is a multiple of NSTAGE)
+        float* A_hi = stage0 + st * STAGE_FLOATS;
+        float* A_lo = A_hi + TILE_M * KC;
+        float* W_hi = A_lo + TILE_M * KC;
+        float* W_lo = W_hi + MAXH * KC;
+        if (pending & (1u << st)) {   // the MMAs that read this stage NSTAGE chunks ago must have finished before it is overwritten
+          ok = mbar_wait(mbar[st], (parity >> st) & 1u) && ok;
+          parity ^= 1u << st; pending &= ~(1u << st);
+          if (!ok) break;
         }
-        // commit: the mbarrier fires when every MMA issued so far has finished reading shared memory / writing TMEM
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mbar) : "memory");
+        store_chunk(ra[p], A_hi, a.precise ? A_lo : nullptr, TILE_M);
+        store_chunk(rw[p], W_hi, a.precise ? W_lo : nullptr, N);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");   // generic-proxy stores -> visible to the MMA
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+#pragma unroll
+          for (int ks = 0; ks < KC / 8; ks++) {
+            uint64_t ah = umma_desc(smem_u32(A_hi) + ks * 2 * lboA, lboA, 128), wh = umma_desc(smem_u32(W_hi) + ks * 2 * lboW, lboW, 128);
+            umma_tf32(tmem, ah, wh, idesc, (k0 | ks) != 0);
+            if (a.precise) {
+              uint64_t al = umma_desc(smem_u32(A_lo) + ks * 2 * lboA, lboA, 128), wl = umma_desc(smem_u32(W_lo) + ks * 2 * lboW, lboW, 128);
+              umma_tf32(tmem, ah, wl, idesc, 1);
+              umma_tf32(tmem, al, wh, idesc, 1);
+            }
+          }
+          // commit: the mbarrier fires when every MMA issued so far has finished reading shared memory / writing TMEM
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(mbar[st]) : "memory");
+        }
+        pending |= 1u << st;
+        if (k0 + PF * KC < K) {
+          load_chunk(ra[p], Asrc, Ald, TILE_M, Avalid, k0 + PF * KC, Abase);
+          load_chunk(rw[p], W, K, N, nout, k0 + PF * KC, 0);
+        }
       }
-      if (k0 + KC < K) {  // next chunk's loads fly while the tensor core works on this one
-        load_chunk(ra, Asrc, Ald, TILE_M, Avalid, k0 + KC, Abase);
-        load_chunk(rw, W, K, N, nout, k0 + KC, 0);
-      }
-      ok = mbar_wait(mbar, parity) && ok;
-      parity ^= 1;
-      if (!ok) break;
     }
+#pragma unroll
+    for (int b = 0; b < NSTAGE; b++)   // drain: the accumulator is complete once every stage's commit has fired
+      if (ok && (pending & (1u << b))) { ok = mbar_wait(mbar[b], (parity >> b) & 1u) && ok; parity ^= 1u << b; pending &= ~(1u << b); }
     if (!ok) break;
     // ---- epilogue: TMEM -> registers -> bias (+ReLU) -> shared activations / global output
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, cgroup = warp >> 2;             // TMEM lane quadrant of the warp, column group
     const int r = quad * 32 + lane;
-    const int ncols = N / 2;                                  // each half of the warps takes half of the columns
+    const int ncols = max(16, N / (NTHREADS / 128));          // the warps of a quadrant split the columns between them
     const float* bias = a.b[net][layer];
-    for (int c0 = half * ncols; c0 < (half + 1) * ncols; c0 += 16) {
+    for (int c0 = cgroup * ncols; c0 < min(N, (cgroup + 1) * ncols); c0 += 16) {
       uint32_t v[16];
       uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
       asm volatile(
@@ -263,7 +311,7 @@ static int launch_mlp(MlpArgs& a, int nnets, void* stream) {
   }
   for (int n = 0; n < nnets; n++)
     if (a.out_dim[n] < 1 || a.out_dim[n] > 32) { g_err_mlp = "out_dim must be in [1, 32]"; return B2H_EUNSUPPORTED; }
-  size_t smem = (size_t)(2 * TILE_M * KC + 2 * MAXH * KC + TILE_M * HSTRIDE) * sizeof(float);
+  size_t smem = (size_t)(NSTAGE * STAGE_FLOATS + TILE_M * HSTRIDE) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,0 +1,66 @@
+#!/usr/bin/env python
+"""BASELINE config 5: env-count sweep 256 ... 65536 envs per GPU (random actions and deterministic random-init policy).
+
+    python tools/sweep_envs.py [--steps 300] [--out profiles/r01_env_sweep.md]       (one GPU; under torchrun: per rank)
+"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from mujocoposelearning_b200.batch import HumanoidBatch  # noqa: E402
+from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams  # noqa: E402
+
+
+def run(E, steps, warmup, with_policy):
+    b = HumanoidBatch(E, frame_skip=3, duration=10.0, reward_type="stand", seed=1234)
+    g = torch.Generator(device="cuda").manual_seed(1234)
+    pool = torch.rand(16, E, b.nu, device="cuda", generator=g) * 2 - 1
+    pol = MlpPolicy(MlpPolicyParams(seed=7), precise=True, seed=11) if with_policy else None
+    obs = b.reset()
+
+    def step(i):
+        if pol is None:
+            return b.step(pool[i % 16])[0]
+        mean, _ = pol.forward(b.obs)
+        _, clipped, _ = pol.sample(mean, i, True)      # deterministic: action = mean
+        return b.step(clipped)[0]
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(warmup + i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    info = b.launch_info()
+    b.close()
+    return E * 3 / (ms * 1e-3), ms, info
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--out", default="")
+    a = ap.parse_args()
+    lines = ["| envs/GPU | warps/CTA | random actions: physics steps/s | ms/step | deterministic policy: physics steps/s | ms/step |",
+             "|---:|---:|---:|---:|---:|---:|"]
+    for E in [256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536]:
+        v0, ms0, info = run(E, a.steps, a.warmup, False)
+        v1, ms1, _ = run(E, a.steps, a.warmup, True)
+        lines.append(f"| {E} | {info['warps_per_cta']} | {v0:.3e} | {ms0:.3f} | {v1:.3e} | {ms1:.3f} |")
+        print(lines[-1], flush=True)
+    if a.out:
+        with open(a.out, "w") as f:
+            f.write("# Env-count sweep (BASELINE config 5), one B200, `stand`, frame_skip 3, control steps "
+                    f"{a.warmup}..{a.warmup + a.steps} of the first episode, device-timed back to back (no L2 flush)\n\n")
+            f.write("\n".join(lines) + "\n")
+
+
+if __name__ == "__main__":
+    main()

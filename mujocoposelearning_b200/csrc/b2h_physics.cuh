@@ -880,7 +880,12 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
       qfrc_smooth = passive - qfrc_bias + act;
     } else st.qfrc_act = 0;
   }
-  if (dbg) for (int i = lane; i < KV * 6; i += 32) dbg->cdofdot[i] = tmp[TMP_CDD + i];
+  if (dbg) {
+    for (int i = lane; i < KV * 6; i += 32) dbg->cdofdot[i] = tmp[TMP_CDD + i];
+    for (int i = lane; i < NCON; i += 32) dbg->con_dist[i] = S.con_dist[i];
+    for (int i = lane; i < NCON * 3; i += 32) dbg->con_pos[i] = S.con_pos[i];
+    for (int i = lane; i < NCON * 9; i += 32) dbg->con_frame[i] = S.con_frame[i];
+  }
   wsync();  // stage scratch in A is dead from here
 
   // =============================================================== acceleration: qacc_smooth = M^-1 qfrc_smooth
@@ -1005,9 +1010,9 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
           }
         }
         wsync();
-        if (lane < LD) {
+        if (lane < LD) {  // H is symmetric: the lane's column is its row (the factorisation reads the lower triangle)
 #pragma unroll
-          for (int i = 0; i < LD; i++) S.A[i * LD + lane] = acc[i];
+          for (int c4 = 0; c4 < LD; c4 += 4) st4(S.A + lane * LD + c4, acc[c4], acc[c4 + 1], acc[c4 + 2], acc[c4 + 3]);
         }
         wsync();
         if ((actl >> lane) & 1u) S.A[lane * LD + lane] += lD;
@@ -1124,9 +1129,6 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
     for (int i = lane; i < KB * 10; i += 32) dbg->cinert[i] = S.cinert[i];
     for (int i = lane; i < KB * 6; i += 32) dbg->cvel[i] = S.cvel[i];
     for (int i = lane; i < KV * 6; i += 32) dbg->cdof[i] = S.cdof[i];
-    for (int i = lane; i < NCON; i += 32) dbg->con_dist[i] = S.con_dist[i];
-    for (int i = lane; i < NCON * 3; i += 32) dbg->con_pos[i] = S.con_pos[i];
-    for (int i = lane; i < NCON * 9; i += 32) dbg->con_frame[i] = S.con_frame[i];
     if (lane < 3) dbg->com[lane] = S.com[lane];
   }
   if (qacc_out) *qacc_out = qacc;

@@ -176,7 +176,10 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback; use --impl reference for the CPU path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_cores = None
     if world > 1:
+        from mujocoposelearning_b200.dist import bind_to_gpu_numa
+        numa_cores = bind_to_gpu_numa(local)     # host loop + pinned result buffers next to this rank's GPU
         dist.init_process_group("nccl", device_id=dev)
     E, K, W = args.n_envs, args.steps, args.warmup
     if W < 3:
@@ -319,7 +322,8 @@ def run_b200(args):
                               "flop_per_physics_step": FLOP_PER_PHYSICS_STEP},
                      "issue": issue},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
-                "api": "B200HumanoidVecEnv.step (numpy in/out, lazy infos)"},
+                "api": "B200HumanoidVecEnv.step (numpy in/out, lazy infos)",
+                "host_cores_rank0": len(numa_cores) if numa_cores else None},
         "gpu_launches": c1["launches"] - c0["launches"], "clocks": clocks,
         "solver": {"newton_iter_per_physics_step": (c1["newton_iter"] - c0["newton_iter"]) / max(1, psteps),
                    "ls_eval_per_physics_step": (c1["ls_eval"] - c0["ls_eval"]) / max(1, psteps),

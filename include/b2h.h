@@ -153,6 +153,9 @@ void b2h_destroy(B2HHandle* h);
 int b2h_obs_dim(const B2HHandle* h);
 /* Launch shape the step kernel uses on this device: CTAs, warps (= envs in flight) per CTA, dynamic smem. */
 int b2h_launch_info(const B2HHandle* h, int* grid, int* warps_per_cta, size_t* smem_bytes);
+/* The shape rule itself (pure host logic, no device needed): env-warps per CTA and dense constraint rows kept in shared
+ * memory for n_envs on a device with n_sm SMs and max_smem_bytes of opt-in shared memory per CTA. */
+int b2h_choose_launch_shape(int n_envs, int n_sm, size_t max_smem_bytes, int dtype, int* warps_per_cta, int* shared_rows);
 
 /* Re-key the reset-noise stream (VecEnv.seed / Env.reset(seed=...), custom_env.py:99-100) and restart the
  * per-env episode counters, so the following resets replay the same noise for the same seed. */

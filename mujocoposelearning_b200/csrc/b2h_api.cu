@@ -203,6 +203,30 @@ static EnvIO<T> make_io(B2HHandle* h, const float* actions, void* obs, void* rew
   return io;
 }
 
+// Launch shape: (env-warps per CTA, dense rows kept in shared memory).  More warps hide more latency but leave
+// fewer shared rows (the rest spill to L1/L2-backed global memory) and make the lockstep group larger; what pays
+// depends on how many rounds of groups each SM runs.  Measured on B200 (fp32): 16 warps x 32 rows steps a group
+// 4.8 % slower than 14 warps x 48 rows, i.e. 8.8 % more envs per second once the SMs stay full.
+template <typename T>
+static void choose_shape(int n_envs, int nsm, size_t max_smem, int* warps_out, int* nrow_s_out) {
+  const int maxw = max_threads<T>() / 32;
+  struct Shape { int warps, nrow_s; double group_time; } shapes[2] = {{maxw, 32, 1.048}, {maxw - maxw / 8, NROW_S, 1.0}};
+  int warps = 0, nrow_s = NROW_S;
+  double best = 0;
+  for (const Shape& sh : shapes) {
+    if (sh.nrow_s > NROW_S || sh.nrow_s < NROW_S_MIN || (size_t)sh.warps * scratch_bytes<T>(sh.nrow_s) > max_smem) continue;
+    double groups = ((double)n_envs + sh.warps - 1) / sh.warps / nsm;       // per SM
+    double rounds = groups <= 3.0 ? ceil(groups - 1e-9) : groups;           // few groups: whole rounds count
+    double t = rounds * sh.group_time;
+    if (!warps || t < best) { warps = sh.warps; nrow_s = sh.nrow_s; best = t; }
+  }
+  if (warps && n_envs < nsm * warps) {  // fewer envs than one full round: spread them over all SMs in smaller groups
+    warps = (n_envs + nsm - 1) / nsm;
+    nrow_s = NROW_S;
+  }
+  *warps_out = warps; *nrow_s_out = nrow_s;
+}
+
 template <typename T>
 static int create_typed(B2HHandle* h) {
   std::vector<unsigned char> buf(sizeof(DevModel<T>));
@@ -215,26 +239,10 @@ static int create_typed(B2HHandle* h) {
   int dev = h->cfg.device, nsm = 0, max_smem = 0;
   CU(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev));
   CU(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  // Launch shape: (env-warps per CTA, dense rows kept in shared memory).  More warps hide more latency but leave
-  // fewer shared rows (the rest spill to L1/L2-backed global memory) and make the lockstep group larger; what pays
-  // depends on how many rounds of groups each SM runs.  Measured on B200 (fp32): 16 warps x 32 rows steps a group
-  // 4.8 % slower than 14 warps x 48 rows, i.e. 8.8 % more envs per second once the SMs stay full.
-  const int maxw = max_threads<T>() / 32;
-  struct Shape { int warps, nrow_s; double group_time; } shapes[2] = {{maxw, 32, 1.048}, {maxw - maxw / 8, NROW_S, 1.0}};
   int warps = 0, nrow_s = NROW_S;
-  double best = 0;
-  for (const Shape& sh : shapes) {
-    if (sh.nrow_s > NROW_S || sh.nrow_s < NROW_S_MIN || (size_t)sh.warps * scratch_bytes<T>(sh.nrow_s) > (size_t)max_smem) continue;
-    double groups = ((double)h->cfg.n_envs + sh.warps - 1) / sh.warps / nsm;       // per SM
-    double rounds = groups <= 3.0 ? ceil(groups - 1e-9) : groups;                  // few groups: whole rounds count
-    double t = rounds * sh.group_time;
-    if (!warps || t < best) { warps = sh.warps; nrow_s = sh.nrow_s; best = t; }
-  }
+  choose_shape<T>(h->cfg.n_envs, nsm, (size_t)max_smem, &warps, &nrow_s);
   if (!warps) return fail(B2H_EUNSUPPORTED, "per-env scratch does not fit in shared memory");
-  if (h->cfg.n_envs < nsm * warps) {  // fewer envs than one full round: spread them over all SMs in smaller groups
-    warps = (h->cfg.n_envs + nsm - 1) / nsm;
-    nrow_s = NROW_S;
-  }
+  const int maxw = max_threads<T>() / 32;
   int ctas_per_sm = 1;
   if (const char* w = getenv("B2H_WARPS_PER_CTA")) {  // tuning knobs: lockstep group size (several CTAs per SM), shared rows
     int req = atoi(w);
@@ -324,6 +332,13 @@ int b2h_set_seed(B2HHandle* h, uint64_t seed) {
   h->cfg.seed = seed; h->P.seed = seed;
   CU(cudaMemset(h->episode, 0, (size_t)h->cfg.n_envs * 4));
   return B2H_OK;
+}
+
+int b2h_choose_launch_shape(int n_envs, int n_sm, size_t max_smem_bytes, int dtype, int* warps_per_cta, int* shared_rows) {
+  if (n_envs <= 0 || n_sm <= 0 || !warps_per_cta || !shared_rows) return fail(B2H_EINVAL, "bad argument");
+  if (dtype == B2H_F64) choose_shape<double>(n_envs, n_sm, max_smem_bytes, warps_per_cta, shared_rows);
+  else choose_shape<float>(n_envs, n_sm, max_smem_bytes, warps_per_cta, shared_rows);
+  return *warps_per_cta > 0 ? B2H_OK : fail(B2H_EUNSUPPORTED, "per-env scratch does not fit in shared memory");
 }
 
 int b2h_launch_info(const B2HHandle* h, int* grid, int* warps_per_cta, size_t* smem_bytes) {

@@ -44,3 +44,23 @@ def reduce_rollout_stats(episode_return_sum, episode_len_sum, episode_count, dev
     s = t.cpu().tolist()
     n = max(s[2], 1.0)
     return s[0] / n, s[1] / n, int(s[2])
+
+
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPU cores NVML reports as local to GPU `local_rank` (same NUMA node / PCIe root), so
+    that the page-locked result buffers the step kernel writes over PCIe are first-touched on that node and the host
+    loop runs next to them.  Returns the core list, or None when NVML or the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1 and 64 * i + b < ncpu]
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0)))
+        if len(allowed) < 2:   # a cpuset that leaves one local core (or none) would only add contention
+            return None
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None

@@ -24,6 +24,7 @@ SIGNATURES = {
     "b2h_obs_dim": (C.c_int, [vp]),
     "b2h_set_seed": (C.c_int, [vp, C.c_uint64]),
     "b2h_launch_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_size_t)]),
+    "b2h_choose_launch_shape": (C.c_int, [C.c_int, C.c_int, C.c_size_t, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "b2h_reset": (C.c_int, [vp, vp, vp, vp]),
     "b2h_set_reset_noise": (C.c_int, [vp, vp, vp]),
     "b2h_get_last_reset_noise": (C.c_int, [vp, vp, vp]),

@@ -54,3 +54,20 @@ def test_bad_arguments(lib, model_struct):
     h = C.c_void_p()
     assert lib.b2h_create(C.byref(model_struct), C.byref(cfg), C.byref(h)) == abi.EINVAL
     assert lib.b2h_gae(None, None, None, None, None, 0.99, 0.95, 4, 4, None, None, None) == abi.EINVAL
+
+
+def test_launch_shape_rule(lib):
+    """b2h_choose_launch_shape is pure host logic: B200 numbers (148 SMs, 227 KB opt-in shared memory per CTA)."""
+    import ctypes as C
+
+    def shape(n_envs, dtype=0):
+        w, r = C.c_int(), C.c_int()
+        assert lib.b2h_choose_launch_shape(n_envs, 148, 232448, dtype, C.byref(w), C.byref(r)) == 0
+        return w.value, r.value
+    assert shape(4096) == (14, 48)            # two rounds either way: the smaller, faster group
+    assert shape(16384) == (16, 32) and shape(65536) == (16, 32)   # SMs stay full: more env-warps, fewer shared rows
+    assert shape(1024) == (7, 48) and shape(256) == (2, 48) and shape(100) == (1, 48)   # below one round: all SMs, small groups
+    assert shape(4096, dtype=1)[0] in (7, 8) and shape(64, dtype=1) == (1, 48)
+    w, r = C.c_int(), C.c_int()
+    assert lib.b2h_choose_launch_shape(4096, 148, 8 * 1024, 0, C.byref(w), C.byref(r)) < 0   # scratch does not fit
+    assert lib.b2h_choose_launch_shape(0, 148, 232448, 0, C.byref(w), C.byref(r)) < 0

@@ -106,8 +106,13 @@ class B200HumanoidVecEnv(_VecEnvBase):
         self._host = [dict(obs=pin((n_envs, b.obs_dim), torch.float64), rew=pin((n_envs,), torch.float64),
                            term=pin((n_envs,), torch.bool), trunc=pin((n_envs,), torch.bool)) for _ in range(2)]
         self._tobs_host = pin((n_envs, b.obs_dim), torch.float64)
+        for hset in self._host:   # numpy views of the page-locked tensors, made once
+            hset["np"] = (hset["obs"].numpy(), hset["rew"].numpy(), hset["term"].numpy(), hset["trunc"].numpy())
+        self._tobs_np = self._tobs_host.numpy()
+        self._actions_np = self.hb["actions"].numpy()
         self._flip = 0
         self._lazy_info = {"TimeLimit.truncated": False}
+        self._lazy_infos = [self._lazy_info] * n_envs
         self.closed = False
 
     # -- VecEnv API (SB3 2.3.2 common/vec_env/base_vec_env.py)
@@ -126,17 +131,15 @@ class B200HumanoidVecEnv(_VecEnvBase):
                 "height": float(o[0]), "forward_velocity": float(o[self.batch.nq - 2]), "truncated": False, "terminated": False}
 
     def step_async(self, actions):
-        a = np.asarray(actions, dtype=np.float32).reshape(self.num_envs, self.batch.nu)
-        self.hb["actions"].numpy()[:] = a
-        self._actions = a
+        self._actions_np[...] = np.asarray(actions).reshape(self.num_envs, self.batch.nu)   # cast + copy into page-locked memory
 
     def step_wait(self):
         out = self._host[self._flip]
         self._flip ^= 1
         n_done = self.batch.step_vecenv(self.hb["actions"], out["obs"], out["rew"], out["term"], out["trunc"], self._tobs_host)
-        obs, rewards, term, trunc = out["obs"].numpy(), out["rew"].numpy(), out["term"].numpy(), out["trunc"].numpy()
+        obs, rewards, term, trunc = out["np"]
         dones = term | trunc
-        tobs = self._tobs_host.numpy() if n_done else None   # rows of the envs that finished (others are stale)
+        tobs = self._tobs_np if n_done else None   # rows of the envs that finished (others are stale)
         self._step_count += 1
         self._total_reward += rewards
         if self.info_mode == "full":
@@ -150,13 +153,15 @@ class B200HumanoidVecEnv(_VecEnvBase):
                 if dones[i]:
                     info["terminal_observation"] = tobs[i].copy()
                 infos.append(info)
+        elif not n_done:
+            infos = self._lazy_infos     # shared, never mutated: one dict for every env of a step without episode ends
         else:
-            infos = [self._lazy_info] * self.num_envs
+            infos = list(self._lazy_infos)
             for i in np.nonzero(dones)[0]:
                 infos[i] = {"terminal_observation": tobs[i].copy(), "terminated": bool(term[i]),
                             "truncated": bool(trunc[i]), "TimeLimit.truncated": bool(trunc[i] and not term[i]),
                             "step_count": int(self._step_count[i]), "total_reward": float(self._total_reward[i])}
-        if dones.any():
+        if n_done:
             self._step_count[dones] = 0
             self._total_reward[dones] = 0
         return obs, rewards, dones, infos

@@ -315,3 +315,41 @@ def test_reference_keyframe_states_single_step(cm, model_struct, dtype, tol):
     c = b.counters()
     assert c["bad_state"] == 0 and c["contact_overflow"] == 0
     b.close()
+
+
+@pytest.mark.parametrize("dtype,n,shape,tol", [("f32", 8192, (16, 32), 1e-5), ("f64", 4096, (8, 32), 1e-9)])
+def test_large_batch_launch_shape_parity(cm, model_struct, dtype, n, shape, tol):
+    """The full-SM launch shapes (16 env-warps x 32 shared rows in fp32, 8 x 32 in fp64) are only chosen for large
+    batches: one control step of a large batch whose sampled envs include prone, contact-rich states (more than 32
+    dense rows: the global row spill) against the oracle."""
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from oracle.oracle import OracleEnv
+    b = HumanoidBatch(n, frame_skip=3, duration=10.0, reward_type="stand", dtype=dtype)
+    info = b.launch_info()
+    assert (info["warps_per_cta"], info["smem_bytes"] // info["warps_per_cta"]) == (shape[0], {"f32": 14512, "f64": 28384}[dtype])
+    rng = np.random.default_rng(12)
+    qpos = np.tile(cm.qpos0, (n, 1)); qpos[:, 2] = 1.282
+    qpos[:, 7:] += rng.uniform(-0.1, 0.1, (n, 21))
+    qvel = rng.normal(0, 0.3, (n, 27))
+    lying = np.arange(n) % 3 == 0                                   # a third of the batch lies face down on the floor
+    qpos[lying, 2] = rng.uniform(0.11, 0.16, lying.sum())           # 9-14 contacts, up to ~56 dense rows (capacity 96)
+    qpos[lying, 3:7] = [np.cos(np.pi / 4), 0, np.sin(np.pi / 4), 0]
+    b.set_state(qpos=qpos, qvel=qvel, warmstart=np.zeros((n, 27)), nstep=np.ones(n, np.int32), step_count=np.zeros(n, np.int32))
+    act = rng.uniform(-1, 1, (n, cm.nu)).astype(np.float32)
+    sample = np.concatenate([np.arange(0, 24), rng.integers(0, n, 24), [n - 1]])
+    nrow = [int(b.debug_forward("nrow", int(i), act)[0]) for i in sample[:6]]
+    assert max(nrow) > 32                                            # rows beyond the shared 32 are in play
+    obs, rew, term, trunc = b.step(torch.as_tensor(act).cuda())
+    got, obs, rew = b.get_state(), obs.cpu().numpy().astype(np.float64), rew.cpu().numpy().astype(np.float64)
+    for i in sample:
+        e = OracleEnv(model_struct, cm.nq, cm.nv, cm.nu)
+        e.set_state(qpos[i], qvel[i], np.zeros(27), 1, 0)
+        o, r, t, tr = e.env_step(act[i], frame_skip=3, duration=10.0, reward_type=0)
+        s = e.get_state()
+        # fp32: a body dropped into the floor is stiff (contact forces of 1e3-1e4 N): the bound is 20x the upright one there
+        k = 20 if (dtype == "f32" and lying[i]) else 1
+        assert _rel(got["qpos"][i], s["qpos"]) < k * tol and _rel(got["qvel"][i], s["qvel"]) < k * tol * 10, (int(i), _rel(got["qpos"][i], s["qpos"]), _rel(got["qvel"][i], s["qvel"]))
+        assert _rel(obs[i], o) < k * tol * 20 and abs(r - rew[i]) < max(tol, 1e-5)
+    c = b.counters()
+    assert c["bad_state"] == 0 and c["contact_overflow"] == 0 and c["physics_steps"] == 3 * n
+    b.close()

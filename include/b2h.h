@@ -11,17 +11,23 @@
  *                         _compute_reward, truncation/termination) + the SubprocVecEnv worker's
  *                         auto-reset / terminal_observation                  custom_env.py:152-261,
  *                                                                           reward_functions.py:66-211
- *   b2h_step_host         the same through host buffers (what VecEnv.step_wait returns, train_sb3.py:203)
+ *   b2h_step_vecenv       the same through host buffers in the form SubprocVecEnv.step_wait returns them
+ *                         (float64 obs / reward, flags, terminal observations), train_sb3.py:203; page-locked
+ *                         buffers are written by the kernel itself.  b2h_step_host: results in the arithmetic dtype
  *   b2h_get_state/set     MjData.qpos/qvel/qacc_warmstart/time field access  custom_env.py:105-117,242-246
  *   b2h_gae               RolloutBuffer.compute_returns_and_advantage (SB3 2.3.2), driven by
  *                         model.learn()                                      train_sb3.py:228
- *   b2h_mlp_forward       MlpPolicy forward during collect_rollouts (SB3 2.3.2) train_sb3.py:208-214
+ *   b2h_mlp_forward / b2h_policy_forward / b2h_policy_sample
+ *                         MlpPolicy forward + DiagGaussian sampling during collect_rollouts (SB3 2.3.2)
+ *                                                                           train_sb3.py:208-214
+ *   b2h_choose_launch_shape, b2h_launch_info, b2h_measure_fp32_peak, b2h_get_counters, b2h_debug_forward
+ *                         no reference counterpart: launch policy, measurement and parity hooks
  *
  * Conventions: every function returns 0 on success or a negative B2H_E* code and never throws; the
  * message for the last failure on the calling thread is b2h_last_error().  Pointers named *_dev are
  * caller-owned device pointers (e.g. torch tensor data_ptr()); *_host are host pointers.  All device
  * work is ordered on the cudaStream_t passed as `void* stream` (NULL = legacy default stream); only the
- * *_host entry points synchronise that stream.  One handle per GPU, one host thread per handle.
+ * *_host / b2h_step_vecenv entry points synchronise that stream.  One handle per GPU, one host thread per handle.
  */
 #ifndef B2H_H_
 #define B2H_H_

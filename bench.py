@@ -268,6 +268,20 @@ def run_b200(args):
     pol.check_error()
     mlp_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(Kp))
     pol_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 2]) for i in range(Kp))
+    # ---- the same rollout with the 53-column observation (qpos[2:] | qvel; SURVEY 8d C3 asks for both), rank-0 time
+    b53 = HumanoidBatch(E, frame_skip=FRAME_SKIP, duration=DURATION, reward_type=REWARD, dtype=args.dtype, device=local,
+                        seed=1234, env_id_offset=rank * E, obs_mode="qpos_qvel")
+    b53.reset()
+    for i in range(W):
+        b53.step(pool[i % 16])
+    K53 = max(10, K // 4)
+    e53 = [torch.cuda.Event(enable_timing=True) for _ in range(2 * K53)]
+    for i in range(K53):
+        flush.zero_()
+        e53[2 * i].record(); b53.step(pool[(W + i) % 16]); e53[2 * i + 1].record()
+    torch.cuda.synchronize()
+    ms53 = sum(e53[2 * i].elapsed_time(e53[2 * i + 1]) for i in range(K53)) / K53
+    b53.close()
     # ---- reduce over ranks: max time
     tt = torch.tensor([total_ms, e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
@@ -331,6 +345,8 @@ def run_b200(args):
         "policy_rollout": {"value": world * E * FRAME_SKIP * Kp / (pol_ms * 1e-3), "unit": UNIT, "ms_per_step": pol_ms / Kp,
                            "mlp_and_sampling_ms_per_step": mlp_ms / Kp, "steps": Kp,
                            "what": "random-init 2x256 ReLU pi/vf MLP forward (tcgen05, tf32 hi/lo split) + Gaussian sampling + b2h_step; rank-0 time"},
+        "obs_qpos_qvel": {"value": world * E * FRAME_SKIP / (ms53 * 1e-3), "unit": UNIT, "ms_per_step": ms53, "steps": K53,
+                          "what": "same rollout, 53-column observation (control steps W..W+steps of the first episode); rank-0 time"},
         "launch": batch.launch_info(), "step_ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],
     }
     if not args.no_cpu_baseline and world == 1:

@@ -175,6 +175,8 @@ struct B2HHandle {
   int* work = nullptr;
   int *effort = nullptr, *perm = nullptr;  // per-env solver effort of the last control step, effort-sorted env order
   int schedule = 1;                        // 1: lockstep groups follow the effort-sorted order
+  bool perm_valid = false;
+  cudaEvent_t step_done = nullptr;         // recorded after the step kernel (b2h_step_vecenv waits on it, not on the sort)
   void* dump = nullptr;
   void* spill = nullptr;  // per-warp dense rows beyond NROW_S
   // staging for the *_host entry points
@@ -282,6 +284,7 @@ void b2h_destroy(B2HHandle* h) {
                   h->tobs_stage, h->rew_stage, h->term_stage, h->trunc_stage, h->mask_stage, h->obs64_stage, h->tobs64_stage,
                   h->rew64_stage};
   for (void* p : ptrs) if (p) cudaFree(p);
+  if (h->step_done) cudaEventDestroy(h->step_done);
   delete h;
 }
 
@@ -318,6 +321,7 @@ int b2h_create(const B2HModel* model, const B2HConfig* cfg, B2HHandle** out) {
   ALLOC(h->actions_stage, E * h->nu * 4); ALLOC(h->obs_stage, E * h->obs_dim * esz); ALLOC(h->tobs_stage, E * h->obs_dim * esz);
   ALLOC(h->rew_stage, E * esz); ALLOC(h->term_stage, E); ALLOC(h->trunc_stage, E); ALLOC(h->mask_stage, E);
 #undef ALLOC
+  CU(cudaEventCreateWithFlags(&h->step_done, cudaEventDisableTiming));
   CU(cudaDeviceSynchronize());
   *out = h;
   return B2H_OK;
@@ -368,12 +372,8 @@ int b2h_reset(B2HHandle* h, const uint8_t* mask_dev, void* obs_dev, void* stream
 static int launch_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward_dev, uint8_t* terminated_dev,
                        uint8_t* truncated_dev, void* terminal_obs_dev, Out64 o64, cudaStream_t s) {
   CU(cudaMemsetAsync(h->work, 0, 4, s));
-  const int* perm = nullptr;
-  if (h->schedule && h->P.sync_mode == 2 && h->cfg.n_envs > h->warps) {
-    order_kernel<<<1, 1024, 0, s>>>(h->effort, h->cfg.n_envs, h->perm);
-    perm = h->perm;
-    h->launches++;
-  }
+  const bool sched = h->schedule && h->P.sync_mode == 2 && h->cfg.n_envs > h->warps;
+  const int* perm = sched && h->perm_valid ? h->perm : nullptr;   // order of the previous step's efforts (first step: env-id order)
   if (h->cfg.dtype == B2H_F64)
     step_kernel<double><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<double>*)h->dmodel, h->P,
         make_io<double>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, o64), h->cfg.n_envs,
@@ -384,6 +384,13 @@ static int launch_step(B2HHandle* h, const float* actions_dev, void* obs_dev, vo
         h->counters, h->work, (float*)h->spill, perm);
   CU(cudaGetLastError());
   h->launches++;
+  if (h->step_done) CU(cudaEventRecord(h->step_done, s));   // results are complete here; the sort below is for the next step
+  if (sched) {  // sorted after the step instead of before the next one: it then overlaps the caller's host work
+    order_kernel<<<1, 1024, 0, s>>>(h->effort, h->cfg.n_envs, h->perm);
+    CU(cudaGetLastError());
+    h->perm_valid = true;
+    h->launches++;
+  }
   return B2H_OK;
 }
 
@@ -429,8 +436,10 @@ int b2h_step_vecenv(B2HHandle* h, const float* actions_host, double* obs_host, d
     CU(cudaMemcpyAsync(reward_host, o64.reward, E * 8, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(terminated_host, term, E, cudaMemcpyDeviceToHost, s));
     CU(cudaMemcpyAsync(truncated_host, trunc, E, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  } else {
+    CU(cudaEventSynchronize(h->step_done));   // the kernel's host writes are complete; the sort for the next step still runs
   }
-  CU(cudaStreamSynchronize(s));
   int nd = 0;
   for (size_t i = 0; i < E; i++) nd += (terminated_host[i] | truncated_host[i]) != 0;
   if (!direct && nd && terminal_obs_host) {

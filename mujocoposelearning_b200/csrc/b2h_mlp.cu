@@ -15,6 +15,7 @@
 // fp32-level accuracy (the reference policy runs in fp32 on the CPU); precise = 0 is a single tf32 pass.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <string>
 
@@ -257,6 +258,205 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_kernel(MlpArgs a) {
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ warp-specialised variant
+// Same math and layouts as mlp_forward_kernel, but the K loop has no CTA barrier: warp 0 only issues tcgen05.mma, the
+// other seven warps only stage operands, and they meet on mbarriers -
+//   full[s]  (224 arrivals): the producers have written stage s and fenced it for the async proxy,
+//   empty[s] (tcgen05.commit): the MMAs that read stage s have finished, the producers may overwrite it,
+//   acc      (tcgen05.commit): the layer's accumulator is complete, everybody runs the TMEM epilogue.
+// The CTA only synchronises once per layer (activations H complete / accumulator drained).
+#ifndef B2H_MLP_WS_PF
+#define B2H_MLP_WS_PF 3
+#endif
+constexpr int WS_PF = B2H_MLP_WS_PF;              // chunks a producer keeps in flight in registers
+constexpr int WS_NS = 2;                          // operand stages
+constexpr int WS_NPROD = NTHREADS - 32;           // producer threads (warps 1..7)
+constexpr int WS_ITEMS = (TILE_M * (KC / 4) + MAXH * (KC / 4) + WS_NPROD - 1) / WS_NPROD;   // float4 per producer per chunk
+
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(mbar) : "memory");
+}
+
+struct WsChunk { float4 v[WS_ITEMS]; };
+
+// item f of a chunk: the first TILE_M * KC/4 items are rows of A, the rest rows of W (chunk_item order inside each)
+__device__ __forceinline__ void ws_load(WsChunk& c, int pt, const float* Asrc, int Ald, int Avalid, int Abase, const float* W, int K,
+                                        int N, int nout, int k0) {
+  constexpr int NA = TILE_M * (KC / 4);
+  const int nitems = NA + N * (KC / 4);
+#pragma unroll
+  for (int i = 0; i < WS_ITEMS; i++) {
+    int f = pt + i * WS_NPROD, r, k4;
+    c.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (f < NA) {
+      chunk_item(f, r, k4);
+      if (r < Avalid) c.v[i] = *reinterpret_cast<const float4*>(Asrc + (size_t)(Abase + r) * Ald + k0 + 4 * k4);
+    } else if (f < nitems) {
+      chunk_item(f - NA, r, k4);
+      if (r < nout) c.v[i] = *reinterpret_cast<const float4*>(W + (size_t)r * K + k0 + 4 * k4);
+    }
+  }
+}
+__device__ __forceinline__ void ws_store(const WsChunk& c, int pt, float* A_hi, float* A_lo, float* W_hi, float* W_lo, int N, bool precise) {
+  constexpr int NA = TILE_M * (KC / 4);
+  const int nitems = NA + N * (KC / 4);
+#pragma unroll
+  for (int i = 0; i < WS_ITEMS; i++) {
+    int f = pt + i * WS_NPROD, r, k4;
+    if (f >= nitems) continue;
+    const bool isA = f < NA;
+    chunk_item(isA ? f : f - NA, r, k4);
+    const int groups = (isA ? TILE_M : N) >> 3;
+    float4 v = c.v[i], hi, lo;
+    hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
+    hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+    hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+    hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+    int off = ((k4 * groups + (r >> 3)) * 32) + (r & 7) * 4;
+    *reinterpret_cast<float4*>((isA ? A_hi : W_hi) + off) = hi;
+    if (precise) *reinterpret_cast<float4*>((isA ? A_lo : W_lo) + off) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_ws_kernel(MlpArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* stage0 = reinterpret_cast<float*>(smem);
+  float* H = stage0 + WS_NS * STAGE_FLOATS;
+  __shared__ __align__(8) unsigned long long bar_storage[2 * WS_NS + 1];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int net = blockIdx.y;
+  const int row0 = blockIdx.x * TILE_M;
+  const int valid = min(TILE_M, a.n_rows - row0);
+  uint32_t full[WS_NS], empty[WS_NS];
+#pragma unroll
+  for (int s = 0; s < WS_NS; s++) { full[s] = smem_u32(&bar_storage[s]); empty[s] = smem_u32(&bar_storage[WS_NS + s]); }
+  const uint32_t accbar = smem_u32(&bar_storage[2 * WS_NS]);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < WS_NS; s++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(full[s]), "r"(WS_NPROD));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(empty[s]));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(accbar));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  bool ok = true;
+  int g = 0;   // chunks since the start of the kernel: stage g % WS_NS, use g / WS_NS (all roles count the same sequence)
+
+  for (int layer = 0; layer < 3; layer++) {
+    const int K = layer == 0 ? a.in_dim : a.hidden;
+    const int nout = layer == 2 ? a.out_dim[net] : a.hidden;
+    const int N = layer == 2 ? 32 : a.hidden;
+    const float* W = a.w[net][layer];
+    const float* Asrc = layer == 0 ? a.x : H;
+    const int Ald = layer == 0 ? a.in_dim : HSTRIDE, Avalid = layer == 0 ? valid : TILE_M, Abase = layer == 0 ? row0 : 0;
+    const int nchunk = K / KC;
+    if (warp == 0) {
+      if (lane == 0) {   // ---- MMA issuer
+        const uint32_t idesc = umma_idesc_tf32(TILE_M, N);
+        const uint32_t lboA = (TILE_M / 8) * 128, lboW = (N / 8) * 128;
+        for (int c = 0; c < nchunk && ok; c++) {
+          const int s = (g + c) % WS_NS, use = (g + c) / WS_NS;
+          ok = mbar_wait(full[s], use & 1);
+          if (!ok) break;
+          asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+          const uint32_t A_hi = smem_u32(stage0 + s * STAGE_FLOATS), A_lo = A_hi + TILE_M * KC * 4, W_hi = A_lo + TILE_M * KC * 4,
+                         W_lo = W_hi + MAXH * KC * 4;
+#pragma unroll
+          for (int ks = 0; ks < KC / 8; ks++) {
+            uint64_t ah = umma_desc(A_hi + ks * 2 * lboA, lboA, 128), wh = umma_desc(W_hi + ks * 2 * lboW, lboW, 128);
+            umma_tf32(tmem, ah, wh, idesc, (c | ks) != 0);
+            if (a.precise) {
+              uint64_t al = umma_desc(A_lo + ks * 2 * lboA, lboA, 128), wl = umma_desc(W_lo + ks * 2 * lboW, lboW, 128);
+              umma_tf32(tmem, ah, wl, idesc, 1);
+              umma_tf32(tmem, al, wh, idesc, 1);
+            }
+          }
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(empty[s]) : "memory");
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(accbar) : "memory");
+      }
+      __syncwarp();      // lanes 1..31 park here instead of polling the accumulator barrier next to the issuing lane
+    } else {             // ---- producers
+      const int pt = threadIdx.x - 32;
+      WsChunk regs[WS_PF];   // register prefetch ring: chunk c + WS_PF is requested as soon as chunk c has been staged
+#pragma unroll
+      for (int p = 0; p < WS_PF; p++)
+        if (p < nchunk) ws_load(regs[p], pt, Asrc, Ald, Avalid, Abase, W, K, N, nout, p * KC);
+      for (int cb = 0; cb < nchunk && ok; cb += WS_PF) {
+#pragma unroll
+        for (int p = 0; p < WS_PF; p++) {
+          const int c = cb + p;
+          if (c >= nchunk || !ok) break;
+          const int s = (g + c) % WS_NS, use = (g + c) / WS_NS;
+          if (use > 0) ok = mbar_wait(empty[s], (use - 1) & 1);
+          if (!ok) break;
+          float* A_hi = stage0 + s * STAGE_FLOATS;
+          float* A_lo = A_hi + TILE_M * KC;
+          float* W_hi = A_lo + TILE_M * KC;
+          float* W_lo = W_hi + MAXH * KC;
+          ws_store(regs[p], pt, A_hi, A_lo, W_hi, W_lo, N, a.precise != 0);
+          asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+          mbar_arrive(full[s]);
+          if (c + WS_PF < nchunk) ws_load(regs[p], pt, Asrc, Ald, Avalid, Abase, W, K, N, nout, (c + WS_PF) * KC);
+        }
+      }
+    }
+    g += nchunk;
+    // ---- everybody: wait for the accumulator, epilogue
+    ok = mbar_wait(accbar, layer & 1) && ok;
+    __syncwarp();
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (ok) {
+      const int quad = warp & 3, cgroup = warp >> 2;
+      const int r = quad * 32 + lane;
+      const int ncols = max(16, N / (NTHREADS / 128));
+      const float* bias = a.b[net][layer];
+      for (int c0 = cgroup * ncols; c0 < min(N, (cgroup + 1) * ncols); c0 += 16) {
+        uint32_t v[16];
+        uint32_t taddr = tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0;
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (layer < 2) {
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            float4 o;
+            o.x = fmaxf(__uint_as_float(v[4 * q + 0]) + __ldg(bias + c0 + 4 * q + 0), 0.f);
+            o.y = fmaxf(__uint_as_float(v[4 * q + 1]) + __ldg(bias + c0 + 4 * q + 1), 0.f);
+            o.z = fmaxf(__uint_as_float(v[4 * q + 2]) + __ldg(bias + c0 + 4 * q + 2), 0.f);
+            o.w = fmaxf(__uint_as_float(v[4 * q + 3]) + __ldg(bias + c0 + 4 * q + 3), 0.f);
+            *reinterpret_cast<float4*>(H + r * HSTRIDE + c0 + 4 * q) = o;
+          }
+        } else if (r < valid) {
+#pragma unroll
+          for (int q = 0; q < 16; q++)
+            if (c0 + q < nout) a.y[net][(size_t)(row0 + r) * nout + c0 + q] = __uint_as_float(v[q]) + __ldg(bias + c0 + q);
+        }
+      }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+    __syncthreads();   // accumulator drained and H complete before the next layer overwrites TMEM / reads H
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    if (!ok) break;
+  }
+  if (!ok && lane == 0) atomicExch(a.error, 1);
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem) : "memory");
+}
+
 // ---- DiagGaussian sampling of SB3 (common/distributions.py): a = mean + exp(log_std) * eps, log_prob summed over
 // action dims, clipped copy for the env (collect_rollouts clips to the Box bounds, the buffer keeps the raw action).
 __device__ __forceinline__ void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
@@ -311,15 +511,19 @@ static int launch_mlp(MlpArgs& a, int nnets, void* stream) {
   }
   for (int n = 0; n < nnets; n++)
     if (a.out_dim[n] < 1 || a.out_dim[n] > 32) { g_err_mlp = "out_dim must be in [1, 32]"; return B2H_EUNSUPPORTED; }
-  size_t smem = (size_t)(NSTAGE * STAGE_FLOATS + TILE_M * HSTRIDE) * sizeof(float);
+  static int use_ws = -1;   // warp-specialised pipeline (default) or the barrier-per-chunk kernel (B2H_MLP_WS=0)
+  if (use_ws < 0) { const char* e = getenv("B2H_MLP_WS"); use_ws = e ? atoi(e) != 0 : 1; }
+  size_t smem = (size_t)((use_ws ? WS_NS : NSTAGE) * STAGE_FLOATS + TILE_M * HSTRIDE) * sizeof(float);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = use_ws ? cudaFuncSetAttribute(mlp_forward_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                           : cudaFuncSetAttribute(mlp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { g_err_mlp = cudaGetErrorString(e); return B2H_ECUDA; }
     attr_set = true;
   }
   dim3 grid((a.n_rows + TILE_M - 1) / TILE_M, nnets);
-  mlp_forward_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+  if (use_ws) mlp_forward_ws_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+  else mlp_forward_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_err_mlp = cudaGetErrorString(e); return B2H_ECUDA; }
   return B2H_OK;

@@ -9,16 +9,20 @@ import sys
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
 
 from mujocoposelearning_b200.batch import HumanoidBatch  # noqa: E402
 from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams  # noqa: E402
 
 
+RANK, WORLD, LOCAL = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+
+
 def run(E, steps, warmup, with_policy):
-    b = HumanoidBatch(E, frame_skip=3, duration=10.0, reward_type="stand", seed=1234)
-    g = torch.Generator(device="cuda").manual_seed(1234)
-    pool = torch.rand(16, E, b.nu, device="cuda", generator=g) * 2 - 1
-    pol = MlpPolicy(MlpPolicyParams(seed=7), precise=True, seed=11) if with_policy else None
+    b = HumanoidBatch(E, frame_skip=3, duration=10.0, reward_type="stand", seed=1234, device=LOCAL, env_id_offset=RANK * E)
+    g = torch.Generator(device=b.device).manual_seed(1234 + RANK)
+    pool = torch.rand(16, E, b.nu, device=b.device, generator=g) * 2 - 1
+    pol = MlpPolicy(MlpPolicyParams(seed=7, device=f"cuda:{LOCAL}"), precise=True, seed=11, row_offset=RANK * E) if with_policy else None
     obs = b.reset()
 
     def step(i):
@@ -30,6 +34,8 @@ def run(E, steps, warmup, with_policy):
     for i in range(warmup):
         step(i)
     torch.cuda.synchronize()
+    if WORLD > 1:
+        dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(steps):
@@ -37,9 +43,13 @@ def run(E, steps, warmup, with_policy):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
+    if WORLD > 1:   # a step is as slow as the slowest rank
+        t = torch.tensor([ms], device=b.device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t[0])
     info = b.launch_info()
     b.close()
-    return E * 3 / (ms * 1e-3), ms, info
+    return WORLD * E * 3 / (ms * 1e-3), ms, info
 
 
 def main():
@@ -48,16 +58,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=100)
     ap.add_argument("--out", default="")
     a = ap.parse_args()
+    torch.cuda.set_device(LOCAL)
+    if WORLD > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", LOCAL))
     lines = ["| envs/GPU | warps/CTA | random actions: physics steps/s | ms/step | deterministic policy: physics steps/s | ms/step |",
              "|---:|---:|---:|---:|---:|---:|"]
     for E in [256, 512, 1024, 2048, 4096, 8192, 16384, 32768, 65536]:
         v0, ms0, info = run(E, a.steps, a.warmup, False)
         v1, ms1, _ = run(E, a.steps, a.warmup, True)
         lines.append(f"| {E} | {info['warps_per_cta']} | {v0:.3e} | {ms0:.3f} | {v1:.3e} | {ms1:.3f} |")
-        print(lines[-1], flush=True)
-    if a.out:
+        if RANK == 0:
+            print(lines[-1], flush=True)
+    if WORLD > 1:
+        dist.destroy_process_group()
+    if a.out and RANK == 0:
         with open(a.out, "w") as f:
-            f.write("# Env-count sweep (BASELINE config 5), one B200, `stand`, frame_skip 3, control steps "
+            f.write(f"# Env-count sweep (BASELINE config 5), {WORLD} B200 (max time over ranks, whole-job steps/s), `stand`, frame_skip 3, control steps "
                     f"{a.warmup}..{a.warmup + a.steps} of the first episode, device-timed back to back (no L2 flush)\n\n")
             f.write("\n".join(lines) + "\n")
 

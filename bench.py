@@ -244,6 +244,22 @@ def run_b200(args):
         obs, rew, dones, infos = venv.step(host_actions[i % 8])
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - te0
+    venv.close()
+    e2e32 = None
+    if args.dtype == "f32":   # opt-in float32 observations (what SB3 casts to anyway): half the bytes on the wire
+        v32 = B200HumanoidVecEnv(env_cfg, n_envs=E, device=local, dtype="f32", seed=99, env_id_offset=rank * E, info_mode="lazy",
+                                 obs_dtype="float32")
+        v32.reset()
+        for i in range(W):
+            v32.step(host_actions[i % 8])
+        torch.cuda.synchronize()
+        K32 = max(10, K // 4)
+        t32 = time.perf_counter()
+        for i in range(K32):
+            v32.step(host_actions[i % 8])
+        torch.cuda.synchronize()
+        e2e32 = world * E * FRAME_SKIP * K32 / (time.perf_counter() - t32)
+        v32.close()
     esz = 8 if args.dtype == "f64" else 4
     h2d = E * batch.nu * 4
     d2h = E * (batch.obs_dim * 8 + 8 + 2)   # float64 observation + reward (observation_space dtype), two flag bytes
@@ -337,7 +353,9 @@ def run_b200(args):
                      "issue": issue},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "api": "B200HumanoidVecEnv.step (numpy in/out, lazy infos)",
-                "host_cores_rank0": len(numa_cores) if numa_cores else None},
+                "host_cores_rank0": len(numa_cores) if numa_cores else None,
+                "obs_float32_option": {"value": e2e32, "unit": UNIT, "d2h_bytes_per_step": E * (batch.obs_dim * 4 + 4 + 2),
+                                       "what": "same call with obs_dtype='float32' (opt-in; rank-0 time, not the headline)"}},
         "gpu_launches": c1["launches"] - c0["launches"], "clocks": clocks,
         "solver": {"newton_iter_per_physics_step": (c1["newton_iter"] - c0["newton_iter"]) / max(1, psteps),
                    "ls_eval_per_physics_step": (c1["ls_eval"] - c0["ls_eval"]) / max(1, psteps),

@@ -186,7 +186,9 @@ int b2h_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward
              uint8_t* terminated_dev, uint8_t* truncated_dev, void* terminal_obs_dev, void* stream);
 
 /* Host-buffer form of b2h_step: copies actions H2D, steps, copies results D2H, synchronises.  obs_host is
- * float [n_envs, obs_dim] for B2H_F32 (double for B2H_F64); reward_host likewise; flags uint8. */
+ * float [n_envs, obs_dim] for B2H_F32 (double for B2H_F64); reward_host likewise; flags uint8.  Page-locked result
+ * buffers are written by the kernel directly (as in b2h_step_vecenv); terminal_obs_host then only receives the rows of
+ * envs whose episode ended. */
 int b2h_step_host(B2HHandle* h, const float* actions_host, void* obs_host, void* reward_host,
                   uint8_t* terminated_host, uint8_t* truncated_host, void* terminal_obs_host, void* stream);
 int b2h_reset_host(B2HHandle* h, const uint8_t* mask_host, void* obs_host, void* stream);

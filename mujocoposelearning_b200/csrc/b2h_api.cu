@@ -457,6 +457,16 @@ int b2h_step_host(B2HHandle* h, const float* actions_host, void* obs_host, void*
   cudaStream_t s = (cudaStream_t)stream;
   size_t E = (size_t)h->cfg.n_envs, esz = (size_t)h->esz;
   CU(cudaMemcpyAsync(h->actions_stage, actions_host, E * h->nu * 4, cudaMemcpyHostToDevice, s));
+  {  // page-locked result buffers: the kernel writes them itself (see b2h_step_vecenv)
+    void *obs_a = mapped_alias(obs_host), *rew_a = mapped_alias(reward_host), *tobs_a = terminal_obs_host ? mapped_alias(terminal_obs_host) : nullptr;
+    uint8_t *term_a = (uint8_t*)mapped_alias(terminated_host), *trunc_a = (uint8_t*)mapped_alias(truncated_host);
+    if (obs_a && rew_a && term_a && trunc_a && (!terminal_obs_host || tobs_a)) {
+      int rc = launch_step(h, h->actions_stage, obs_a, rew_a, term_a, trunc_a, tobs_a, Out64(), s);
+      if (rc != B2H_OK) return rc;
+      CU(cudaEventSynchronize(h->step_done));
+      return B2H_OK;
+    }
+  }
   int rc = b2h_step(h, h->actions_stage, h->obs_stage, h->rew_stage, h->term_stage, h->trunc_stage,
                     terminal_obs_host ? h->tobs_stage : nullptr, stream);
   if (rc != B2H_OK) return rc;

@@ -80,13 +80,18 @@ class B200HumanoidVecEnv(_VecEnvBase):
     metadata = {"render_modes": ["rgb_array"], "render_fps": 60}
 
     def __init__(self, env_config, n_envs=8, device=0, dtype="f32", obs_mode="full352", seed=0, env_id_offset=0,
-                 info_mode="auto"):
+                 info_mode="auto", obs_dtype="float64"):
+        """obs_dtype: "float64" is the reference's observation_space dtype (custom_env.py:80-85, the default);
+        "float32" returns what SB3 casts the observation to anyway and halves the bytes crossing PCIe per step."""
         self.cfg = parse_env_config(env_config)
         if self.cfg["render_mode"] is not None:
             raise NotImplementedError("rendering is outside the rollout hot path (custom_env.py:273-321)")
         self.batch = _make_batch(self.cfg, n_envs, device, dtype, obs_mode, seed, env_id_offset)
         self.num_envs = n_envs
-        self.observation_space = _box(-np.inf, np.inf, (self.batch.obs_dim,), np.float64)  # custom_env.py:80-85
+        if obs_dtype not in ("float64", "float32") or (obs_dtype == "float32" and dtype != "f32"):
+            raise ValueError("obs_dtype must be 'float64', or 'float32' with the f32 arithmetic build")
+        self.obs_dtype = obs_dtype
+        self.observation_space = _box(-np.inf, np.inf, (self.batch.obs_dim,), np.dtype(obs_dtype))  # custom_env.py:80-85
         self.action_space = _box(-1.0, 1.0, (self.batch.nu,), np.float32)                 # custom_env.py:87-93
         self.render_mode = None
         self.reset_infos = [{} for _ in range(n_envs)]
@@ -103,9 +108,10 @@ class B200HumanoidVecEnv(_VecEnvBase):
         # other envs are still being stepped, and the host does no per-step conversion or allocation.
         b = self.batch
         pin = lambda shape, dt: torch.zeros(shape, dtype=dt).pin_memory()
-        self._host = [dict(obs=pin((n_envs, b.obs_dim), torch.float64), rew=pin((n_envs,), torch.float64),
+        odt = torch.float64 if obs_dtype == "float64" else torch.float32
+        self._host = [dict(obs=pin((n_envs, b.obs_dim), odt), rew=pin((n_envs,), odt),
                            term=pin((n_envs,), torch.bool), trunc=pin((n_envs,), torch.bool)) for _ in range(2)]
-        self._tobs_host = pin((n_envs, b.obs_dim), torch.float64)
+        self._tobs_host = pin((n_envs, b.obs_dim), odt)
         for hset in self._host:   # numpy views of the page-locked tensors, made once
             hset["np"] = (hset["obs"].numpy(), hset["rew"].numpy(), hset["term"].numpy(), hset["trunc"].numpy())
         self._tobs_np = self._tobs_host.numpy()
@@ -123,7 +129,7 @@ class B200HumanoidVecEnv(_VecEnvBase):
         self.reset_infos = [self._reset_info(i) for i in range(self.num_envs)] if self.info_mode == "full" else [{} for _ in range(self.num_envs)]
         self._seeds = [None] * self.num_envs
         self._options = [{} for _ in range(self.num_envs)]
-        return self.hb["obs"].numpy().astype(np.float64)
+        return self.hb["obs"].numpy().astype(self.obs_dtype)
 
     def _reset_info(self, i):  # custom_env.py:133-145
         o = self.hb["obs"][i]
@@ -136,9 +142,16 @@ class B200HumanoidVecEnv(_VecEnvBase):
     def step_wait(self):
         out = self._host[self._flip]
         self._flip ^= 1
-        n_done = self.batch.step_vecenv(self.hb["actions"], out["obs"], out["rew"], out["term"], out["trunc"], self._tobs_host)
+        if self.obs_dtype == "float64":
+            n_done = self.batch.step_vecenv(self.hb["actions"], out["obs"], out["rew"], out["term"], out["trunc"], self._tobs_host)
+        else:   # results in the arithmetic dtype (float32), same zero-copy path
+            self.batch.step_host(dict(actions=self.hb["actions"], obs=out["obs"], reward=out["rew"], terminated=out["term"],
+                                      truncated=out["trunc"], terminal_obs=self._tobs_host))
+            n_done = -1
         obs, rewards, term, trunc = out["np"]
         dones = term | trunc
+        if n_done < 0:
+            n_done = int(dones.sum())
         tobs = self._tobs_np if n_done else None   # rows of the envs that finished (others are stale)
         self._step_count += 1
         self._total_reward += rewards

@@ -391,3 +391,22 @@ def test_full_size_batch_is_shard_and_schedule_invariant():
         del os.environ["B2H_SCHEDULE"]
     assert torch.equal(whole, plain)
     assert float(whole[7, :, 353].sum()) == n and float(whole[:7, :, 353].sum()) == 0      # every env terminates at step 8
+
+
+def test_vec_env_float32_observation_option():
+    """obs_dtype='float32' (opt-in, half the PCIe bytes): same values as the default float64 VecEnv, rounded once."""
+    from mujocoposelearning_b200.vec_env import B200HumanoidVecEnv
+    cfg = {"model_path": None, "duration": 0.049, "frame_skip": 3, "reward_config": {"type": "stand"}}
+    e64, e32 = B200HumanoidVecEnv(cfg, n_envs=32, seed=3), B200HumanoidVecEnv(cfg, n_envs=32, seed=3, obs_dtype="float32")
+    o64, o32 = e64.reset(), e32.reset()
+    assert o32.dtype == np.float32 and e32.observation_space.dtype == np.float32 and np.array_equal(o64.astype(np.float32), o32)
+    rng = np.random.default_rng(1)
+    for k in range(4):
+        a = rng.uniform(-1, 1, (32, 21)).astype(np.float32)
+        o64, r64, d64, i64 = e64.step(a)
+        o32, r32, d32, i32 = e32.step(a)
+        assert o32.dtype == np.float32 and np.array_equal(o64.astype(np.float32), o32) and np.array_equal(r64.astype(np.float32), r32)
+        assert np.array_equal(d64, d32)
+        if d64.all():
+            assert np.array_equal(i64[5]["terminal_observation"].astype(np.float32), i32[5]["terminal_observation"])
+    e64.close(); e32.close()

@@ -410,3 +410,38 @@ def test_vec_env_float32_observation_option():
         if d64.all():
             assert np.array_equal(i64[5]["terminal_observation"].astype(np.float32), i32[5]["terminal_observation"])
     e64.close(); e32.close()
+
+
+def test_step_is_cuda_graph_capturable():
+    """b2h_step is stream-ordered with no hidden synchronisation or allocation: one control step captured into a CUDA
+    graph and replayed gives the same states as eager stepping (launch-bound loops at small batches can be graphed)."""
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    n = 512
+    mk = lambda: HumanoidBatch(n, frame_skip=3, duration=10.0, reward_type="stand", seed=21)
+    eager, graphed = mk(), mk()
+    eager.reset(); graphed.reset()
+    g = torch.Generator(device="cuda").manual_seed(2)
+    acts = torch.rand(6, n, 21, device="cuda", generator=g) * 2 - 1
+    static_a = torch.zeros(n, 21, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):           # warm-up step on the side stream (also applied to the eager twin below)
+        static_a.copy_(acts[0])
+        graphed.step(static_a)
+    torch.cuda.current_stream().wait_stream(side)
+    eager.step(acts[0])
+    graph = torch.cuda.CUDAGraph()
+    static_a.copy_(acts[1])
+    with torch.cuda.graph(graph):
+        graphed.step(static_a)
+    eager.step(acts[1])                      # capture does not execute: replay once for step 1
+    graph.replay()
+    for t in range(2, 6):
+        static_a.copy_(acts[t])
+        graph.replay()
+        o, r, te, tr = eager.step(acts[t])
+    torch.cuda.synchronize()
+    assert torch.equal(graphed.obs, eager.obs) and torch.equal(graphed.reward, eager.reward)
+    a, b = graphed.get_state(), eager.get_state()
+    assert np.array_equal(a["qpos"], b["qpos"]) and np.array_equal(a["qvel"], b["qvel"]) and np.array_equal(a["nstep"], b["nstep"])
+    graphed.close(); eager.close()

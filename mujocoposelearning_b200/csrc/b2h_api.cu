@@ -21,14 +21,22 @@ using namespace b2h;
 // Up to 16 env-warps of fp32 scratch (8 of fp64) share the 227 KB of shared memory of one SM; 512 threads leave
 // 128 registers per thread (fp64: 256 threads, 255 registers)
 extern __shared__ __align__(16) unsigned char b2h_smem[];
+#ifndef B2H_MAX_THREADS
 #define B2H_MAX_THREADS 512
+#endif
 template <typename T> constexpr int max_threads() { return sizeof(T) == 8 ? B2H_MAX_THREADS / 2 : B2H_MAX_THREADS; }
 template <typename T> __device__ __forceinline__ Scratch<T>& my_scratch(const DevModel<T>* model) {
   return *reinterpret_cast<Scratch<T>*>(b2h_smem + (threadIdx.x >> 5) * (sizeof(Scratch<T>) - (size_t)(NROW_S - model->nrow_s) * LD * sizeof(T)));
 }
 
+#ifdef B2H_STAGE_CLOCKS
+__device__ unsigned long long g_stage_clk[12];
+#endif
 __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long long* g) {
   if (lane_id() == 0) {
+#ifdef B2H_STAGE_CLOCKS
+    for (int i = 0; i < 12; i++) atomicAdd(&g_stage_clk[i], (unsigned long long)c.clk[i]);
+#endif
     if (c.physics_steps) atomicAdd(g + 0, (unsigned long long)c.physics_steps);
     if (c.contact_overflow) atomicAdd(g + 1, (unsigned long long)c.contact_overflow);
     if (c.iter_cap) atomicAdd(g + 2, (unsigned long long)c.iter_cap);
@@ -48,9 +56,11 @@ step_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, int
   __shared__ int s_base;
   const int nwarps = blockDim.x >> 5;
   for (;;) {  // the CTA claims one env per warp at a time and steps them in lockstep (see env_step)
+    B2H_CLK(tk);
     __syncthreads();
     if (threadIdx.x == 0) s_base = atomicAdd(work, nwarps);
     __syncthreads();
+    B2H_CLK_ADD(10, tk);
     const int base = s_base;
     if (base >= n_envs) break;
     // lockstep groups are taken from the effort-sorted order (order_kernel): warps that wait for each other at the
@@ -619,6 +629,15 @@ int b2h_measure_fp32_peak(int device, double* tflops) {
   *tflops = best;
   return B2H_OK;
 }
+
+#ifdef B2H_STAGE_CLOCKS
+int b2h_debug_stage_clocks(uint64_t out[12], int reset) {   // tuning build only (not part of include/b2h.h)
+  CU(cudaDeviceSynchronize());
+  CU(cudaMemcpyFromSymbol(out, g_stage_clk, 12 * 8));
+  if (reset) { unsigned long long z[12] = {0}; CU(cudaMemcpyToSymbol(g_stage_clk, z, 12 * 8)); }
+  return B2H_OK;
+}
+#endif
 
 int b2h_get_counters(B2HHandle* h, uint64_t counters_host[8]) {
   if (!h || !counters_host) return fail(B2H_EINVAL, "null argument");

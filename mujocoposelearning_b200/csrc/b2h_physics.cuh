@@ -226,7 +226,17 @@ static_assert(TMP_CDD + KV * 6 <= LD * LD, "velocity-stage scratch must fit in A
 struct Counters {  // per-warp tallies of one launch (32-bit: a warp sees a few thousand events), flushed with atomics
   unsigned physics_steps, contact_overflow, iter_cap, bad_state, newton_iter, ls_eval;
   unsigned work;  // solver effort of the env in flight (Newton iterations weighted by row slots): next launch's schedule key
+#ifdef B2H_STAGE_CLOCKS
+  long long clk[12];  // tuning build: cycles per stage (tools/stage_clocks.py)
+#endif
 };
+#ifdef B2H_STAGE_CLOCKS
+#define B2H_CLK(var) long long var = clock64()
+#define B2H_CLK_ADD(i, t0) do { long long t1_ = clock64(); cnt.clk[i] += t1_ - (t0); (t0) = t1_; } while (0)
+#else
+#define B2H_CLK(var)
+#define B2H_CLK_ADD(i, t0)
+#endif
 
 // per-row soft-constraint parameters (mj_makeImpedance + mj_referenceConstraint)
 template <typename T> struct RowParam { T D, aref; };
@@ -401,6 +411,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
   // dense row r lives in shared memory below nrow_s and in this warp's global spill area above it
   const int nrow_s = B2H_LDG(m.nrow_s);
   auto jrow = [&](int r) -> T* { return r < nrow_s ? S.J + r * LD : Jspill + (size_t)(r - nrow_s) * LD; };
+  B2H_CLK(tc);
 
   // ---- mj_checkPos / mj_checkVel: NaN or |x| > 1e10 resets mjData (qpos0, zero velocity, time 0)
   {
@@ -913,9 +924,11 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
   wsync();  // stage scratch in A is dead from here
 
   // =============================================================== acceleration: qacc_smooth = M^-1 qfrc_smooth
+  B2H_CLK_ADD(0, tc);
   for (int i = lane; i < LD * LD; i += 32) S.A[i] = S.M[i];
   wsync();
   T qacc_smooth = chol_solve_fused(S.A, nv, lane, qfrc_smooth);
+  B2H_CLK_ADD(1, tc);
 
   // =============================================================== mj_fwdConstraint: Newton solver (primal)
   T qacc = qacc_smooth, qfrc_con = 0;
@@ -1014,6 +1027,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
 #pragma unroll
       for (int s = 0; s < NSLOT; s++) pact[s] = act[s];
       pactl = actl;
+      B2H_CLK_ADD(5, tc);
       // -- Hessian H = M + J^T diag(D active) J, built per column (lane j owns column j), then factored
       {
         T acc[LD];
@@ -1044,7 +1058,9 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
       }
       // -- PrimalUpdateGradient + Newton direction: search = -H^-1 grad
       grad = lane < nv ? Ma - qfrc_smooth - qfrc_con : T(0);
+      B2H_CLK_ADD(6, tc);
       search = -chol_solve_fused(S.A, nv, lane, grad);
+      B2H_CLK_ADD(7, tc);
       // -- PrimalSearch: exact line search on the piecewise-quadratic cost along `search`
       T snorm = m_sqrt(wsum(lane < nv ? search * search : T(0)));
       T alpha = 0;
@@ -1126,6 +1142,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
         }
         cnt.ls_eval += lsiter;
       }
+      B2H_CLK_ADD(8, tc);
       if (alpha == T(0)) break;
       if (Tol<T>::step_rel > T(0)) {  // step below the resolution of qacc
         T amax = m_abs(qacc), smax = m_abs(alpha * search);
@@ -1137,6 +1154,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
       for (int s = 0; s < NSLOT; s++) Jaref[s] += alpha * Jv[s];
       lJaref += alpha * lJv;
     }
+    B2H_CLK_ADD(5, tc);
     cnt.newton_iter += niter;
     cnt.work += niter * (8 + (nrow >> 2));
     st.warm = qacc;
@@ -1167,6 +1185,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
   }
 
   // =============================================================== mj_Euler (implicit joint damping) + mj_advance
+  B2H_CLK_ADD(2, tc);
   wsync();
   for (int i = lane; i < LD * LD; i += 32) S.A[i] = S.M[i];
   wsync();
@@ -1197,6 +1216,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
   st.nstep++;
   cnt.physics_steps++;
   wsync();
+  B2H_CLK_ADD(3, tc);
   return false;
 }
 template <typename T>
@@ -1355,9 +1375,12 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     step_count = io.step_count[env] + 1;
   }
   cnt.work = 0;
+  B2H_CLK(te);
   if (P.sync_mode == 1) cta_sync();
   for (int s = 0; s < P.frame_skip; s++) {
+    B2H_CLK_ADD(9, te);
     if (P.sync_mode == 2) cta_sync();
+    B2H_CLK_ADD(4, te);
     if (active) {
       // data.ctrl[:] = action before every mj_step (a bad-state reset inside the previous sub-step zeroed it)
       st.ctrl = a >= 0 ? T(io.actions[(size_t)env * nu + a]) : T(0);
@@ -1381,7 +1404,9 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     if (done && io.terminal_obs) write_obs(m, S, st, P.obs_mode, io.terminal_obs + (size_t)env * io.obs_dim, lane);
     if (done && io.terminal_obs64) write_obs(m, S, st, P.obs_mode, io.terminal_obs64 + (size_t)env * io.obs_dim, lane);
   }
+  B2H_CLK_ADD(9, te);
   if (P.sync_mode == 2) cta_sync();
+  B2H_CLK_ADD(4, te);
   if (active && done) {
     env_reset<T>(m, S, Jspill, st, cnt, P, io, env, lane);
     step_count = 0; total = 0;
@@ -1396,6 +1421,7 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
       if (io.work) io.work[env] = (int)cnt.work;
     }
   }
+  B2H_CLK_ADD(9, te);
 }
 
 // reset path on its own (b2h_reset): reset env, write the first observation

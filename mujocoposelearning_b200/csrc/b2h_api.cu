@@ -25,17 +25,31 @@ extern __shared__ __align__(16) unsigned char b2h_smem[];
 #define B2H_MAX_THREADS 512
 #endif
 template <typename T> constexpr int max_threads() { return sizeof(T) == 8 ? B2H_MAX_THREADS / 2 : B2H_MAX_THREADS; }
+// The model tables (12 KB in fp32) lead the CTA's shared memory, one copy for all env-warps; the per-warp scratch
+// slices follow.  Read through the L1 instead, they compete with the row spill and the state traffic for the ~24 KB
+// of L1 this launch leaves (measured: +2.1 % at 4096 envs, +2.2 % at 16384 with the tables in shared memory, although
+// 5-7 constraint rows per env move from shared memory to the spill area to make room).
+template <typename T> __host__ __device__ constexpr size_t model_smem_bytes() { return (sizeof(DevModel<T>) + 15) / 16 * 16; }
+template <typename T> __device__ __forceinline__ const DevModel<T>* stage_model(const DevModel<T>* g) {
+  const uint4* src = reinterpret_cast<const uint4*>(g);
+  uint4* dst = reinterpret_cast<uint4*>(b2h_smem);
+  for (int i = threadIdx.x; i < (int)(model_smem_bytes<T>() / 16); i += blockDim.x) dst[i] = src[i];
+  __syncthreads();
+  return reinterpret_cast<const DevModel<T>*>(b2h_smem);
+}
 template <typename T> __device__ __forceinline__ Scratch<T>& my_scratch(const DevModel<T>* model) {
-  return *reinterpret_cast<Scratch<T>*>(b2h_smem + (threadIdx.x >> 5) * (sizeof(Scratch<T>) - (size_t)(NROW_S - model->nrow_s) * LD * sizeof(T)));
+  return *reinterpret_cast<Scratch<T>*>(b2h_smem + model_smem_bytes<T>() +
+                                        (threadIdx.x >> 5) * (sizeof(Scratch<T>) - (size_t)(NROW_S - model->nrow_s) * LD * sizeof(T)));
 }
 
 #ifdef B2H_STAGE_CLOCKS
-__device__ unsigned long long g_stage_clk[12];
+__device__ unsigned long long g_stage_clk[24];
+__device__ unsigned long long g_cta_exit[1024];  // globaltimer at which each CTA of the last step launch left the claim loop
 #endif
 __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long long* g) {
   if (lane_id() == 0) {
 #ifdef B2H_STAGE_CLOCKS
-    for (int i = 0; i < 12; i++) atomicAdd(&g_stage_clk[i], (unsigned long long)c.clk[i]);
+    for (int i = 0; i < 24; i++) atomicAdd(&g_stage_clk[i], (unsigned long long)c.clk[i]);
 #endif
     if (c.physics_steps) atomicAdd(g + 0, (unsigned long long)c.physics_steps);
     if (c.contact_overflow) atomicAdd(g + 1, (unsigned long long)c.contact_overflow);
@@ -48,8 +62,9 @@ __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long 
 
 template <typename T>
 __global__ void __launch_bounds__(max_threads<T>(), 1)
-step_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, int n_envs, unsigned long long* counters,
+step_kernel(const DevModel<T>* __restrict__ gmodel, EnvParams P, EnvIO<T> io, int n_envs, unsigned long long* counters,
             int* work, T* spill, const int* __restrict__ perm) {
+  const DevModel<T>* model = stage_model<T>(gmodel);
   Scratch<T>& S = my_scratch<T>(model);
   T* Jspill = spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ((NROW - model->nrow_s) * LD);
   Counters cnt = {0, 0, 0, 0, 0, 0, 0};
@@ -70,6 +85,13 @@ step_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, int
     const int env = active ? (perm ? perm[slot] : slot) : 0;
     env_step<T>(*model, S, Jspill, cnt, P, io, env, active);
   }
+#ifdef B2H_STAGE_CLOCKS
+  if (threadIdx.x == 0) {  // when this CTA ran out of work (tail imbalance of the launch)
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_cta_exit[blockIdx.x] = t;
+  }
+#endif
   flush_counters(cnt, counters);
 }
 
@@ -92,8 +114,9 @@ __global__ void __launch_bounds__(1024, 1) order_kernel(const int* __restrict__ 
 
 template <typename T>
 __global__ void __launch_bounds__(max_threads<T>(), 1)
-reset_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, int n_envs, const uint8_t* mask,
+reset_kernel(const DevModel<T>* __restrict__ gmodel, EnvParams P, EnvIO<T> io, int n_envs, const uint8_t* mask,
              unsigned long long* counters, int* work, T* spill) {
+  const DevModel<T>* model = stage_model<T>(gmodel);
   Scratch<T>& S = my_scratch<T>(model);
   T* Jspill = spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ((NROW - model->nrow_s) * LD);
   Counters cnt = {0, 0, 0, 0, 0, 0, 0};
@@ -110,8 +133,9 @@ reset_kernel(const DevModel<T>* __restrict__ model, EnvParams P, EnvIO<T> io, in
 
 template <typename T>
 __global__ void __launch_bounds__(32, 1)
-debug_kernel(const DevModel<T>* __restrict__ model, EnvIO<T> io, int env, DebugDump<T>* out, T* Jspill) {
-  Scratch<T>& S = reinterpret_cast<Scratch<T>*>(b2h_smem)[0];
+debug_kernel(const DevModel<T>* model, EnvIO<T> io, int env, DebugDump<T>* out, T* Jspill) {
+  model = stage_model<T>(model);
+  Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(b2h_smem + model_smem_bytes<T>());
   const int lane = lane_id(), nq = model->nq, nv = model->nv, nu = model->nu;
   Counters cnt = {0, 0, 0, 0, 0, 0, 0};
   EnvState<T> st;
@@ -218,14 +242,19 @@ static EnvIO<T> make_io(B2HHandle* h, const float* actions, void* obs, void* rew
 // Launch shape: (env-warps per CTA, dense rows kept in shared memory).  More warps hide more latency but leave
 // fewer shared rows (the rest spill to L1/L2-backed global memory) and make the lockstep group larger; what pays
 // depends on how many rounds of groups each SM runs.  Measured on B200 (fp32): 16 warps x 32 rows steps a group
-// 4.8 % slower than 14 warps x 48 rows, i.e. 8.8 % more envs per second once the SMs stay full.
+// 4.8 % slower than 14 warps x 48 rows, i.e. 8.8 % more envs per second once the SMs stay full.  The row counts of
+// the two shapes are upper bounds: each shape keeps as many rows as fit beside the model tables (fp32 on B200:
+// 14 x 44 and 16 x 26).
 template <typename T>
 static void choose_shape(int n_envs, int nsm, size_t max_smem, int* warps_out, int* nrow_s_out) {
   const int maxw = max_threads<T>() / 32;
   struct Shape { int warps, nrow_s; double group_time; } shapes[2] = {{maxw, 32, 1.048}, {maxw - maxw / 8, NROW_S, 1.0}};
   int warps = 0, nrow_s = NROW_S;
   double best = 0;
-  for (const Shape& sh : shapes) {
+  if (max_smem > model_smem_bytes<T>()) max_smem -= model_smem_bytes<T>(); else max_smem = 0;
+  for (Shape& sh : shapes) {
+    // as many shared rows as the shape's warp count leaves room for beside the model tables
+    while (sh.nrow_s > NROW_S_MIN && (size_t)sh.warps * scratch_bytes<T>(sh.nrow_s) > max_smem) sh.nrow_s--;
     if (sh.nrow_s > NROW_S || sh.nrow_s < NROW_S_MIN || (size_t)sh.warps * scratch_bytes<T>(sh.nrow_s) > max_smem) continue;
     double groups = ((double)n_envs + sh.warps - 1) / sh.warps / nsm;       // per SM
     double rounds = groups <= 3.0 ? ceil(groups - 1e-9) : groups;           // few groups: whole rounds count
@@ -235,6 +264,7 @@ static void choose_shape(int n_envs, int nsm, size_t max_smem, int* warps_out, i
   if (warps && n_envs < nsm * warps) {  // fewer envs than one full round: spread them over all SMs in smaller groups
     warps = (n_envs + nsm - 1) / nsm;
     nrow_s = NROW_S;
+    while (nrow_s > NROW_S_MIN && (size_t)warps * scratch_bytes<T>(nrow_s) > max_smem) nrow_s--;
   }
   *warps_out = warps; *nrow_s_out = nrow_s;
 }
@@ -261,21 +291,22 @@ static int create_typed(B2HHandle* h) {
     if (req >= 1 && req <= maxw) { warps = req; }
   }
   if (const char* r = getenv("B2H_NROW_SHARED")) { int req = atoi(r); if (req >= NROW_S_MIN && req <= NROW_S) nrow_s = req; }
-  while (warps > 1 && (size_t)warps * scratch_bytes<T>(nrow_s) > (size_t)max_smem) warps--;
+  const size_t msm = model_smem_bytes<T>();
+  while (warps > 1 && (size_t)warps * scratch_bytes<T>(nrow_s) + msm > (size_t)max_smem) warps--;
   if (getenv("B2H_WARPS_PER_CTA")) {
-    ctas_per_sm = (int)((size_t)max_smem / ((size_t)warps * scratch_bytes<T>(nrow_s)));
+    ctas_per_sm = (int)((size_t)max_smem / ((size_t)warps * scratch_bytes<T>(nrow_s) + msm));
     if (ctas_per_sm * warps > maxw) ctas_per_sm = maxw / warps;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
   dm->nrow_s = nrow_s;
   CU(cudaMemcpy(h->dmodel, dm, sizeof(DevModel<T>), cudaMemcpyHostToDevice));
   h->warps = warps;
-  h->smem = (size_t)warps * scratch_bytes<T>(nrow_s);
+  h->smem = (size_t)warps * scratch_bytes<T>(nrow_s) + msm;
   h->grid = nsm * ctas_per_sm;
   CU(cudaMalloc(&h->spill, (size_t)(h->grid * warps + 1) * (NROW - nrow_s) * LD * sizeof(T)));
   CU(cudaFuncSetAttribute(step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   CU(cudaFuncSetAttribute(reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-  CU(cudaFuncSetAttribute(debug_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Scratch<T>)));
+  CU(cudaFuncSetAttribute(debug_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Scratch<T>) + msm)));
   return B2H_OK;
 }
 
@@ -579,7 +610,7 @@ int b2h_set_state(B2HHandle* h, const double* qpos, const double* qvel, const do
 }  // extern "C"
 template <typename T>
 static int debug_typed(B2HHandle* h, const float* actions_dev, int env, const char* what, double* out, int max_out) {
-  debug_kernel<T><<<1, 32, sizeof(Scratch<T>)>>>((const DevModel<T>*)h->dmodel,
+  debug_kernel<T><<<1, 32, sizeof(Scratch<T>) + model_smem_bytes<T>()>>>((const DevModel<T>*)h->dmodel,
       make_io<T>(h, actions_dev, nullptr, nullptr, nullptr, nullptr, nullptr), env, (DebugDump<T>*)h->dump, (T*)h->spill);
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
@@ -631,10 +662,18 @@ int b2h_measure_fp32_peak(int device, double* tflops) {
 }
 
 #ifdef B2H_STAGE_CLOCKS
-int b2h_debug_stage_clocks(uint64_t out[12], int reset) {   // tuning build only (not part of include/b2h.h)
+int b2h_debug_stage_clocks(uint64_t out[24], int reset) {   // tuning build only (not part of include/b2h.h)
   CU(cudaDeviceSynchronize());
-  CU(cudaMemcpyFromSymbol(out, g_stage_clk, 12 * 8));
-  if (reset) { unsigned long long z[12] = {0}; CU(cudaMemcpyToSymbol(g_stage_clk, z, 12 * 8)); }
+  CU(cudaMemcpyFromSymbol(out, g_stage_clk, 24 * 8));
+  {  // out[22], out[23]: mean and max CTA exit time of the last launch, in ns after the earliest exit... relative to the min
+    static unsigned long long ex[1024];
+    CU(cudaMemcpyFromSymbol(ex, g_cta_exit, sizeof(ex)));
+    unsigned long long mn = ~0ull, mx = 0, sum = 0; int n = 0;
+    for (int i = 0; i < 1024; i++) if (ex[i]) { if (ex[i] < mn) mn = ex[i]; if (ex[i] > mx) mx = ex[i]; n++; }
+    for (int i = 0; i < 1024; i++) if (ex[i]) sum += ex[i] - mn;
+    out[22] = n ? sum / n : 0; out[23] = n ? mx - mn : 0;
+  }
+  if (reset) { unsigned long long z[24] = {0}; CU(cudaMemcpyToSymbol(g_stage_clk, z, 24 * 8)); }
   return B2H_OK;
 }
 #endif

@@ -27,7 +27,8 @@ void sync();
 #else
 #define B2H_DEV __device__ __forceinline__
 #define B2H_DEV_NOINLINE __device__ __noinline__
-#define B2H_LDG(x) __ldg(&(x))
+#define B2H_LDG(x) (x)   // model tables: every kernel stages them at the start of the CTA's shared memory (stage_model)
+extern __shared__ __align__(16) unsigned char b2h_model_smem[];  // the CTA's dynamic shared memory (model tables first)
 #endif
 
 namespace b2h {
@@ -227,14 +228,16 @@ struct Counters {  // per-warp tallies of one launch (32-bit: a warp sees a few 
   unsigned physics_steps, contact_overflow, iter_cap, bad_state, newton_iter, ls_eval;
   unsigned work;  // solver effort of the env in flight (Newton iterations weighted by row slots): next launch's schedule key
 #ifdef B2H_STAGE_CLOCKS
-  long long clk[12];  // tuning build: cycles per stage (tools/stage_clocks.py)
+  long long clk[24];  // tuning build: cycles per stage (tools/stage_clocks.py)
 #endif
 };
 #ifdef B2H_STAGE_CLOCKS
 #define B2H_CLK(var) long long var = clock64()
+#define B2H_CLK_FROM(var, src) long long var = (src)
 #define B2H_CLK_ADD(i, t0) do { long long t1_ = clock64(); cnt.clk[i] += t1_ - (t0); (t0) = t1_; } while (0)
 #else
 #define B2H_CLK(var)
+#define B2H_CLK_FROM(var, src)
 #define B2H_CLK_ADD(i, t0)
 #endif
 
@@ -399,8 +402,16 @@ struct DebugDump {  // named views of one mj_forward (parity / debug only)
 // If `integrate` is false this is mj_forward: state untouched, qacc returned in *qacc_out.
 // Returns true when mj_checkAcc tripped: the state was reset and the caller must run the step once more.
 template <typename T>
-B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, bool integrate,
+B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, bool integrate,
                                    StepStats* stats, T* qacc_out, DebugDump<T>* dbg /* optional named dump */) {
+#ifndef B2H_HOST_EMU
+  // the kernels stage the model tables at the start of the CTA's dynamic shared memory: address them as such
+  // (LDS with immediate offsets) instead of through the generic reference this non-inlined function receives
+  const DevModel<T>& m = *reinterpret_cast<const DevModel<T>*>(b2h_model_smem);
+  (void)m_arg;
+#else
+  const DevModel<T>& m = m_arg;
+#endif
   const int lane = lane_id();
   const int nv = B2H_LDG(m.nv), nq = B2H_LDG(m.nq), nbody = B2H_LDG(m.nbody), njnt = B2H_LDG(m.njnt);
   const T h = B2H_LDG(m.timestep);
@@ -486,6 +497,8 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
     }
     wsync();
   }
+  B2H_CLK_FROM(tp, tc);
+  B2H_CLK_ADD(12, tp);
   // inertial frames (lane = body), joint anchors/axes in the world (lane = joint), geoms (lane = geom)
   T my_mass = 0;
   if (lane > 0 && lane < nbody) {
@@ -568,6 +581,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
   }
   if (lane < KV) for (int k = 0; k < 6; k++) S.cdof[6 * lane + k] = cd[k];
   wsync();
+  B2H_CLK_ADD(13, tp);
   // ---- mj_crb: composite inertia = sum over the depth-first subtree range; M over ancestor chains
   if (lane > 0 && lane < nbody) {
     T c[10];
@@ -592,6 +606,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
   }
   wsync();
 
+  B2H_CLK_ADD(14, tp);
   // =============================================================== collision (lane = candidate pair)
   int ncon = 0;
   {
@@ -620,6 +635,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
       ncand += popc(km);
     }
     wsync();
+    B2H_CLK_ADD(15, tp);
     for (int base = 0; base < ncand; base += 32) {
       int p = base + lane < ncand ? cand[base + lane] : npair;
       int n = 0;
@@ -742,6 +758,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
     for (int i = lane; i < POS_END; i += 32) dbg->pos[i] = S.J[i];
     wsync();
   }
+  B2H_CLK_ADD(16, tp);
   // =============================================================== constraint rows
   // dense rows: tendon limits first, then contacts (1 row frictionless, 4 rows pyramidal condim 3)
   int nrow = 0;
@@ -805,6 +822,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
   S.vec[1][lane] = lane < nv ? st.qv : T(0);
   wsync();
 
+  B2H_CLK_ADD(17, tp);
   // per-row parameters; lane owns dense rows lane, lane+32, lane+64 (slots) and the joint limit of dof `lane`
   const int nslot = (nrow + 31) >> 5;
   T rD[NSLOT] = {0, 0, 0}, raref[NSLOT] = {0, 0, 0};
@@ -862,6 +880,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
   const unsigned limit_mask = ballot(lsign != T(0));
   const int nefc = nrow + popc(limit_mask);
 
+  B2H_CLK_ADD(18, tp);
   // =============================================================== velocity stage
   // ---- mj_comVel as sums over ancestor chains: vprev[d] = sum of cdof*qvel over the dofs before d
   if (lane < KV) for (int k = 0; k < 6; k++) tmp[TMP_DOFW + 6 * lane + k] = cd[k] * (lane < nv ? st.qv : T(0));
@@ -922,6 +941,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m, Scratch<T>& S, T* Jspil
     for (int i = lane; i < NCON * 9; i += 32) dbg->con_frame[i] = S.con_frame[i];
   }
   wsync();  // stage scratch in A is dead from here
+  B2H_CLK_ADD(19, tp);
 
   // =============================================================== acceleration: qacc_smooth = M^-1 qfrc_smooth
   B2H_CLK_ADD(0, tc);

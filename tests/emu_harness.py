@@ -6,6 +6,7 @@ the fp64 oracle without a GPU.
 from __future__ import annotations
 
 import ctypes as C
+import os
 import subprocess
 from pathlib import Path
 
@@ -23,7 +24,7 @@ def build(nrow_s=None, force=False):
     deps = [SRC] + list(CSRC.glob("*.h")) + list(CSRC.glob("*.cuh")) + [HERE.parent / "include" / "b2h.h"]
     if force or not out.exists() or out.stat().st_mtime < max(p.stat().st_mtime for p in deps):
         out.parent.mkdir(exist_ok=True)
-        extra = [f"-DB2H_NROW_S={nrow_s}"] if nrow_s else []
+        extra = ([f"-DB2H_NROW_S={nrow_s}"] if nrow_s else []) + os.environ.get("B2H_EMU_EXTRA", "").split()   # tuning variants
         subprocess.run(["g++", "-O1", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas"] + extra +
                        ["-o", str(out), str(SRC), "-lpthread"], check=True, capture_output=True)
     return out

@@ -64,9 +64,11 @@ def test_launch_shape_rule(lib):
         w, r = C.c_int(), C.c_int()
         assert lib.b2h_choose_launch_shape(n_envs, 148, 232448, dtype, C.byref(w), C.byref(r)) == 0
         return w.value, r.value
-    assert shape(4096) == (14, 48)            # two rounds either way: the smaller, faster group
-    assert shape(16384) == (16, 32) and shape(65536) == (16, 32)   # SMs stay full: more env-warps, fewer shared rows
+    # shared rows: as many as fit beside the model tables (12 KB in fp32) that lead the CTA's shared memory
+    assert shape(4096) == (14, 44)            # two rounds either way: the smaller, faster group
+    assert shape(16384) == (16, 26) and shape(65536) == (16, 26)   # SMs stay full: more env-warps, fewer shared rows
     assert shape(1024) == (7, 48) and shape(256) == (2, 48) and shape(100) == (1, 48)   # below one round: all SMs, small groups
+    assert shape(2048) == (14, 44)            # exactly one round
     assert shape(4096, dtype=1)[0] in (7, 8) and shape(64, dtype=1) == (1, 48)
     w, r = C.c_int(), C.c_int()
     assert lib.b2h_choose_launch_shape(4096, 148, 8 * 1024, 0, C.byref(w), C.byref(r)) < 0   # scratch does not fit

@@ -32,7 +32,7 @@ pool = torch.rand(16, E, b.nu, device="cuda", generator=g) * 2 - 1
 b.reset()
 for i in range(W):
     b.step(pool[i % 16])
-out = (C.c_uint64 * 12)()
+out = (C.c_uint64 * 24)()
 fn(out, 1)
 c0 = b.counters()
 for i in range(K):
@@ -46,4 +46,8 @@ res = {"n_envs": E, "steps": K, "launch": b.launch_info(), "warp_cycles_per_phys
        "newton_iter_per_step": (c1["newton_iter"] - c0["newton_iter"]) / psteps,
        "frac": {NAMES[i]: round(clk[i] / total, 4) for i in range(11)}}
 res["frac"]["env epilogue + io (rest)"] = round((clk[9] - sum(clk[i] for i in (0, 1, 2, 3, 5, 6, 7, 8))) / total, 4)
+PRE = {12: "kinematics", 13: "frames + com + cinert + cdof", 14: "crb", 15: "collision broad phase", 16: "collision narrow phase",
+       17: "constraint rows (J)", 18: "row parameters + limits", 19: "velocity stage (comvel, rne, passive, actuation)"}
+res["pre-solver split"] = {v: round(clk[k] / total, 4) for k, v in PRE.items()}
+res["cta_exit_spread_ns"] = {"mean_after_first": clk[22], "last_after_first": clk[23]}   # tail imbalance of the last launch
 print(json.dumps(res, indent=1))

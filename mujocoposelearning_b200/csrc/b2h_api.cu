@@ -43,13 +43,13 @@ template <typename T> __device__ __forceinline__ Scratch<T>& my_scratch(const De
 }
 
 #ifdef B2H_STAGE_CLOCKS
-__device__ unsigned long long g_stage_clk[24];
+__device__ unsigned long long g_stage_clk[48];
 __device__ unsigned long long g_cta_exit[1024];  // globaltimer at which each CTA of the last step launch left the claim loop
 #endif
 __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long long* g) {
   if (lane_id() == 0) {
 #ifdef B2H_STAGE_CLOCKS
-    for (int i = 0; i < 24; i++) atomicAdd(&g_stage_clk[i], (unsigned long long)c.clk[i]);
+    for (int i = 0; i < 48; i++) atomicAdd(&g_stage_clk[i], (unsigned long long)c.clk[i]);
 #endif
     if (c.physics_steps) atomicAdd(g + 0, (unsigned long long)c.physics_steps);
     if (c.contact_overflow) atomicAdd(g + 1, (unsigned long long)c.contact_overflow);
@@ -97,16 +97,25 @@ step_kernel(const DevModel<T>* __restrict__ gmodel, EnvParams P, EnvIO<T> io, in
 
 // Counting sort of the envs by the solver effort of their previous control step, costliest first (one CTA).
 // Which warp steps which env never changes a result; the order inside a bucket is left to the atomics.
+// It also re-arms the claim counter of the next step launch (no memset node on the stream).
 constexpr int ORDER_BUCKETS = 256;
-__global__ void __launch_bounds__(1024, 1) order_kernel(const int* __restrict__ effort, int n, int* __restrict__ perm) {
+__global__ void __launch_bounds__(1024, 1) order_kernel(const int* __restrict__ effort, int n, int* __restrict__ perm, int* work) {
   __shared__ int hist[ORDER_BUCKETS], start[ORDER_BUCKETS];
+  if (threadIdx.x == 0) *work = 0;
   for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[min(effort[i] >> 2, ORDER_BUCKETS - 1)], 1);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    int acc = 0;
-    for (int b = ORDER_BUCKETS - 1; b >= 0; b--) { start[b] = acc; acc += hist[b]; }
+  if (threadIdx.x < 32) {  // exclusive prefix over the buckets in descending order: 8 buckets per lane + one warp scan
+    constexpr int PER = ORDER_BUCKETS / 32;
+    const int lane = threadIdx.x, top = ORDER_BUCKETS - 1 - lane * PER;
+    int loc[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) { loc[k] = sum; sum += hist[top - k]; }
+    int incl = sum;
+    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+#pragma unroll
+    for (int k = 0; k < PER; k++) start[top - k] = incl - sum + loc[k];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) perm[atomicAdd(&start[min(effort[i] >> 2, ORDER_BUCKETS - 1)], 1)] = i;
@@ -210,6 +219,7 @@ struct B2HHandle {
   int *effort = nullptr, *perm = nullptr;  // per-env solver effort of the last control step, effort-sorted env order
   int schedule = 1;                        // 1: lockstep groups follow the effort-sorted order
   bool perm_valid = false;
+  bool work_armed = false;                 // the claim counter was zeroed by the sort that followed the previous step launch
   cudaEvent_t step_done = nullptr;         // recorded after the step kernel (b2h_step_vecenv waits on it, not on the sort)
   void* dump = nullptr;
   void* spill = nullptr;  // per-warp dense rows beyond NROW_S
@@ -399,6 +409,7 @@ int b2h_reset(B2HHandle* h, const uint8_t* mask_dev, void* obs_dev, void* stream
   CU(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   CU(cudaMemsetAsync(h->work, 0, 4, s));
+  h->work_armed = false;   // the reset kernel claims envs through the same counter
   if (h->cfg.dtype == B2H_F64)
     reset_kernel<double><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<double>*)h->dmodel, h->P,
         make_io<double>(h, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr), h->cfg.n_envs, mask_dev, h->counters, h->work, (double*)h->spill);
@@ -412,8 +423,8 @@ int b2h_reset(B2HHandle* h, const uint8_t* mask_dev, void* obs_dev, void* stream
 
 static int launch_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward_dev, uint8_t* terminated_dev,
                        uint8_t* truncated_dev, void* terminal_obs_dev, Out64 o64, cudaStream_t s) {
-  CU(cudaMemsetAsync(h->work, 0, 4, s));
   const bool sched = h->schedule && h->P.sync_mode == 2 && h->cfg.n_envs > h->warps;
+  if (!sched || !h->work_armed) CU(cudaMemsetAsync(h->work, 0, 4, s));   // otherwise the last sort re-armed the claim counter
   const int* perm = sched && h->perm_valid ? h->perm : nullptr;   // order of the previous step's efforts (first step: env-id order)
   if (h->cfg.dtype == B2H_F64)
     step_kernel<double><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<double>*)h->dmodel, h->P,
@@ -427,9 +438,10 @@ static int launch_step(B2HHandle* h, const float* actions_dev, void* obs_dev, vo
   h->launches++;
   if (h->step_done) CU(cudaEventRecord(h->step_done, s));   // results are complete here; the sort below is for the next step
   if (sched) {  // sorted after the step instead of before the next one: it then overlaps the caller's host work
-    order_kernel<<<1, 1024, 0, s>>>(h->effort, h->cfg.n_envs, h->perm);
+    order_kernel<<<1, 1024, 0, s>>>(h->effort, h->cfg.n_envs, h->perm, h->work);
     CU(cudaGetLastError());
     h->perm_valid = true;
+    h->work_armed = true;
     h->launches++;
   }
   return B2H_OK;
@@ -662,9 +674,9 @@ int b2h_measure_fp32_peak(int device, double* tflops) {
 }
 
 #ifdef B2H_STAGE_CLOCKS
-int b2h_debug_stage_clocks(uint64_t out[24], int reset) {   // tuning build only (not part of include/b2h.h)
+int b2h_debug_stage_clocks(uint64_t out[48], int reset) {   // tuning build only (not part of include/b2h.h)
   CU(cudaDeviceSynchronize());
-  CU(cudaMemcpyFromSymbol(out, g_stage_clk, 24 * 8));
+  CU(cudaMemcpyFromSymbol(out, g_stage_clk, 48 * 8));
   {  // out[22], out[23]: mean and max CTA exit time of the last launch, in ns after the earliest exit... relative to the min
     static unsigned long long ex[1024];
     CU(cudaMemcpyFromSymbol(ex, g_cta_exit, sizeof(ex)));
@@ -673,7 +685,7 @@ int b2h_debug_stage_clocks(uint64_t out[24], int reset) {   // tuning build only
     for (int i = 0; i < 1024; i++) if (ex[i]) sum += ex[i] - mn;
     out[22] = n ? sum / n : 0; out[23] = n ? mx - mn : 0;
   }
-  if (reset) { unsigned long long z[24] = {0}; CU(cudaMemcpyToSymbol(g_stage_clk, z, 24 * 8)); }
+  if (reset) { unsigned long long z[48] = {0}; CU(cudaMemcpyToSymbol(g_stage_clk, z, 24 * 8)); }
   return B2H_OK;
 }
 #endif

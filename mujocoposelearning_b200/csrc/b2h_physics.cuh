@@ -228,14 +228,16 @@ struct Counters {  // per-warp tallies of one launch (32-bit: a warp sees a few 
   unsigned physics_steps, contact_overflow, iter_cap, bad_state, newton_iter, ls_eval;
   unsigned work;  // solver effort of the env in flight (Newton iterations weighted by row slots): next launch's schedule key
 #ifdef B2H_STAGE_CLOCKS
-  long long clk[24];  // tuning build: cycles per stage (tools/stage_clocks.py)
+  long long clk[48];  // tuning build: cycles per stage (tools/stage_clocks.py)
 #endif
 };
 #ifdef B2H_STAGE_CLOCKS
 #define B2H_CLK(var) long long var = clock64()
 #define B2H_CLK_FROM(var, src) long long var = (src)
 #define B2H_CLK_ADD(i, t0) do { long long t1_ = clock64(); cnt.clk[i] += t1_ - (t0); (t0) = t1_; } while (0)
+#define B2H_TALLY(i) (cnt.clk[i] += 1)
 #else
+#define B2H_TALLY(i)
 #define B2H_CLK(var)
 #define B2H_CLK_FROM(var, src)
 #define B2H_CLK_ADD(i, t0)
@@ -1039,6 +1041,12 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* J
         T improvement = scale * (oldcost - cost);
         T gn = m_sqrt(wsum(lane < nv ? (Ma - qfrc_smooth - qfrc_con) * (Ma - qfrc_smooth - qfrc_con) : T(0)));
         niter++;
+#ifdef B2H_STAGE_CLOCKS
+        if (improvement < m_max(tolerance, Tol<T>::cost_rel * scale * m_abs(cost))) { B2H_TALLY(24); B2H_TALLY(32 + (niter < 15 ? niter : 15)); if ((full_step || tiny_step) && act[0] == pact[0] && act[1] == pact[1] && act[2] == pact[2] && actl == pactl) B2H_TALLY(29); }
+        else if (scale * gn < tolerance) { B2H_TALLY(25); B2H_TALLY(32 + (niter < 15 ? niter : 15)); }
+        else if (Tol<T>::exact_stop && (full_step || tiny_step) && act[0] == pact[0] && act[1] == pact[1] && act[2] == pact[2] && actl == pactl) { B2H_TALLY(26); B2H_TALLY(32 + (niter < 15 ? niter : 15)); }
+        if (act[0] == pact[0] && act[1] == pact[1] && act[2] == pact[2] && actl == pactl) B2H_TALLY(31);
+#endif
         if (improvement < m_max(tolerance, Tol<T>::cost_rel * scale * m_abs(cost)) || scale * gn < tolerance) break;
         if (Tol<T>::exact_stop && (full_step || tiny_step) && act[0] == pact[0] && act[1] == pact[1] && act[2] == pact[2] && actl == pactl) break;
         if (niter >= Tol<T>::maxiter) { cnt.iter_cap++; break; }
@@ -1120,6 +1128,9 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* J
         bool done = false;
         if (m_abs(p1.d0) < gtol) { alpha = p1.alpha; done = true; }
         else full_step = false;
+        B2H_TALLY(27);                     // line searches
+        if (full_step) B2H_TALLY(28);      // ... that took the exact Newton step at once
+        if (done) B2H_TALLY(30);           // ... that ended after two evaluations
         if (!done) {
           int dir = p1.d0 < T(0) ? 1 : -1;
           bool p2update = false;

@@ -32,7 +32,7 @@ pool = torch.rand(16, E, b.nu, device="cuda", generator=g) * 2 - 1
 b.reset()
 for i in range(W):
     b.step(pool[i % 16])
-out = (C.c_uint64 * 24)()
+out = (C.c_uint64 * 48)()
 fn(out, 1)
 c0 = b.counters()
 for i in range(K):
@@ -49,5 +49,9 @@ res["frac"]["env epilogue + io (rest)"] = round((clk[9] - sum(clk[i] for i in (0
 PRE = {12: "kinematics", 13: "frames + com + cinert + cdof", 14: "crb", 15: "collision broad phase", 16: "collision narrow phase",
        17: "constraint rows (J)", 18: "row parameters + limits", 19: "velocity stage (comvel, rne, passive, actuation)"}
 res["pre-solver split"] = {v: round(clk[k] / total, 4) for k, v in PRE.items()}
+res["newton exits"] = {"improvement": clk[24], "gradient": clk[25], "exact_stop": clk[26], "improvement exits that exact_stop would also take": clk[29],
+                       "top-of-iteration checks with unchanged active set": clk[31]}
+res["line searches"] = {"count": clk[27], "exact newton step accepted": clk[28], "done after two evaluations": clk[30]}
+res["iterations at exit (histogram)"] = clk[32:48]
 res["cta_exit_spread_ns"] = {"mean_after_first": clk[22], "last_after_first": clk[23]}   # tail imbalance of the last launch
 print(json.dumps(res, indent=1))

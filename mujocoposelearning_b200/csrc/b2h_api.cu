@@ -367,7 +367,7 @@ int b2h_create(const B2HModel* model, const B2HConfig* cfg, B2HHandle** out) {
   ALLOC(h->qpos, E * h->nq * esz); ALLOC(h->qvel, E * h->nv * esz); ALLOC(h->warm, E * h->nv * esz);
   ALLOC(h->total_reward, E * esz); ALLOC(h->nstep, E * 4); ALLOC(h->step_count, E * 4); ALLOC(h->episode, E * 4);
   ALLOC(h->reset_noise, E * (h->nq + h->nv) * 8); ALLOC(h->noise_injected, E);
-  ALLOC(h->counters, 8 * 8); ALLOC(h->work, 4); ALLOC(h->effort, E * 4); ALLOC(h->perm, E * 4);
+  ALLOC(h->counters, 8 * 8); ALLOC(h->work, 8); /* [0] step claim counter, [1] reset claim counter */ ALLOC(h->effort, E * 4); ALLOC(h->perm, E * 4);
   if (const char* sc = getenv("B2H_SCHEDULE")) h->schedule = atoi(sc);  // tuning knob: 0 = env-id order
   ALLOC(h->actions_stage, E * h->nu * 4); ALLOC(h->obs_stage, E * h->obs_dim * esz); ALLOC(h->tobs_stage, E * h->obs_dim * esz);
   ALLOC(h->rew_stage, E * esz); ALLOC(h->term_stage, E); ALLOC(h->trunc_stage, E); ALLOC(h->mask_stage, E);
@@ -408,14 +408,13 @@ int b2h_reset(B2HHandle* h, const uint8_t* mask_dev, void* obs_dev, void* stream
   if (!h) return fail(B2H_EINVAL, "null handle");
   CU(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
-  CU(cudaMemsetAsync(h->work, 0, 4, s));
-  h->work_armed = false;   // the reset kernel claims envs through the same counter
+  CU(cudaMemsetAsync(h->work + 1, 0, 4, s));   // the reset kernel's own claim counter: a captured step graph stays valid across resets
   if (h->cfg.dtype == B2H_F64)
     reset_kernel<double><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<double>*)h->dmodel, h->P,
-        make_io<double>(h, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr), h->cfg.n_envs, mask_dev, h->counters, h->work, (double*)h->spill);
+        make_io<double>(h, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr), h->cfg.n_envs, mask_dev, h->counters, h->work + 1, (double*)h->spill);
   else
     reset_kernel<float><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<float>*)h->dmodel, h->P,
-        make_io<float>(h, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr), h->cfg.n_envs, mask_dev, h->counters, h->work, (float*)h->spill);
+        make_io<float>(h, nullptr, obs_dev, nullptr, nullptr, nullptr, nullptr), h->cfg.n_envs, mask_dev, h->counters, h->work + 1, (float*)h->spill);
   CU(cudaGetLastError());
   h->launches++;
   return B2H_OK;

@@ -444,4 +444,15 @@ def test_step_is_cuda_graph_capturable():
     assert torch.equal(graphed.obs, eager.obs) and torch.equal(graphed.reward, eager.reward)
     a, b = graphed.get_state(), eager.get_state()
     assert np.array_equal(a["qpos"], b["qpos"]) and np.array_equal(a["qvel"], b["qvel"]) and np.array_equal(a["nstep"], b["nstep"])
+    # a reset between replays must not disturb the captured step (the reset kernel claims envs through its own counter,
+    # the step's claim counter is re-armed by the sort that follows every step launch)
+    noise = np.random.default_rng(4).uniform(-0.01, 0.01, (n, 55))
+    for hb in (graphed, eager):
+        hb.set_reset_noise(noise)
+        hb.reset()
+    static_a.copy_(acts[2])
+    graph.replay()
+    eager.step(acts[2])
+    torch.cuda.synchronize()
+    assert torch.equal(graphed.obs, eager.obs) and torch.equal(graphed.reward, eager.reward)
     graphed.close(); eager.close()

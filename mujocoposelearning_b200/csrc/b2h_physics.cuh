@@ -1397,12 +1397,14 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
   EnvState<T> st;
   st.qp = 0; st.qv = 0; st.warm = 0; st.ctrl = 0; st.qfrc_act = 0; st.nstep = 0;
   int a = -1, step_count = 0;
+  T action = 0;   // this lane's motor command: read once per control step (the array may be page-locked host memory)
   if (active) {
     st.qp = lane < nq ? io.qpos[(size_t)env * nq + lane] : T(0);
     st.qv = lane < nv ? io.qvel[(size_t)env * nv + lane] : T(0);
     st.warm = lane < nv ? io.warm[(size_t)env * nv + lane] : T(0);
     st.nstep = io.nstep[env];
     a = lane < nv ? B2H_LDG(m.dof_act[lane]) : -1;
+    if (a >= 0) action = T(io.actions[(size_t)env * nu + a]);
     step_count = io.step_count[env] + 1;
   }
   cnt.work = 0;
@@ -1414,7 +1416,7 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     B2H_CLK_ADD(4, te);
     if (active) {
       // data.ctrl[:] = action before every mj_step (a bad-state reset inside the previous sub-step zeroed it)
-      st.ctrl = a >= 0 ? T(io.actions[(size_t)env * nu + a]) : T(0);
+      st.ctrl = action;
       mj_step<T>(m, S, Jspill, st, cnt);
     }
   }

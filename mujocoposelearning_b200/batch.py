@@ -100,6 +100,22 @@ class HumanoidBatch:
                                        p(terminal_obs) if terminal_obs is not None else None, C.byref(nd), self._stream()))
         return nd.value
 
+    def vecenv_call(self, actions, obs, reward, terminated, truncated, terminal_obs):
+        """The b2h_step_vecenv call bound to one fixed set of (page-locked) CPU tensors: pointers are marshalled once,
+        a step is then a single foreign call.  Returns a function () -> number of envs whose episode ended."""
+        p = lambda t: C.c_void_p(t.data_ptr())
+        nd = C.c_int(0)
+        args = (self.h, p(actions), p(obs), p(reward), p(terminated), p(truncated),
+                p(terminal_obs) if terminal_obs is not None else None, C.byref(nd))
+        fn, dev = self.lib.b2h_step_vecenv, self.device
+
+        def call():
+            rc = fn(*args, torch.cuda.current_stream(dev).cuda_stream)
+            if rc < 0:
+                check(rc)
+            return nd.value
+        return call
+
     def reset_host(self, hb, mask=None):
         mp = None
         if mask is not None:

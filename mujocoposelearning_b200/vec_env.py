@@ -115,6 +115,10 @@ class B200HumanoidVecEnv(_VecEnvBase):
         for hset in self._host:   # numpy views of the page-locked tensors, made once
             hset["np"] = (hset["obs"].numpy(), hset["rew"].numpy(), hset["term"].numpy(), hset["trunc"].numpy())
         self._tobs_np = self._tobs_host.numpy()
+        if obs_dtype == "float64":
+            for hset in self._host:   # the foreign call of a step, argument pointers marshalled once per buffer set
+                hset["call"] = self.batch.vecenv_call(self.hb["actions"], hset["obs"], hset["rew"], hset["term"], hset["trunc"],
+                                                      self._tobs_host)
         self._actions_np = self.hb["actions"].numpy()
         self._flip = 0
         self._lazy_info = {"TimeLimit.truncated": False}
@@ -143,7 +147,7 @@ class B200HumanoidVecEnv(_VecEnvBase):
         out = self._host[self._flip]
         self._flip ^= 1
         if self.obs_dtype == "float64":
-            n_done = self.batch.step_vecenv(self.hb["actions"], out["obs"], out["rew"], out["term"], out["trunc"], self._tobs_host)
+            n_done = out["call"]()
         else:   # results in the arithmetic dtype (float32), same zero-copy path
             self.batch.step_host(dict(actions=self.hb["actions"], obs=out["obs"], reward=out["rew"], terminated=out["term"],
                                       truncated=out["trunc"], terminal_obs=self._tobs_host))

@@ -88,7 +88,11 @@ B2H_DEV float m_min(float a, float b) { return fminf(a, b); }
 B2H_DEV double m_min(double a, double b) { return fmin(a, b); }
 B2H_DEV float m_max(float a, float b) { return fmaxf(a, b); }
 B2H_DEV double m_max(double a, double b) { return fmax(a, b); }
+#ifdef B2H_HOST_EMU
 B2H_DEV float m_exp(float x) { return expf(x); }
+#else
+B2H_DEV float m_exp(float x) { return __expf(x); }   // reward terms only (2 ulp + range reduction in the MUFU path)
+#endif
 B2H_DEV double m_exp(double x) { return exp(x); }
 B2H_DEV float m_pow(float a, float b) { return powf(a, b); }
 B2H_DEV double m_pow(double a, double b) { return pow(a, b); }
@@ -96,7 +100,13 @@ B2H_DEV float m_atan2(float a, float b) { return atan2f(a, b); }
 B2H_DEV double m_atan2(double a, double b) { return atan2(a, b); }
 B2H_DEV float m_asin(float a) { return asinf(a); }
 B2H_DEV double m_asin(double a) { return asin(a); }
+#ifdef B2H_HOST_EMU
 B2H_DEV void m_sincos(float x, float* s, float* c) { *s = sinf(x); *c = cosf(x); }
+#else
+// half joint angles and h * |omega| / 2: always inside [-pi, pi], where the MUFU sine / cosine are good to 2^-21.4
+// absolute -- below fp32 resolution of a unit quaternion component; sinf / cosf carry a 350-instruction slow path
+B2H_DEV void m_sincos(float x, float* s, float* c) { __sincosf(x, s, c); }
+#endif
 B2H_DEV void m_sincos(double x, double* s, double* c) { *s = sin(x); *c = cos(x); }
 template <typename T> B2H_DEV T clampT(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
 template <typename T> B2H_DEV bool is_bad(T x) { return !(x == x) || x > T(1e10) || x < T(-1e10); }

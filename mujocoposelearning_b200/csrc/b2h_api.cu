@@ -157,7 +157,7 @@ debug_kernel(const DevModel<T>* model, EnvIO<T> io, int env, DebugDump<T>* out, 
   st.ctrl = (a >= 0 && io.actions) ? T(io.actions[(size_t)env * nu + a]) : T(0);
   T qacc;
   StepStats stats;
-  physics_step<T>(*model, S, Jspill, st, cnt, false, &stats, &qacc, out);
+  physics_step<T, true>(*model, S, Jspill, st, cnt, false, &stats, &qacc, out);
   __syncwarp();
   if (lane == 0) out->stats = stats;
 }

@@ -253,6 +253,11 @@ struct Counters {  // per-warp tallies of one launch (32-bit: a warp sees a few 
 #define B2H_CLK_ADD(i, t0)
 #endif
 
+// impedance curve for a general power (solimp[4] other than 1 or 2): kept out of line, the model on the path uses 2
+template <typename T>
+B2H_DEV_NOINLINE T imp_power_curve(T x, T p, T mid) {
+  return x <= mid ? m_pow(x, p) / m_pow(mid, p - 1) : T(1) - m_pow(T(1) - x, p) / m_pow(T(1) - mid, p - 1);
+}
 // per-row soft-constraint parameters (mj_makeImpedance + mj_referenceConstraint)
 template <typename T> struct RowParam { T D, aref; };
 template <typename T>
@@ -269,7 +274,7 @@ B2H_DEV_NOINLINE RowParam<T> row_params(T solref0, T solref1, T solimp0, T solim
       T y, p = solimp[4], mid = solimp[3];
       if (p == T(1)) y = x;
       else if (p == T(2)) y = x <= mid ? x * x / mid : T(1) - (T(1) - x) * (T(1) - x) / (T(1) - mid);
-      else y = x <= mid ? m_pow(x, p) / m_pow(mid, p - 1) : T(1) - m_pow(T(1) - x, p) / m_pow(T(1) - mid, p - 1);
+      else y = imp_power_curve(x, p, mid);
       imp = solimp[0] + y * (solimp[1] - solimp[0]);
     }
   }
@@ -413,9 +418,16 @@ struct DebugDump {  // named views of one mj_forward (parity / debug only)
 // values of this step, which is what the reference's observation and rewards read.
 // If `integrate` is false this is mj_forward: state untouched, qacc returned in *qacc_out.
 // Returns true when mj_checkAcc tripped: the state was reset and the caller must run the step once more.
-template <typename T>
-B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, bool integrate,
-                                   StepStats* stats, T* qacc_out, DebugDump<T>* dbg /* optional named dump */) {
+// DBG = true is the instantiation of the debug / parity kernel (mj_forward with named dumps); the step and reset
+// kernels use DBG = false, whose instruction stream carries none of the dump code (cold code inside the lockstep
+// stream costs fetch slots even when it is branched over).
+template <typename T, bool DBG = false>
+B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, bool integrate_arg,
+                                   StepStats* stats_arg, T* qacc_out_arg, DebugDump<T>* dbg_arg /* optional named dump */) {
+  const bool integrate = DBG ? integrate_arg : true;
+  StepStats* const stats = DBG ? stats_arg : nullptr;
+  T* const qacc_out = DBG ? qacc_out_arg : nullptr;
+  DebugDump<T>* const dbg = DBG ? dbg_arg : nullptr;
 #ifndef B2H_HOST_EMU
   // the kernels stage the model tables at the start of the CTA's dynamic shared memory: address them as such
   // (LDS with immediate offsets) instead of through the generic reference this non-inlined function receives
@@ -1263,7 +1275,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* J
 template <typename T>
 B2H_DEV void mj_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt) {
   for (int tries = 0; tries < 2; tries++)
-    if (!physics_step<T>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr)) break;
+    if (!physics_step<T, false>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr)) break;
 }
 
 // ------------------------------------------------------------------------------------------------ env layer

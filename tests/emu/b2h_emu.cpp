@@ -73,7 +73,7 @@ static void* lane_main(void* arg) {
       int a = lane < nv ? j->m->dof_act[lane] : -1;
       st.ctrl = (a >= 0 && j->io.actions) ? T(j->io.actions[(size_t)e * nu + a]) : T(0);
       T qacc;
-      physics_step<T>(*j->m, *j->S, j->Jspill, st, cnt, false, &j->dump->stats, &qacc, j->dump);
+      physics_step<T, true>(*j->m, *j->S, j->Jspill, st, cnt, false, &j->dump->stats, &qacc, j->dump);
       emu::sync();
     }
   }

@@ -1310,7 +1310,7 @@ template <typename T> B2H_DEV void quat_to_euler(const T* q, T* roll, T* pitch) 
 // reward_functions.py: stand (:156-211), kneeling (:66-154), walk (:213-261); cfrc_ext and subtree_linvel are
 // identically zero in the reference (no sensors), so the foot / com-velocity terms are the constants below.
 template <typename T>
-B2H_DEV T compute_reward(const DevModel<T>& m, const Scratch<T>& S, const EnvState<T>& st, const EnvParams& P, int lane) {
+B2H_DEV_NOINLINE T compute_reward(const DevModel<T>& m, const Scratch<T>& S, const EnvState<T>& st, const EnvParams& P, int lane) {
   const int nv = B2H_LDG(m.nv);
   T hgt = shfl(st.qp, 2), vx = shfl(st.qv, 0), q[4], roll, pitch;
   for (int k = 0; k < 4; k++) q[k] = shfl(st.qp, 3 + k);
@@ -1378,7 +1378,7 @@ struct EnvIO {  // device arrays, all [n_envs, dim] row-major
 
 // HumanoidEnv.reset (custom_env.py:97-150): qpos0 + masked U(-0.01,0.01) noise, one settle step with ctrl = 0
 template <typename T>
-B2H_DEV void env_reset(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, const EnvParams& P,
+B2H_DEV_NOINLINE void env_reset(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, const EnvParams& P,
                        const EnvIO<T>& io, int env, int lane) {
   const int nq = B2H_LDG(m.nq), nv = B2H_LDG(m.nv);
   const int nqv = nq + nv;

@@ -421,9 +421,15 @@ struct DebugDump {  // named views of one mj_forward (parity / debug only)
 // DBG = true is the instantiation of the debug / parity kernel (mj_forward with named dumps); the step and reset
 // kernels use DBG = false, whose instruction stream carries none of the dump code (cold code inside the lockstep
 // stream costs fetch slots even when it is branched over).
-template <typename T, bool DBG = false>
-B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, bool integrate_arg,
+// NS = dense-row slots per lane compiled in (capacity 32 * NS rows).  The bench workload needs more than 32 dense rows
+// in one step out of a thousand (oracle: 99th percentile of nefc, joint limits included, is 24), so mj_step runs the
+// NS = 1 instantiation -- no slot 1 / slot 2 copies of the row loops in the instruction stream -- and falls back to
+// the full-capacity one (a separate, out-of-line function) when the rows do not fit: return value 2, state untouched.
+enum { B2H_STEP_OK = 0, B2H_STEP_BAD_ACC = 1, B2H_STEP_MORE_ROWS = 2 };
+template <typename T, bool DBG = false, int NS = NSLOT>
+B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, bool integrate_arg,
                                    StepStats* stats_arg, T* qacc_out_arg, DebugDump<T>* dbg_arg /* optional named dump */) {
+  constexpr int NSLOT = NS;   // shadows the capacity constant for everything below (arrays, B2H_SLOTS)
   const bool integrate = DBG ? integrate_arg : true;
   StepStats* const stats = DBG ? stats_arg : nullptr;
   T* const qacc_out = DBG ? qacc_out_arg : nullptr;
@@ -814,6 +820,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* J
     int keep_rows = drop ? 0 : nr;
     nrow += wsum(keep_rows);
   }
+  if (NS * 32 < NROW && nrow > NS * 32) return B2H_STEP_MORE_ROWS;   // warp-uniform
   wsync();
   // contact Jacobians (lane = dof): J_k[d] = frame_k . (jacp_body2[d] - jacp_body1[d]), mj_jac about the com
   for (int c = 0; c < ncon; c++) {
@@ -849,7 +856,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* J
   B2H_CLK_ADD(17, tp);
   // per-row parameters; lane owns dense rows lane, lane+32, lane+64 (slots) and the joint limit of dof `lane`
   const int nslot = (nrow + 31) >> 5;
-  T rD[NSLOT] = {0, 0, 0}, raref[NSLOT] = {0, 0, 0};
+  T rD[NSLOT] = {}, raref[NSLOT] = {};
   B2H_SLOTS(s) {
     int r = lane + 32 * s;
     if (r < nrow) {
@@ -1006,7 +1013,7 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* J
       return wsum(c);
     };
     // ---- warmstart(): the cheaper of qacc_warmstart and qacc_smooth; J*x and M*x of the chosen point are kept
-    T jar[NSLOT] = {0, 0, 0}, ljar, jar_s[NSLOT] = {0, 0, 0}, ljar_s;
+    T jar[NSLOT] = {}, ljar, jar_s[NSLOT] = {}, ljar_s;
     jar_of(st.warm, jar, &ljar);
     T cost_warm = row_cost(jar, ljar);
     T Ma = mat_vec(S.M, S.vec[2], nv, lane);
@@ -1030,11 +1037,11 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* J
     const int ls_iterations = 50;
     T cost = 0, gauss = 0, grad = 0, search = 0;
     bool first = true, full_step = false, tiny_step = false;
-    unsigned pact[NSLOT] = {0, 0, 0}, pactl = 0;  // active sets the current Hessian was built from
+    unsigned pact[NSLOT] = {}, pactl = 0;  // active sets the current Hessian was built from
     for (;;) {
       // -- PrimalUpdateConstraint: active rows, forces, cost
-      unsigned act[NSLOT] = {0, 0, 0}, actl;
-      T f[NSLOT] = {0, 0, 0}, lf = 0, c = 0;
+      unsigned act[NSLOT] = {}, actl;
+      T f[NSLOT] = {}, lf = 0, c = 0;
       B2H_SLOTS(s) {
         bool on = lane + 32 * s < nrow && Jaref[s] < T(0);
         if (on) { f[s] = -rD[s] * Jaref[s]; c += T(0.5) * rD[s] * Jaref[s] * Jaref[s]; }
@@ -1063,14 +1070,17 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* J
         T improvement = scale * (oldcost - cost);
         T gn = m_sqrt(wsum(lane < nv ? (Ma - qfrc_smooth - qfrc_con) * (Ma - qfrc_smooth - qfrc_con) : T(0)));
         niter++;
+        bool same_set = actl == pactl;
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) same_set = same_set && act[s] == pact[s];
 #ifdef B2H_STAGE_CLOCKS
-        if (improvement < m_max(tolerance, Tol<T>::cost_rel * scale * m_abs(cost))) { B2H_TALLY(24); B2H_TALLY(32 + (niter < 15 ? niter : 15)); if ((full_step || tiny_step) && act[0] == pact[0] && act[1] == pact[1] && act[2] == pact[2] && actl == pactl) B2H_TALLY(29); }
+        if (improvement < m_max(tolerance, Tol<T>::cost_rel * scale * m_abs(cost))) { B2H_TALLY(24); B2H_TALLY(32 + (niter < 15 ? niter : 15)); if ((full_step || tiny_step) && same_set) B2H_TALLY(29); }
         else if (scale * gn < tolerance) { B2H_TALLY(25); B2H_TALLY(32 + (niter < 15 ? niter : 15)); }
-        else if (Tol<T>::exact_stop && (full_step || tiny_step) && act[0] == pact[0] && act[1] == pact[1] && act[2] == pact[2] && actl == pactl) { B2H_TALLY(26); B2H_TALLY(32 + (niter < 15 ? niter : 15)); }
-        if (act[0] == pact[0] && act[1] == pact[1] && act[2] == pact[2] && actl == pactl) B2H_TALLY(31);
+        else if (Tol<T>::exact_stop && (full_step || tiny_step) && same_set) { B2H_TALLY(26); B2H_TALLY(32 + (niter < 15 ? niter : 15)); }
+        if (same_set) B2H_TALLY(31);
 #endif
         if (improvement < m_max(tolerance, Tol<T>::cost_rel * scale * m_abs(cost)) || scale * gn < tolerance) break;
-        if (Tol<T>::exact_stop && (full_step || tiny_step) && act[0] == pact[0] && act[1] == pact[1] && act[2] == pact[2] && actl == pactl) break;
+        if (Tol<T>::exact_stop && (full_step || tiny_step) && same_set) break;
         if (niter >= Tol<T>::maxiter) { cnt.iter_cap++; break; }
       }
       first = false;
@@ -1114,14 +1124,14 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* J
       // -- PrimalSearch: exact line search on the piecewise-quadratic cost along `search`
       T snorm = m_sqrt(wsum(lane < nv ? search * search : T(0)));
       T alpha = 0;
-      T Jv[NSLOT] = {0, 0, 0}, lJv = 0, Mv = 0;
+      T Jv[NSLOT] = {}, lJv = 0, Mv = 0;
       if (snorm >= B2H_MINVAL) {
         T gtol = tolerance * ls_tolerance * snorm / scale;
         jar_of(search, Jv, &lJv);
         Mv = mat_vec(S.M, S.vec[2], nv, lane);
         T qg1 = wsum(lane < nv ? search * (Ma - qfrc_smooth) : T(0));
         T qg2 = wsum(lane < nv ? T(0.5) * search * Mv : T(0));
-        T q0r[NSLOT + 1] = {0, 0, 0, 0}, q1r[NSLOT + 1] = {0, 0, 0, 0}, q2r[NSLOT + 1] = {0, 0, 0, 0};  // per-row quadratics (slots + limit)
+        T q0r[NSLOT + 1] = {}, q1r[NSLOT + 1] = {}, q2r[NSLOT + 1] = {};  // per-row quadratics (slots + limit)
         B2H_SLOTS(s) {
           if (lane + 32 * s < nrow) {
             q0r[s] = T(0.5) * rD[s] * Jaref[s] * Jaref[s]; q1r[s] = rD[s] * Jaref[s] * Jv[s]; q2r[s] = T(0.5) * rD[s] * Jv[s] * Jv[s];
@@ -1227,14 +1237,14 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* J
     if (lane < 3) dbg->com[lane] = S.com[lane];
   }
   if (qacc_out) *qacc_out = qacc;
-  if (!integrate) return false;
+  if (!integrate) return B2H_STEP_OK;
 
   // ---- mj_checkAcc: MuJoCo resets mjData and re-runs mj_forward before integrating
   if (ballot(lane < nv && is_bad(qacc))) {
     st.qp = lane < nq ? B2H_LDG(m.qpos0[lane]) : T(0);
     st.qv = 0; st.warm = 0; st.ctrl = 0; st.nstep = 0;
     cnt.bad_state++;
-    return true;
+    return B2H_STEP_BAD_ACC;
   }
 
   // =============================================================== mj_Euler (implicit joint damping) + mj_advance
@@ -1270,12 +1280,15 @@ B2H_DEV_NOINLINE bool physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* J
   cnt.physics_steps++;
   wsync();
   B2H_CLK_ADD(3, tc);
-  return false;
+  return B2H_STEP_OK;
 }
 template <typename T>
 B2H_DEV void mj_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt) {
-  for (int tries = 0; tries < 2; tries++)
-    if (!physics_step<T, false>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr)) break;
+  for (int tries = 0; tries < 2; tries++) {
+    int rc = physics_step<T, false, 1>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
+    if (rc == B2H_STEP_MORE_ROWS) rc = physics_step<T, false, NSLOT>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
+    if (rc == B2H_STEP_OK) break;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ env layer

@@ -669,7 +669,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
     for (int base = 0; base < ncand; base += 32) {
       int p = base + lane < ncand ? cand[base + lane] : npair;
       int n = 0;
-      T cdist[2], cpos[2][3], cnrm[2][3], chint[3] = {0, 0, 0};
+      T cdist[2] = {}, cpos[2][3] = {}, cnrm[2][3] = {}, chint[3] = {0, 0, 0};
       uint32_t info = 0;
       if (p < npair) {
         uint32_t pw = B2H_LDG(m.pair[p]);
@@ -702,7 +702,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
           T r1 = B2H_LDG(m.geom_size[g1][0]), h1 = B2H_LDG(m.geom_size[g1][1]);
           const T* p1 = gpos + 3 * g1;
           const T* a1 = gaxis + 3 * g1;
-          T v1[2][3], v2[2][3];
+          T v1[2][3] = {}, v2[2][3] = {};
           int ncand = 1;
           if (h1 == T(0)) {  // mjc_SphereSphere / mjc_SphereCapsule
             T d[3] = {p1[0] - p2[0], p1[1] - p2[1], p1[2] - p2[2]};
@@ -713,7 +713,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
             T ma = dot3(a1, a1), mb = -dot3(a1, a2), mc = dot3(a2, a2), u = -dot3(a1, dif), v = dot3(a2, dif);
             cross3(cr, a1, a2);
             T det = dot3(cr, cr);  // = ma*mc - mb*mb without the cancellation
-            if (det >= B2H_MINVAL) {
+            if (__builtin_expect(det >= B2H_MINVAL, 1)) {
               T x1 = (mc * u - mb * v) / det, x2 = (ma * v - mb * u) / det;
               if (x1 > h1) { x1 = h1; x2 = (v - mb * h1) / mc; }
               else if (x1 < -h1) { x1 = -h1; x2 = (v + mb * h1) / mc; }
@@ -743,26 +743,31 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
             }
           }
           T mind = margin + r1 + r2;
+          // one copy of the body (a second candidate only exists for parallel axes): candidate 1 moves into slot 0
+#pragma unroll 1
           for (int e = 0; e < ncand; e++) {
-            T d[3] = {v2[e][0] - v1[e][0], v2[e][1] - v1[e][1], v2[e][2] - v1[e][2]};
+            T d[3] = {v2[0][0] - v1[0][0], v2[0][1] - v1[0][1], v2[0][2] - v1[0][2]};
             if (dot3(d, d) <= mind * mind) {
               T dist = normalize3(d) - r1 - r2;
               if (dist < margin) {
-                cdist[n] = dist;
-                for (int k = 0; k < 3; k++) { cnrm[n][k] = d[k]; cpos[n][k] = v1[e][k] + d[k] * (r1 + dist * T(0.5)); }
+                if (n == 0) { cdist[0] = dist; for (int k = 0; k < 3; k++) { cnrm[0][k] = d[k]; cpos[0][k] = v1[0][k] + d[k] * (r1 + dist * T(0.5)); } }
+                else { cdist[1] = dist; for (int k = 0; k < 3; k++) { cnrm[1][k] = d[k]; cpos[1][k] = v1[0][k] + d[k] * (r1 + dist * T(0.5)); } }
                 n++;
               }
             }
+            for (int k = 0; k < 3; k++) { v1[0][k] = v1[1][k]; v2[0][k] = v2[1][k]; }
           }
         }
       }
       int slot = ncon + wscan_excl(n, lane);
       int total = shfl(slot + n, 31) - ncon;
+      // one copy of the body: the second contact of a pair (both ends of a capsule on the plane) moves into slot 0
+#pragma unroll 1
       for (int e = 0; e < n; e++) {
         int c = slot + e;
         if (c < NCON) {
           T f[9];  // mju_makeFrame
-          for (int k = 0; k < 3; k++) { f[k] = cnrm[e][k]; f[3 + k] = chint[k]; }
+          for (int k = 0; k < 3; k++) { f[k] = cnrm[0][k]; f[3 + k] = chint[k]; }
           normalize3(f);
           if (m_sqrt(dot3(f + 3, f + 3)) < T(0.5)) {
             f[3] = f[4] = f[5] = 0;
@@ -772,11 +777,13 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
           for (int k = 0; k < 3; k++) f[3 + k] -= f[k] * dp;
           normalize3(f + 3);
           cross3(f + 6, f, f + 3);
-          S.con_dist[c] = cdist[e];
-          for (int k = 0; k < 3; k++) S.con_pos[3 * c + k] = cpos[e][k];
+          S.con_dist[c] = cdist[0];
+          for (int k = 0; k < 3; k++) S.con_pos[3 * c + k] = cpos[0][k];
           for (int k = 0; k < 9; k++) S.con_frame[9 * c + k] = f[k];
           S.con_info[c] = info;
         }
+        cdist[0] = cdist[1];
+        for (int k = 0; k < 3; k++) { cnrm[0][k] = cnrm[1][k]; cpos[0][k] = cpos[1][k]; }
       }
       ncon += total;
     }

@@ -451,7 +451,11 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
   T* const gpos = S.J + POS_GPOS; T* const gaxis = S.J + POS_GAXIS;
   // dense row r lives in shared memory below nrow_s and in this warp's global spill area above it
   const int nrow_s = B2H_LDG(m.nrow_s);
-  auto jrow = [&](int r) -> T* { return r < nrow_s ? S.J + r * LD : Jspill + (size_t)(r - nrow_s) * LD; };
+  // (the one-slot instantiation only runs when every row is in shared memory: no select, no generic pointer)
+  auto jrow = [&](int r) -> T* {
+    if constexpr (NS == 1) return S.J + r * LD;
+    else return r < nrow_s ? S.J + r * LD : Jspill + (size_t)(r - nrow_s) * LD;
+  };
   B2H_CLK(tc);
 
   // ---- mj_checkPos / mj_checkVel: NaN or |x| > 1e10 resets mjData (qpos0, zero velocity, time 0)
@@ -827,7 +831,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
     int keep_rows = drop ? 0 : nr;
     nrow += wsum(keep_rows);
   }
-  if (NS * 32 < NROW && nrow > NS * 32) return B2H_STEP_MORE_ROWS;   // warp-uniform
+  if (NS * 32 < NROW && nrow > (NS == 1 && nrow_s < 32 ? nrow_s : NS * 32)) return B2H_STEP_MORE_ROWS;   // warp-uniform
   wsync();
   // contact Jacobians (lane = dof): J_k[d] = frame_k . (jacp_body2[d] - jacp_body1[d]), mj_jac about the com
   for (int c = 0; c < ncon; c++) {

@@ -600,7 +600,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
     for (int k = 0; k < 3; k++) off[k] = com[k] - xanchor[3 * j + k];
     if (B2H_LDG(m.jnt_type[j]) == B2H_JNT_FREE) {
       int k = lane - B2H_LDG(m.jnt_dadr[j]);
-      if (k < 3) cd[3 + k] = 1;
+      if (k < 3) { cd[3] = k == 0 ? T(1) : T(0); cd[4] = k == 1 ? T(1) : T(0); cd[5] = k == 2 ? T(1) : T(0); }   // (static indices: cd stays in registers)
       else {
         const T* R = xmat + 9 * my_dbody;
         ax[0] = R[k - 3]; ax[1] = R[k]; ax[2] = R[k + 3];
@@ -695,8 +695,8 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
             if (cd_ <= margin + r2) {
               T dist = cd_ - r2;
               if (dist < margin) {
-                cdist[n] = dist;
-                for (int k = 0; k < 3; k++) { cnrm[n][k] = pn[k]; cpos[n][k] = c[k] - pn[k] * (dist * T(0.5) + r2); }
+                if (n == 0) { cdist[0] = dist; for (int k = 0; k < 3; k++) { cnrm[0][k] = pn[k]; cpos[0][k] = c[k] - pn[k] * (dist * T(0.5) + r2); } }
+                else { cdist[1] = dist; for (int k = 0; k < 3; k++) { cnrm[1][k] = pn[k]; cpos[1][k] = c[k] - pn[k] * (dist * T(0.5) + r2); } }
                 n++;
               }
             }
@@ -740,7 +740,8 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
                 }
                 T d[3] = {b[0] - a[0], b[1] - a[1], b[2] - a[2]};
                 if (dot3(d, d) <= mind * mind) {
-                  for (int k = 0; k < 3; k++) { v1[ncand][k] = a[k]; v2[ncand][k] = b[k]; }
+                  if (ncand == 0) { for (int k = 0; k < 3; k++) { v1[0][k] = a[k]; v2[0][k] = b[k]; } }
+                  else { for (int k = 0; k < 3; k++) { v1[1][k] = a[k]; v2[1][k] = b[k]; } }
                   ncand++;
                 }
               }
@@ -805,8 +806,10 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
   int nrow = 0;
   T ten_pos[KT];   // signed distance of an active tendon limit (uniform)
   int ten_row[KT], ten_side[KT];
-  for (int t = 0; t < B2H_LDG(m.ntendon); t++) {
+#pragma unroll
+  for (int t = 0; t < KT; t++) {
     ten_row[t] = -1; ten_side[t] = 0; ten_pos[t] = 0;
+    if (t >= B2H_LDG(m.ntendon)) continue;
     T len = wsum(lane < nq ? B2H_LDG(m.ten_qcoef[t][lane]) * st.qp : T(0));
     if (B2H_LDG(m.ten_limited[t])) {
       T lo = B2H_LDG(m.ten_range[t][0]), hi = B2H_LDG(m.ten_range[t][1]), mg = B2H_LDG(m.ten_margin[t]);
@@ -884,7 +887,10 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
         int t = -1 - rc;
         sr0 = B2H_LDG(m.ten_solref[t][0]); sr1 = B2H_LDG(m.ten_solref[t][1]);
         for (int k = 0; k < 5; k++) si[k] = B2H_LDG(m.ten_solimp[t][k]);
-        pos = ten_pos[t]; mg = B2H_LDG(m.ten_margin[t]); dA = B2H_LDG(m.ten_invw[t]);
+        pos = 0;
+#pragma unroll
+        for (int k = 0; k < KT; k++) if (k == t) pos = ten_pos[k];
+        mg = B2H_LDG(m.ten_margin[t]); dA = B2H_LDG(m.ten_invw[t]);
       } else {
         uint32_t info = S.con_info[rc];
         int cls = info >> 16;
@@ -1193,7 +1199,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
               T bestcost = 0; int best = -1;
               for (int i = 0; i < 3; i++)
                 if (m_abs(cand[i].d0) < gtol && (best == -1 || cand[i].cost < bestcost)) { bestcost = cand[i].cost; best = i; }
-              if (best >= 0) { alpha = cand[best].alpha; done = true; break; }
+              if (best >= 0) { alpha = best == 0 ? cand[0].alpha : best == 1 ? cand[1].alpha : cand[2].alpha; done = true; break; }
               int b1 = 0, b2 = 0;
               for (int i = 0; i < 3; i++) {
                 if (p1.d0 < T(0) && cand[i].d0 < T(0) && p1.d0 < cand[i].d0) { p1 = cand[i]; b1 = 1; }
@@ -1284,7 +1290,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
       normalize4(q);
       T out[4];
       mul_quat(out, q, qr);
-      st.qp = out[lane - 3];
+      st.qp = lane == 3 ? out[0] : lane == 4 ? out[1] : lane == 5 ? out[2] : out[3];
     }
   }
   st.nstep++;

@@ -60,7 +60,7 @@ __device__ __forceinline__ void flush_counters(const Counters& c, unsigned long 
   }
 }
 
-template <typename T>
+template <typename T, int OUT>
 __global__ void __launch_bounds__(max_threads<T>(), 1)
 step_kernel(const DevModel<T>* __restrict__ gmodel, EnvParams P, EnvIO<T> io, int n_envs, unsigned long long* counters,
             int* work, T* spill, const int* __restrict__ perm) {
@@ -83,7 +83,7 @@ step_kernel(const DevModel<T>* __restrict__ gmodel, EnvParams P, EnvIO<T> io, in
     const int slot = base + (threadIdx.x >> 5);
     const bool active = slot < n_envs;
     const int env = active ? (perm ? perm[slot] : slot) : 0;
-    env_step<T>(*model, S, Jspill, cnt, P, io, env, active);
+    env_step<T, OUT>(*model, S, Jspill, cnt, P, io, env, active);
   }
 #ifdef B2H_STAGE_CLOCKS
   if (threadIdx.x == 0) {  // when this CTA ran out of work (tail imbalance of the launch)
@@ -314,7 +314,8 @@ static int create_typed(B2HHandle* h) {
   h->smem = (size_t)warps * scratch_bytes<T>(nrow_s) + msm;
   h->grid = nsm * ctas_per_sm;
   CU(cudaMalloc(&h->spill, (size_t)(h->grid * warps + 1) * (NROW - nrow_s) * LD * sizeof(T)));
-  CU(cudaFuncSetAttribute(step_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  CU(cudaFuncSetAttribute(step_kernel<T, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  CU(cudaFuncSetAttribute(step_kernel<T, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   CU(cudaFuncSetAttribute(reset_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
   CU(cudaFuncSetAttribute(debug_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(Scratch<T>) + msm)));
   return B2H_OK;
@@ -425,14 +426,14 @@ static int launch_step(B2HHandle* h, const float* actions_dev, void* obs_dev, vo
   const bool sched = h->schedule && h->P.sync_mode == 2 && h->cfg.n_envs > h->warps;
   if (!sched || !h->work_armed) CU(cudaMemsetAsync(h->work, 0, 4, s));   // otherwise the last sort re-armed the claim counter
   const int* perm = sched && h->perm_valid ? h->perm : nullptr;   // order of the previous step's efforts (first step: env-id order)
-  if (h->cfg.dtype == B2H_F64)
-    step_kernel<double><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<double>*)h->dmodel, h->P,
-        make_io<double>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, o64), h->cfg.n_envs,
-        h->counters, h->work, (double*)h->spill, perm);
-  else
-    step_kernel<float><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<float>*)h->dmodel, h->P,
-        make_io<float>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, o64), h->cfg.n_envs,
-        h->counters, h->work, (float*)h->spill, perm);
+  // one instantiation per result kind: the arithmetic-type arrays (device rollouts, b2h_step_host) or the float64 VecEnv ones
+#define B2H_LAUNCH_STEP(T, OUT) step_kernel<T, OUT><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<T>*)h->dmodel, h->P, \
+      make_io<T>(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, o64), h->cfg.n_envs, \
+      h->counters, h->work, (T*)h->spill, perm)
+  const bool out64 = o64.obs != nullptr;
+  if (h->cfg.dtype == B2H_F64) { if (out64) B2H_LAUNCH_STEP(double, 1); else B2H_LAUNCH_STEP(double, 0); }
+  else { if (out64) B2H_LAUNCH_STEP(float, 1); else B2H_LAUNCH_STEP(float, 0); }
+#undef B2H_LAUNCH_STEP
   CU(cudaGetLastError());
   h->launches++;
   if (h->step_done) CU(cudaEventRecord(h->step_done, s));   // results are complete here; the sort below is for the next step

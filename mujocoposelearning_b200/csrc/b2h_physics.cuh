@@ -1438,9 +1438,12 @@ B2H_DEV_NOINLINE void env_reset(const DevModel<T>& m, Scratch<T>& S, T* Jspill, 
 }
 
 // HumanoidEnv.step + SubprocVecEnv auto-reset for one env (custom_env.py:152-230; SB3 subproc_vec_env._worker)
-template <typename T>
+// OUT: which result arrays this instantiation writes -- 0 the arithmetic-type ones (io.obs, ...), 1 the float64
+// VecEnv ones (io.obs64, ...), -1 whichever are non-null (the unused variants then sit in the claim loop's stream).
+template <typename T, int OUT = -1>
 B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& cnt, const EnvParams& P, const EnvIO<T>& io, int env,
                       bool active) {
+  constexpr bool kOutT = OUT != 1, kOut64 = OUT != 0;
   // All warps of a CTA enter every sub-step together (cta_sync): they then walk the same instructions at about
   // the same time, which keeps the (large, mostly straight-line) step code resident in the instruction cache.
   // `active` is warp-uniform; inactive warps (tail of the env list) only take part in the barriers.
@@ -1481,13 +1484,13 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     bool terminated = (double)st.nstep * P.timestep >= P.duration;
     total = io.total_reward[env] + reward;
     if (lane == 0) {
-      if (io.reward) io.reward[env] = reward;
-      if (io.reward64) io.reward64[env] = (double)reward;
+      if (kOutT && io.reward) io.reward[env] = reward;
+      if (kOut64 && io.reward64) io.reward64[env] = (double)reward;
       io.terminated[env] = terminated; io.truncated[env] = truncated;
     }
     done = terminated || truncated;
-    if (done && io.terminal_obs) write_obs(m, S, st, P.obs_mode, io.terminal_obs + (size_t)env * io.obs_dim, lane);
-    if (done && io.terminal_obs64) write_obs(m, S, st, P.obs_mode, io.terminal_obs64 + (size_t)env * io.obs_dim, lane);
+    if (kOutT && done && io.terminal_obs) write_obs(m, S, st, P.obs_mode, io.terminal_obs + (size_t)env * io.obs_dim, lane);
+    if (kOut64 && done && io.terminal_obs64) write_obs(m, S, st, P.obs_mode, io.terminal_obs64 + (size_t)env * io.obs_dim, lane);
   }
   B2H_CLK_ADD(9, te);
   if (P.sync_mode == 2) cta_sync();
@@ -1497,8 +1500,8 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     step_count = 0; total = 0;
   }
   if (active) {
-    if (io.obs) write_obs(m, S, st, P.obs_mode, io.obs + (size_t)env * io.obs_dim, lane);
-    if (io.obs64) write_obs(m, S, st, P.obs_mode, io.obs64 + (size_t)env * io.obs_dim, lane);
+    if (kOutT && io.obs) write_obs(m, S, st, P.obs_mode, io.obs + (size_t)env * io.obs_dim, lane);
+    if (kOut64 && io.obs64) write_obs(m, S, st, P.obs_mode, io.obs64 + (size_t)env * io.obs_dim, lane);
     if (lane < nq) io.qpos[(size_t)env * nq + lane] = st.qp;
     if (lane < nv) { io.qvel[(size_t)env * nv + lane] = st.qv; io.warm[(size_t)env * nv + lane] = st.warm; }
     if (lane == 0) {

@@ -83,7 +83,11 @@ step_kernel(const DevModel<T>* __restrict__ gmodel, EnvParams P, EnvIO<T> io, in
     const int slot = base + (threadIdx.x >> 5);
     const bool active = slot < n_envs;
     const int env = active ? (perm ? perm[slot] : slot) : 0;
-    env_step<T, OUT>(*model, S, Jspill, cnt, P, io, env, active);
+    // row slots of the group: what the neediest of its envs used in its previous control step (plus a margin); an env
+    // that outgrows them falls back on its own (mj_step)
+    const int rows = active && io.work ? (int)((unsigned)io.work[env] >> B2H_EFFORT_BITS) : 0;
+    const int ns = __syncthreads_or(rows > 60) ? 3 : (__syncthreads_or(rows > 28) ? 2 : 1);
+    env_step<T, OUT>(*model, S, Jspill, cnt, P, io, env, active, ns);
   }
 #ifdef B2H_STAGE_CLOCKS
   if (threadIdx.x == 0) {  // when this CTA ran out of work (tail imbalance of the launch)
@@ -99,12 +103,15 @@ step_kernel(const DevModel<T>* __restrict__ gmodel, EnvParams P, EnvIO<T> io, in
 // Which warp steps which env never changes a result; the order inside a bucket is left to the atomics.
 // It also re-arms the claim counter of the next step launch (no memset node on the stream).
 constexpr int ORDER_BUCKETS = 256;
+__device__ __forceinline__ int order_bucket(int packed) {   // the solver effort (EnvIO::work also carries the row hint)
+  return min((int)((unsigned)packed & B2H_EFFORT_MASK) >> 2, ORDER_BUCKETS - 1);
+}
 __global__ void __launch_bounds__(1024, 1) order_kernel(const int* __restrict__ effort, int n, int* __restrict__ perm, int* work) {
   __shared__ int hist[ORDER_BUCKETS], start[ORDER_BUCKETS];
   if (threadIdx.x == 0) *work = 0;
   for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) hist[i] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[min(effort[i] >> 2, ORDER_BUCKETS - 1)], 1);
+  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[order_bucket(effort[i])], 1);
   __syncthreads();
   if (threadIdx.x < 32) {  // exclusive prefix over the buckets in descending order: 8 buckets per lane + one warp scan
     constexpr int PER = ORDER_BUCKETS / 32;
@@ -118,7 +125,7 @@ __global__ void __launch_bounds__(1024, 1) order_kernel(const int* __restrict__ 
     for (int k = 0; k < PER; k++) start[top - k] = incl - sum + loc[k];
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[atomicAdd(&start[min(effort[i] >> 2, ORDER_BUCKETS - 1)], 1)] = i;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[atomicAdd(&start[order_bucket(effort[i])], 1)] = i;
 }
 
 template <typename T>

@@ -234,9 +234,12 @@ constexpr int TMP_DOFW = 0, TMP_DOFA = TMP_DOFW + KV * 6, TMP_CFRC = TMP_DOFA + 
 static_assert(TMP_CRB + KB * 10 <= LD * LD, "position-stage scratch must fit in A");
 static_assert(TMP_CDD + KV * 6 <= LD * LD, "velocity-stage scratch must fit in A");
 
+constexpr int B2H_EFFORT_BITS = 20;   // EnvIO::work packs the effort (low bits) and the rows of the last control step
+constexpr unsigned B2H_EFFORT_MASK = (1u << B2H_EFFORT_BITS) - 1u;
 struct Counters {  // per-warp tallies of one launch (32-bit: a warp sees a few thousand events), flushed with atomics
   unsigned physics_steps, contact_overflow, iter_cap, bad_state, newton_iter, ls_eval;
   unsigned work;  // solver effort of the env in flight (Newton iterations weighted by row slots): next launch's schedule key
+  unsigned rows;  // most dense constraint rows of a physics step of the env in flight: next launch's slot-count hint
 #ifdef B2H_STAGE_CLOCKS
   long long clk[48];  // tuning build: cycles per stage (tools/stage_clocks.py)
 #endif
@@ -835,6 +838,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
     nrow += wsum(keep_rows);
   }
   if (NS * 32 < NROW && nrow > (NS == 1 && nrow_s < 32 ? nrow_s : NS * 32)) return B2H_STEP_MORE_ROWS;   // warp-uniform
+  cnt.rows = (unsigned)nrow > cnt.rows ? (unsigned)nrow : cnt.rows;
   wsync();
   // contact Jacobians (lane = dof): J_k[d] = frame_k . (jacp_body2[d] - jacp_body1[d]), mj_jac about the com
   for (int c = 0; c < ncon; c++) {
@@ -1299,10 +1303,15 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
   B2H_CLK_ADD(3, tc);
   return B2H_STEP_OK;
 }
+// ns: slots to start with (warp-uniform; the step kernel makes it CTA-uniform from the rows the group's envs needed in
+// their previous control step, so that a lockstep group walks ONE instantiation); too few slots fall back to all.
 template <typename T>
-B2H_DEV void mj_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt) {
+B2H_DEV void mj_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, int ns = 1) {
   for (int tries = 0; tries < 2; tries++) {
-    int rc = physics_step<T, false, 1>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
+    int rc;
+    if (ns <= 1) rc = physics_step<T, false, 1>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
+    else if (ns == 2) rc = physics_step<T, false, 2>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
+    else rc = B2H_STEP_MORE_ROWS;
     if (rc == B2H_STEP_MORE_ROWS) rc = physics_step<T, false, NSLOT>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
     if (rc == B2H_STEP_OK) break;
   }
@@ -1442,7 +1451,7 @@ B2H_DEV_NOINLINE void env_reset(const DevModel<T>& m, Scratch<T>& S, T* Jspill, 
 // VecEnv ones (io.obs64, ...), -1 whichever are non-null (the unused variants then sit in the claim loop's stream).
 template <typename T, int OUT = -1>
 B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& cnt, const EnvParams& P, const EnvIO<T>& io, int env,
-                      bool active) {
+                      bool active, int ns = 1 /* row slots the lockstep group starts with, see mj_step */) {
   constexpr bool kOutT = OUT != 1, kOut64 = OUT != 0;
   // All warps of a CTA enter every sub-step together (cta_sync): they then walk the same instructions at about
   // the same time, which keeps the (large, mostly straight-line) step code resident in the instruction cache.
@@ -1462,7 +1471,7 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     if (a >= 0) action = T(io.actions[(size_t)env * nu + a]);
     step_count = io.step_count[env] + 1;
   }
-  cnt.work = 0;
+  cnt.work = 0; cnt.rows = 0;
   B2H_CLK(te);
   if (P.sync_mode == 1) cta_sync();
   for (int s = 0; s < P.frame_skip; s++) {
@@ -1472,7 +1481,7 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     if (active) {
       // data.ctrl[:] = action before every mj_step (a bad-state reset inside the previous sub-step zeroed it)
       st.ctrl = action;
-      mj_step<T>(m, S, Jspill, st, cnt);
+      mj_step<T>(m, S, Jspill, st, cnt, ns);
     }
   }
   bool done = false;
@@ -1506,7 +1515,7 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     if (lane < nv) { io.qvel[(size_t)env * nv + lane] = st.qv; io.warm[(size_t)env * nv + lane] = st.warm; }
     if (lane == 0) {
       io.nstep[env] = st.nstep; io.step_count[env] = step_count; io.total_reward[env] = total;
-      if (io.work) io.work[env] = (int)cnt.work;
+      if (io.work) io.work[env] = (int)((cnt.work & B2H_EFFORT_MASK) | (cnt.rows << B2H_EFFORT_BITS));
     }
   }
   B2H_CLK_ADD(9, te);

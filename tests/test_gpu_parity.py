@@ -352,6 +352,22 @@ def test_large_batch_launch_shape_parity(cm, model_struct, dtype, n, shape, tol)
         assert _rel(obs[i], o) < k * tol * 20 and abs(r - rew[i]) < max(tol, 1e-5)
     c = b.counters()
     assert c["bad_state"] == 0 and c["contact_overflow"] == 0 and c["physics_steps"] == 3 * n
+    # second control step: the lockstep groups now start in the row-slot instantiation their envs' first step asked for
+    # (one slot for the upright envs, two or three for the prone ones) instead of falling back env by env; the oracle
+    # starts from the states the first step left on the device
+    act2 = rng.uniform(-1, 1, (n, cm.nu)).astype(np.float32)
+    obs2, rew2, _, _ = b.step(torch.as_tensor(act2).cuda())
+    got2, obs2, rew2 = b.get_state(), obs2.cpu().numpy().astype(np.float64), rew2.cpu().numpy().astype(np.float64)
+    for i in sample:
+        e = OracleEnv(model_struct, cm.nq, cm.nv, cm.nu)
+        e.set_state(got["qpos"][i], got["qvel"][i], got["warmstart"][i], int(got["nstep"][i]), int(got["step_count"][i]))
+        o, r, t, tr = e.env_step(act2[i], frame_skip=3, duration=10.0, reward_type=0)
+        s = e.get_state()
+        k = 20 if (dtype == "f32" and lying[i]) else 1
+        assert _rel(got2["qpos"][i], s["qpos"]) < k * tol and _rel(got2["qvel"][i], s["qvel"]) < k * tol * 10, (int(i), _rel(got2["qpos"][i], s["qpos"]), _rel(got2["qvel"][i], s["qvel"]))
+        assert _rel(obs2[i], o) < k * tol * 20 and abs(r - rew2[i]) < max(tol, 1e-5)
+    c = b.counters()
+    assert c["bad_state"] == 0 and c["contact_overflow"] == 0 and c["physics_steps"] == 6 * n
     b.close()
 
 

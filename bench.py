@@ -7,6 +7,10 @@ One "step" = one control step of all envs = frame_skip physics steps per env, th
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--n-envs E] [--dtype f32|f64] [--impl reference]
 
+Timed state: the envs' episode phases are spread uniformly over the 667-step episode by an untimed pre-roll
+(`stagger`), so every timed window -- 20 steps or 2000 -- sees the episode-average workload (upright, falling, prone,
+and E/667 auto-resets per step) instead of whatever phase `--warmup` happens to leave the synchronised batch in.
+
 Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` goes through the
 public VecEnv.step (host numpy actions in, host numpy obs/reward/done out, pinned staging, copies inside the
 timed region); `cpu_baseline` times the CPU oracle port on the box's host cores on a bounded sample;
@@ -34,6 +38,9 @@ FRAME_SKIP, DURATION, REWARD = 3, 10.0, "stand"
 BYTES_PER_PHYSICS_STEP = 724.0
 FLOP_PER_PHYSICS_STEP = 1.0e5
 FP32_NOMINAL_TFLOPS = 74.5
+EPISODE_STEPS = 667          # control steps per episode: time = (1 + 3 n) h >= 10 s first at n = 667
+CPU_NOTE = ("dense fp64 C port of mj_step written for clarity (oracle/humanoid_oracle.c), one pthread per core, no Python in the "
+            "loop: NOT MuJoCo's sparse engine (faster per core) and NOT the reference's Python + SubprocVecEnv pipe path (slower)")
 
 
 def parse():
@@ -47,17 +54,32 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="tuning runs: only the device-timed leg (no e2e / policy / CPU legs)")
+    ap.add_argument("--no-stagger", action="store_true", help="keep the batch's episodes synchronised (SURVEY 8d C3 as written); the "
+                    "timed window then depends on --warmup / --steps")
     return ap.parse_args()
 
 
 def workload_config(args, world):
     return {"workload": f"random-action rollout, humanoid `stand`, {args.n_envs} envs/GPU, frame_skip {FRAME_SKIP}, duration {DURATION}s "
                         f"(BASELINE config 3)", "n_envs_per_gpu": args.n_envs, "frame_skip": FRAME_SKIP, "obs_dim": 352,
-            "parallelism": f"env-sharded x{world} (no data-path collective)", "l2": "256 MiB device memset between timed steps (outside the event pairs)"}
+            "parallelism": f"env-sharded x{world} (no data-path collective)", "l2": "256 MiB device memset between timed steps (outside the event pairs)",
+            "episode_phase": "synchronised (as reset)" if args.no_stagger else f"staggered uniformly over the {EPISODE_STEPS}-step episode by an untimed pre-roll"}
 
 
 # ------------------------------------------------------------------------------------------------ CPU (oracle) legs
-def cpu_rollout(n_envs, nthreads, budget_s, seed=0, min_steps=2):
+def cpu_stagger(env, rng, n_envs, nqv, nu):
+    """Untimed pre-roll of the CPU arm: env i is reset again at pre-roll step i * 667 // n, so the episode phases end up
+    spread uniformly (the same timed state as the B200 arm)."""
+    phase = np.arange(n_envs) * EPISODE_STEPS // n_envs
+    noise = rng.uniform(-0.01, 0.01, (n_envs, nqv))
+    for t in range(EPISODE_STEPS):
+        if t:
+            for i in np.nonzero(phase == t)[0]:
+                env.envs[i].env_reset(noise[i])
+        env.step(rng.uniform(-1, 1, (n_envs, nu)).astype(np.float32), noise)
+
+
+def cpu_rollout(n_envs, nthreads, budget_s, seed=0, min_steps=2, stagger=True):
     """Times the CPU oracle port (SubprocVecEnv semantics, one pthread per core, no Python in the loop)."""
     from mujocoposelearning_b200.abi import pack_model
     from mujocoposelearning_b200.mjcf import compile_mjcf
@@ -67,6 +89,8 @@ def cpu_rollout(n_envs, nthreads, budget_s, seed=0, min_steps=2):
                        nthreads=nthreads)
     rng = np.random.default_rng(seed)
     env.reset(rng.uniform(-0.01, 0.01, (n_envs, cm.nq + cm.nv)))
+    if stagger:
+        cpu_stagger(env, rng, n_envs, cm.nq + cm.nv, cm.nu)
     noise = rng.uniform(-0.01, 0.01, (n_envs, cm.nq + cm.nv))
     acts = rng.uniform(-1, 1, (8, n_envs, cm.nu)).astype(np.float32)
     env.step(acts[0], noise)  # warm-up
@@ -92,10 +116,11 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     n_envs = args.n_envs
     # bounded sample: time warm-up + K steps of the full env count if one step stays under ~2 s, else fewer envs
-    v, steps, dt = cpu_rollout(min(n_envs, 8 * cores), cores, 1.0)
+    v, steps, dt = cpu_rollout(min(n_envs, 8 * cores), cores, 1.0, stagger=False)
     est_step = n_envs * FRAME_SKIP / v
-    if est_step * (args.steps + args.warmup) > 150.0:
-        n_envs = max(cores, int(150.0 * v / (FRAME_SKIP * (args.steps + args.warmup))))
+    total_steps = args.steps + args.warmup + (0 if args.no_stagger else EPISODE_STEPS)
+    if est_step * total_steps > 150.0:
+        n_envs = max(cores, int(150.0 * v / (FRAME_SKIP * total_steps)))
     from mujocoposelearning_b200.abi import pack_model
     from mujocoposelearning_b200.mjcf import compile_mjcf
     from oracle.oracle import OracleVecEnv
@@ -103,6 +128,8 @@ def run_reference(args):
     env = OracleVecEnv(pack_model(cm), cm.nq, cm.nv, cm.nu, n_envs, frame_skip=FRAME_SKIP, duration=DURATION, reward_type=0, nthreads=cores)
     rng = np.random.default_rng(0)
     env.reset(rng.uniform(-0.01, 0.01, (n_envs, cm.nq + cm.nv)))
+    if not args.no_stagger:
+        cpu_stagger(env, rng, n_envs, cm.nq + cm.nv, cm.nu)
     noise = rng.uniform(-0.01, 0.01, (n_envs, cm.nq + cm.nv))
     acts = rng.uniform(-1, 1, (8, n_envs, cm.nu)).astype(np.float32)
     for i in range(args.warmup):
@@ -116,7 +143,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, 1),
-           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "note": CPU_NOTE},
            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out), flush=True)
 
@@ -159,10 +186,23 @@ class ClockSampler:
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm),
+                "window": "untimed pre-roll (same kernel, same load) + warm-up + timed region; 100 ms nvidia-smi samples"}
 
 
 # ------------------------------------------------------------------------------------------------ B200 arm
+def stagger(batch, pool):
+    """Untimed pre-roll: env i is reset again at pre-roll step i * 667 // E (masked b2h_reset), all envs keep stepping
+    with the workload's random actions; afterwards the steps-since-reset are uniform over the episode."""
+    import torch
+    E = batch.n_envs
+    phase = (torch.arange(E, device=batch.device, dtype=torch.int64) * EPISODE_STEPS) // E
+    for t in range(EPISODE_STEPS):
+        if t:
+            batch.reset((phase == t).to(torch.uint8))
+        batch.step(pool[t % pool.shape[0]])
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -194,14 +234,17 @@ def run_b200(args):
     if os.environ.get("B2H_BENCH_IDENTICAL"):   # tuning experiment: every env gets the same noise and actions (no work variance)
         pool = pool[:, :1].expand(16, E, batch.nu).contiguous()
         batch.set_reset_noise(np.tile(np.random.default_rng(0).uniform(-0.01, 0.01, (1, batch.nq + batch.nv)), (E, 1)))
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    t_load = time.perf_counter()
     batch.reset()
+    if not args.no_stagger:
+        stagger(batch, pool)
     for i in range(W):
         batch.step(pool[i % 16])
     torch.cuda.synchronize()
     c0 = batch.counters()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     if world > 1:
@@ -219,7 +262,7 @@ def run_b200(args):
     t1 = time.perf_counter()
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
     total_ms = float(step_ms.sum())
-    clocks = sampler.stop(t0, t1) if rank == 0 else None
+    clocks = sampler.stop(t_load, t1) if rank == 0 else None
     c1 = batch.counters()
     if args.quick:
         if rank == 0:
@@ -232,6 +275,8 @@ def run_b200(args):
     # ---- e2e: the public VecEnv.step with host numpy actions / results (pinned staging, copies timed)
     venv = B200HumanoidVecEnv(env_cfg, n_envs=E, device=local, dtype=args.dtype, seed=99, env_id_offset=rank * E, info_mode="lazy")
     venv.reset()
+    if not args.no_stagger:
+        stagger(venv.batch, pool)
     host_actions = np.random.default_rng(rank).uniform(-1, 1, (8, E, batch.nu)).astype(np.float32)
     for i in range(W):
         venv.step(host_actions[i % 8])
@@ -250,6 +295,8 @@ def run_b200(args):
         v32 = B200HumanoidVecEnv(env_cfg, n_envs=E, device=local, dtype="f32", seed=99, env_id_offset=rank * E, info_mode="lazy",
                                  obs_dtype="float32")
         v32.reset()
+        if not args.no_stagger:
+            stagger(v32.batch, pool)
         for i in range(W):
             v32.step(host_actions[i % 8])
         torch.cuda.synchronize()
@@ -288,6 +335,8 @@ def run_b200(args):
     b53 = HumanoidBatch(E, frame_skip=FRAME_SKIP, duration=DURATION, reward_type=REWARD, dtype=args.dtype, device=local,
                         seed=1234, env_id_offset=rank * E, obs_mode="qpos_qvel")
     b53.reset()
+    if not args.no_stagger:
+        stagger(b53, pool)
     for i in range(W):
         b53.step(pool[i % 16])
     K53 = max(10, K // 4)
@@ -321,7 +370,8 @@ def run_b200(args):
     psteps = c1["physics_steps"] - c0["physics_steps"]
     traffic, issue = None, None
     try:   # dram bytes / warp instructions of one step-kernel launch from the committed ncu capture (same env count only)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        tname = "r02_traffic.json" if os.path.exists(os.path.join(ROOT, "profiles", "r02_traffic.json")) else "r01_traffic.json"
+        tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
         if tj["n_envs"] == E and args.dtype == "f32":
             traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
             sm_hz = 1e6 * float((clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0))
@@ -344,12 +394,16 @@ def run_b200(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": kernel_ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": workload_config(args, world),
-        "roofline": {"bound": "hbm", "achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
-                     "traffic": traffic, "algorithmic_bytes_per_launch": BYTES_PER_PHYSICS_STEP * E * FRAME_SKIP, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback",
-                     "note": "latency/issue-bound irregular FP32 work, not HBM-bound (SURVEY 8d); see fp32 block",
-                     "fp32": {"achieved_tflops": fp32_tflops, "peak_tflops": fp32_peak, "peak_source": fp32_src,
-                              "nominal_peak_tflops": FP32_NOMINAL_TFLOPS, "frac": fp32_tflops / fp32_peak,
-                              "flop_per_physics_step": FLOP_PER_PHYSICS_STEP},
+        # the path is FP32 issue / latency-bound: the headline roofline is the FP32 pipe against the FFMA peak
+        # measured on this GPU; the HBM figure the base contract asks for is the sub-block
+        "roofline": {"bound": "fp32", "achieved": fp32_tflops, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_tflops / fp32_peak,
+                     "traffic": traffic, "peak_source": fp32_src, "nominal_peak_tflops": FP32_NOMINAL_TFLOPS,
+                     "flop_per_physics_step": FLOP_PER_PHYSICS_STEP, "algorithmic_flop_per_launch": FLOP_PER_PHYSICS_STEP * E * FRAME_SKIP,
+                     "kernel": "step_kernel<float, 0> (one launch per control step)",
+                     "note": "irregular FP32 work bound by instruction issue and dependent latency, not by HBM (see hbm / issue)",
+                     "hbm": {"achieved": achieved_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": achieved_gbs / hbm_peak,
+                             "algorithmic_bytes_per_launch": BYTES_PER_PHYSICS_STEP * E * FRAME_SKIP,
+                             "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (measured)" if peaks else "fallback"},
                      "issue": issue},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": Ke,
                 "api": "B200HumanoidVecEnv.step (numpy in/out, lazy infos)",
@@ -371,7 +425,7 @@ def run_b200(args):
         cores = os.cpu_count() or 1
         nenv = min(E, 8 * cores)
         v, steps, dt = cpu_rollout(nenv, cores, args.cpu_seconds)
-        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+        out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "note": CPU_NOTE,
                                "sample": f"{nenv} envs x {steps} control steps x frame_skip {FRAME_SKIP} in {dt:.1f}s, oracle port on {cores} threads"}
     print(json.dumps(out), flush=True)
     if world > 1:

@@ -227,6 +227,7 @@ struct B2HHandle {
   int schedule = 1;                        // 1: lockstep groups follow the effort-sorted order
   bool perm_valid = false;
   bool work_armed = false;                 // the claim counter was zeroed by the sort that followed the previous step launch
+  cudaStream_t armed_stream = nullptr;     // ... on this stream: a step on another stream zeroes the counter itself
   cudaEvent_t step_done = nullptr;         // recorded after the step kernel (b2h_step_vecenv waits on it, not on the sort)
   void* dump = nullptr;
   void* spill = nullptr;  // per-warp dense rows beyond NROW_S
@@ -431,7 +432,8 @@ int b2h_reset(B2HHandle* h, const uint8_t* mask_dev, void* obs_dev, void* stream
 static int launch_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward_dev, uint8_t* terminated_dev,
                        uint8_t* truncated_dev, void* terminal_obs_dev, Out64 o64, cudaStream_t s) {
   const bool sched = h->schedule && h->P.sync_mode == 2 && h->cfg.n_envs > h->warps;
-  if (!sched || !h->work_armed) CU(cudaMemsetAsync(h->work, 0, 4, s));   // otherwise the last sort re-armed the claim counter
+  // the last sort re-armed the claim counter -- in stream order, so only a launch on that same stream may rely on it
+  if (!sched || !h->work_armed || h->armed_stream != s) CU(cudaMemsetAsync(h->work, 0, 4, s));
   const int* perm = sched && h->perm_valid ? h->perm : nullptr;   // order of the previous step's efforts (first step: env-id order)
   // one instantiation per result kind: the arithmetic-type arrays (device rollouts, b2h_step_host) or the float64 VecEnv ones
 #define B2H_LAUNCH_STEP(T, OUT) step_kernel<T, OUT><<<h->grid, h->warps * 32, h->smem, s>>>((const DevModel<T>*)h->dmodel, h->P, \
@@ -449,6 +451,7 @@ static int launch_step(B2HHandle* h, const float* actions_dev, void* obs_dev, vo
     CU(cudaGetLastError());
     h->perm_valid = true;
     h->work_armed = true;
+    h->armed_stream = s;
     h->launches++;
   }
   return B2H_OK;

@@ -137,9 +137,9 @@ std::string build_dev_model(const B2HModel& m, DevModel<T>& d) {
     for (int k = 0; k < 4; k++) d.body_quat[b][k] = (T)m.body_quat[b][k];
     for (int k = 0; k < 6; k++) d.body_inertia[b][k] = (T)m.body_inertia_full[b][k];
     d.body_mass[b] = (T)m.body_mass[b];
-    int w = b;  // mj_diagApprox uses the weld body's translational invweight0
-    while (w > 0 && m.body_jntnum[w] == 0) w = m.body_parentid[w];
-    d.body_invw[b] = (T)m.body_invweight0[w][0];
+    // mj_diagApprox (engine_core_constraint.c, contact cases) indexes body_invweight0 with geom_bodyid itself, not with
+    // the weld parent: a jointless child (head, hands) carries its own value  [UNVERIFIED-vs-3.2.5, see oracle]
+    d.body_invw[b] = (T)m.body_invweight0[b][0];
   }
   for (int k = 0; k < KQ; k++) d.qpos_dof[k] = -1;
   for (int i = 0; i < KV; i++) { d.dof_parent[i] = -1; d.dof_vparent[i] = -1; d.dof_act[i] = -1; d.dof_qadr[i] = 0; d.dof_cdotzero[i] = 1; }

@@ -335,6 +335,38 @@ template <typename T> B2H_DEV void st4(T* p, T x, T y, T z, T w) {
 template <typename T>
 B2H_DEV_NOINLINE T chol_solve_fused(T* A, int n, int lane, T b) {
   constexpr int N = KV - 1;
+#if defined(B2H_HOST_EMU) && defined(B2H_EXP_CHOL_F64)
+  // EXPERIMENT (CPU lane emulation only): the same factor + solve carried in double, to separate
+  // the round-off of the fp32 solve from the round-off already present in its fp32 inputs (M, J, D, right-hand side)
+  if constexpr (sizeof(T) == 4) {
+    static double D[LD * LD];
+    if (lane < LD) A[N * LD + lane] = lane < n ? b : T(0);
+    if (lane >= n && lane < N) A[lane * LD + lane] = 1;
+    wsync();
+    double a[LD];
+    for (int c = 0; c < LD; c++) a[c] = (double)A[(lane < LD ? lane : 0) * LD + c];
+    wsync();
+    for (int j = 0; j < N; j++) {
+      if (lane < LD) D[j * LD + lane] = a[j];
+      wsync();
+      double piv = D[j * LD + j] > 1e-15 ? D[j * LD + j] : 1e-15, r = 1.0 / sqrt(piv), lr = a[j] * r * r;
+      a[j] = a[j] * r;
+      for (int k = j + 1; k < N; k++) a[k] -= lr * D[j * LD + k];
+    }
+    wsync();
+    if (lane < LD) for (int c = 0; c < LD; c++) D[lane * LD + c] = a[c];
+    wsync();
+    const int me = lane < N ? lane : 0;
+    double dinv = 1.0 / D[me * LD + me], y = D[N * LD + me], acc = 0;
+    for (int k = N - 1; k > 0; k--) {
+      double xk = shfl((y - acc) * dinv, k);
+      if (lane < k) acc += D[k * LD + lane] * xk;
+    }
+    double x = (y - acc) * dinv;
+    wsync();
+    return lane < n ? (T)x : T(0);
+  }
+#endif
   if (lane < LD) A[N * LD + lane] = lane < n ? b : T(0);
   if (lane >= n && lane < N) A[lane * LD + lane] = 1;  // unused dof slots factor as identity
   wsync();

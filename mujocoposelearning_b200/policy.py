@@ -157,7 +157,8 @@ class RolloutCollector:
             mean, value = pol.forward(self.last_obs)
             actions, clipped, logp = pol.sample(mean, self.num_timesteps // b.n_envs, self.det)
             obs, rew, term, trunc = b.step(clipped)
-            rew = rew.to(torch.float32).clone()
+            raw = rew.to(torch.float32)      # what the env returned: episode statistics use this (SB3's Monitor does too)
+            rew = raw.clone()
             done = (term | trunc).to(torch.float32)
             if self.can_truncate:   # bootstrap with V(terminal_obs) where the episode was cut by the step limit only
                 tl = (trunc.bool() & ~term.bool()).to(torch.float32)
@@ -168,7 +169,7 @@ class RolloutCollector:
             self.values[t].copy_(value)
             self.log_probs[t].copy_(logp)
             self.episode_starts[t].copy_(self.last_episode_starts)
-            self.ep_return += rew
+            self.ep_return += raw
             self.ep_len += 1
             self.stats += torch.stack([(self.ep_return * done).sum(), (self.ep_len * done).sum(), done.sum()]).to(torch.float64)
             self.ep_return *= 1 - done

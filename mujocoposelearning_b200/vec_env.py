@@ -69,8 +69,8 @@ def _make_batch(cfg, n_envs, device, dtype, obs_mode, seed, env_id_offset):
     rc = cfg["reward_config"] or {"type": "default"}
     import os
     mp = cfg["model_path"]
-    if mp is not None and not os.path.exists(mp):
-        mp = None  # the packaged humanoid is the model the reference ships (XML/humanoid.xml)
+    if mp is not None and not os.path.exists(mp):   # mujoco.MjModel.from_xml_path raises here too (custom_env.py:53)
+        raise FileNotFoundError(f"model_path {mp!r} does not exist (pass None for the packaged XML/humanoid.xml)")
     return HumanoidBatch(n_envs, model_path=mp, frame_skip=cfg["frame_skip"], duration=float(cfg["duration"]),
                          reward_type=rc.get("type", "default"), reward_params=rc.get("params"), obs_mode=obs_mode,
                          dtype=dtype, device=device, seed=seed, env_id_offset=env_id_offset)

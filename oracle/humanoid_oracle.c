@@ -473,10 +473,6 @@ static void collision(OrcEnv* d) {
 }
 
 /* ------------------------------------------------------------------------------------------ constraints */
-static int body_weldid(const B2HModel* m, int b) {
-  while (b > 0 && m->body_jntnum[b] == 0) b = m->body_parentid[b];
-  return b;
-}
 /* translational Jacobian of `point` on `body` (mj_jac) */
 static void jac_point(const OrcEnv* d, double jacp[3][NV], const double* point, int body) {
   const B2HModel* m = &d->m;
@@ -547,8 +543,12 @@ static void make_constraint(OrcEnv* d) {
       for (int k = 0; k < nv; k++)
         jc[r][k] = c->frame[3 * r] * (j2[0][k] - j1[0][k]) + c->frame[3 * r + 1] * (j2[1][k] - j1[1][k]) +
                    c->frame[3 * r + 2] * (j2[2][k] - j1[2][k]);
-    int w1 = body_weldid(m, b1), w2 = body_weldid(m, b2);
-    double tran = m->body_invweight0[w1][0] + m->body_invweight0[w2][0];
+    /* [UNVERIFIED-vs-3.2.5] mj_diagApprox (engine_core_constraint.c, contact cases): the body weights are indexed
+       with the geoms' own bodies, `bid = m->geom_bodyid[con->geom[side]]; tran += m->body_invweight0[2*bid]` --
+       NOT the weld parent.  mj_setConst computes a distinct body_invweight0 for a jointless child (head, hands:
+       mj_jacBodyCom at its own inertial frame), so the two readings differ for head / hand contacts.  Round 1 used
+       the weld body; round 2 follows the upstream indexing as recalled from the 2.x and 3.x sources. */
+    double tran = m->body_invweight0[b1][0] + m->body_invweight0[b2][0];
     c->efc_address = d->nefc;
     if (c->dim == 1) {
       memset(J, 0, sizeof J);

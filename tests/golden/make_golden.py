@@ -191,14 +191,19 @@ def make_env_fixtures():
     # truncation at step 750 needs duration > 11.255 s: jump the counters instead of stepping 750 times
     np.random.seed(15)
     env = HumanoidEnv({"model_path": xml, "duration": 30.0, "frame_skip": 3, "reward_config": {"type": "stand"}})
+    np.random.seed(15)                # the draws of the reset inside __init__: pos first, then vel (custom_env.py:109-110)
+    noise = np.concatenate([np.random.uniform(-0.01, 0.01, 28), np.random.uniform(-0.01, 0.01, 27)])
     env.step_count = 748
-    rows = []
+    rows, obs, acts = [], [], []
+    rng = np.random.default_rng(15)
     for k in range(2):
-        o, r, te, tr, info = env.step(np.zeros(21, np.float32))
+        a = np.clip(rng.normal(0, 0.7, 21), -1, 1).astype(np.float32)
+        o, r, te, tr, info = env.step(a)
         rows.append((r, te, tr, info["step_count"]))
-    np.savez_compressed(OUT / "env_truncation.npz", rows=np.array(rows, dtype=np.float64))
+        obs.append(o); acts.append(a)
+    np.savez_compressed(OUT / "env_truncation.npz", rows=np.array(rows, dtype=np.float64), reset_noise=noise,
+                        actions=np.array(acts), obs=np.array(obs), frame_skip=3, duration=30.0, reward_type="stand")
     print("env_truncation", rows)
-
 
 if __name__ == "__main__":
     if not REF.exists():

@@ -137,3 +137,24 @@ def test_reference_keyframe_state_step_f64(cm, model_struct, idx):
     assert np.abs(obs[0] - o).max() < 1e-9 * max(1.0, np.abs(o).max()) and abs(rew[0] - r) < 1e-10
     s = e.get_state()
     assert np.abs(emu.qpos[0] - s["qpos"]).max() < 1e-9 and np.abs(emu.qvel[0] - s["qvel"]).max() < 1e-8
+
+
+def test_truncation_branch_f64(cm, model_struct):
+    """custom_env.py:201-213 on the kernel source: at step_count 750 the env truncates (not terminates), the reward is
+    exactly 0.0 and the reward function is skipped, the terminal observation is the last one of the episode and the env
+    auto-resets (fixture recorded through the reference's own HumanoidEnv class, duration 30 s)."""
+    g = np.load(GOLD / "env_truncation.npz")
+    emu = EmuBatch(model_struct, make_config(1, frame_skip=3, reward_type="stand", dtype="f64", duration=30.0), cm.nq, cm.nv, cm.nu)
+    emu.set_reset_noise(g["reset_noise"])
+    emu.reset()
+    emu.step_count[0] = 748
+    rows = g["rows"]
+    for k in range(2):
+        emu.set_reset_noise(g["reset_noise"])
+        obs, rew, term, trunc, tobs = emu.step(g["actions"][k][None])
+        assert bool(term[0]) == bool(rows[k][1]) and bool(trunc[0]) == bool(rows[k][2])
+        last = tobs[0] if trunc[0] else obs[0]
+        assert np.abs(last - g["obs"][k]).max() < 1e-9 * max(1.0, np.abs(g["obs"][k]).max())
+        assert abs(rew[0] - rows[k][0]) < 1e-10
+    assert trunc[0] and not term[0] and rew[0] == 0.0
+    assert emu.step_count[0] == 0 and emu.nstep[0] == 1 and emu.total_reward[0] == 0.0     # auto-reset happened

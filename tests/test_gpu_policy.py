@@ -122,3 +122,31 @@ def test_ppo_minibatch_update_matches_sb3_recipe():
     for got, want in zip(tr.tensors, ref):
         assert float((got - want).abs().max()) < 2e-6
     b.close()
+
+
+def test_rollout_collector_timeout_bootstrap():
+    """OnPolicyAlgorithm.collect_rollouts (SB3 2.3.2): where an episode is cut by the step limit only
+    (TimeLimit.truncated) the stored reward is the env reward plus gamma * V(terminal_observation); the episode
+    statistics keep the raw env reward (custom_env.py:201-206 sets it to 0.0 on that step)."""
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams, RolloutCollector
+    n = 64
+    b = HumanoidBatch(n, frame_skip=3, duration=30.0, reward_type="stand", seed=6)
+    pol = MlpPolicy(MlpPolicyParams(seed=2), seed=4)
+    col = RolloutCollector(b, pol, n_steps=4)
+    assert col.can_truncate
+    col.reset()
+    b.set_state(step_count=np.full(n, 747, np.int32))
+    col.collect()
+    torch.cuda.synchronize()
+    pol.check_error()
+    es = col.episode_starts.cpu().numpy()
+    assert es[0].all() and es[3].all() and not es[1].any() and not es[2].any()      # truncated on the third step (750)
+    _, v_term = pol.forward_torch(b.terminal_obs.to(torch.float32))                 # rows of the step that truncated
+    want = 0.99 * v_term
+    assert float((col.rewards[2] - want).abs().max()) < 2e-5 * max(1.0, float(want.abs().max()))
+    assert float(col.rewards[2].abs().min()) > 0 and float(col.rewards[:2].min()) > 0
+    ep = col.stats.cpu().numpy()                                                     # sum of returns, sum of lengths, episodes
+    raw_return = float(col.rewards[:2].sum())                                        # the truncating step's env reward is 0.0
+    assert ep[2] == n and ep[1] == 3 * n and abs(ep[0] - raw_return) < 1e-3 * max(1.0, abs(raw_return))
+    b.close()

@@ -49,15 +49,19 @@ def test_env_semantics_match_reference_class(env, name):
 
 
 def test_truncation_at_step_750(env, cm):
-    g = np.load(GOLD / "env_truncation.npz")["rows"]
-    np.random.seed(15)
-    env.env_reset(np.zeros(55))
+    """custom_env.py:201-206: step_count >= 750 truncates, forces the reward to 0.0 and skips the reward function."""
+    g = np.load(GOLD / "env_truncation.npz")
+    rows = g["rows"]
+    env.env_reset(g["reset_noise"])
     env.set_state(step_count=748)
     for k in range(2):
-        o, r, te, tr = env.env_step(np.zeros(21, np.float32), frame_skip=3, duration=30.0, reward_type=0)
-        assert (te, tr, env.get_state()["step_count"]) == (bool(g[k][1]), bool(g[k][2]), int(g[k][3]))
+        o, r, te, tr = env.env_step(g["actions"][k], frame_skip=3, duration=30.0, reward_type=0)
+        assert (te, tr, env.get_state()["step_count"]) == (bool(rows[k][1]), bool(rows[k][2]), int(rows[k][3]))
+        np.testing.assert_allclose(o, g["obs"][k], rtol=0, atol=1e-11)
+        assert abs(r - rows[k][0]) < 1e-13
         if tr:
             assert r == 0.0                                   # reward forced to 0 at truncation (quirk D5)
+    assert bool(rows[1][2]) and not bool(rows[0][2]) and not bool(rows[1][1])
 
 
 def test_episode_length_is_667_control_steps(env):

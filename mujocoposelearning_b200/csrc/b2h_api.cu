@@ -315,6 +315,7 @@ static int create_typed(B2HHandle* h) {
     ctas_per_sm = (int)((size_t)max_smem / ((size_t)warps * scratch_bytes<T>(nrow_s) + msm));
     if (ctas_per_sm * warps > maxw) ctas_per_sm = maxw / warps;
     if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (const char* c = getenv("B2H_CTAS_PER_SM")) { int req = atoi(c); if (req >= 1 && req < ctas_per_sm) ctas_per_sm = req; }
   }
   dm->nrow_s = nrow_s;
   CU(cudaMemcpy(h->dmodel, dm, sizeof(DevModel<T>), cudaMemcpyHostToDevice));

@@ -145,6 +145,7 @@ class CompiledModel:
                 f"mass={self.body_mass.sum():.4f}")
 
 
+# [UNVERIFIED-vs-3.2.5] capsule mass / inertia closed form (user_objects.cc mjCGeom::SetInertia)
 def _capsule_inertia(r, half, density):
     """Solid capsule about its centre, axis z (MuJoCo user_objects.cc mjCGeom::SetInertia)."""
     height = 2 * half
@@ -203,7 +204,7 @@ def compile_mjcf(path=None) -> CompiledModel:
             quat = z_to_quat(_floats(a["zaxis"]))
         if "fromto" in a and gtype == GEOM_CAPSULE:
             ft = _floats(a["fromto"])
-            vec = ft[0:3] - ft[3:6]  # MuJoCo orients geom z from 'to' towards 'from'
+            vec = ft[0:3] - ft[3:6]  # MuJoCo orients geom z from 'to' towards 'from'  [UNVERIFIED-vs-3.2.5: sign of the axis]
             size = np.array([size[0], np.linalg.norm(vec) / 2, 0.0])
             pos = 0.5 * (ft[0:3] + ft[3:6])
             quat = z_to_quat(vec)
@@ -454,6 +455,7 @@ def compile_mjcf(path=None) -> CompiledModel:
     m.actuator_ctrlrange = np.array([a["ctrlrange"] for a in acts]).reshape(-1, 2)
     m.actuator_ctrllimited = np.array([a["ctrllimited"] for a in acts], dtype=np.int32)
     # ---- collision candidates (engine_collision_driver.c filtering, all static for this subset)
+    # [UNVERIFIED-vs-3.2.5] same body / same weld id / weld-parent-child (neither the world) / <exclude>; contype & conaffinity either way
     bname = {b["name"]: i for i, b in enumerate(bodies)}
     excludes = set()
     con = root.find("contact")
@@ -493,6 +495,7 @@ def compile_mjcf(path=None) -> CompiledModel:
     m.pair_solimp = np.zeros((m.npair, 5))
     m.pair_margin = np.zeros(m.npair)
     m.pair_gap = np.zeros(m.npair)
+    # [UNVERIFIED-vs-3.2.5] mj_contactParam: condim / friction / margin / gap = max, solref / solimp mixed with solmix weights (equal priority)
     for i, (a, b) in enumerate(pairs):
         ga, gb = geoms[a], geoms[b]
         if ga["priority"] != gb["priority"]:
@@ -606,6 +609,9 @@ def mass_matrix_np(m: CompiledModel, qpos):
     return M, cdof, k
 
 
+# [UNVERIFIED-vs-3.2.5] mj_setConst: dof_invweight0 = diag(M^-1) with the free joint's translational / rotational triples averaged,
+# body_invweight0 = mean diagonal of J M^-1 J^T at the body's own inertial frame (every body, welded children included),
+# tendon_invweight0 = J M^-1 J^T, meaninertia = trace(M) / nv
 def _set_const(m: CompiledModel):
     M, cdof, k = mass_matrix_np(m, m.qpos0)
     Minv = np.linalg.inv(M)

@@ -191,6 +191,7 @@ static void chol_solve(double* x, double L[NV][NV], const double* b, int n) {
 
 /* ------------------------------------------------------------------------------------------ position */
 /* mj_kinematics (engine_core_smooth.c) */
+/* [UNVERIFIED-vs-3.2.5] mj_kinematics: hinge anchor bookkeeping (xpos corrected so that the anchor stays fixed), quaternion renormalisation points */
 static void kinematics(OrcEnv* d) {
   const B2HModel* m = &d->m;
   memset(d->xpos[0], 0, sizeof d->xpos[0]);
@@ -258,6 +259,7 @@ static int body_rootid(const B2HModel* m, int b) {
 }
 
 /* mj_comPos: subtree_com, cinert (mju_inertCom), cdof (mju_dofCom) */
+/* [UNVERIFIED-vs-3.2.5] mj_comPos: cinert about the subtree com via mju_inertCom, cdof via mju_dofCom (free joint: world-axis translations, body-axis rotations) */
 static void com_pos(OrcEnv* d) {
   const B2HModel* m = &d->m;
   memset(d->subtree_com, 0, sizeof d->subtree_com);
@@ -368,6 +370,7 @@ static int plane_sphere(OrcContact* c, double margin, const double* ppos, const 
   c->frame[3] = c->frame[4] = c->frame[5] = 0;
   return 1;
 }
+/* [UNVERIFIED-vs-3.2.5] mjc_PlaneCapsule: two end-sphere tests in the order +axis, -axis; contact frame seeded with the capsule axis as second axis */
 static int plane_capsule(OrcContact* c, double margin, const double* ppos, const double* pmat, const double* cpos,
                          const double* cmat, const double* size) {
   double axis[3] = {cmat[2], cmat[5], cmat[8]}, pos[3];
@@ -388,6 +391,7 @@ static int sphere_capsule(OrcContact* c, double margin, const double* spos, doub
   double pos[3] = {cpos[0] + axis[0] * x, cpos[1] + axis[1] * x, cpos[2] + axis[2] * x};
   return sphere_sphere(c, margin, spos, sr, pos, size[0]);
 }
+/* [UNVERIFIED-vs-3.2.5] mjc_CapsuleCapsule: closest-point solve (ma, mb, mc, u, v, det), clamping order, parallel-axis branch (|det| < mjMINVAL: up to two contacts) */
 static int capsule_capsule(OrcContact* c, double margin, const double* pos1, const double* mat1, const double* size1,
                            const double* pos2, const double* mat2, const double* size2) {
   double axis1[3] = {mat1[2], mat1[5], mat1[8]}, axis2[3] = {mat2[2], mat2[5], mat2[8]};
@@ -422,6 +426,7 @@ static int capsule_capsule(OrcContact* c, double margin, const double* pos1, con
   }
   return n;
 }
+/* [UNVERIFIED-vs-3.2.5] mju_makeFrame: fallback second axis (y unless |normal.y| >= 0.5, then z), Gram-Schmidt, third = cross */
 static void make_frame(double* f) { /* mju_makeFrame */
   normalize3(f);
   if (sqrt(dot3(f + 3, f + 3)) < 0.5) {
@@ -435,6 +440,7 @@ static void make_frame(double* f) { /* mju_makeFrame */
 }
 
 /* mj_collision over the static candidate list (engine_collision_driver.c; broadphase only culls) */
+/* [UNVERIFIED-vs-3.2.5] mj_collision: contact ORDER follows this repo's pair list (mjcf.py), which may differ from MuJoCo's body-pair sweep; order changes no result, only summation order */
 static void collision(OrcEnv* d) {
   const B2HModel* m = &d->m;
   d->ncon = 0;
@@ -494,6 +500,7 @@ static int add_row(OrcEnv* d, const double* J, double pos, double margin, int ty
   d->efc_diagApprox[r] = diagApprox;
   return r;
 }
+/* [UNVERIFIED-vs-3.2.5] getimpedance: x = |pos - margin| / width, power curve with midpoint, clamps at 0 / 1 */
 static void get_impedance(const double* solimp, double pos, double margin, double* imp) {
   if (solimp[0] == solimp[1] || solimp[2] <= MINVAL) { *imp = 0.5 * (solimp[0] + solimp[1]); return; }
   double x = fabs((pos - margin) / solimp[2]);
@@ -505,6 +512,7 @@ static void get_impedance(const double* solimp, double pos, double margin, doubl
   *imp = solimp[0] + y * (solimp[1] - solimp[0]);
 }
 /* mj_makeConstraint: limits (joint, tendon) then contacts; then mj_makeImpedance */
+/* [UNVERIFIED-vs-3.2.5] mj_makeConstraint / mj_makeImpedance / mj_diagApprox: limit distance and Jacobian sign, pyramidal rows (n + mu t, n - mu t per tangent), diagApprox = tran (+ mu^2 tran), refsafe clamp, K / B from solref with dmax, R = max(mjMINVAL, (1 - imp) / imp * diagApprox), pyramidal Rpy = 2 mu^2 R[first row] */
 static void make_constraint(OrcEnv* d) {
   const B2HModel* m = &d->m;
   int nv = m->nv;
@@ -607,6 +615,7 @@ static void make_constraint(OrcEnv* d) {
 }
 
 /* ------------------------------------------------------------------------------------------ velocity */
+/* [UNVERIFIED-vs-3.2.5] mj_comVel: free-joint special case (translational cdof_dot = 0, the three rotational ones see cvel after the translations only) */
 static void com_vel(OrcEnv* d) { /* mj_comVel */
   const B2HModel* m = &d->m;
   memset(d->cvel[0], 0, sizeof d->cvel[0]);
@@ -641,6 +650,7 @@ static void passive(OrcEnv* d) { /* mj_passive: joint springs and dampers only *
     d->qfrc_passive[m->jnt_dofadr[j]] += -m->jnt_stiffness[j] * (d->qpos[qa] - m->qpos_spring[qa]);
   }
 }
+/* [UNVERIFIED-vs-3.2.5] aref = -B vel - K imp (pos - margin) */
 static void reference_constraint(OrcEnv* d) { /* mj_referenceConstraint */
   int nv = d->m.nv;
   for (int i = 0; i < d->nefc; i++) {
@@ -772,6 +782,7 @@ static int update_bracket(Primal* c, PrimalPnt* p, const PrimalPnt cand[3], Prim
   return flag;
 }
 /* PrimalSearch (engine_solver.c): exact line search on the piecewise-quadratic cost along `search` */
+/* [UNVERIFIED-vs-3.2.5] PrimalSearch (engine_solver.c): gtol = tolerance * ls_tolerance * snorm / scale, bracketing with p1 / p2 / midpoint candidates, the exit rules */
 static double primal_search(Primal* c, double tolerance, double ls_tolerance, int ls_iterations) {
   OrcEnv* d = c->d;
   int nv = c->nv;
@@ -833,6 +844,7 @@ static double primal_search(Primal* c, double tolerance, double ls_tolerance, in
 }
 
 /* mj_fwdConstraint: warmstart selection + mj_solNewton (solver Newton, 100 iterations, tolerance 1e-8) */
+/* [UNVERIFIED-vs-3.2.5] mj_fwdConstraint + mj_solNewton: warm start = the cheaper of qacc_warmstart and qacc_smooth, scale = 1 / (meaninertia * max(1, nv)), stop on improvement or gradient < tolerance */
 static void fwd_constraint(OrcEnv* d) {
   const B2HModel* m = &d->m;
   int nv = m->nv, nefc = d->nefc;
@@ -925,6 +937,7 @@ void orc_forward(OrcEnv* d) { /* mj_forward */
   com_vel(d); passive(d); reference_constraint(d); rne_bias(d);
   actuation(d); acceleration(d); fwd_constraint(d);
 }
+/* [UNVERIFIED-vs-3.2.5] mj_Euler: implicit damping (M + h B) qacc = qfrc_smooth + qfrc_constraint whenever a dof has damping and eulerdamp is on; mj_advance: qvel first, then qpos with the NEW qvel; qacc_warmstart = qacc of the unmodified forward pass */
 static void euler(OrcEnv* d) { /* mj_Euler with implicit joint damping + mj_advance */
   const B2HModel* m = &d->m;
   int nv = m->nv;

@@ -331,6 +331,30 @@ def run_b200(args):
     pol.check_error()
     mlp_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 1]) for i in range(Kp))
     pol_ms = sum(ev[3 * i].elapsed_time(ev[3 * i + 2]) for i in range(Kp))
+    # ---- collect_rollouts + GAE as the library runs it (P1: one foreign call per rollout, CUDA graph, buffers written in place)
+    from mujocoposelearning_b200.policy import RolloutCollector
+    T_ROLL = 64
+    col = RolloutCollector(batch, pol, n_steps=T_ROLL, cuda_graph=True)
+    col.start_from_current()
+    col.collect()                                    # captures the graph and runs one rollout (warm-up)
+    torch.cuda.synchronize()
+    R = max(2, min(8, K // T_ROLL))
+    cev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    cev[0].record()
+    for _ in range(R):
+        col.collect()
+    cev[1].record()
+    torch.cuda.synchronize()
+    col.check_error()
+    col_ms = cev[0].elapsed_time(cev[1])
+    col_launches = 5 if col.can_truncate else 4      # graph nodes per control step: MLP, sampler, env step, record + effort sort (+ V(terminal_obs))
+    ceg = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    col.collect_eager()
+    ceg[0].record()
+    col.collect_eager()
+    ceg[1].record()
+    torch.cuda.synchronize()
+    col_eager_ms = ceg[0].elapsed_time(ceg[1])
     # ---- the same rollout with the 53-column observation (qpos[2:] | qvel; SURVEY 8d C3 asks for both), rank-0 time
     b53 = HumanoidBatch(E, frame_skip=FRAME_SKIP, duration=DURATION, reward_type=REWARD, dtype=args.dtype, device=local,
                         seed=1234, env_id_offset=rank * E, obs_mode="qpos_qvel")
@@ -417,6 +441,11 @@ def run_b200(args):
         "policy_rollout": {"value": world * E * FRAME_SKIP * Kp / (pol_ms * 1e-3), "unit": UNIT, "ms_per_step": pol_ms / Kp,
                            "mlp_and_sampling_ms_per_step": mlp_ms / Kp, "steps": Kp,
                            "what": "random-init 2x256 ReLU pi/vf MLP forward (tcgen05, tf32 hi/lo split) + Gaussian sampling + b2h_step; rank-0 time"},
+        "collect_rollouts": {"value": world * E * FRAME_SKIP * T_ROLL * R / (col_ms * 1e-3), "unit": UNIT, "n_steps": T_ROLL, "rollouts": R,
+                             "ms_per_step": col_ms / (R * T_ROLL), "kernel_launches_per_control_step": col_launches,
+                             "op_by_op_python_loop": {"value": world * E * FRAME_SKIP * T_ROLL / (col_eager_ms * 1e-3), "ms_per_step": col_eager_ms / T_ROLL},
+                             "what": "b2h_rollout_collect: policy/value MLP + sampling + env step + buffer record for 64 steps, last values and GAE, "
+                                     "one CUDA graph per rollout (SB3 collect_rollouts + compute_returns_and_advantage); rank-0 time"},
         "obs_qpos_qvel": {"value": world * E * FRAME_SKIP / (ms53 * 1e-3), "unit": UNIT, "ms_per_step": ms53, "steps": K53,
                           "what": "same rollout, 53-column observation (control steps W..W+steps of the first episode); rank-0 time"},
         "launch": batch.launch_info(), "step_ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],

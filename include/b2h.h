@@ -17,6 +17,7 @@
  *   b2h_get_state/set     MjData.qpos/qvel/qacc_warmstart/time field access  custom_env.py:105-117,242-246
  *   b2h_gae               RolloutBuffer.compute_returns_and_advantage (SB3 2.3.2), driven by
  *                         model.learn()                                      train_sb3.py:228
+ *   b2h_rollout_collect   collect_rollouts + GAE as one device-resident loop (SB3 2.3.2)  train_sb3.py:228
  *   b2h_mlp_forward / b2h_policy_forward / b2h_policy_sample
  *                         MlpPolicy forward + DiagGaussian sampling during collect_rollouts (SB3 2.3.2)
  *                                                                           train_sb3.py:208-214
@@ -254,6 +255,53 @@ const char* b2h_mlp_last_error(void);
  * eps is Philox4x32-10 keyed by (seed, row_offset + row, step); deterministic != 0 gives actions = mean. */
 int b2h_policy_sample(const float* mean_dev, const float* log_std_dev, int n_rows, int act_dim, uint64_t seed, uint64_t step,
                       int row_offset, int deterministic, float* actions_dev, float* clipped_dev, float* log_prob_dev, void* stream);
+
+/* As b2h_policy_sample, with the step counter read from device memory (step = *step_dev + step_offset): a captured
+ * CUDA graph of the rollout loop then draws fresh noise on every replay. */
+int b2h_policy_sample_dev(const float* mean_dev, const float* log_std_dev, int n_rows, int act_dim, uint64_t seed,
+                          const uint64_t* step_dev, uint64_t step_offset, int row_offset, int deterministic, float* actions_dev,
+                          float* clipped_dev, float* log_prob_dev, void* stream);
+
+/* OnPolicyAlgorithm.collect_rollouts + RolloutBuffer.compute_returns_and_advantage (SB3 2.3.2, driven by
+ * train_sb3.py:228) for n_steps control steps, entirely on the device and without a host round trip per step:
+ *   per step t: policy / value forward on obs[t] (tcgen05) -> DiagGaussian sample -> clip -> env step -> record.
+ * The kernels write the SB3 buffer layout in place: the step kernel puts the next observation into obs[t + 1] and
+ * the reward into rewards[t]; the sampler puts the raw action into actions[t] and its log-probability into
+ * log_probs[t]; the value head writes values[t]; the record kernel (fused with the effort sort that follows every
+ * step launch) writes episode_starts[t + 1] = done, adds gamma * V(terminal_obs) to the reward where the episode was
+ * cut by the step limit only (TimeLimit.truncated), and keeps the episode statistics (raw env rewards, as SB3's
+ * Monitor would).  Four kernel launches per control step (five with the time-limit bootstrap).  Then
+ * last_values = V(obs[n_steps]) and the GAE scan.  Slot 0 of obs / episode_starts is the caller's carry-over from the
+ * previous rollout (copy slot n_steps there, or fill it after b2h_reset).  float32 build (dtype B2H_F32) only.
+ * All pointers are device pointers owned by the caller. */
+typedef struct B2HRollout {
+  int32_t n_steps;
+  int32_t hidden, precise, deterministic, row_offset, bootstrap_timeouts;
+  uint64_t seed;
+  double gamma, gae_lambda;
+  float* obs;             /* [n_steps + 1, E, obs_dim]                                    */
+  float* actions;         /* [n_steps, E, nu]  raw (unclipped) actions                     */
+  float* rewards;         /* [n_steps, E]                                                  */
+  float* values;          /* [n_steps, E]                                                  */
+  float* log_probs;       /* [n_steps, E]                                                  */
+  float* episode_starts;  /* [n_steps + 1, E]                                              */
+  float* advantages;      /* [n_steps, E]                                                  */
+  float* returns;         /* [n_steps, E]                                                  */
+  float* last_values;     /* [E]                                                           */
+  float* mean;            /* [E, nu] scratch                                               */
+  float* clipped;         /* [E, nu] scratch                                               */
+  float* v_term;          /* [E] scratch (bootstrap_timeouts != 0)                         */
+  float* ep_return;       /* [E] running return of the episode in flight                   */
+  float* ep_len;          /* [E] running length                                            */
+  double* stats;          /* [4] sum of finished returns, sum of lengths, episodes, unused */
+  uint64_t* step_counter; /* [1] control steps taken so far (sampling noise counter)       */
+  int32_t* mlp_error;     /* [1] set by the MLP kernel if its tensor pipeline timed out    */
+  const float* pi[6];     /* W1 b1 W2 b2 W3 b3 of the policy network                       */
+  const float* vf[6];     /* ... of the value network                                      */
+  const float* log_std;   /* [nu]                                                          */
+} B2HRollout;
+size_t b2h_sizeof_rollout(void);
+int b2h_rollout_collect(B2HHandle* h, const B2HRollout* r, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,6 +56,19 @@ class B2HConfig(C.Structure):
     ]
 
 
+class B2HRollout(C.Structure):
+    """include/b2h.h B2HRollout: buffers (device pointers) and parameters of b2h_rollout_collect."""
+    _fields_ = [
+        ("n_steps", i32), ("hidden", i32), ("precise", i32), ("deterministic", i32), ("row_offset", i32), ("bootstrap_timeouts", i32),
+        ("seed", C.c_uint64), ("gamma", f64), ("gae_lambda", f64),
+        ("obs", C.c_void_p), ("actions", C.c_void_p), ("rewards", C.c_void_p), ("values", C.c_void_p), ("log_probs", C.c_void_p),
+        ("episode_starts", C.c_void_p), ("advantages", C.c_void_p), ("returns", C.c_void_p), ("last_values", C.c_void_p),
+        ("mean", C.c_void_p), ("clipped", C.c_void_p), ("v_term", C.c_void_p), ("ep_return", C.c_void_p), ("ep_len", C.c_void_p),
+        ("stats", C.c_void_p), ("step_counter", C.c_void_p), ("mlp_error", C.c_void_p),
+        ("pi", C.c_void_p * 6), ("vf", C.c_void_p * 6), ("log_std", C.c_void_p),
+    ]
+
+
 KNEELING_DEFAULTS = (1.282, 0.85, float(np.pi / 6), 0.1, 0.3, 0.3, 0.2, 0.1, 0.1)  # reward_functions.py:71-81
 KNEELING_KEYS = ("target_height", "min_height", "max_roll_pitch", "com_radius", "energy_weight", "posture_weight",
                  "com_weight", "foot_weight", "alive_weight")

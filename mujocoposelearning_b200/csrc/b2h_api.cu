@@ -106,26 +106,66 @@ constexpr int ORDER_BUCKETS = 256;
 __device__ __forceinline__ int order_bucket(int packed) {   // the solver effort (EnvIO::work also carries the row hint)
   return min((int)((unsigned)packed & B2H_EFFORT_MASK) >> 2, ORDER_BUCKETS - 1);
 }
-__global__ void __launch_bounds__(1024, 1) order_kernel(const int* __restrict__ effort, int n, int* __restrict__ perm, int* work) {
+// What collect_rollouts does with the result of one env.step (SB3 2.3.2 on_policy_algorithm.py), per env, after the step
+// kernel: episode_starts of the next slot, the time-limit bootstrap of the stored reward, the episode statistics.
+struct RecordArgs {
+  float* rewards_t;             // [E] slot t of the reward buffer (the step kernel wrote the env reward there)
+  float* episode_starts_next;   // [E] slot t + 1
+  const uint8_t *terminated, *truncated;
+  const float* v_term;          // [E] V(terminal_obs), or null (no step-limit truncation possible)
+  float gamma;
+  float *ep_return, *ep_len;    // [E]
+  double* stats;                // sum of finished returns, sum of finished lengths, finished episodes
+  unsigned long long* step_counter;
+};
+__global__ void __launch_bounds__(1024, 1) post_step_kernel(const int* __restrict__ effort, int n, int* __restrict__ perm, int* work,
+                                                            int do_sort, int do_record, RecordArgs rec) {
   __shared__ int hist[ORDER_BUCKETS], start[ORDER_BUCKETS];
-  if (threadIdx.x == 0) *work = 0;
-  for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) hist[i] = 0;
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[order_bucket(effort[i])], 1);
-  __syncthreads();
-  if (threadIdx.x < 32) {  // exclusive prefix over the buckets in descending order: 8 buckets per lane + one warp scan
-    constexpr int PER = ORDER_BUCKETS / 32;
-    const int lane = threadIdx.x, top = ORDER_BUCKETS - 1 - lane * PER;
-    int loc[PER], sum = 0;
+  __shared__ double red[3][32];
+  if (do_sort) {
+    if (threadIdx.x == 0) *work = 0;
+    for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[order_bucket(effort[i])], 1);
+    __syncthreads();
+    if (threadIdx.x < 32) {  // exclusive prefix over the buckets in descending order: 8 buckets per lane + one warp scan
+      constexpr int PER = ORDER_BUCKETS / 32;
+      const int lane = threadIdx.x, top = ORDER_BUCKETS - 1 - lane * PER;
+      int loc[PER], sum = 0;
 #pragma unroll
-    for (int k = 0; k < PER; k++) { loc[k] = sum; sum += hist[top - k]; }
-    int incl = sum;
-    for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+      for (int k = 0; k < PER; k++) { loc[k] = sum; sum += hist[top - k]; }
+      int incl = sum;
+      for (int o = 1; o < 32; o <<= 1) { int y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
 #pragma unroll
-    for (int k = 0; k < PER; k++) start[top - k] = incl - sum + loc[k];
+      for (int k = 0; k < PER; k++) start[top - k] = incl - sum + loc[k];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) perm[atomicAdd(&start[order_bucket(effort[i])], 1)] = i;
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) perm[atomicAdd(&start[order_bucket(effort[i])], 1)] = i;
+  if (do_record) {
+    double sr = 0, sl = 0, sn = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const float raw = rec.rewards_t[i];
+      const bool te = rec.terminated[i] != 0, tr = rec.truncated[i] != 0, done = te || tr;
+      if (rec.v_term && tr && !te) rec.rewards_t[i] = raw + rec.gamma * rec.v_term[i];   // TimeLimit.truncated: bootstrap
+      rec.episode_starts_next[i] = done ? 1.0f : 0.0f;
+      const float er = rec.ep_return[i] + raw, el = rec.ep_len[i] + 1.0f;   // statistics on the raw env reward
+      if (done) { sr += er; sl += el; sn += 1; }
+      rec.ep_return[i] = done ? 0.0f : er;
+      rec.ep_len[i] = done ? 0.0f : el;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      sr += __shfl_xor_sync(0xffffffffu, sr, o); sl += __shfl_xor_sync(0xffffffffu, sl, o); sn += __shfl_xor_sync(0xffffffffu, sn, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = sr; red[1][threadIdx.x >> 5] = sl; red[2][threadIdx.x >> 5] = sn; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+      double t = 0;
+      for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += red[threadIdx.x][w];
+      rec.stats[threadIdx.x] += t;
+    }
+    if (threadIdx.x == 0) *rec.step_counter += 1ull;
+  }
 }
 
 template <typename T>
@@ -173,12 +213,12 @@ debug_kernel(const DevModel<T>* model, EnvIO<T> io, int env, DebugDump<T>* out, 
 // Explicit _rn intrinsics keep the rounding sequence of the numpy float32 expression (no FMA contraction).
 __global__ void gae_kernel(const float* __restrict__ rewards, const float* __restrict__ values,
                            const float* __restrict__ episode_starts, const float* __restrict__ last_values,
-                           const uint8_t* __restrict__ dones, float gamma, float gl, int T, int E,
+                           const uint8_t* __restrict__ dones, const float* __restrict__ dones_f, float gamma, float gl, int T, int E,
                            float* __restrict__ adv, float* __restrict__ ret) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= E) return;
   float last_gae = 0.0f;
-  float nnt = 1.0f - (float)dones[e], nv = last_values[e];
+  float nnt = 1.0f - (dones ? (float)dones[e] : dones_f[e]), nv = last_values[e];   // last dones as bytes or as 0 / 1 floats
   for (int t = T - 1; t >= 0; t--) {
     size_t i = (size_t)t * E + e;
     float v = values[i];
@@ -430,8 +470,11 @@ int b2h_reset(B2HHandle* h, const uint8_t* mask_dev, void* obs_dev, void* stream
   return B2H_OK;
 }
 
-static int launch_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward_dev, uint8_t* terminated_dev,
-                       uint8_t* truncated_dev, void* terminal_obs_dev, Out64 o64, cudaStream_t s) {
+// A control step = the step kernel, then (on the same stream) whatever has to see its results before the next step:
+// the effort sort that orders the next launch's lockstep groups and re-arms its claim counter, and -- for the
+// device-resident rollout -- the record of collect_rollouts.  One small single-CTA kernel does both.
+static int launch_step_kernel(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward_dev, uint8_t* terminated_dev,
+                              uint8_t* truncated_dev, void* terminal_obs_dev, Out64 o64, cudaStream_t s) {
   const bool sched = h->schedule && h->P.sync_mode == 2 && h->cfg.n_envs > h->warps;
   // the last sort re-armed the claim counter -- in stream order, so only a launch on that same stream may rely on it
   if (!sched || !h->work_armed || h->armed_stream != s) CU(cudaMemsetAsync(h->work, 0, 4, s));
@@ -447,15 +490,22 @@ static int launch_step(B2HHandle* h, const float* actions_dev, void* obs_dev, vo
   CU(cudaGetLastError());
   h->launches++;
   if (h->step_done) CU(cudaEventRecord(h->step_done, s));   // results are complete here; the sort below is for the next step
-  if (sched) {  // sorted after the step instead of before the next one: it then overlaps the caller's host work
-    order_kernel<<<1, 1024, 0, s>>>(h->effort, h->cfg.n_envs, h->perm, h->work);
-    CU(cudaGetLastError());
-    h->perm_valid = true;
-    h->work_armed = true;
-    h->armed_stream = s;
-    h->launches++;
-  }
   return B2H_OK;
+}
+static int launch_post_step(B2HHandle* h, const RecordArgs* rec, cudaStream_t s) {
+  const bool sched = h->schedule && h->P.sync_mode == 2 && h->cfg.n_envs > h->warps;
+  if (!sched && !rec) return B2H_OK;
+  // sorted after the step instead of before the next one: it then overlaps the caller's host work
+  post_step_kernel<<<1, 1024, 0, s>>>(h->effort, h->cfg.n_envs, h->perm, h->work, sched ? 1 : 0, rec ? 1 : 0, rec ? *rec : RecordArgs());
+  CU(cudaGetLastError());
+  if (sched) { h->perm_valid = true; h->work_armed = true; h->armed_stream = s; }
+  h->launches++;
+  return B2H_OK;
+}
+static int launch_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward_dev, uint8_t* terminated_dev,
+                       uint8_t* truncated_dev, void* terminal_obs_dev, Out64 o64, cudaStream_t s) {
+  int rc = launch_step_kernel(h, actions_dev, obs_dev, reward_dev, terminated_dev, truncated_dev, terminal_obs_dev, o64, s);
+  return rc != B2H_OK ? rc : launch_post_step(h, nullptr, s);
 }
 
 int b2h_step(B2HHandle* h, const float* actions_dev, void* obs_dev, void* reward_dev, uint8_t* terminated_dev,
@@ -718,7 +768,56 @@ int b2h_gae(const float* rewards_dev, const float* values_dev, const float* epis
   if (T <= 0 || E <= 0) return fail(B2H_EINVAL, "T and E must be positive");
   // numpy float32 semantics: python-float scalars round to float32 once (gamma, and the double product gamma*lambda)
   gae_kernel<<<(E + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rewards_dev, values_dev, episode_starts_dev, last_values_dev,
-      last_dones_dev, (float)gamma, (float)(gamma * gae_lambda), T, E, advantages_dev, returns_dev);
+      last_dones_dev, nullptr, (float)gamma, (float)(gamma * gae_lambda), T, E, advantages_dev, returns_dev);
+  CU(cudaGetLastError());
+  return B2H_OK;
+}
+
+size_t b2h_sizeof_rollout(void) { return sizeof(B2HRollout); }
+
+int b2h_rollout_collect(B2HHandle* h, const B2HRollout* r, void* stream) {
+  if (!h || !r) return fail(B2H_EINVAL, "null argument");
+  if (h->cfg.dtype != B2H_F32) return fail(B2H_EUNSUPPORTED, "the device-resident rollout runs on the float32 build");
+  if (r->n_steps <= 0 || !r->obs || !r->actions || !r->rewards || !r->values || !r->log_probs || !r->episode_starts || !r->advantages ||
+      !r->returns || !r->last_values || !r->mean || !r->clipped || !r->ep_return || !r->ep_len || !r->stats || !r->step_counter ||
+      !r->mlp_error || !r->log_std || (r->bootstrap_timeouts && !r->v_term))
+    return fail(B2H_EINVAL, "null buffer in B2HRollout");
+  for (int k = 0; k < 6; k++) if (!r->pi[k] || !r->vf[k]) return fail(B2H_EINVAL, "null network parameter in B2HRollout");
+  CU(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t E = (size_t)h->cfg.n_envs, od = (size_t)h->obs_dim, nu = (size_t)h->nu;
+  const int T = r->n_steps;
+  for (int t = 0; t < T; t++) {
+    const float* obs_t = r->obs + (size_t)t * E * od;
+    int rc = b2h_policy_forward(obs_t, r->pi, r->vf, r->mean, r->values + (size_t)t * E, (int)E, (int)od, r->hidden, (int)nu, r->precise,
+                                r->mlp_error, stream);
+    if (rc != B2H_OK) return fail(rc, std::string("b2h_policy_forward: ") + b2h_mlp_last_error());
+    rc = b2h_policy_sample_dev(r->mean, r->log_std, (int)E, (int)nu, r->seed, r->step_counter, 0, r->row_offset, r->deterministic,
+                               r->actions + (size_t)t * E * nu, r->clipped, r->log_probs + (size_t)t * E, stream);
+    if (rc != B2H_OK) return fail(rc, std::string("b2h_policy_sample: ") + b2h_mlp_last_error());
+    // the env step writes the next observation and the reward straight into the rollout buffers
+    rc = launch_step_kernel(h, r->clipped, r->obs + (size_t)(t + 1) * E * od, r->rewards + (size_t)t * E, h->term_stage, h->trunc_stage,
+                            h->tobs_stage, Out64(), s);
+    if (rc != B2H_OK) return rc;
+    if (r->bootstrap_timeouts) {   // V(terminal_obs): rows of envs that did not finish are stale and unused
+      rc = b2h_mlp_forward((const float*)h->tobs_stage, r->vf[0], r->vf[1], r->vf[2], r->vf[3], r->vf[4], r->vf[5], r->v_term, (int)E,
+                           (int)od, r->hidden, 1, r->precise, r->mlp_error, stream);
+      if (rc != B2H_OK) return fail(rc, std::string("b2h_mlp_forward: ") + b2h_mlp_last_error());
+    }
+    RecordArgs rec;
+    rec.rewards_t = r->rewards + (size_t)t * E; rec.episode_starts_next = r->episode_starts + (size_t)(t + 1) * E;
+    rec.terminated = h->term_stage; rec.truncated = h->trunc_stage; rec.v_term = r->bootstrap_timeouts ? r->v_term : nullptr;
+    rec.gamma = (float)r->gamma; rec.ep_return = r->ep_return; rec.ep_len = r->ep_len; rec.stats = r->stats;
+    rec.step_counter = reinterpret_cast<unsigned long long*>(r->step_counter);
+    rc = launch_post_step(h, &rec, s);
+    if (rc != B2H_OK) return rc;
+  }
+  int rc = b2h_mlp_forward(r->obs + (size_t)T * E * od, r->vf[0], r->vf[1], r->vf[2], r->vf[3], r->vf[4], r->vf[5], r->last_values, (int)E,
+                           (int)od, r->hidden, 1, r->precise, r->mlp_error, stream);
+  if (rc != B2H_OK) return fail(rc, std::string("b2h_mlp_forward: ") + b2h_mlp_last_error());
+  // last dones = episode_starts[T] (the dones of the final step), as collect_rollouts passes them
+  gae_kernel<<<((int)E + 255) / 256, 256, 0, s>>>(r->rewards, r->values, r->episode_starts, r->last_values, nullptr, r->episode_starts + (size_t)T * E,
+                                                  (float)r->gamma, (float)(r->gamma * r->gae_lambda), T, (int)E, r->advantages, r->returns);
   CU(cudaGetLastError());
   return B2H_OK;
 }

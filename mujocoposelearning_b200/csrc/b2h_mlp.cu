@@ -469,9 +469,11 @@ __device__ __forceinline__ void philox(uint32_t c[4], uint32_t k0, uint32_t k1) 
 }
 __global__ void policy_sample_kernel(const float* __restrict__ mean, const float* __restrict__ log_std, int n_rows, int act_dim,
                                      unsigned long long seed, unsigned long long step, int row_offset, int deterministic,
-                                     float* __restrict__ actions, float* __restrict__ clipped, float* __restrict__ log_prob) {
+                                     float* __restrict__ actions, float* __restrict__ clipped, float* __restrict__ log_prob,
+                                     const unsigned long long* __restrict__ step_dev) {
   int row = blockIdx.x * blockDim.x + threadIdx.x;
   if (row >= n_rows) return;
+  if (step_dev) step += *step_dev;   // counter kept on the device (graph-captured rollout loops)
   float lp = 0.f;
   for (int j0 = 0; j0 < act_dim; j0 += 4) {
     uint32_t c[4] = {(uint32_t)(row + row_offset), (uint32_t)step, (uint32_t)(step >> 32), (uint32_t)(j0 >> 2) ^ 0x504F4C49u};
@@ -557,7 +559,18 @@ int b2h_policy_sample(const float* mean_dev, const float* log_std_dev, int n_row
                       int row_offset, int deterministic, float* actions_dev, float* clipped_dev, float* log_prob_dev, void* stream) {
   if (!mean_dev || !log_std_dev || !actions_dev || !clipped_dev || !log_prob_dev || n_rows <= 0 || act_dim <= 0) { g_err_mlp = "bad argument"; return B2H_EINVAL; }
   policy_sample_kernel<<<(n_rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean_dev, log_std_dev, n_rows, act_dim, seed, step,
-                                                                                row_offset, deterministic, actions_dev, clipped_dev, log_prob_dev);
+                                                                                row_offset, deterministic, actions_dev, clipped_dev, log_prob_dev, nullptr);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_err_mlp = cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
+}
+
+int b2h_policy_sample_dev(const float* mean_dev, const float* log_std_dev, int n_rows, int act_dim, uint64_t seed, const uint64_t* step_dev,
+                          uint64_t step_offset, int row_offset, int deterministic, float* actions_dev, float* clipped_dev,
+                          float* log_prob_dev, void* stream) {
+  if (!mean_dev || !log_std_dev || !actions_dev || !clipped_dev || !log_prob_dev || !step_dev || n_rows <= 0 || act_dim <= 0) { g_err_mlp = "bad argument"; return B2H_EINVAL; }
+  policy_sample_kernel<<<(n_rows + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean_dev, log_std_dev, n_rows, act_dim, seed, step_offset,
+      row_offset, deterministic, actions_dev, clipped_dev, log_prob_dev, reinterpret_cast<const unsigned long long*>(step_dev));
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_err_mlp = cudaGetErrorString(e); return B2H_ECUDA; }
   return B2H_OK;

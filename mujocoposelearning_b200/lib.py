@@ -42,6 +42,9 @@ SIGNATURES = {
     "b2h_policy_forward": (C.c_int, [vp, vp, vp, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "b2h_mlp_last_error": (C.c_char_p, []),
     "b2h_policy_sample": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "b2h_policy_sample_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_uint64, vp, C.c_uint64, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "b2h_sizeof_rollout": (C.c_size_t, []),
+    "b2h_rollout_collect": (C.c_int, [vp, C.POINTER(abi.B2HRollout), vp]),
 }
 
 
@@ -61,7 +64,8 @@ def load():
                 raise B2HError(f"libb2h.so does not export {name}")
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
-        if L.b2h_sizeof_model() != C.sizeof(abi.B2HModel) or L.b2h_sizeof_config() != C.sizeof(abi.B2HConfig):
+        if (L.b2h_sizeof_model() != C.sizeof(abi.B2HModel) or L.b2h_sizeof_config() != C.sizeof(abi.B2HConfig)
+                or L.b2h_sizeof_rollout() != C.sizeof(abi.B2HRollout)):
             raise B2HError("struct layout mismatch between abi.py and libb2h.so")
         _lib = L
     return _lib

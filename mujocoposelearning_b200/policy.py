@@ -124,38 +124,118 @@ class MlpPolicy:
 
 
 class RolloutCollector:
-    """collect_rollouts + GAE with the SB3 buffer layout ([T, E, ...] float32), all on the device."""
+    """collect_rollouts + GAE with the SB3 buffer layout ([T, E, ...] float32), all on the device.
 
-    def __init__(self, batch, policy: MlpPolicy, n_steps=64, gamma=0.99, gae_lambda=0.95, deterministic=False):
+    ``collect()`` is ONE foreign call (``b2h_rollout_collect``): the loop over the T control steps runs in the library, four
+    kernel launches per step (policy / value MLP, sampler, env step, record + effort sort), the kernels write the buffers in
+    place (the env step puts the next observation into ``obs[t + 1]``, the reward into ``rewards[t]``).  With
+    ``cuda_graph=True`` the whole rollout is captured once and replayed: the sampler's noise counter lives on the device.
+    ``collect_eager()`` is the same loop written with the single-op entry points (tests compare the two)."""
+
+    def __init__(self, batch, policy: MlpPolicy, n_steps=64, gamma=0.99, gae_lambda=0.95, deterministic=False, cuda_graph=False):
+        from . import abi
         from .batch import gae
         self.b, self.pol, self.T, self.gamma, self.lam, self.det = batch, policy, n_steps, gamma, gae_lambda, deterministic
         self._gae = gae
+        if batch.tdtype != torch.float32:
+            raise ValueError("the device-resident rollout runs on the float32 build (dtype='f32')")
         E, dev, f32 = batch.n_envs, batch.device, torch.float32
-        self.obs = torch.zeros(n_steps, E, batch.obs_dim, device=dev, dtype=f32)
-        self.actions = torch.zeros(n_steps, E, batch.nu, device=dev, dtype=f32)
-        self.rewards, self.values, self.log_probs, self.episode_starts = (torch.zeros(n_steps, E, device=dev, dtype=f32) for _ in range(4))
+        z = lambda *shape, dt=f32: torch.zeros(*shape, device=dev, dtype=dt)
+        self._obs = z(n_steps + 1, E, batch.obs_dim)            # slot t: observation before step t; slot T: carry-over
+        self._starts = z(n_steps + 1, E)
+        self.obs, self.episode_starts = self._obs[:n_steps], self._starts[:n_steps]
+        self.actions = z(n_steps, E, batch.nu)
+        self.rewards, self.values, self.log_probs, self.advantages, self.returns = (z(n_steps, E) for _ in range(5))
+        self._mean, self._clipped = z(E, batch.nu), z(E, batch.nu)
+        self._v_term, self._last_values = z(E), z(E)
         self.last_obs = None
-        self.last_episode_starts = torch.ones(E, device=dev, dtype=f32)      # _setup_learn: ones
         self.num_timesteps = 0
         h = float(batch.cm.timestep)
         # TimeLimit.truncated (step_count >= 750 while not terminated) can only happen when the duration outlasts 750 steps
         self.can_truncate = batch.cfg.duration > (1 + batch.cfg.frame_skip * batch.cfg.max_steps) * h
-        # on-device episode statistics ("rollout statistics" of the north star)
-        self.ep_return = torch.zeros(E, device=dev, dtype=f32)
-        self.ep_len = torch.zeros(E, device=dev, dtype=f32)
-        self.stats = torch.zeros(3, device=dev, dtype=torch.float64)        # sum of returns, sum of lengths, episodes
+        # on-device episode statistics ("rollout statistics" of the north star); stats[3] is unused
+        self.ep_return, self.ep_len = z(E), z(E)
+        self.stats = z(4, dt=torch.float64)        # sum of returns, sum of lengths, episodes
+        self._counter = z(1, dt=torch.int64)       # control steps taken (noise counter of the sampler)
+        p = policy.p
+        r = abi.B2HRollout()
+        r.n_steps, r.hidden, r.precise, r.deterministic = n_steps, p.hidden, policy.precise, int(deterministic)
+        r.row_offset, r.bootstrap_timeouts, r.seed = policy.row_offset, int(self.can_truncate), policy.seed
+        r.gamma, r.gae_lambda = float(gamma), float(gae_lambda)
+        for name, t in (("obs", self._obs), ("actions", self.actions), ("rewards", self.rewards), ("values", self.values),
+                        ("log_probs", self.log_probs), ("episode_starts", self._starts), ("advantages", self.advantages),
+                        ("returns", self.returns), ("last_values", self._last_values), ("mean", self._mean), ("clipped", self._clipped),
+                        ("v_term", self._v_term), ("ep_return", self.ep_return), ("ep_len", self.ep_len), ("stats", self.stats),
+                        ("step_counter", self._counter), ("mlp_error", policy.err), ("log_std", p.log_std)):
+            setattr(r, name, t.data_ptr())
+        for k in range(6):
+            r.pi[k], r.vf[k] = p.pi[k].data_ptr(), p.vf[k].data_ptr()
+        self._args = r
+        self.cuda_graph = bool(cuda_graph)
+        self._graph = None
+
+    @property
+    def last_episode_starts(self):
+        return self._starts[self.T] if self.last_obs is not None else self._starts[0]
 
     def reset(self):
-        self.last_obs = self.b.reset().to(torch.float32).clone()
-        self.last_episode_starts.fill_(1.0)
+        self._obs[0].copy_(self.b.reset().to(torch.float32))
+        self._starts[0].fill_(1.0)                  # _setup_learn: ones
+        self.last_obs = self._obs[0]
+
+    def start_from_current(self):
+        """Continue from the batch's present state instead of resetting it (the observation of its last step / reset)."""
+        self._obs[0].copy_(self.b.obs.to(torch.float32))
+        self._starts[0].zero_()
+        self.last_obs = self._obs[0]
+        self._obs[self.T].copy_(self._obs[0])
+        self._starts[self.T].zero_()
+
+    def _launch(self):
+        check(self.pol.lib.b2h_rollout_collect(self.b.h, C.byref(self._args),
+                                               C.c_void_p(torch.cuda.current_stream(self.b.device).cuda_stream)))
 
     def collect(self):
         if self.last_obs is None:
             self.reset()
+        else:                                       # carry the last observation / dones of the previous rollout into slot 0
+            self._obs[0].copy_(self._obs[self.T])
+            self._starts[0].copy_(self._starts[self.T])
+        if self.cuda_graph:
+            if self._graph is None:
+                # the only lazy initialisation on the path is the MLP kernel's shared-memory attribute: one stateless
+                # forward before the capture (a capture does not execute, and must not contain that call)
+                self.pol.forward(self._obs[0])
+                torch.cuda.current_stream(self.b.device).synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch()
+                self._graph = g
+            self._graph.replay()
+        else:
+            self._launch()
+        self.last_obs = self._obs[self.T]
+        self.num_timesteps += self.T * self.b.n_envs
+        return self.advantages, self.returns
+
+    def check_error(self):
+        """Raises if the tcgen05 MLP pipeline reported a timeout during any rollout so far (device flag, one sync)."""
+        self.pol.check_error()
+
+    def collect_eager(self):
+        """The same rollout written op by op in Python (~15 torch ops per step): the round-1 formulation, kept as the
+        cross-check of ``collect`` (same kernels, same noise counters -> identical buffers)."""
+        if self.last_obs is None:
+            self.reset()
+        else:
+            self._obs[0].copy_(self._obs[self.T])
+            self._starts[0].copy_(self._starts[self.T])
         b, pol = self.b, self.pol
+        last_obs, starts = self._obs[0].clone(), self._starts[0].clone()
+        step0 = int(self._counter.item())
         for t in range(self.T):
-            mean, value = pol.forward(self.last_obs)
-            actions, clipped, logp = pol.sample(mean, self.num_timesteps // b.n_envs, self.det)
+            mean, value = pol.forward(last_obs)
+            actions, clipped, logp = pol.sample(mean, step0 + t, self.det)
             obs, rew, term, trunc = b.step(clipped)
             raw = rew.to(torch.float32)      # what the env returned: episode statistics use this (SB3's Monitor does too)
             rew = raw.clone()
@@ -163,21 +243,25 @@ class RolloutCollector:
             if self.can_truncate:   # bootstrap with V(terminal_obs) where the episode was cut by the step limit only
                 tl = (trunc.bool() & ~term.bool()).to(torch.float32)
                 rew += self.gamma * pol.values(b.terminal_obs.to(torch.float32)) * tl
-            self.obs[t].copy_(self.last_obs)
+            self._obs[t].copy_(last_obs)
             self.actions[t].copy_(actions)
             self.rewards[t].copy_(rew)
             self.values[t].copy_(value)
             self.log_probs[t].copy_(logp)
-            self.episode_starts[t].copy_(self.last_episode_starts)
+            self._starts[t].copy_(starts)
             self.ep_return += raw
             self.ep_len += 1
-            self.stats += torch.stack([(self.ep_return * done).sum(), (self.ep_len * done).sum(), done.sum()]).to(torch.float64)
+            self.stats[:3] += torch.stack([(self.ep_return * done).sum(), (self.ep_len * done).sum(), done.sum()]).to(torch.float64)
             self.ep_return *= 1 - done
             self.ep_len *= 1 - done
-            self.last_obs = obs.to(torch.float32).clone()
-            self.last_episode_starts = done
-            self.num_timesteps += b.n_envs
+            last_obs = obs.to(torch.float32).clone()
+            starts = done
+        self._obs[self.T].copy_(last_obs)
+        self._starts[self.T].copy_(starts)
+        self._counter += self.T
+        self.last_obs = self._obs[self.T]
+        self.num_timesteps += self.T * b.n_envs
         last_values = pol.values(self.last_obs)
-        self.advantages, self.returns = self._gae(self.rewards, self.values, self.episode_starts, last_values,
-                                                  self.last_episode_starts.to(torch.uint8), self.gamma, self.lam)
+        adv, ret = self._gae(self.rewards, self.values, self.episode_starts, last_values, starts.to(torch.uint8), self.gamma, self.lam)
+        self.advantages.copy_(adv); self.returns.copy_(ret)
         return self.advantages, self.returns

@@ -172,10 +172,14 @@ class PPOTrainer:
             d = self.col.stats - before
         stats = self.update()
         self.iterations += 1
-        ep = d.clone()
-        if self.world > 1:                       # rollout statistics: the only other collective
+        # rollout statistics (the only other collective); the MLP kernel's pipeline-timeout flag rides along, so a
+        # corrupted rollout cannot go unnoticed (one sync per iteration, which the statistics need anyway)
+        ep = torch.cat([d[:3], self.policy.err.to(torch.float64)])
+        if self.world > 1:
             dist.all_reduce(ep)
         ep = ep.tolist()
+        if ep[3] != 0:
+            raise RuntimeError("tcgen05 MLP pipeline timed out during the rollout (mbarrier wait exceeded its bound)")
         stats.update(ep_rew_mean=ep[0] / max(ep[2], 1.0), ep_len_mean=ep[1] / max(ep[2], 1.0), episodes=int(ep[2]),
                      timesteps=self.col.num_timesteps * self.world)
         return stats

@@ -124,22 +124,55 @@ def test_ppo_minibatch_update_matches_sb3_recipe():
     b.close()
 
 
+def _twin_collectors(n, n_steps, duration, seed, **kw):
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams, RolloutCollector
+    out = []
+    for _ in range(2):
+        b = HumanoidBatch(n, frame_skip=3, duration=duration, reward_type="stand", seed=seed)
+        out.append(RolloutCollector(b, MlpPolicy(MlpPolicyParams(seed=2), seed=4), n_steps=n_steps, **kw))
+    return out
+
+
+def _same_buffers(a, b):
+    for name in ("obs", "actions", "rewards", "values", "log_probs", "episode_starts", "advantages", "returns", "ep_return", "ep_len"):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.allclose(a.stats[:3], b.stats[:3], rtol=1e-6, atol=0) and torch.equal(a.last_obs, b.last_obs)   # sums: order of addition differs
+    assert torch.equal(a.last_episode_starts, b.last_episode_starts) and a.num_timesteps == b.num_timesteps
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_library_rollout_loop_equals_op_by_op_loop(graph):
+    """b2h_rollout_collect (one foreign call, four launches per control step, buffers written in place; optionally one
+    CUDA graph per rollout) against the same rollout issued op by op from Python: bit-identical SB3 buffers, statistics
+    and carry-over across two consecutive rollouts that cross episode ends (13-step episodes)."""
+    fast, slow = _twin_collectors(192, 20, 0.2, 6, cuda_graph=graph)
+    for _ in range(2):
+        fast.collect()
+        slow.collect_eager()
+        torch.cuda.synchronize()
+        _same_buffers(fast, slow)
+    fast.check_error()
+    assert float(fast.stats[2]) == 3 * 192                    # episodes end at steps 13, 26, 39 of the 40 collected
+    fast.b.close(); slow.b.close()
+
+
 def test_rollout_collector_timeout_bootstrap():
     """OnPolicyAlgorithm.collect_rollouts (SB3 2.3.2): where an episode is cut by the step limit only
     (TimeLimit.truncated) the stored reward is the env reward plus gamma * V(terminal_observation); the episode
     statistics keep the raw env reward (custom_env.py:201-206 sets it to 0.0 on that step)."""
-    from mujocoposelearning_b200.batch import HumanoidBatch
-    from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams, RolloutCollector
     n = 64
-    b = HumanoidBatch(n, frame_skip=3, duration=30.0, reward_type="stand", seed=6)
-    pol = MlpPolicy(MlpPolicyParams(seed=2), seed=4)
-    col = RolloutCollector(b, pol, n_steps=4)
+    fast, col = _twin_collectors(n, 4, 30.0, 6)
+    b, pol = col.b, col.pol
     assert col.can_truncate
-    col.reset()
-    b.set_state(step_count=np.full(n, 747, np.int32))
-    col.collect()
+    for c in (fast, col):
+        c.reset()
+        c.b.set_state(step_count=np.full(n, 747, np.int32))
+    col.collect_eager()
+    fast.collect()
     torch.cuda.synchronize()
     pol.check_error()
+    _same_buffers(fast, col)                                                         # the in-library loop takes the same branch
     es = col.episode_starts.cpu().numpy()
     assert es[0].all() and es[3].all() and not es[1].any() and not es[2].any()      # truncated on the third step (750)
     _, v_term = pol.forward_torch(b.terminal_obs.to(torch.float32))                 # rows of the step that truncated
@@ -149,4 +182,4 @@ def test_rollout_collector_timeout_bootstrap():
     ep = col.stats.cpu().numpy()                                                     # sum of returns, sum of lengths, episodes
     raw_return = float(col.rewards[:2].sum())                                        # the truncating step's env reward is 0.0
     assert ep[2] == n and ep[1] == 3 * n and abs(ep[0] - raw_return) < 1e-3 * max(1.0, abs(raw_return))
-    b.close()
+    b.close(); fast.b.close()

@@ -54,6 +54,11 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--quick", action="store_true", help="tuning runs: only the device-timed leg (no e2e / policy / CPU legs)")
+    ap.add_argument("--ppo", action="store_true", help="BASELINE config 4 leg: full PPO `stand` training iterations (rollout + GAE + update + "
+                    "NCCL gradient all-reduce), 16384 envs/GPU unless --n-envs is given; --steps / --warmup count ITERATIONS")
+    ap.add_argument("--ppo-batch", type=int, default=16384, help="PPO minibatch size per GPU")
+    ap.add_argument("--ppo-epochs", type=int, default=4)
+    ap.add_argument("--ppo-tf32", action="store_true", help="run the update's library GEMMs on the tf32 tensor cores")
     ap.add_argument("--no-stagger", action="store_true", help="keep the batch's episodes synchronised (SURVEY 8d C3 as written); the "
                     "timed window then depends on --warmup / --steps")
     return ap.parse_args()
@@ -461,9 +466,76 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+def run_ppo(args):
+    """BASELINE config 4: full PPO `stand` training, E envs per GPU (16384), n_steps 64, NCCL gradient all-reduce.
+    The reference gives no batch / epoch figures for this scale (config.py's batch 256 would be 4096 minibatches per
+    iteration): minibatch 16384 per GPU and 4 epochs are this repo's choice, stated in the line.  One "step" here is
+    one training iteration; the line reports the time split rollout (incl. GAE) / update / all-reduce."""
+    import torch
+    import torch.distributed as dist
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from mujocoposelearning_b200.ppo import PPOTrainer
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    E, T = args.n_envs, 64
+    K, W = max(1, args.steps), max(1, args.warmup)
+    b = HumanoidBatch(E, frame_skip=FRAME_SKIP, duration=DURATION, reward_type=REWARD, dtype="f32", device=local, seed=1234, env_id_offset=rank * E)
+    tr = PPOTrainer(b, n_steps=T, batch_size=args.ppo_batch, n_epochs=args.ppo_epochs, lr=3e-4, seed=3, update_tf32=args.ppo_tf32)
+    tr.col.cuda_graph = True
+    tr.time_allreduce = world > 1
+    for _ in range(W):
+        tr.iterate()
+    tr.allreduce_ms()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    roll, upd, ar, n_ar = 0.0, 0.0, 0.0, 0
+    t0 = time.perf_counter()
+    for _ in range(K):
+        tm = {}
+        stats = tr.iterate(timing=tm)
+        a_ms, a_n = tr.allreduce_ms()
+        roll += tm["rollout_ms"]; upd += tm["update_ms"]; ar += a_ms; n_ar += a_n
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    tt = torch.tensor([roll, upd, ar, wall * 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    roll, upd, ar, wall_ms = (float(x) for x in tt)
+    if rank == 0:
+        n_mb = args.ppo_epochs * (T * E // args.ppo_batch)
+        out = {"leg": "ppo", "metric": METRIC, "unit": UNIT, "value": world * E * FRAME_SKIP * T * K / (wall_ms * 1e-3), "n_gpus": world,
+               "steps": K, "warmup": W, "ms_per_step": wall_ms / K, "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
+               "config": {"workload": f"full PPO `stand` training, {E} envs/GPU x {world} GPU, n_steps {T} (BASELINE config 4)", "n_envs_per_gpu": E,
+                          "n_steps": T, "minibatch_per_gpu": args.ppo_batch, "epochs": args.ppo_epochs, "minibatches_per_iteration": n_mb,
+                          "gradient_allreduce": "one flat 1.27 MB NCCL all-reduce per minibatch" if world > 1 else "none (1 GPU)",
+                          "update": "PyTorch autograd + library GEMMs (" + ("tf32" if args.ppo_tf32 else "fp32") + "), CUDA-graphed; NOT a hand-written kernel"},
+               "split_ms_per_iteration": {"rollout_incl_gae": roll / K, "update_incl_allreduce": upd / K, "allreduce": ar / K,
+                                          "allreduce_calls": n_ar // max(1, K), "wall": wall_ms / K},
+               "rollout_value": world * E * FRAME_SKIP * T * K / (roll * 1e-3),
+               "train": {"ep_rew_mean": stats.get("ep_rew_mean"), "episodes": stats.get("episodes"), "value_loss": float(stats["value_loss"]),
+                         "policy_loss": float(stats["policy_loss"]), "clip_fraction": float(stats["clip_fraction"])}}
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
-    if args.impl == "reference":
+    if args.ppo:
+        if "--n-envs" not in sys.argv:
+            args.n_envs = 16384
+        if "--steps" not in sys.argv:
+            args.steps = 3
+        if "--warmup" not in sys.argv:
+            args.warmup = 1
+        run_ppo(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

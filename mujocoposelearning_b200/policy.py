@@ -149,6 +149,7 @@ class RolloutCollector:
         self._mean, self._clipped = z(E, batch.nu), z(E, batch.nu)
         self._v_term, self._last_values = z(E), z(E)
         self.last_obs = None
+        self._slot0_valid = False                   # slot 0 already holds the carry-over (after reset / start_from_current)
         self.num_timesteps = 0
         h = float(batch.cm.timestep)
         # TimeLimit.truncated (step_count >= 750 while not terminated) can only happen when the duration outlasts 750 steps
@@ -176,31 +177,35 @@ class RolloutCollector:
 
     @property
     def last_episode_starts(self):
-        return self._starts[self.T] if self.last_obs is not None else self._starts[0]
+        return self._starts[0] if (self.last_obs is None or self._slot0_valid) else self._starts[self.T]
 
     def reset(self):
         self._obs[0].copy_(self.b.reset().to(torch.float32))
         self._starts[0].fill_(1.0)                  # _setup_learn: ones
         self.last_obs = self._obs[0]
+        self._slot0_valid = True
 
     def start_from_current(self):
         """Continue from the batch's present state instead of resetting it (the observation of its last step / reset)."""
         self._obs[0].copy_(self.b.obs.to(torch.float32))
         self._starts[0].zero_()
         self.last_obs = self._obs[0]
-        self._obs[self.T].copy_(self._obs[0])
-        self._starts[self.T].zero_()
+        self._slot0_valid = True
+
+    def _carry_over(self):
+        if self.last_obs is None:
+            self.reset()
+        elif not self._slot0_valid:                 # the last observation / dones of the previous rollout go into slot 0
+            self._obs[0].copy_(self._obs[self.T])
+            self._starts[0].copy_(self._starts[self.T])
+        self._slot0_valid = False
 
     def _launch(self):
         check(self.pol.lib.b2h_rollout_collect(self.b.h, C.byref(self._args),
                                                C.c_void_p(torch.cuda.current_stream(self.b.device).cuda_stream)))
 
     def collect(self):
-        if self.last_obs is None:
-            self.reset()
-        else:                                       # carry the last observation / dones of the previous rollout into slot 0
-            self._obs[0].copy_(self._obs[self.T])
-            self._starts[0].copy_(self._starts[self.T])
+        self._carry_over()
         if self.cuda_graph:
             if self._graph is None:
                 # the only lazy initialisation on the path is the MLP kernel's shared-memory attribute: one stateless
@@ -225,11 +230,7 @@ class RolloutCollector:
     def collect_eager(self):
         """The same rollout written op by op in Python (~15 torch ops per step): the round-1 formulation, kept as the
         cross-check of ``collect`` (same kernels, same noise counters -> identical buffers)."""
-        if self.last_obs is None:
-            self.reset()
-        else:
-            self._obs[0].copy_(self._obs[self.T])
-            self._starts[0].copy_(self._starts[self.T])
+        self._carry_over()
         b, pol = self.b, self.pol
         last_obs, starts = self._obs[0].clone(), self._starts[0].clone()
         step0 = int(self._counter.item())

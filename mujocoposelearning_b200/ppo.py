@@ -52,6 +52,8 @@ class PPOTrainer:
         self.gen = torch.Generator(device=batch.device).manual_seed(seed + 17 + rank)
         self.iterations = 0
         self.update_tf32 = bool(update_tf32)   # library GEMMs of the update on the tf32 tensor cores (default: fp32 like the reference)
+        self.time_allreduce = False            # bench: CUDA events around every gradient all-reduce (adds two event records each)
+        self._ar_events = []
 
     def _evaluate(self, obs, actions):
         p = self.params
@@ -155,7 +157,13 @@ class PPOTrainer:
                     self.flat_grad.zero_()
                     loss.backward()              # accumulates into the views of flat_grad
                 if self.world > 1:               # average gradients: one flat NCCL all-reduce over NVLink
+                    if self.time_allreduce:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
                     dist.all_reduce(self.flat_grad)
+                    if self.time_allreduce:
+                        e1.record()
+                        self._ar_events.append((e0, e1))
                     self.flat_grad /= self.world
                 if use_graph:
                     self._graphs["g2"].replay()
@@ -164,13 +172,31 @@ class PPOTrainer:
                 stats = dict(policy_loss=pl, value_loss=vl, clip_fraction=cf)
         return {k: v.clone() for k, v in stats.items()}
 
-    def iterate(self):
-        """collect_rollouts + train, as one iteration of ``model.learn`` (train_sb3.py:228)."""
+    def allreduce_ms(self):
+        """Device time spent in the gradient all-reduces since the last call (needs ``time_allreduce``; synchronises)."""
+        torch.cuda.synchronize(self.b.device)
+        ms = sum(a.elapsed_time(b) for a, b in self._ar_events)
+        n = len(self._ar_events)
+        self._ar_events = []
+        return ms, n
+
+    def iterate(self, timing=None):
+        """collect_rollouts + train, as one iteration of ``model.learn`` (train_sb3.py:228).  ``timing``: a dict that
+        receives the device time of the two halves (CUDA events; one extra synchronisation)."""
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timing is not None else None
+        if ev:
+            ev[0].record()
         with torch.no_grad():
             before = self.col.stats.clone()
             self.col.collect()
             d = self.col.stats - before
+        if ev:
+            ev[1].record()
         stats = self.update()
+        if ev:
+            ev[2].record()
+            torch.cuda.synchronize(self.b.device)
+            timing["rollout_ms"], timing["update_ms"] = ev[0].elapsed_time(ev[1]), ev[1].elapsed_time(ev[2])
         self.iterations += 1
         # rollout statistics (the only other collective); the MLP kernel's pipeline-timeout flag rides along, so a
         # corrupted rollout cannot go unnoticed (one sync per iteration, which the statistics need anyway)

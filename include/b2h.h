@@ -256,6 +256,19 @@ const char* b2h_mlp_last_error(void);
 int b2h_policy_sample(const float* mean_dev, const float* log_std_dev, int n_rows, int act_dim, uint64_t seed, uint64_t step,
                       int row_offset, int deterministic, float* actions_dev, float* clipped_dev, float* log_prob_dev, void* stream);
 
+/* The same forward with the weights prepared once per policy update (the round-2 kernel, mlp_forward_v2_kernel):
+ * b2h_policy_pack splits both networks' weights into tf32 hi / lo parts laid out in the tensor cores' core-matrix order
+ * (0.6 MB per network); b2h_policy_forward_packed then streams them with the TMA engine (cp.async.bulk.tensor) while the
+ * activations flow TMEM -> shared-memory operand ring between the layers.  Call b2h_policy_pack again whenever the
+ * weights changed; the biases are read from pi_dev / vf_dev ({W1, b1, W2, b2, W3, b3}) on every forward.  mean_dev or
+ * value_dev may be null (only the other network runs: SB3 predict_values).  Any in_dim; hidden a multiple of 32 up to 256. */
+typedef struct B2HPolicyPacked B2HPolicyPacked;
+int b2h_policy_packed_create(int in_dim, int hidden, int act_dim, B2HPolicyPacked** out);
+void b2h_policy_packed_destroy(B2HPolicyPacked* p);
+int b2h_policy_pack(B2HPolicyPacked* p, const float* const pi_dev[6], const float* const vf_dev[6], void* stream);
+int b2h_policy_forward_packed(B2HPolicyPacked* p, const float* x_dev, const float* const pi_dev[6], const float* const vf_dev[6],
+                              float* mean_dev, float* value_dev, int n_rows, int precise, int* error_flag_dev, void* stream);
+
 /* As b2h_policy_sample, with the step counter read from device memory (step = *step_dev + step_offset): a captured
  * CUDA graph of the rollout loop then draws fresh noise on every replay. */
 int b2h_policy_sample_dev(const float* mean_dev, const float* log_std_dev, int n_rows, int act_dim, uint64_t seed,
@@ -299,6 +312,7 @@ typedef struct B2HRollout {
   const float* pi[6];     /* W1 b1 W2 b2 W3 b3 of the policy network                       */
   const float* vf[6];     /* ... of the value network                                      */
   const float* log_std;   /* [nu]                                                          */
+  B2HPolicyPacked* packed; /* b2h_policy_packed_create(obs_dim, hidden, nu): re-packed at the start of every rollout; null: the round-1 kernel */
 } B2HRollout;
 size_t b2h_sizeof_rollout(void);
 int b2h_rollout_collect(B2HHandle* h, const B2HRollout* r, void* stream);

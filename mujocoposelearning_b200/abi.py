@@ -65,7 +65,7 @@ class B2HRollout(C.Structure):
         ("episode_starts", C.c_void_p), ("advantages", C.c_void_p), ("returns", C.c_void_p), ("last_values", C.c_void_p),
         ("mean", C.c_void_p), ("clipped", C.c_void_p), ("v_term", C.c_void_p), ("ep_return", C.c_void_p), ("ep_len", C.c_void_p),
         ("stats", C.c_void_p), ("step_counter", C.c_void_p), ("mlp_error", C.c_void_p),
-        ("pi", C.c_void_p * 6), ("vf", C.c_void_p * 6), ("log_std", C.c_void_p),
+        ("pi", C.c_void_p * 6), ("vf", C.c_void_p * 6), ("log_std", C.c_void_p), ("packed", C.c_void_p),
     ]
 
 

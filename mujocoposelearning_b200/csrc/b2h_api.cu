@@ -787,10 +787,16 @@ int b2h_rollout_collect(B2HHandle* h, const B2HRollout* r, void* stream) {
   cudaStream_t s = (cudaStream_t)stream;
   const size_t E = (size_t)h->cfg.n_envs, od = (size_t)h->obs_dim, nu = (size_t)h->nu;
   const int T = r->n_steps;
+  if (r->packed) {   // weights are constant within a rollout: split / lay them out for the tensor cores once
+    int rc = b2h_policy_pack(r->packed, r->pi, r->vf, stream);
+    if (rc != B2H_OK) return fail(rc, std::string("b2h_policy_pack: ") + b2h_mlp_last_error());
+  }
   for (int t = 0; t < T; t++) {
     const float* obs_t = r->obs + (size_t)t * E * od;
-    int rc = b2h_policy_forward(obs_t, r->pi, r->vf, r->mean, r->values + (size_t)t * E, (int)E, (int)od, r->hidden, (int)nu, r->precise,
-                                r->mlp_error, stream);
+    int rc = r->packed ? b2h_policy_forward_packed(r->packed, obs_t, r->pi, r->vf, r->mean, r->values + (size_t)t * E, (int)E, r->precise,
+                                                   r->mlp_error, stream)
+                       : b2h_policy_forward(obs_t, r->pi, r->vf, r->mean, r->values + (size_t)t * E, (int)E, (int)od, r->hidden, (int)nu,
+                                            r->precise, r->mlp_error, stream);
     if (rc != B2H_OK) return fail(rc, std::string("b2h_policy_forward: ") + b2h_mlp_last_error());
     rc = b2h_policy_sample_dev(r->mean, r->log_std, (int)E, (int)nu, r->seed, r->step_counter, 0, r->row_offset, r->deterministic,
                                r->actions + (size_t)t * E * nu, r->clipped, r->log_probs + (size_t)t * E, stream);
@@ -800,8 +806,10 @@ int b2h_rollout_collect(B2HHandle* h, const B2HRollout* r, void* stream) {
                             h->tobs_stage, Out64(), s);
     if (rc != B2H_OK) return rc;
     if (r->bootstrap_timeouts) {   // V(terminal_obs): rows of envs that did not finish are stale and unused
-      rc = b2h_mlp_forward((const float*)h->tobs_stage, r->vf[0], r->vf[1], r->vf[2], r->vf[3], r->vf[4], r->vf[5], r->v_term, (int)E,
-                           (int)od, r->hidden, 1, r->precise, r->mlp_error, stream);
+      rc = r->packed ? b2h_policy_forward_packed(r->packed, (const float*)h->tobs_stage, r->pi, r->vf, nullptr, r->v_term, (int)E, r->precise,
+                                                 r->mlp_error, stream)
+                     : b2h_mlp_forward((const float*)h->tobs_stage, r->vf[0], r->vf[1], r->vf[2], r->vf[3], r->vf[4], r->vf[5], r->v_term, (int)E,
+                                       (int)od, r->hidden, 1, r->precise, r->mlp_error, stream);
       if (rc != B2H_OK) return fail(rc, std::string("b2h_mlp_forward: ") + b2h_mlp_last_error());
     }
     RecordArgs rec;
@@ -812,8 +820,10 @@ int b2h_rollout_collect(B2HHandle* h, const B2HRollout* r, void* stream) {
     rc = launch_post_step(h, &rec, s);
     if (rc != B2H_OK) return rc;
   }
-  int rc = b2h_mlp_forward(r->obs + (size_t)T * E * od, r->vf[0], r->vf[1], r->vf[2], r->vf[3], r->vf[4], r->vf[5], r->last_values, (int)E,
-                           (int)od, r->hidden, 1, r->precise, r->mlp_error, stream);
+  int rc = r->packed ? b2h_policy_forward_packed(r->packed, r->obs + (size_t)T * E * od, r->pi, r->vf, nullptr, r->last_values, (int)E, r->precise,
+                                                 r->mlp_error, stream)
+                     : b2h_mlp_forward(r->obs + (size_t)T * E * od, r->vf[0], r->vf[1], r->vf[2], r->vf[3], r->vf[4], r->vf[5], r->last_values,
+                                       (int)E, (int)od, r->hidden, 1, r->precise, r->mlp_error, stream);
   if (rc != B2H_OK) return fail(rc, std::string("b2h_mlp_forward: ") + b2h_mlp_last_error());
   // last dones = episode_starts[T] (the dones of the final step), as collect_rollouts passes them
   gae_kernel<<<((int)E + 255) / 256, 256, 0, s>>>(r->rewards, r->values, r->episode_starts, r->last_values, nullptr, r->episode_starts + (size_t)T * E,

@@ -13,6 +13,7 @@
 //     ReLU and writes the next layer's input (or the network output).
 // precise = 1 splits every operand into tf32 hi + lo parts and issues hi*hi + hi*lo + lo*hi, which recovers
 // fp32-level accuracy (the reference policy runs in fp32 on the CPU); precise = 0 is a single tf32 pass.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -457,6 +458,295 @@ __global__ void __launch_bounds__(NTHREADS, 1) mlp_forward_ws_kernel(MlpArgs a) 
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ packed-weight TMA pipeline (v2)
+// The round-2 kernel.  What changed against mlp_forward_ws_kernel, and why (profiles/r01_mlp_kernel_tcgen05.txt: tensor
+// pipe 25.6 % active, 64 us per 128-row tile, the time in 54 operand hand-offs):
+//   * the weights are split into tf32 hi / lo and laid out in the canonical UMMA core-matrix order ONCE per policy update
+//     (pack_weights_kernel), not by every CTA on every call; a K chunk of W then is one contiguous 32 KB block that the
+//     TMA engine drops into shared memory (cp.async.bulk.tensor through a 2-D tensor map: rows = 128-byte core matrices)
+//     while the threads do something else;
+//   * K chunks are 32 wide (four MMA K-steps, 12 MMAs in precise mode): 11 + 8 + 8 hand-offs per tile instead of 54;
+//   * there is no activation buffer: the epilogue of layer l reads the accumulator 32 columns at a time, applies bias +
+//     ReLU, splits into hi / lo and writes the result straight into the operand ring as the next K chunk of layer l + 1,
+//     whose MMAs (into the other half of TMEM) start while the rest of the epilogue is still running;
+//   * roles: warp 0 issues tcgen05.mma, warp 1 issues the TMA loads, warps 4-7 (one thread per tile row, TMEM lane
+//     quadrant = warp % 4) produce every A chunk -- from global memory for layer 0, from TMEM afterwards.
+// Accumulators: layer 0 -> TMEM columns [0, 256), layer 1 -> [256, 512), layer 2 -> [0, 32).
+// One operand ring of two stages; a stage holds a whole K chunk of 32 columns: A hi + lo (2 x 16 KB) and W hi + lo (2 x 32 KB),
+// and ONE mbarrier says it is full (128 producer arrivals + the TMA thread's expect_tx bytes).  Measured alternatives
+// (profiles/r02_mlp_v2_ring_variants.txt): separate A / W barriers +4 us per tile, a third A stage +8 us, W in half chunks
+// through a five-deep ring +10 us -- every extra hand-off costs the single MMA-issuing thread more than the deeper
+// prefetch returns; with a single tf32 pass instead of three the tile still takes 31 us, i.e. the tile is bound by ~27
+// hand-off round trips of ~1 us, not by the tensor pipe.
+constexpr int KC2 = 32;                                 // K columns of a chunk
+constexpr int V2_NS = 2;                                // stages
+constexpr int V2_A_PART = TILE_M * KC2;                 // floats of the hi (or lo) part of an A chunk: 16 KB
+constexpr int V2_W_PART = MAXH * KC2;                   // ... of a W chunk: 32 KB
+constexpr int V2_STAGE_FLOATS = 2 * V2_A_PART + 2 * V2_W_PART;
+constexpr int V2_SMEM_FLOATS = V2_NS * V2_STAGE_FLOATS; // 192 KB
+constexpr int V2_NPROD = 128;                           // A producers: warps 4..7
+
+struct PackedNet {         // one trunk + head: offsets (floats) of the packed layers inside the buffer, chunk counts
+  int chunks[3];           // K chunks of 32 per layer
+  int n[3];                // UMMA N per layer (hidden, hidden, 32)
+  int nout;                // real output features of the head
+};
+struct V2Args {
+  const float* x;
+  const float* bias[2][3];
+  float* y[2];
+  PackedNet net[2];
+  int n_rows, in_dim, precise;
+  int* error;
+};
+struct alignas(64) V2Maps { CUtensorMap m[2][3]; };
+
+__device__ __forceinline__ void split_tf32(float4 v, float4& hi, float4& lo) {
+  hi.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); lo.x = v.x - hi.x;
+  hi.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); lo.y = v.y - hi.y;
+  hi.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); lo.z = v.z - hi.z;
+  hi.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); lo.w = v.w - hi.w;
+}
+
+// W [nout, K] (nn.Linear layout) -> per K chunk of 32: [hi | lo] x [k4 group 0..7] x [row group 0..N/8) x 8 rows x 4 floats
+struct PackJob { const float* W; float* dst; int nout, K, N, chunks; };
+struct PackJobs { PackJob j[6]; };                       // both networks' three layers in one launch (blockIdx.y)
+__global__ void pack_weights_kernel(PackJobs jobs) {
+  const PackJob jb = jobs.j[blockIdx.y];
+  const float* __restrict__ W = jb.W;
+  float* __restrict__ dst = jb.dst;
+  const int nout = jb.nout, K = jb.K, N = jb.N, halves = jb.chunks;
+  constexpr int G = KC2 / 4;                             // 16-byte K groups per chunk
+  const int total = halves * G * N;                      // float4 items per part
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ri = i & 7, rg = (i >> 3) % (N >> 3), k4 = (i / N) % G, c = i / (G * N);
+    const int row = rg * 8 + ri, col = c * KC2 + k4 * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < nout) {
+      const float* src = W + (size_t)row * K + col;
+      if (col + 0 < K) v.x = src[0];
+      if (col + 1 < K) v.y = src[1];
+      if (col + 2 < K) v.z = src[2];
+      if (col + 3 < K) v.w = src[3];
+    }
+    float4 hi, lo;
+    split_tf32(v, hi, lo);
+    const size_t part = (size_t)G * N * 4;               // floats per part of one chunk
+    float* base = dst + (size_t)c * 2 * part + ((size_t)(k4 * (N >> 3) + rg) * 32 + ri * 4);
+    *reinterpret_cast<float4*>(base) = hi;
+    *reinterpret_cast<float4*>(base + part) = lo;
+  }
+}
+
+__device__ __forceinline__ void v2_store_row_chunk(const float4 (&v)[8], int r, float* A_hi, float* A_lo, bool precise) {
+#pragma unroll
+  for (int k4 = 0; k4 < 8; k4++) {
+    float4 hi, lo;
+    split_tf32(v[k4], hi, lo);
+    const int off = ((k4 * (TILE_M / 8) + (r >> 3)) * 32) + (r & 7) * 4;
+    *reinterpret_cast<float4*>(A_hi + off) = hi;
+    if (precise) *reinterpret_cast<float4*>(A_lo + off) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(256, 1) mlp_forward_v2_kernel(const __grid_constant__ V2Maps maps, V2Args a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* stage0 = reinterpret_cast<float*>(smem);
+  __shared__ __align__(8) unsigned long long bar_storage[2 * V2_NS + 3];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int net = blockIdx.y;
+  const int row0 = blockIdx.x * TILE_M;
+  const int valid = min(TILE_M, a.n_rows - row0);
+  const PackedNet pn = a.net[net];
+  const bool precise = a.precise != 0;
+  uint32_t full[V2_NS], empty[V2_NS], acc[3];
+#pragma unroll
+  for (int s = 0; s < V2_NS; s++) { full[s] = smem_u32(&bar_storage[s]); empty[s] = smem_u32(&bar_storage[V2_NS + s]); }
+#pragma unroll
+  for (int l = 0; l < 3; l++) acc[l] = smem_u32(&bar_storage[2 * V2_NS + l]);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < V2_NS; s++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(full[s]), "r"(V2_NPROD + 1));   // 128 A producers + the TMA thread
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(empty[s]));
+    }
+#pragma unroll
+    for (int l = 0; l < 3; l++) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(acc[l]));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  bool ok = true;
+  const int c0end = pn.chunks[0], c1end = c0end + pn.chunks[1], c2end = c1end + pn.chunks[2];   // global chunk sequence
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---------------------------------------------------------------- MMA issuer
+      for (int g = 0; g < c2end && ok; g++) {
+        const int layer = g < c0end ? 0 : (g < c1end ? 1 : 2);
+        const int c = g - (layer == 0 ? 0 : (layer == 1 ? c0end : c1end));
+        const int N = pn.n[layer];
+        const int s = g % V2_NS, use = g / V2_NS;
+        ok = mbar_wait(full[s], use & 1);
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t idesc = umma_idesc_tf32(TILE_M, N);
+        const uint32_t lboA = (TILE_M / 8) * 128, lboW = (uint32_t)(N / 8) * 128;
+        const uint32_t A_hi = smem_u32(stage0 + s * V2_STAGE_FLOATS), A_lo = A_hi + V2_A_PART * 4, W_hi = A_lo + V2_A_PART * 4,
+                       W_lo = W_hi + V2_W_PART * 4;
+        const uint32_t d = tmem + (layer == 1 ? 256u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < KC2 / 8; ks++) {
+          uint64_t ah = umma_desc(A_hi + ks * 2 * lboA, lboA, 128), wh = umma_desc(W_hi + ks * 2 * lboW, lboW, 128);
+          umma_tf32(d, ah, wh, idesc, (c | ks) != 0);
+          if (precise) {
+            uint64_t al = umma_desc(A_lo + ks * 2 * lboA, lboA, 128), wl = umma_desc(W_lo + ks * 2 * lboW, lboW, 128);
+            umma_tf32(d, ah, wl, idesc, 1);
+            umma_tf32(d, al, wh, idesc, 1);
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(empty[s]) : "memory");
+        if (g + 1 == c0end || g + 1 == c1end || g + 1 == c2end)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(acc[layer]) : "memory");
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {   // ---------------------------------------------------------------- TMA: weight chunks
+      for (int g = 0; g < c2end && ok; g++) {
+        const int layer = g < c0end ? 0 : (g < c1end ? 1 : 2);
+        const int c = g - (layer == 0 ? 0 : (layer == 1 ? c0end : c1end));
+        const int N = pn.n[layer];
+        const int s = g % V2_NS, use = g / V2_NS;
+        if (use > 0) ok = mbar_wait(empty[s], (use - 1) & 1);
+        if (!ok) break;
+        const uint32_t part_bytes = (uint32_t)N * KC2 * 4;
+        const uint32_t W_hi = smem_u32(stage0 + s * V2_STAGE_FLOATS + 2 * V2_A_PART), W_lo = W_hi + V2_W_PART * 4;
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(full[s]),
+                     "r"(precise ? 2 * part_bytes : part_bytes) : "memory");
+        const CUtensorMap* tm = &maps.m[net][layer];
+        const int row_hi = c * 2 * N, row_lo = row_hi + N;      // rows of the map = 128-byte core matrices
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                     ::"r"(W_hi), "l"(tm), "r"(0), "r"(row_hi), "r"(full[s]) : "memory");
+        if (precise)
+          asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+                       ::"r"(W_lo), "l"(tm), "r"(0), "r"(row_lo), "r"(full[s]) : "memory");
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {   // ------------------------------------------------------------- A producers / epilogue (thread = tile row)
+    const int r = threadIdx.x - 128;
+    const int quad = warp & 3;
+    int g = 0;
+    // layer 0: x[row0 + r, :] -> chunks (zero rows beyond the batch, zero columns beyond in_dim)
+    {
+      const float* xr = a.x + (size_t)(row0 + (r < valid ? r : 0)) * a.in_dim;
+      const bool vec = (a.in_dim & 3) == 0;
+      float4 cur[8], nxt[8];
+      auto load = [&](float4 (&v)[8], int c) {
+#pragma unroll
+        for (int k4 = 0; k4 < 8; k4++) {
+          const int col = c * KC2 + 4 * k4;
+          v[k4] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (r < valid) {
+            if (vec && col + 3 < a.in_dim) v[k4] = *reinterpret_cast<const float4*>(xr + col);
+            else {
+              if (col + 0 < a.in_dim) v[k4].x = xr[col + 0];
+              if (col + 1 < a.in_dim) v[k4].y = xr[col + 1];
+              if (col + 2 < a.in_dim) v[k4].z = xr[col + 2];
+              if (col + 3 < a.in_dim) v[k4].w = xr[col + 3];
+            }
+          }
+        }
+      };
+      load(cur, 0);
+      for (int c = 0; c < pn.chunks[0] && ok; c++, g++) {
+        if (c + 1 < pn.chunks[0]) load(nxt, c + 1);
+        const int s = g % V2_NS, use = g / V2_NS;
+        if (use > 0) ok = mbar_wait(empty[s], (use - 1) & 1);
+        if (!ok) break;
+        float* A_hi = stage0 + s * V2_STAGE_FLOATS;
+        v2_store_row_chunk(cur, r, A_hi, A_hi + V2_A_PART, precise);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        mbar_arrive(full[s]);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; k4++) cur[k4] = nxt[k4];
+      }
+    }
+    // layers 1 and 2: the previous layer's accumulator, 32 columns at a time -> bias + ReLU -> next K chunk
+    for (int layer = 1; layer < 3 && ok; layer++) {
+      ok = mbar_wait(acc[layer - 1], 0);
+      if (!ok) break;
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const float* bias = a.bias[net][layer - 1];
+      const uint32_t dsrc = tmem + ((uint32_t)(quad * 32) << 16) + (layer == 2 ? 256u : 0u);
+      for (int c = 0; c < pn.chunks[layer] && ok; c++, g++) {
+        uint32_t v[32];
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+              : "=r"(v[16 * h + 0]), "=r"(v[16 * h + 1]), "=r"(v[16 * h + 2]), "=r"(v[16 * h + 3]), "=r"(v[16 * h + 4]), "=r"(v[16 * h + 5]),
+                "=r"(v[16 * h + 6]), "=r"(v[16 * h + 7]), "=r"(v[16 * h + 8]), "=r"(v[16 * h + 9]), "=r"(v[16 * h + 10]), "=r"(v[16 * h + 11]),
+                "=r"(v[16 * h + 12]), "=r"(v[16 * h + 13]), "=r"(v[16 * h + 14]), "=r"(v[16 * h + 15])
+              : "r"(dsrc + (uint32_t)(c * KC2 + 16 * h)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        float4 o[8];
+#pragma unroll
+        for (int k4 = 0; k4 < 8; k4++) {
+          const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + c * KC2 + 4 * k4));
+          o[k4].x = fmaxf(__uint_as_float(v[4 * k4 + 0]) + b4.x, 0.f);
+          o[k4].y = fmaxf(__uint_as_float(v[4 * k4 + 1]) + b4.y, 0.f);
+          o[k4].z = fmaxf(__uint_as_float(v[4 * k4 + 2]) + b4.z, 0.f);
+          o[k4].w = fmaxf(__uint_as_float(v[4 * k4 + 3]) + b4.w, 0.f);
+        }
+        const int s = g % V2_NS, use = g / V2_NS;
+        if (use > 0) ok = mbar_wait(empty[s], (use - 1) & 1);
+        if (!ok) break;
+        float* A_hi = stage0 + s * V2_STAGE_FLOATS;
+        v2_store_row_chunk(o, r, A_hi, A_hi + V2_A_PART, precise);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");   // the TMEM reads above precede whoever this releases
+        mbar_arrive(full[s]);
+      }
+    }
+    // output head: accumulator columns [0, 32) + bias -> global
+    if (ok) ok = mbar_wait(acc[2], 0);
+    if (ok) {
+      asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+      const float* bias = a.bias[net][2];
+      const int nout = pn.nout;
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        if (16 * h >= nout) break;
+        uint32_t v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(16 * h)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        if (r < valid) {
+#pragma unroll
+          for (int q = 0; q < 16; q++)
+            if (16 * h + q < nout) a.y[net][(size_t)(row0 + r) * nout + 16 * h + q] = __uint_as_float(v[q]) + __ldg(bias + 16 * h + q);
+        }
+      }
+    }
+  }
+  if (!ok) atomicExch(a.error, 1);
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(tmem) : "memory");
+}
+
 // ---- DiagGaussian sampling of SB3 (common/distributions.py): a = mean + exp(log_std) * eps, log_prob summed over
 // action dims, clipped copy for the env (collect_rollouts clips to the Box bounds, the buffer keeps the raw action).
 __device__ __forceinline__ void philox(uint32_t c[4], uint32_t k0, uint32_t k1) {
@@ -553,6 +843,124 @@ int b2h_policy_forward(const float* x_dev, const float* const pi_dev[6], const f
   a.y[0] = mean_dev; a.y[1] = value_dev; a.out_dim[0] = act_dim; a.out_dim[1] = 1;
   a.n_rows = n_rows; a.in_dim = in_dim; a.hidden = hidden; a.precise = precise; a.error = error_flag_dev;
   return launch_mlp(a, 2, stream);
+}
+
+// ---- packed-weight pipeline (mlp_forward_v2_kernel)
+struct B2HPolicyPacked {
+  int in_dim, hidden, act_dim;
+  float* buf;
+  size_t off[2][3];        // floats
+  PackedNet net[2];
+  V2Maps maps;
+};
+
+void b2h_policy_packed_destroy(B2HPolicyPacked* p) {
+  if (!p) return;
+  if (p->buf) cudaFree(p->buf);
+  delete p;
+}
+
+int b2h_policy_packed_create(int in_dim, int hidden, int act_dim, B2HPolicyPacked** out) {
+  if (!out || in_dim < 1 || hidden < 32 || hidden > MAXH || hidden % 32 || act_dim < 1 || act_dim > 32) {
+    g_err_mlp = "unsupported MLP shape (hidden a multiple of 32 in [32, 256], act_dim <= 32)";
+    return B2H_EUNSUPPORTED;
+  }
+  B2HPolicyPacked* p = new B2HPolicyPacked();
+  p->in_dim = in_dim; p->hidden = hidden; p->act_dim = act_dim; p->buf = nullptr;
+  size_t total = 0;
+  for (int n = 0; n < 2; n++) {
+    const int K[3] = {in_dim, hidden, hidden}, N[3] = {hidden, hidden, 32};
+    for (int l = 0; l < 3; l++) {
+      p->net[n].chunks[l] = (K[l] + KC2 - 1) / KC2;
+      p->net[n].n[l] = N[l];
+      p->off[n][l] = total;
+      total += (size_t)p->net[n].chunks[l] * 2 * N[l] * KC2;      // hi + lo, K padded to whole chunks
+    }
+    p->net[n].nout = n == 0 ? act_dim : 1;
+  }
+  if (cudaMalloc(&p->buf, total * sizeof(float)) != cudaSuccess) { g_err_mlp = "cudaMalloc failed"; delete p; return B2H_ENOMEM; }
+  // the driver entry point is looked up at run time: the library must load (and export its symbols) on a machine without
+  // libcuda.so, e.g. the CPU-only build container
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                               const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeFn encode = nullptr;
+  {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+      g_err_mlp = "cuTensorMapEncodeTiled is not available from this driver";
+      b2h_policy_packed_destroy(p);
+      return B2H_ECUDA;
+    }
+    encode = reinterpret_cast<EncodeFn>(fn);
+  }
+  cudaMemset(p->buf, 0, total * sizeof(float));
+  for (int n = 0; n < 2; n++)
+    for (int l = 0; l < 3; l++) {
+      // the packed layer as a 2-D tensor: rows = 128-byte core matrices (32 floats), one box = one part (hi or lo) of a K chunk
+      const cuuint64_t dims[2] = {32, (cuuint64_t)p->net[n].chunks[l] * 2 * p->net[n].n[l]};
+      const cuuint64_t strides[1] = {128};
+      const cuuint32_t box[2] = {32, (cuuint32_t)p->net[n].n[l]};
+      const cuuint32_t estr[2] = {1, 1};
+      CUresult r = encode(&p->maps.m[n][l], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, p->buf + p->off[n][l], dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { g_err_mlp = "cuTensorMapEncodeTiled failed"; b2h_policy_packed_destroy(p); return B2H_ECUDA; }
+    }
+  const size_t smem = (size_t)V2_SMEM_FLOATS * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(mlp_forward_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { g_err_mlp = cudaGetErrorString(e); b2h_policy_packed_destroy(p); return B2H_ECUDA; }
+  *out = p;
+  return B2H_OK;
+}
+
+int b2h_policy_pack(B2HPolicyPacked* p, const float* const pi_dev[6], const float* const vf_dev[6], void* stream) {
+  if (!p || !pi_dev || !vf_dev) { g_err_mlp = "null argument"; return B2H_EINVAL; }
+  PackJobs jobs;
+  int max_items = 0;
+  for (int n = 0; n < 2; n++) {
+    const float* const* w = n == 0 ? pi_dev : vf_dev;
+    const int K[3] = {p->in_dim, p->hidden, p->hidden}, nout[3] = {p->hidden, p->hidden, p->net[n].nout};
+    for (int l = 0; l < 3; l++) {
+      if (!w[2 * l]) { g_err_mlp = "null argument"; return B2H_EINVAL; }
+      PackJob& jb = jobs.j[3 * n + l];
+      jb.W = w[2 * l]; jb.dst = p->buf + p->off[n][l]; jb.nout = nout[l]; jb.K = K[l]; jb.N = p->net[n].n[l]; jb.chunks = p->net[n].chunks[l];
+      const int items = jb.chunks * (KC2 / 4) * jb.N;
+      if (items > max_items) max_items = items;
+    }
+  }
+  pack_weights_kernel<<<dim3((max_items + 255) / 256, 6), 256, 0, (cudaStream_t)stream>>>(jobs);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_err_mlp = cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
+}
+
+int b2h_policy_forward_packed(B2HPolicyPacked* p, const float* x_dev, const float* const pi_dev[6], const float* const vf_dev[6],
+                              float* mean_dev, float* value_dev, int n_rows, int precise, int* error_flag_dev, void* stream) {
+  if (!p || !x_dev || !pi_dev || !vf_dev || !error_flag_dev || n_rows <= 0 || (!mean_dev && !value_dev)) { g_err_mlp = "bad argument"; return B2H_EINVAL; }
+  V2Args a = {};
+  a.x = x_dev; a.n_rows = n_rows; a.in_dim = p->in_dim; a.precise = precise; a.error = error_flag_dev;
+  // blockIdx.y walks the requested networks: both, or only the value trunk (predict_values) / only the policy trunk
+  V2Maps maps;
+  int nn = 0;
+  for (int n = 0; n < 2; n++) {
+    float* y = n == 0 ? mean_dev : value_dev;
+    if (!y) continue;
+    const float* const* w = n == 0 ? pi_dev : vf_dev;
+    for (int l = 0; l < 3; l++) {
+      if (!w[2 * l + 1]) { g_err_mlp = "null argument"; return B2H_EINVAL; }
+      a.bias[nn][l] = w[2 * l + 1];
+      maps.m[nn][l] = p->maps.m[n][l];
+    }
+    a.y[nn] = y; a.net[nn] = p->net[n];
+    nn++;
+  }
+  const size_t smem = (size_t)V2_SMEM_FLOATS * sizeof(float);
+  dim3 grid((n_rows + TILE_M - 1) / TILE_M, nn);
+  mlp_forward_v2_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(maps, a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_err_mlp = cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
 }
 
 int b2h_policy_sample(const float* mean_dev, const float* log_std_dev, int n_rows, int act_dim, uint64_t seed, uint64_t step,

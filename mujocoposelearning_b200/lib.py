@@ -43,6 +43,10 @@ SIGNATURES = {
     "b2h_mlp_last_error": (C.c_char_p, []),
     "b2h_policy_sample": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_int, C.c_int, vp, vp, vp, vp]),
     "b2h_policy_sample_dev": (C.c_int, [vp, vp, C.c_int, C.c_int, C.c_uint64, vp, C.c_uint64, C.c_int, C.c_int, vp, vp, vp, vp]),
+    "b2h_policy_packed_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(vp)]),
+    "b2h_policy_packed_destroy": (None, [vp]),
+    "b2h_policy_pack": (C.c_int, [vp, vp, vp, vp]),
+    "b2h_policy_forward_packed": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
     "b2h_sizeof_rollout": (C.c_size_t, []),
     "b2h_rollout_collect": (C.c_int, [vp, C.POINTER(abi.B2HRollout), vp]),
 }

@@ -56,12 +56,47 @@ class MlpPolicyParams:
 
 
 class MlpPolicy:
-    """Forward-only policy used during rollout."""
+    """Forward-only policy used during rollout.
 
-    def __init__(self, params: MlpPolicyParams, precise=True, seed=0, row_offset=0):
+    ``kernel="v2"`` (default): weights packed once per update into tf32 hi / lo core-matrix order, streamed by TMA, activations
+    kept on chip between the layers (``b2h_policy_pack`` + ``b2h_policy_forward_packed``).  ``forward`` / ``values`` re-pack
+    before every call (a few microseconds; always correct after an in-place weight update); the in-library rollout loop
+    packs once per rollout.  ``kernel="v1"`` is the round-1 warp-specialised kernel (needs in_dim % 16 == 0)."""
+
+    def __init__(self, params: MlpPolicyParams, precise=True, seed=0, row_offset=0, kernel="v2"):
         self.p, self.precise, self.seed, self.row_offset = params, int(precise), int(seed), int(row_offset)
         self.lib = load()
         self.err = torch.zeros(1, dtype=torch.int32, device=params.device)
+        self.kernel = kernel
+        self.packed = None
+        if kernel == "v2":
+            with torch.cuda.device(params.device):
+                h = C.c_void_p()
+                rc = self.lib.b2h_policy_packed_create(params.obs_dim, params.hidden, params.act_dim, C.byref(h))
+                if rc < 0:
+                    raise RuntimeError(f"b2h_policy_packed_create: {self.lib.b2h_mlp_last_error().decode()}")
+                self.packed = h
+        self._pi = (C.c_void_p * 6)(*[t.data_ptr() for t in params.pi])
+        self._vf = (C.c_void_p * 6)(*[t.data_ptr() for t in params.vf])
+
+    def __del__(self):
+        if getattr(self, "packed", None):
+            self.lib.b2h_policy_packed_destroy(self.packed)
+            self.packed = None
+
+    def pack(self):
+        """Prepare the current weights for the tensor cores (call after the weights changed; forward() does it itself)."""
+        s = C.c_void_p(torch.cuda.current_stream(self.p.device).cuda_stream)
+        rc = self.lib.b2h_policy_pack(self.packed, self._pi, self._vf, s)
+        if rc < 0:
+            raise RuntimeError(f"b2h_policy_pack: {self.lib.b2h_mlp_last_error().decode()}")
+
+    def _forward_packed(self, obs, mean, value):
+        s = C.c_void_p(torch.cuda.current_stream(self.p.device).cuda_stream)
+        rc = self.lib.b2h_policy_forward_packed(self.packed, _p(obs), self._pi, self._vf, _p(mean) if mean is not None else None,
+                                                _p(value) if value is not None else None, obs.shape[0], self.precise, _p(self.err), s)
+        if rc < 0:
+            raise RuntimeError(f"b2h_policy_forward_packed: {self.lib.b2h_mlp_last_error().decode()}")
 
     def _net(self, net, x, out_dim):
         p = self.p
@@ -81,6 +116,10 @@ class MlpPolicy:
         E = obs.shape[0]
         mean = torch.empty(E, p.act_dim, device=p.device, dtype=torch.float32)
         value = torch.empty(E, device=p.device, dtype=torch.float32)
+        if self.packed:
+            self.pack()
+            self._forward_packed(obs, mean, value)
+            return mean, value
         pi = (C.c_void_p * 6)(*[t.data_ptr() for t in p.pi])
         vf = (C.c_void_p * 6)(*[t.data_ptr() for t in p.vf])
         s = C.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)
@@ -93,6 +132,11 @@ class MlpPolicy:
     def values(self, obs):
         if obs.dtype != torch.float32 or not obs.is_contiguous():
             obs = obs.to(torch.float32).contiguous()
+        if self.packed:
+            value = torch.empty(obs.shape[0], device=self.p.device, dtype=torch.float32)
+            self.pack()
+            self._forward_packed(obs, None, value)
+            return value
         return self._net(self.p.vf, obs, 1).squeeze(1)
 
     def sample(self, mean, step, deterministic=False):
@@ -171,6 +215,7 @@ class RolloutCollector:
             setattr(r, name, t.data_ptr())
         for k in range(6):
             r.pi[k], r.vf[k] = p.pi[k].data_ptr(), p.vf[k].data_ptr()
+        r.packed = policy.packed
         self._args = r
         self.cuda_graph = bool(cuda_graph)
         self._graph = None

@@ -8,22 +8,50 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
+@pytest.mark.parametrize("kernel", ["v2", "v1"])
 @pytest.mark.parametrize("n_rows", [1, 127, 128, 1000, 4096])
 @pytest.mark.parametrize("precise,tol", [(True, 2e-5), (False, 5e-3)])
-def test_mlp_forward_matches_torch_fp32(n_rows, precise, tol):
+def test_mlp_forward_matches_torch_fp32(n_rows, precise, tol, kernel):
     from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams
     p = MlpPolicyParams(seed=3)
     g = torch.Generator(device="cuda").manual_seed(1)
     for t in p.pi[1::2] + p.vf[1::2]:                        # non-zero biases so the epilogue is exercised
         t.copy_(torch.randn(t.shape, device="cuda", generator=g) * 0.1)
-    pol = MlpPolicy(p, precise=precise)
+    pol = MlpPolicy(p, precise=precise, kernel=kernel)
     obs = torch.randn(n_rows, 352, device="cuda", generator=g) * 2.0
     mean, value = pol.forward(obs)
+    v_only = pol.values(obs)
     torch.cuda.synchronize()
     pol.check_error()
     mref, vref = pol.forward_torch(obs)
     scale_m, scale_v = float(mref.abs().max()), float(vref.abs().max())
     assert float((mean - mref).abs().max()) < tol * max(1.0, scale_m) and float((value - vref).abs().max()) < tol * max(1.0, scale_v)
+    assert torch.equal(v_only, value)                        # predict_values: the value trunk on its own
+
+
+@pytest.mark.parametrize("obs_dim,hidden,act_dim", [(53, 256, 21), (352, 64, 21), (40, 128, 3), (352, 256, 32)])
+def test_mlp_v2_shapes(obs_dim, hidden, act_dim):
+    """The packed-weight kernel pads K chunks itself: any observation width (obs_mode='qpos_qvel' = 53 columns), the
+    64 x 64 nets of the reference's config.py:26-32, other head widths -- against the PyTorch fp32 forward."""
+    from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams
+    p = MlpPolicyParams(obs_dim=obs_dim, act_dim=act_dim, hidden=hidden, seed=5)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    for t in p.pi[1::2] + p.vf[1::2]:
+        t.copy_(torch.randn(t.shape, device="cuda", generator=g) * 0.1)
+    pol = MlpPolicy(p, precise=True)
+    obs = torch.randn(300, obs_dim, device="cuda", generator=g)
+    mean, value = pol.forward(obs)
+    torch.cuda.synchronize()
+    pol.check_error()
+    mref, vref = pol.forward_torch(obs)
+    assert float((mean - mref).abs().max()) < 2e-5 * max(1.0, float(mref.abs().max()))
+    assert float((value - vref).abs().max()) < 2e-5 * max(1.0, float(vref.abs().max()))
+    # an in-place weight update is seen by the next forward (forward() re-packs)
+    with torch.no_grad():
+        p.pi[4].mul_(2.0)
+    mean2, _ = pol.forward(obs)
+    mref2, _ = pol.forward_torch(obs)
+    assert float((mean2 - mref2).abs().max()) < 2e-5 * max(1.0, float(mref2.abs().max())) and not torch.equal(mean, mean2)
 
 
 def test_policy_sample_statistics_and_logprob():

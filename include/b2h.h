@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define B2H_ABI_VERSION 1
+#define B2H_ABI_VERSION 2
 
 #define B2H_MAX_BODY 32
 #define B2H_MAX_JNT 32
@@ -146,6 +146,10 @@ typedef struct B2HConfig {
   double duration;         /* custom_env.py:22 (terminated = time >= duration, :213)               */
   uint64_t seed;           /* reset-noise Philox key                                               */
   double kneeling_params[9]; /* target_height,min_height,max_roll_pitch,com_radius,energy_w,posture_w,com_w,foot_w,alive_w */
+  int32_t sensor_terms;    /* 0 (default) = the reference: data.cfrc_ext / data.subtree_linvel are identically zero (the model has
+                              no sensor, so MuJoCo never computes them: reward_functions.py:109,121-122,176-177 read zeros).
+                              1 = compute what mj_rnePostConstraint (contact part) / mj_subtreeVel would give and feed the rewards. */
+  int32_t reserved_;
 } B2HConfig;
 
 typedef struct B2HHandle B2HHandle;

@@ -189,7 +189,7 @@ reset_kernel(const DevModel<T>* __restrict__ gmodel, EnvParams P, EnvIO<T> io, i
 
 template <typename T>
 __global__ void __launch_bounds__(32, 1)
-debug_kernel(const DevModel<T>* model, EnvIO<T> io, int env, DebugDump<T>* out, T* Jspill) {
+debug_kernel(const DevModel<T>* model, EnvIO<T> io, int env, DebugDump<T>* out, T* Jspill, int ext) {
   model = stage_model<T>(model);
   Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(b2h_smem + model_smem_bytes<T>());
   const int lane = lane_id(), nq = model->nq, nv = model->nv, nu = model->nu;
@@ -204,7 +204,8 @@ debug_kernel(const DevModel<T>* model, EnvIO<T> io, int env, DebugDump<T>* out, 
   st.ctrl = (a >= 0 && io.actions) ? T(io.actions[(size_t)env * nu + a]) : T(0);
   T qacc;
   StepStats stats;
-  physics_step<T, true>(*model, S, Jspill, st, cnt, false, &stats, &qacc, out);
+  if (ext) physics_step<T, true, NSLOT, true>(*model, S, Jspill, st, cnt, false, &stats, &qacc, out);
+  else physics_step<T, true>(*model, S, Jspill, st, cnt, false, &stats, &qacc, out);
   __syncwarp();
   if (lane == 0) out->stats = stats;
 }
@@ -409,6 +410,7 @@ int b2h_create(const B2HModel* model, const B2HConfig* cfg, B2HHandle** out) {
   for (int k = 0; k < 9; k++) h->P.kneel[k] = cfg->kneeling_params[k];
   h->P.seed = cfg->seed; h->P.env_id_offset = cfg->env_id_offset;
   h->P.sync_mode = 2;
+  h->P.sensor_terms = cfg->sensor_terms != 0;
   if (const char* sm = getenv("B2H_SYNC_MODE")) h->P.sync_mode = atoi(sm);  // tuning knob, see env_step
   int rc = cfg->dtype == B2H_F64 ? create_typed<double>(h) : create_typed<float>(h);
   if (rc != B2H_OK) { b2h_destroy(h); return rc; }
@@ -684,7 +686,7 @@ int b2h_set_state(B2HHandle* h, const double* qpos, const double* qvel, const do
 template <typename T>
 static int debug_typed(B2HHandle* h, const float* actions_dev, int env, const char* what, double* out, int max_out) {
   debug_kernel<T><<<1, 32, sizeof(Scratch<T>) + model_smem_bytes<T>()>>>((const DevModel<T>*)h->dmodel,
-      make_io<T>(h, actions_dev, nullptr, nullptr, nullptr, nullptr, nullptr), env, (DebugDump<T>*)h->dump, (T*)h->spill);
+      make_io<T>(h, actions_dev, nullptr, nullptr, nullptr, nullptr, nullptr), env, (DebugDump<T>*)h->dump, (T*)h->spill, h->P.sensor_terms);
   CU(cudaGetLastError());
   CU(cudaDeviceSynchronize());
   h->launches++;

@@ -34,6 +34,8 @@ int extract_named(const DevModel<T>& m, const DebugDump<T>& d, const char* what,
   else if (!strcmp(what, "qfrc_actuator")) lanes(5, m.nv);
   else if (!strcmp(what, "limit_D")) lanes(6, m.nv);
   else if (!strcmp(what, "limit_aref")) lanes(7, m.nv);
+  else if (!strcmp(what, "cfrc_ext")) arr(d.cfrc_ext, 6 * m.nbody);
+  else if (!strcmp(what, "subtree_linvel0")) arr(d.sub_linvel, 3);
   else if (!strcmp(what, "ncon")) put((T)d.stats.ncon);
   else if (!strcmp(what, "nrow")) put((T)d.stats.nrow);
   else if (!strcmp(what, "nefc")) put((T)(d.stats.nrow + d.stats.nlimit));

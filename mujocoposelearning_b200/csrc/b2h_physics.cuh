@@ -446,6 +446,7 @@ struct DebugDump {  // named views of one mj_forward (parity / debug only)
   T cinert[KB * 10], cvel[KB * 6], cdof[KV * 6], cdofdot[KV * 6];
   T con_dist[NCON], con_pos[NCON * 3], con_frame[NCON * 9], com[4];
   T lane[32][8];       // per-lane: qfrc_bias, qfrc_smooth, qacc_smooth, qacc, qfrc_constraint, qfrc_actuator, limit D, limit aref
+  T cfrc_ext[KB * 6], sub_linvel[4];   // EXT instantiation only (section 8 f4)
   StepStats stats;
 };
 
@@ -461,7 +462,10 @@ struct DebugDump {  // named views of one mj_forward (parity / debug only)
 // NS = 1 instantiation -- no slot 1 / slot 2 copies of the row loops in the instruction stream -- and falls back to
 // the full-capacity one (a separate, out-of-line function) when the rows do not fit: return value 2, state untouched.
 enum { B2H_STEP_OK = 0, B2H_STEP_BAD_ACC = 1, B2H_STEP_MORE_ROWS = 2 };
-template <typename T, bool DBG = false, int NS = NSLOT>
+// EXT = true (B2HConfig::sensor_terms, section 8 f4; never on the bench path) also computes what the rewards read from
+// data.cfrc_ext[-2], [-1] and data.subtree_linvel[0] (reward_functions.py:109,121-122,176-177) if MuJoCo computed them:
+// the contact part of mj_rnePostConstraint and the whole-model row of mj_subtreeVel; results in S.vec[0][0..4].
+template <typename T, bool DBG = false, int NS = NSLOT, bool EXT = false>
 B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, bool integrate_arg,
                                    StepStats* stats_arg, T* qacc_out_arg, DebugDump<T>* dbg_arg /* optional named dump */) {
   constexpr int NSLOT = NS;   // shadows the capacity constant for everything below (arrays, B2H_SLOTS)
@@ -979,6 +983,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
   if (lane < KV) for (int k = 0; k < 6; k++) { tmp[TMP_CDD + 6 * lane + k] = cdd[k]; tmp[TMP_DOFA + 6 * lane + k] = cdd[k] * (lane < nv ? st.qv : T(0)); }
   wsync();
   // ---- cvel, cacc (lane = body) as chain sums; cfrc_body = I cacc + cvel x* (I cvel)   (mj_rne, flg_acc = 0)
+  T bmom[3] = {0, 0, 0};
   if (lane > 0 && lane < nbody) {
     T cv[6] = {0, 0, 0, 0, 0, 0}, ca[6] = {0, 0, 0, 0, 0, 0};
     for (int j = B2H_LDG(m.body_lastdof[lane]); j >= 0; j = B2H_LDG(m.dof_parent[j]))
@@ -988,6 +993,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
     T f[6], t1[6], t2[6];
     mul_inert_vec(f, S.cinert + 10 * lane, ca);
     mul_inert_vec(t1, S.cinert + 10 * lane, cv);
+    if constexpr (EXT) { bmom[0] = t1[3]; bmom[1] = t1[4]; bmom[2] = t1[5]; }   // the body's linear momentum
     cross_force(t2, cv, t1);
     for (int k = 0; k < 6; k++) tmp[TMP_CFRC + 6 * lane + k] = f[k] + t2[k];
   }
@@ -1037,6 +1043,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
   // =============================================================== mj_fwdConstraint: Newton solver (primal)
   T qacc = qacc_smooth, qfrc_con = 0;
   int niter = 0;
+  T fin[NSLOT] = {};   // EXT: the dense rows' forces at the solution
   if (nefc > 0) {
     // J*x - aref for the dense rows of this lane and its limit row; x is read from S.vec[2]
     auto jar_of = [&](T x_lane, T* jar, T* ljar) {
@@ -1104,6 +1111,10 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
         bool on = lsign != T(0) && lJaref < T(0);
         if (on) { lf = -lD * lJaref; c += T(0.5) * lD * lJaref * lJaref; }
         actl = ballot(on);
+      }
+      if constexpr (EXT) {
+#pragma unroll
+        for (int s = 0; s < NSLOT; s++) fin[s] = f[s];
       }
       T oldcost = cost;
       gauss = wsum(lane < nv ? T(0.5) * (Ma - qfrc_smooth) * (qacc - qacc_smooth) : T(0));
@@ -1277,6 +1288,47 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
   } else {
     st.warm = qacc_smooth;
   }
+  if constexpr (EXT) {
+    // ---- mj_subtreeVel, whole-model row: total linear momentum / total mass
+    T lv[3];
+    for (int k = 0; k < 3; k++) lv[k] = wsum(bmom[k]) * B2H_LDG(m.inv_total_mass);
+    // ---- mj_rnePostConstraint, contact part (lane = body): the contact force in the world as a spatial force about the
+    // tree's centre of mass, subtracted from body 1 (unless it is the world), added to body 2
+    T ce[6] = {0, 0, 0, 0, 0, 0};
+    auto row_force = [&](int r) {
+      T v = 0;
+#pragma unroll
+      for (int s = 0; s < NSLOT; s++) { T t = shfl(fin[s], r & 31); if ((r >> 5) == s) v = t; }
+      return v;
+    };
+    for (int c = 0; c < ncon; c++) {
+      int r0 = S.con_row[c];
+      if (r0 < 0) continue;
+      uint32_t info = S.con_info[c];
+      int b1 = info & 255, b2 = (info >> 8) & 255, cls = info >> 16;
+      T lf[3] = {0, 0, 0};
+      if (B2H_LDG(m.cls_condim[cls]) == 1) lf[0] = row_force(r0);
+      else {   // mj_contactForce, pyramidal: normal = sum of the edge forces, tangents mu * (f0 - f1), mu * (f2 - f3)
+        T f0 = row_force(r0), f1 = row_force(r0 + 1), f2 = row_force(r0 + 2), f3 = row_force(r0 + 3), mu = B2H_LDG(m.cls_mu[cls]);
+        lf[0] = f0 + f1 + f2 + f3; lf[1] = mu * (f0 - f1); lf[2] = mu * (f2 - f3);
+      }
+      const T* fr = S.con_frame + 9 * c;
+      T fw[3], off[3], tq[3];
+      for (int k = 0; k < 3; k++) { fw[k] = fr[k] * lf[0] + fr[3 + k] * lf[1] + fr[6 + k] * lf[2]; off[k] = S.con_pos[3 * c + k] - com[k]; }
+      cross3(tq, off, fw);
+      T sg = T(lane == b2 && b2 != 0 ? 1 : 0) - T(lane == b1 && b1 != 0 ? 1 : 0);
+      for (int k = 0; k < 3; k++) { ce[k] += sg * tq[k]; ce[3 + k] += sg * fw[k]; }
+    }
+    T l1 = m_abs(ce[0]) + m_abs(ce[1]) + m_abs(ce[2]) + m_abs(ce[3]) + m_abs(ce[4]) + m_abs(ce[5]);
+    T lf_ = shfl(l1, nbody - 2), rf_ = shfl(l1, nbody - 1);
+    wsync();
+    if (lane == 0) { S.vec[0][0] = lf_; S.vec[0][1] = rf_; S.vec[0][2] = lv[0]; S.vec[0][3] = lv[1]; S.vec[0][4] = lv[2]; }
+    if (dbg) {
+      if (lane < KB) for (int k = 0; k < 6; k++) dbg->cfrc_ext[6 * lane + k] = ce[k];
+      if (lane < 3) dbg->sub_linvel[lane] = lv[lane];
+    }
+    wsync();
+  }
   if (stats) { stats->ncon = ncon; stats->nrow = nrow; stats->nlimit = popc(limit_mask); stats->niter = niter; }
   if (dbg) {
     T* dl = dbg->lane[lane];
@@ -1338,13 +1390,16 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
 // ns: slots to start with (warp-uniform; the step kernel makes it CTA-uniform from the rows the group's envs needed in
 // their previous control step, so that a lockstep group walks ONE instantiation); too few slots fall back to all.
 template <typename T>
-B2H_DEV void mj_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, int ns = 1) {
+B2H_DEV void mj_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, int ns = 1, bool ext = false) {
   for (int tries = 0; tries < 2; tries++) {
     int rc;
-    if (ns <= 1) rc = physics_step<T, false, 1>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
-    else if (ns == 2) rc = physics_step<T, false, 2>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
-    else rc = B2H_STEP_MORE_ROWS;
-    if (rc == B2H_STEP_MORE_ROWS) rc = physics_step<T, false, NSLOT>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
+    if (ext) rc = physics_step<T, false, NSLOT, true>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);   // section 8 f4, not the bench path
+    else {
+      if (ns <= 1) rc = physics_step<T, false, 1>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
+      else if (ns == 2) rc = physics_step<T, false, 2>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
+      else rc = B2H_STEP_MORE_ROWS;
+      if (rc == B2H_STEP_MORE_ROWS) rc = physics_step<T, false, NSLOT>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
+    }
     if (rc == B2H_STEP_OK) break;
   }
 }
@@ -1370,6 +1425,7 @@ struct EnvParams {
   uint64_t seed;
   int env_id_offset;
   int sync_mode;  // CTA lockstep: 0 none, 1 once per control step, 2 before every physics sub-step
+  int sensor_terms;  // B2HConfig::sensor_terms (section 8 f4): 0 = the reference (cfrc_ext / subtree_linvel read as zeros)
 };
 
 template <typename T> B2H_DEV void quat_to_euler(const T* q, T* roll, T* pitch) {  // utils.py:3-20 (pitch unclamped)
@@ -1388,12 +1444,15 @@ B2H_DEV_NOINLINE T compute_reward(const DevModel<T>& m, const Scratch<T>& S, con
   T ctrl2 = wsum(lane < nv ? st.ctrl * st.ctrl : T(0));
   T power = wsum(lane >= 6 && lane < nv ? (st.qfrc_act * st.qv) * (st.qfrc_act * st.qv) : T(0));
   quat_to_euler(q, &roll, &pitch);
+  // sum |cfrc_ext[-2]|, sum |cfrc_ext[-1]|, subtree_linvel[0]: zeros in the reference (no sensors), see physics_step<EXT>
+  T lff = 0, rff = 0, lv2 = 0;
+  if (P.sensor_terms) { lff = S.vec[0][0]; rff = S.vec[0][1]; lv2 = S.vec[0][2] * S.vec[0][2] + S.vec[0][3] * S.vec[0][3] + S.vec[0][4] * S.vec[0][4]; }
   if (P.reward_type == B2H_REWARD_STAND) {
     if (hgt < T(0.8)) return T(0);
     T vr = m_exp(T(-2) * (vx - T(1)) * (vx - T(1)));
     T hr = m_exp(T(-2) * (hgt - T(1.282)) * (hgt - T(1.282)));
     T orr = m_exp(T(-3) * (roll * roll + pitch * pitch));
-    T foot = T(1) - m_min(T(0), T(0)) / (T(0) + T(0) + T(1e-8));
+    T foot = T(1) - m_min(lff, rff) / (lff + rff + T(1e-8));
     return T(0.4) * vr + T(0.3) * (T(0.5) * hr + T(0.5) * orr) + T(0.2) * foot + T(0.1) * m_exp(T(-0.05) * ctrl2);
   }
   if (P.reward_type == B2H_REWARD_WALK) {
@@ -1408,8 +1467,8 @@ B2H_DEV_NOINLINE T compute_reward(const DevModel<T>& m, const Scratch<T>& S, con
   T oerr = (roll * roll + pitch * pitch) / (mrp * mrp);
   T posture = T(0.7) * m_exp(T(-5) * oerr) + T(0.3) * m_exp(T(-5) * (hgt - th) * (hgt - th));
   T dist = m_sqrt(S.com[0] * S.com[0] + S.com[1] * S.com[1]);
-  T com_score = T(0.7) * m_exp(T(-10) * (dist / crad)) + T(0.3) * m_exp(T(-0.1) * T(0));
-  T foot_balance = m_min(T(0), T(0)) / (T(0) + T(0) + T(1e-8));
+  T com_score = T(0.7) * m_exp(T(-10) * (dist / crad)) + T(0.3) * m_exp(T(-0.1) * lv2);
+  T foot_balance = m_min(lff, rff) / (lff + rff + T(1e-8));
   T energy = m_exp(T(-0.01) * power);
   T alive = T(1) - m_exp(T(-0.5) * T((double)st.nstep * P.timestep));
   return T(P.kneel[5]) * posture + T(P.kneel[6]) * com_score + T(P.kneel[7]) * foot_balance + T(P.kneel[4]) * energy +
@@ -1475,7 +1534,7 @@ B2H_DEV_NOINLINE void env_reset(const DevModel<T>& m, Scratch<T>& S, T* Jspill, 
   st.qp = lane < nq ? T(q0 + npos) : T(0);
   st.qv = lane < nv ? T(nvel) : T(0);
   st.warm = 0; st.ctrl = 0; st.qfrc_act = 0; st.nstep = 0;
-  mj_step<T>(m, S, Jspill, st, cnt);
+  mj_step<T>(m, S, Jspill, st, cnt, 1, P.sensor_terms != 0);
 }
 
 // HumanoidEnv.step + SubprocVecEnv auto-reset for one env (custom_env.py:152-230; SB3 subproc_vec_env._worker)
@@ -1513,7 +1572,7 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     if (active) {
       // data.ctrl[:] = action before every mj_step (a bad-state reset inside the previous sub-step zeroed it)
       st.ctrl = action;
-      mj_step<T>(m, S, Jspill, st, cnt, ns);
+      mj_step<T>(m, S, Jspill, st, cnt, ns, P.sensor_terms != 0);
     }
   }
   bool done = false;

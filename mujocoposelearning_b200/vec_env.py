@@ -65,7 +65,7 @@ def parse_env_config(env_config):
                 reward_config={"type": "default"}, frame_skip=5, run_name=None)
 
 
-def _make_batch(cfg, n_envs, device, dtype, obs_mode, seed, env_id_offset):
+def _make_batch(cfg, n_envs, device, dtype, obs_mode, seed, env_id_offset, sensor_terms=False):
     rc = cfg["reward_config"] or {"type": "default"}
     import os
     mp = cfg["model_path"]
@@ -73,20 +73,21 @@ def _make_batch(cfg, n_envs, device, dtype, obs_mode, seed, env_id_offset):
         raise FileNotFoundError(f"model_path {mp!r} does not exist (pass None for the packaged XML/humanoid.xml)")
     return HumanoidBatch(n_envs, model_path=mp, frame_skip=cfg["frame_skip"], duration=float(cfg["duration"]),
                          reward_type=rc.get("type", "default"), reward_params=rc.get("params"), obs_mode=obs_mode,
-                         dtype=dtype, device=device, seed=seed, env_id_offset=env_id_offset)
+                         dtype=dtype, device=device, seed=seed, env_id_offset=env_id_offset, sensor_terms=sensor_terms)
 
 
 class B200HumanoidVecEnv(_VecEnvBase):
     metadata = {"render_modes": ["rgb_array"], "render_fps": 60}
 
     def __init__(self, env_config, n_envs=8, device=0, dtype="f32", obs_mode="full352", seed=0, env_id_offset=0,
-                 info_mode="auto", obs_dtype="float64"):
-        """obs_dtype: "float64" is the reference's observation_space dtype (custom_env.py:80-85, the default);
+                 info_mode="auto", obs_dtype="float64", sensor_terms=False):
+        """sensor_terms: False = the reference (cfrc_ext / subtree_linvel read as zeros by the rewards); True = compute them.
+        obs_dtype: "float64" is the reference's observation_space dtype (custom_env.py:80-85, the default);
         "float32" returns what SB3 casts the observation to anyway and halves the bytes crossing PCIe per step."""
         self.cfg = parse_env_config(env_config)
         if self.cfg["render_mode"] is not None:
             raise NotImplementedError("rendering is outside the rollout hot path (custom_env.py:273-321)")
-        self.batch = _make_batch(self.cfg, n_envs, device, dtype, obs_mode, seed, env_id_offset)
+        self.batch = _make_batch(self.cfg, n_envs, device, dtype, obs_mode, seed, env_id_offset, sensor_terms)
         self.num_envs = n_envs
         if obs_dtype not in ("float64", "float32") or (obs_dtype == "float32" and dtype != "f32"):
             raise ValueError("obs_dtype must be 'float64', or 'float32' with the f32 arithmetic build")

@@ -59,6 +59,10 @@ typedef struct OrcEnv {
   int step_count;
   double total_reward;
   int n_bad; /* mj_check* resets */
+  /* section 8(f4): what MuJoCo would compute if the model had the sensors the rewards assume (off = reference behaviour:
+     both arrays stay zero because XML/humanoid.xml has no sensor) */
+  int sensor_terms;
+  double cfrc_ext[NB][6], subtree_linvel[NB][3];
   /* position stage */
   double xpos[NB][3], xquat[NB][4], xmat[NB][9], xipos[NB][3], ximat[NB][9];
   double xanchor[NJ][3], xaxis[NJ][3];
@@ -930,12 +934,71 @@ void orc_reset_data(OrcEnv* d) { /* mj_resetData */
   memset(d->cvel, 0, sizeof d->cvel);
   memset(d->subtree_com, 0, sizeof d->subtree_com);
   memset(d->qfrc_actuator, 0, sizeof d->qfrc_actuator);
+  memset(d->cfrc_ext, 0, sizeof d->cfrc_ext);
+  memset(d->subtree_linvel, 0, sizeof d->subtree_linvel);
   d->time = 0; d->nstep = 0; d->ncon = 0; d->nefc = 0;
+}
+/* [UNVERIFIED-vs-3.2.5] mj_subtreeVel (linear part): body momentum m * (cvel_lin + omega x (xipos - subtree_com[root])) summed over
+   each subtree, divided by the subtree mass */
+static void subtree_vel(OrcEnv* d) {
+  const B2HModel* m = &d->m;
+  double mom[NB][3], mass[NB];
+  for (int b = 0; b < m->nbody; b++) {
+    double dif[3], v[3];
+    const double* com = d->subtree_com[b ? body_rootid(m, b) : 0];
+    for (int k = 0; k < 3; k++) dif[k] = d->xipos[b][k] - com[k];
+    cross3(v, d->cvel[b], dif);
+    for (int k = 0; k < 3; k++) mom[b][k] = m->body_mass[b] * (d->cvel[b][3 + k] + v[k]);
+    mass[b] = m->body_mass[b];
+  }
+  for (int b = m->nbody - 1; b > 0; b--) {
+    int p = m->body_parentid[b];
+    for (int k = 0; k < 3; k++) mom[p][k] += mom[b][k];
+    mass[p] += mass[b];
+  }
+  for (int b = 0; b < m->nbody; b++)
+    for (int k = 0; k < 3; k++) d->subtree_linvel[b][k] = mass[b] > MINVAL ? mom[b][k] / mass[b] : 0.0;
+}
+/* [UNVERIFIED-vs-3.2.5] mj_rnePostConstraint, contact part of cfrc_ext: the contact force (mj_contactForce: frictionless = the
+   row's force; pyramidal = normal sum of the four edge forces, tangents mu * (f0 - f1), mu * (f2 - f3)) rotated to the
+   world, as a spatial force [torque; force] about the subtree com of the body's tree, subtracted from body 1, added to body 2 */
+static void rne_post_constraint(OrcEnv* d) {
+  const B2HModel* m = &d->m;
+  memset(d->cfrc_ext, 0, sizeof d->cfrc_ext);
+  for (int ci = 0; ci < d->ncon; ci++) {
+    const OrcContact* c = &d->con[ci];
+    int r = c->efc_address;
+    double lf[3] = {0, 0, 0};
+    if (c->dim == 1) lf[0] = d->efc_force[r];
+    else {
+      lf[0] = d->efc_force[r] + d->efc_force[r + 1] + d->efc_force[r + 2] + d->efc_force[r + 3];
+      lf[1] = c->friction[0] * (d->efc_force[r] - d->efc_force[r + 1]);
+      lf[2] = c->friction[1] * (d->efc_force[r + 2] - d->efc_force[r + 3]);
+    }
+    double f[3];
+    for (int k = 0; k < 3; k++) f[k] = c->frame[k] * lf[0] + c->frame[3 + k] * lf[1] + c->frame[6 + k] * lf[2];
+    int bb[2] = {m->geom_bodyid[c->geom1], m->geom_bodyid[c->geom2]};
+    for (int side = 0; side < 2; side++) {
+      int b = bb[side];
+      if (b == 0) continue;
+      const double* com = d->subtree_com[body_rootid(m, b)];
+      double off[3], tq[3], sg = side ? 1.0 : -1.0;
+      for (int k = 0; k < 3; k++) off[k] = c->pos[k] - com[k];
+      cross3(tq, off, f);
+      for (int k = 0; k < 3; k++) { d->cfrc_ext[b][k] += sg * tq[k]; d->cfrc_ext[b][3 + k] += sg * f[k]; }
+    }
+  }
+}
+void orc_set_sensor_terms(OrcEnv* d, int on) {
+  d->sensor_terms = on;
+  memset(d->cfrc_ext, 0, sizeof d->cfrc_ext);
+  memset(d->subtree_linvel, 0, sizeof d->subtree_linvel);
 }
 void orc_forward(OrcEnv* d) { /* mj_forward */
   kinematics(d); com_pos(d); tendon(d); crb(d); collision(d); make_constraint(d);
   com_vel(d); passive(d); reference_constraint(d); rne_bias(d);
   actuation(d); acceleration(d); fwd_constraint(d);
+  if (d->sensor_terms) { subtree_vel(d); rne_post_constraint(d); }
 }
 /* [UNVERIFIED-vs-3.2.5] mj_Euler: implicit damping (M + h B) qacc = qfrc_smooth + qfrc_constraint whenever a dof has damping and eulerdamp is on; mj_advance: qvel first, then qpos with the NEW qvel; qacc_warmstart = qacc of the unmodified forward pass */
 static void euler(OrcEnv* d) { /* mj_Euler with implicit joint damping + mj_advance */
@@ -996,7 +1059,9 @@ static void quat_to_euler(const double* q, double* roll, double* pitch) { /* uti
 static double reward_stand(const OrcEnv* d) { /* reward_functions.py:156-211 */
   double h = d->qpos[2], vx = d->qvel[0], roll, pitch;
   quat_to_euler(d->qpos + 3, &roll, &pitch);
-  double lf = 0, rf = 0;
+  const int nb = d->m.nbody;
+  double lf = 0, rf = 0;   /* np.sum(np.abs(cfrc_ext[-2])), [-1]: identically zero unless sensor_terms */
+  for (int k = 0; k < 6; k++) { lf += fabs(d->cfrc_ext[nb - 2][k]); rf += fabs(d->cfrc_ext[nb - 1][k]); }
   if (h < 0.8) return 0.0;
   double vr = exp(-2.0 * (vx - 1.0) * (vx - 1.0));
   double hr = exp(-2.0 * (h - 1.282) * (h - 1.282));
@@ -1031,8 +1096,12 @@ static double reward_kneeling(const OrcEnv* d, const double* p) { /* reward_func
   double posture = 0.7 * exp(-5.0 * oerr) + 0.3 * exp(-5.0 * (h - p[0]) * (h - p[0]));
   const double* com = d->subtree_com[0];
   double dist = sqrt(com[0] * com[0] + com[1] * com[1]);
-  double com_score = 0.7 * exp(-10.0 * (dist / p[3])) + 0.3 * exp(-0.1 * 0.0);
-  double foot_balance = fmin(0.0, 0.0) / (0.0 + 0.0 + 1e-8);
+  const double* lv = d->subtree_linvel[0];
+  double com_score = 0.7 * exp(-10.0 * (dist / p[3])) + 0.3 * exp(-0.1 * (lv[0] * lv[0] + lv[1] * lv[1] + lv[2] * lv[2]));
+  const int nb = d->m.nbody;
+  double lf = 0, rf = 0;
+  for (int k = 0; k < 6; k++) { lf += fabs(d->cfrc_ext[nb - 2][k]); rf += fabs(d->cfrc_ext[nb - 1][k]); }
+  double foot_balance = fmin(lf, rf) / (lf + rf + 1e-8);
   double power = 0;
   for (int i = 6; i < d->m.nv; i++) { double t = d->qfrc_actuator[i] * d->qvel[i]; power += t * t; }
   double energy = exp(-0.01 * power);
@@ -1140,6 +1209,8 @@ int orc_get(const OrcEnv* d, const char* what, double* out, int max_out) {
   if (!strcmp(what, "cdof_dot")) { for (int i = 0; i < nv; i++) for (int k = 0; k < 6; k++) tmp[n++] = d->cdof_dot[i][k]; OUT(tmp, n); }
   if (!strcmp(what, "qM")) { for (int i = 0; i < nv; i++) for (int k = 0; k < nv; k++) tmp[n++] = d->qM[i][k]; OUT(tmp, n); }
   if (!strcmp(what, "ten_length")) OUT(d->ten_length, m->ntendon);
+  if (!strcmp(what, "cfrc_ext")) OUT(d->cfrc_ext[0], 6 * m->nbody);
+  if (!strcmp(what, "subtree_linvel")) OUT(d->subtree_linvel[0], 3 * m->nbody);
   if (!strcmp(what, "qfrc_passive")) OUT(d->qfrc_passive, nv);
   if (!strcmp(what, "qfrc_bias")) OUT(d->qfrc_bias, nv);
   if (!strcmp(what, "qfrc_actuator")) OUT(d->qfrc_actuator, nv);

@@ -40,6 +40,7 @@ def lib():
         L.orc_get.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int]
         L.orc_obs_dim.restype = C.c_int
         L.orc_obs_dim.argtypes = [C.c_void_p]
+        L.orc_set_sensor_terms.argtypes = [C.c_void_p, C.c_int]
         for f in ("orc_forward", "orc_mj_step", "orc_reset_data"):
             getattr(L, f).argtypes = [C.c_void_p]
         L.orc_set_state.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
@@ -101,6 +102,10 @@ class OracleEnv:
         c[:self.nu] = ctrl
         lib().orc_set_ctrl(self.h, _p(c))
 
+    def set_sensor_terms(self, on=True):
+        """section 8(f4): compute cfrc_ext / subtree_linvel (off = the reference: both stay zero)."""
+        lib().orc_set_sensor_terms(self.h, int(bool(on)))
+
     def forward(self):
         lib().orc_forward(self.h)
 
@@ -151,9 +156,12 @@ class OracleVecEnv:
     """n independent OracleEnv stepped with SubprocVecEnv auto-reset semantics (optionally multi-threaded)."""
 
     def __init__(self, model_struct, nq, nv, nu, n_envs, frame_skip=3, duration=10.0, reward_type=0, max_steps=750,
-                 kneel_params=None, nthreads=1):
+                 kneel_params=None, nthreads=1, sensor_terms=False):
         from mujocoposelearning_b200.abi import KNEELING_DEFAULTS
         self.envs = [OracleEnv(model_struct, nq, nv, nu) for _ in range(n_envs)]
+        if sensor_terms:
+            for e in self.envs:
+                e.set_sensor_terms(True)
         self.n, self.nq, self.nv, self.nu = n_envs, nq, nv, nu
         self.obs_dim = self.envs[0].obs_dim
         self._harr = (C.c_void_p * n_envs)(*[e.h for e in self.envs])

@@ -28,7 +28,7 @@ def test_exports_every_declared_symbol(lib):
 
 def test_struct_layouts_match(lib):
     from mujocoposelearning_b200 import abi
-    assert lib.b2h_abi_version() == 1
+    assert lib.b2h_abi_version() == 2      # 2: B2HConfig::sensor_terms, the rollout / packed-policy entry points
     assert lib.b2h_sizeof_model() == C.sizeof(abi.B2HModel) and lib.b2h_sizeof_config() == C.sizeof(abi.B2HConfig)
 
 

@@ -149,7 +149,9 @@ typedef struct B2HConfig {
   int32_t sensor_terms;    /* 0 (default) = the reference: data.cfrc_ext / data.subtree_linvel are identically zero (the model has
                               no sensor, so MuJoCo never computes them: reward_functions.py:109,121-122,176-177 read zeros).
                               1 = compute what mj_rnePostConstraint (contact part) / mj_subtreeVel would give and feed the rewards. */
-  int32_t reserved_;
+  int32_t no_auto_reset;   /* 0 (default) = SubprocVecEnv worker semantics: a finished env is reset inside the step and the step returns
+                              the first observation of the new episode.  1 = gymnasium Env.step semantics (custom_env.py:152-230):
+                              the env stays in its terminal state (state, observation) until b2h_reset is called for it. */
 } B2HConfig;
 
 typedef struct B2HHandle B2HHandle;

@@ -52,7 +52,7 @@ class B2HConfig(C.Structure):
     _fields_ = [
         ("n_envs", i32), ("env_id_offset", i32), ("frame_skip", i32), ("reward_type", i32), ("obs_mode", i32),
         ("dtype", i32), ("max_steps", i32), ("device", i32), ("duration", f64), ("seed", C.c_uint64),
-        ("kneeling_params", f64 * 9), ("sensor_terms", i32), ("reserved_", i32),
+        ("kneeling_params", f64 * 9), ("sensor_terms", i32), ("no_auto_reset", i32),
     ]
 
 
@@ -102,7 +102,7 @@ def pack_model(cm) -> B2HModel:
 
 
 def make_config(n_envs, *, frame_skip=5, reward_type="default", reward_params=None, obs_mode="full352", dtype="f32",
-                duration=15.0, max_steps=750, device=0, seed=0, env_id_offset=0, sensor_terms=False) -> B2HConfig:
+                duration=15.0, max_steps=750, device=0, seed=0, env_id_offset=0, sensor_terms=False, auto_reset=True) -> B2HConfig:
     rt = {"default": REWARD_STAND, "stand": REWARD_STAND, "kneeling": REWARD_KNEELING, "walk": REWARD_WALK}
     if reward_type not in rt:
         raise ValueError(f"Unknown reward type: {reward_type}")  # custom_env.py:268-269
@@ -113,6 +113,7 @@ def make_config(n_envs, *, frame_skip=5, reward_type="default", reward_params=No
     c.dtype = {"f32": F32, "f64": F64}[dtype]
     c.max_steps, c.device, c.duration, c.seed = int(max_steps), int(device), float(duration), int(seed)
     c.sensor_terms = int(bool(sensor_terms))
+    c.no_auto_reset = int(not auto_reset)
     kp = dict(zip(KNEELING_KEYS, KNEELING_DEFAULTS))
     kp.update(reward_params or {})
     for i, k in enumerate(KNEELING_KEYS):

@@ -18,7 +18,7 @@ from .mjcf import compile_mjcf
 
 class HumanoidBatch:
     def __init__(self, n_envs, *, model_path=None, frame_skip=5, duration=15.0, reward_type="default", reward_params=None,
-                 obs_mode="full352", dtype="f32", device=0, seed=0, env_id_offset=0, max_steps=750, sensor_terms=False):
+                 obs_mode="full352", dtype="f32", device=0, seed=0, env_id_offset=0, max_steps=750, sensor_terms=False, auto_reset=True):
         if not torch.cuda.is_available():
             raise B2HError("no CUDA device visible: the B200 humanoid batch has no CPU fallback")
         self.lib = load()
@@ -26,7 +26,7 @@ class HumanoidBatch:
         self.model = abi.pack_model(self.cm)
         self.cfg = abi.make_config(n_envs, frame_skip=frame_skip, reward_type=reward_type, reward_params=reward_params,
                                    obs_mode=obs_mode, dtype=dtype, duration=duration, max_steps=max_steps, device=device,
-                                   seed=seed, env_id_offset=env_id_offset, sensor_terms=sensor_terms)
+                                   seed=seed, env_id_offset=env_id_offset, sensor_terms=sensor_terms, auto_reset=auto_reset)
         self.n_envs, self.nq, self.nv, self.nu = n_envs, self.cm.nq, self.cm.nv, self.cm.nu
         self.device = torch.device("cuda", device)
         self.tdtype = torch.float64 if dtype == "f64" else torch.float32

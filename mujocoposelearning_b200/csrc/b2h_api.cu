@@ -411,6 +411,7 @@ int b2h_create(const B2HModel* model, const B2HConfig* cfg, B2HHandle** out) {
   h->P.seed = cfg->seed; h->P.env_id_offset = cfg->env_id_offset;
   h->P.sync_mode = 2;
   h->P.sensor_terms = cfg->sensor_terms != 0;
+  h->P.auto_reset = cfg->no_auto_reset == 0;
   if (const char* sm = getenv("B2H_SYNC_MODE")) h->P.sync_mode = atoi(sm);  // tuning knob, see env_step
   int rc = cfg->dtype == B2H_F64 ? create_typed<double>(h) : create_typed<float>(h);
   if (rc != B2H_OK) { b2h_destroy(h); return rc; }

@@ -1426,6 +1426,7 @@ struct EnvParams {
   int env_id_offset;
   int sync_mode;  // CTA lockstep: 0 none, 1 once per control step, 2 before every physics sub-step
   int sensor_terms;  // B2HConfig::sensor_terms (section 8 f4): 0 = the reference (cfrc_ext / subtree_linvel read as zeros)
+  int auto_reset;    // 1: SubprocVecEnv worker semantics (reset inside the step); 0: gymnasium Env.step (stay terminal)
 };
 
 template <typename T> B2H_DEV void quat_to_euler(const T* q, T* roll, T* pitch) {  // utils.py:3-20 (pitch unclamped)
@@ -1595,7 +1596,7 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
   B2H_CLK_ADD(9, te);
   if (P.sync_mode == 2) cta_sync();
   B2H_CLK_ADD(4, te);
-  if (active && done) {
+  if (active && done && P.auto_reset) {
     env_reset<T>(m, S, Jspill, st, cnt, P, io, env, lane);
     step_count = 0; total = 0;
   }

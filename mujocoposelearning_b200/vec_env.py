@@ -65,7 +65,7 @@ def parse_env_config(env_config):
                 reward_config={"type": "default"}, frame_skip=5, run_name=None)
 
 
-def _make_batch(cfg, n_envs, device, dtype, obs_mode, seed, env_id_offset, sensor_terms=False):
+def _make_batch(cfg, n_envs, device, dtype, obs_mode, seed, env_id_offset, sensor_terms=False, auto_reset=True):
     rc = cfg["reward_config"] or {"type": "default"}
     import os
     mp = cfg["model_path"]
@@ -73,7 +73,8 @@ def _make_batch(cfg, n_envs, device, dtype, obs_mode, seed, env_id_offset, senso
         raise FileNotFoundError(f"model_path {mp!r} does not exist (pass None for the packaged XML/humanoid.xml)")
     return HumanoidBatch(n_envs, model_path=mp, frame_skip=cfg["frame_skip"], duration=float(cfg["duration"]),
                          reward_type=rc.get("type", "default"), reward_params=rc.get("params"), obs_mode=obs_mode,
-                         dtype=dtype, device=device, seed=seed, env_id_offset=env_id_offset, sensor_terms=sensor_terms)
+                         dtype=dtype, device=device, seed=seed, env_id_offset=env_id_offset, sensor_terms=sensor_terms,
+                         auto_reset=auto_reset)
 
 
 class B200HumanoidVecEnv(_VecEnvBase):
@@ -89,11 +90,18 @@ class B200HumanoidVecEnv(_VecEnvBase):
             raise NotImplementedError("rendering is outside the rollout hot path (custom_env.py:273-321)")
         self.batch = _make_batch(self.cfg, n_envs, device, dtype, obs_mode, seed, env_id_offset, sensor_terms)
         self.num_envs = n_envs
+        self._base_init = False
         if obs_dtype not in ("float64", "float32") or (obs_dtype == "float32" and dtype != "f32"):
             raise ValueError("obs_dtype must be 'float64', or 'float32' with the f32 arithmetic build")
         self.obs_dtype = obs_dtype
         self.observation_space = _box(-np.inf, np.inf, (self.batch.obs_dim,), np.dtype(obs_dtype))  # custom_env.py:80-85
         self.action_space = _box(-1.0, 1.0, (self.batch.nu,), np.float32)                 # custom_env.py:87-93
+        if _VecEnvBase is not object:   # real SB3 base class: let it set its own bookkeeping (render_mode, reset_infos, _seeds, _options)
+            try:
+                _VecEnvBase.__init__(self, n_envs, self.observation_space, self.action_space)
+                self._base_init = True
+            except Exception:            # a different SB3 version's signature: the attributes below are what 2.3.2 sets
+                pass
         self.render_mode = None
         self.reset_infos = [{} for _ in range(n_envs)]
         self._seeds = [None] * n_envs
@@ -250,7 +258,9 @@ class HumanoidEnv:
         self.cfg = parse_env_config(env_config)
         for k, v in self.cfg.items():
             setattr(self, k, v)
-        self.batch = _make_batch(self.cfg, 1, device, dtype, "full352", seed, 0)
+        # gymnasium Env.step semantics: no reset inside step() -- after a terminal step .data is the terminal state
+        # (generate_trajectories.py:54-64 reads env.data.qpos / qvel right after the step that ended the episode)
+        self.batch = _make_batch(self.cfg, 1, device, dtype, "full352", seed, 0, auto_reset=False)
         self.observation_space = _box(-np.inf, np.inf, (self.batch.obs_dim,), np.float64)
         self.action_space = _box(-1.0, 1.0, (self.batch.nu,), np.float32)
         self.hb = self.batch.make_host_buffers()
@@ -283,8 +293,7 @@ class HumanoidEnv:
         self.batch.step_host(self.hb)
         terminated = bool(self.hb["terminated"][0])
         truncated = bool(self.hb["truncated"][0])
-        src = self.hb["terminal_obs"] if (terminated or truncated) else self.hb["obs"]
-        obs = src.numpy()[0].astype(np.float64)
+        obs = self.hb["obs"].numpy()[0].astype(np.float64)       # no auto-reset: the observation of the state just reached
         reward = float(self.hb["reward"][0])
         self.total_reward += reward
         info = {"reward_components": {}, "height": float(obs[0]), "step_count": self.step_count, "truncated": truncated,

@@ -117,7 +117,7 @@ static int emu_run(int mode, const B2HModel* model, const B2HConfig* cfg, double
   job.P.frame_skip = cfg->frame_skip; job.P.reward_type = cfg->reward_type; job.P.obs_mode = cfg->obs_mode;
   job.P.max_steps = cfg->max_steps; job.P.duration = cfg->duration; job.P.timestep = model->timestep;
   for (int k = 0; k < 9; k++) job.P.kneel[k] = cfg->kneeling_params[k];
-  job.P.seed = cfg->seed; job.P.env_id_offset = cfg->env_id_offset; job.P.sync_mode = 0; job.P.sensor_terms = cfg->sensor_terms != 0;
+  job.P.seed = cfg->seed; job.P.env_id_offset = cfg->env_id_offset; job.P.sync_mode = 0; job.P.sensor_terms = cfg->sensor_terms != 0; job.P.auto_reset = cfg->no_auto_reset == 0;
   job.io.qpos = q.data(); job.io.qvel = v.data(); job.io.warm = w.data(); job.io.nstep = nstep; job.io.step_count = step_count;
   job.io.episode = episode; job.io.total_reward = tr.data(); job.io.reset_noise = reset_noise; job.io.noise_injected = noise_injected;
   job.io.actions = actions; job.io.obs = ob.data(); job.io.reward = rw.data(); job.io.terminal_obs = tob.data();

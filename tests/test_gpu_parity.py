@@ -573,3 +573,27 @@ def test_true_single_mj_step_parity(cm, model_struct, dtype, tol_norm, tol_elem,
     assert worst["obs_norm"] < tol_norm * (1 if dtype == "f32" else 10) and worst["reward"] < max(tol_norm, 1e-5 if dtype == "f32" else 0), worst
     assert max(worst["qpos_elem"], worst["qvel_elem"], worst["obs_elem"]) < tol_elem, worst
     b.close()
+
+
+def test_gymnasium_facade_keeps_the_terminal_state(cm, model_struct):
+    """HumanoidEnv.step has gymnasium semantics (custom_env.py:152-230): no reset inside step().  After the step that
+    ends the episode, obs / .data are the terminal state (generate_trajectories.py:54-64 reads env.data right there),
+    the env keeps stepping if asked to, and reset() starts a new episode."""
+    from mujocoposelearning_b200.vec_env import HumanoidEnv
+    from oracle.oracle import OracleEnv
+    env = HumanoidEnv({"model_path": None, "duration": 0.049, "frame_skip": 3, "reward_config": {"type": "stand"}}, dtype="f64", seed=5)
+    noise = env.batch.last_reset_noise()[0]
+    ref = OracleEnv(model_struct, cm.nq, cm.nv, cm.nu)
+    ref.env_reset(noise)
+    rng = np.random.default_rng(3)
+    for k in range(4):
+        a = rng.uniform(-1, 1, cm.nu).astype(np.float32)
+        obs, r, term, trunc, info = env.step(a)
+        o, rr, te, tr = ref.env_step(a, frame_skip=3, duration=0.049, reward_type=0)
+        assert term == te and trunc == tr and term == (k >= 2) and info["step_count"] == k + 1
+        assert _rel(obs, o) < 1e-9 and abs(r - rr) < 1e-9
+        s = ref.get_state()
+        assert _rel(env.data.qpos, s["qpos"]) < 1e-9 and _rel(env.data.qvel, s["qvel"]) < 1e-9      # terminal state, not a reset one
+    obs0, info0 = env.reset()
+    assert env.step_count == 0 and abs(env.data.time - cm.timestep) < 1e-12 and abs(obs0[0] - 1.282) < 0.01
+    env.close()

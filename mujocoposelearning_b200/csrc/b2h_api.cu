@@ -67,7 +67,7 @@ step_kernel(const DevModel<T>* __restrict__ gmodel, EnvParams P, EnvIO<T> io, in
   const DevModel<T>* model = stage_model<T>(gmodel);
   Scratch<T>& S = my_scratch<T>(model);
   T* Jspill = spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ((NROW - model->nrow_s) * LD);
-  Counters cnt = {0, 0, 0, 0, 0, 0, 0};
+  Counters cnt = {};
   __shared__ int s_base;
   const int nwarps = blockDim.x >> 5;
   for (;;) {  // the CTA claims one env per warp at a time and steps them in lockstep (see env_step)
@@ -87,7 +87,12 @@ step_kernel(const DevModel<T>* __restrict__ gmodel, EnvParams P, EnvIO<T> io, in
     // that outgrows them falls back on its own (mj_step)
     const int rows = active && io.work ? (int)((unsigned)io.work[env] >> B2H_EFFORT_BITS) : 0;
     const int ns = __syncthreads_or(rows > 60) ? 3 : (__syncthreads_or(rows > 28) ? 2 : 1);
-    env_step<T, OUT>(*model, S, Jspill, cnt, P, io, env, active, ns);
+#ifdef B2H_EXP_NEWTON_BARRIER
+    const int group_threads = 32 * min(nwarps, n_envs - base);
+#else
+    const int group_threads = 0;
+#endif
+    env_step<T, OUT>(*model, S, Jspill, cnt, P, io, env, active, ns, group_threads);
   }
 #ifdef B2H_STAGE_CLOCKS
   if (threadIdx.x == 0) {  // when this CTA ran out of work (tail imbalance of the launch)
@@ -103,8 +108,23 @@ step_kernel(const DevModel<T>* __restrict__ gmodel, EnvParams P, EnvIO<T> io, in
 // Which warp steps which env never changes a result; the order inside a bucket is left to the atomics.
 // It also re-arms the claim counter of the next step launch (no memset node on the stream).
 constexpr int ORDER_BUCKETS = 256;
-__device__ __forceinline__ int order_bucket(int packed) {   // the solver effort (EnvIO::work also carries the row hint)
-  return min((int)((unsigned)packed & B2H_EFFORT_MASK) >> 2, ORDER_BUCKETS - 1);
+__device__ __forceinline__ int order_bucket(int packed, int mode = 0) {   // EnvIO::work: effort | joint limits | dense rows
+  const int effort = (int)((unsigned)packed & 16383u), nlim = (int)(((unsigned)packed >> 14) & 63u), rows = (int)((unsigned)packed >> B2H_EFFORT_BITS);
+  // Sort key of the lockstep schedule.  Round 1 sorted by the solver effort (Newton iterations x row weight) of the env's last control
+  // step; its iteration count is nearly unpredictable (rho = 0.3 from step to step) and scrambles what IS persistent: the contact
+  // configuration.  Sorting by the dense row count (ties: active joint limits) makes the groups homogeneous in per-iteration and
+  // pre-solver cost: +2.2 % at 4096 envs, +1.7 % at 16384 against the effort key (profiles/r02_schedule_key_ab.txt; no sort: -2.7 %).
+  // B2H_ORDER_KEY: 0 effort; 1 rows; 2 effort + rows; 5 rows + limits; 6 (default) rows, ties by limits; 7 rows, ties by effort
+  int key;
+  switch (mode) {
+    case 0: key = effort >> 2; break;
+    case 2: key = (effort >> 2) + rows; break;
+    case 5: key = 2 * (rows + nlim); break;
+    case 6: key = 4 * rows + min(nlim, 3); break;
+    case 7: key = 3 * rows + (effort >> 5); break;
+    default: key = 2 * rows; break;
+  }
+  return min(key, ORDER_BUCKETS - 1);
 }
 // What collect_rollouts does with the result of one env.step (SB3 2.3.2 on_policy_algorithm.py), per env, after the step
 // kernel: episode_starts of the next slot, the time-limit bootstrap of the stored reward, the episode statistics.
@@ -119,14 +139,14 @@ struct RecordArgs {
   unsigned long long* step_counter;
 };
 __global__ void __launch_bounds__(1024, 1) post_step_kernel(const int* __restrict__ effort, int n, int* __restrict__ perm, int* work,
-                                                            int do_sort, int do_record, RecordArgs rec) {
+                                                            int do_sort, int do_record, RecordArgs rec, int key_mode) {
   __shared__ int hist[ORDER_BUCKETS], start[ORDER_BUCKETS];
   __shared__ double red[3][32];
   if (do_sort) {
     if (threadIdx.x == 0) *work = 0;
     for (int i = threadIdx.x; i < ORDER_BUCKETS; i += blockDim.x) hist[i] = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[order_bucket(effort[i])], 1);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) atomicAdd(&hist[order_bucket(effort[i], key_mode)], 1);
     __syncthreads();
     if (threadIdx.x < 32) {  // exclusive prefix over the buckets in descending order: 8 buckets per lane + one warp scan
       constexpr int PER = ORDER_BUCKETS / 32;
@@ -140,7 +160,7 @@ __global__ void __launch_bounds__(1024, 1) post_step_kernel(const int* __restric
       for (int k = 0; k < PER; k++) start[top - k] = incl - sum + loc[k];
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) perm[atomicAdd(&start[order_bucket(effort[i])], 1)] = i;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) perm[atomicAdd(&start[order_bucket(effort[i], key_mode)], 1)] = i;
   }
   if (do_record) {
     double sr = 0, sl = 0, sn = 0;
@@ -175,7 +195,7 @@ reset_kernel(const DevModel<T>* __restrict__ gmodel, EnvParams P, EnvIO<T> io, i
   const DevModel<T>* model = stage_model<T>(gmodel);
   Scratch<T>& S = my_scratch<T>(model);
   T* Jspill = spill + (size_t)(blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ((NROW - model->nrow_s) * LD);
-  Counters cnt = {0, 0, 0, 0, 0, 0, 0};
+  Counters cnt = {};
   for (;;) {
     int env = 0;
     if (lane_id() == 0) env = atomicAdd(work, 1);
@@ -193,7 +213,7 @@ debug_kernel(const DevModel<T>* model, EnvIO<T> io, int env, DebugDump<T>* out, 
   model = stage_model<T>(model);
   Scratch<T>& S = *reinterpret_cast<Scratch<T>*>(b2h_smem + model_smem_bytes<T>());
   const int lane = lane_id(), nq = model->nq, nv = model->nv, nu = model->nu;
-  Counters cnt = {0, 0, 0, 0, 0, 0, 0};
+  Counters cnt = {};
   EnvState<T> st;
   st.qp = lane < nq ? io.qpos[(size_t)env * nq + lane] : T(0);
   st.qv = lane < nv ? io.qvel[(size_t)env * nv + lane] : T(0);
@@ -266,6 +286,7 @@ struct B2HHandle {
   int* work = nullptr;
   int *effort = nullptr, *perm = nullptr;  // per-env solver effort of the last control step, effort-sorted env order
   int schedule = 1;                        // 1: lockstep groups follow the effort-sorted order
+  int order_key = 6;                       // sort key of that order: dense rows, ties by joint limits (tuning knob B2H_ORDER_KEY, see order_bucket)
   bool perm_valid = false;
   bool work_armed = false;                 // the claim counter was zeroed by the sort that followed the previous step launch
   cudaStream_t armed_stream = nullptr;     // ... on this stream: a step on another stream zeroes the counter itself
@@ -422,6 +443,7 @@ int b2h_create(const B2HModel* model, const B2HConfig* cfg, B2HHandle** out) {
   ALLOC(h->reset_noise, E * (h->nq + h->nv) * 8); ALLOC(h->noise_injected, E);
   ALLOC(h->counters, 8 * 8); ALLOC(h->work, 8); /* [0] step claim counter, [1] reset claim counter */ ALLOC(h->effort, E * 4); ALLOC(h->perm, E * 4);
   if (const char* sc = getenv("B2H_SCHEDULE")) h->schedule = atoi(sc);  // tuning knob: 0 = env-id order
+  if (const char* ok = getenv("B2H_ORDER_KEY")) h->order_key = atoi(ok);
   ALLOC(h->actions_stage, E * h->nu * 4); ALLOC(h->obs_stage, E * h->obs_dim * esz); ALLOC(h->tobs_stage, E * h->obs_dim * esz);
   ALLOC(h->rew_stage, E * esz); ALLOC(h->term_stage, E); ALLOC(h->trunc_stage, E); ALLOC(h->mask_stage, E);
 #undef ALLOC
@@ -499,7 +521,7 @@ static int launch_post_step(B2HHandle* h, const RecordArgs* rec, cudaStream_t s)
   const bool sched = h->schedule && h->P.sync_mode == 2 && h->cfg.n_envs > h->warps;
   if (!sched && !rec) return B2H_OK;
   // sorted after the step instead of before the next one: it then overlaps the caller's host work
-  post_step_kernel<<<1, 1024, 0, s>>>(h->effort, h->cfg.n_envs, h->perm, h->work, sched ? 1 : 0, rec ? 1 : 0, rec ? *rec : RecordArgs());
+  post_step_kernel<<<1, 1024, 0, s>>>(h->effort, h->cfg.n_envs, h->perm, h->work, sched ? 1 : 0, rec ? 1 : 0, rec ? *rec : RecordArgs(), h->order_key);
   CU(cudaGetLastError());
   if (sched) { h->perm_valid = true; h->work_armed = true; h->armed_stream = s; }
   h->launches++;

@@ -240,6 +240,8 @@ struct Counters {  // per-warp tallies of one launch (32-bit: a warp sees a few 
   unsigned physics_steps, contact_overflow, iter_cap, bad_state, newton_iter, ls_eval;
   unsigned work;  // solver effort of the env in flight (Newton iterations weighted by row slots): next launch's schedule key
   unsigned rows;  // most dense constraint rows of a physics step of the env in flight: next launch's slot-count hint
+  unsigned nlim;  // most active joint limits of a physics step of the env in flight (schedule key experiments)
+  int sync_threads;  // tuning experiment (B2H_EXP_NEWTON_BARRIER): threads of the lockstep group that meet again before the solver, 0 = none
 #ifdef B2H_STAGE_CLOCKS
   long long clk[48];  // tuning build: cycles per stage (tools/stage_clocks.py)
 #endif
@@ -967,6 +969,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
   }
   const unsigned limit_mask = ballot(lsign != T(0));
   const int nefc = nrow + popc(limit_mask);
+  cnt.nlim = (unsigned)popc(limit_mask) > cnt.nlim ? (unsigned)popc(limit_mask) : cnt.nlim;
 
   B2H_CLK_ADD(18, tp);
   // =============================================================== velocity stage
@@ -1040,6 +1043,10 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
   T qacc_smooth = chol_solve_fused(S.A, nv, lane, qfrc_smooth);
   B2H_CLK_ADD(1, tc);
 
+#if defined(B2H_EXP_NEWTON_BARRIER) && !defined(B2H_HOST_EMU)
+  // experiment: the lockstep group re-aligns before the Newton loop (the pre-solver stages drift with the contact count)
+  if (cnt.sync_threads) asm volatile("bar.sync 1, %0;" ::"r"(cnt.sync_threads) : "memory");
+#endif
   // =============================================================== mj_fwdConstraint: Newton solver (primal)
   T qacc = qacc_smooth, qfrc_con = 0;
   int niter = 0;
@@ -1393,6 +1400,7 @@ template <typename T>
 B2H_DEV void mj_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, EnvState<T>& st, Counters& cnt, int ns = 1, bool ext = false) {
   for (int tries = 0; tries < 2; tries++) {
     int rc;
+    if (tries) cnt.sync_threads = 0;   // a retry after mj_checkAcc already met the group once
     if (ext) rc = physics_step<T, false, NSLOT, true>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);   // section 8 f4, not the bench path
     else {
       if (ns <= 1) rc = physics_step<T, false, 1>(m, S, Jspill, st, cnt, true, nullptr, nullptr, nullptr);
@@ -1535,6 +1543,7 @@ B2H_DEV_NOINLINE void env_reset(const DevModel<T>& m, Scratch<T>& S, T* Jspill, 
   st.qp = lane < nq ? T(q0 + npos) : T(0);
   st.qv = lane < nv ? T(nvel) : T(0);
   st.warm = 0; st.ctrl = 0; st.qfrc_act = 0; st.nstep = 0;
+  cnt.sync_threads = 0;   // only the envs that finished run this step
   mj_step<T>(m, S, Jspill, st, cnt, 1, P.sensor_terms != 0);
 }
 
@@ -1543,7 +1552,7 @@ B2H_DEV_NOINLINE void env_reset(const DevModel<T>& m, Scratch<T>& S, T* Jspill, 
 // VecEnv ones (io.obs64, ...), -1 whichever are non-null (the unused variants then sit in the claim loop's stream).
 template <typename T, int OUT = -1>
 B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& cnt, const EnvParams& P, const EnvIO<T>& io, int env,
-                      bool active, int ns = 1 /* row slots the lockstep group starts with, see mj_step */) {
+                      bool active, int ns = 1 /* row slots the lockstep group starts with, see mj_step */, int group_threads = 0) {
   constexpr bool kOutT = OUT != 1, kOut64 = OUT != 0;
   // All warps of a CTA enter every sub-step together (cta_sync): they then walk the same instructions at about
   // the same time, which keeps the (large, mostly straight-line) step code resident in the instruction cache.
@@ -1563,7 +1572,7 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     if (a >= 0) action = T(io.actions[(size_t)env * nu + a]);
     step_count = io.step_count[env] + 1;
   }
-  cnt.work = 0; cnt.rows = 0;
+  cnt.work = 0; cnt.rows = 0; cnt.nlim = 0;
   B2H_CLK(te);
   if (P.sync_mode == 1) cta_sync();
   for (int s = 0; s < P.frame_skip; s++) {
@@ -1573,6 +1582,7 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     if (active) {
       // data.ctrl[:] = action before every mj_step (a bad-state reset inside the previous sub-step zeroed it)
       st.ctrl = action;
+      cnt.sync_threads = group_threads;
       mj_step<T>(m, S, Jspill, st, cnt, ns, P.sensor_terms != 0);
     }
   }
@@ -1607,7 +1617,8 @@ B2H_DEV void env_step(const DevModel<T>& m, Scratch<T>& S, T* Jspill, Counters& 
     if (lane < nv) { io.qvel[(size_t)env * nv + lane] = st.qv; io.warm[(size_t)env * nv + lane] = st.warm; }
     if (lane == 0) {
       io.nstep[env] = st.nstep; io.step_count[env] = step_count; io.total_reward[env] = total;
-      if (io.work) io.work[env] = (int)((cnt.work & B2H_EFFORT_MASK) | (cnt.rows << B2H_EFFORT_BITS));
+      // effort (14 bits) | joint limits (6 bits) | dense rows (12 bits)
+      if (io.work) io.work[env] = (int)((cnt.work < 16383u ? cnt.work : 16383u) | ((cnt.nlim & 63u) << 14) | (cnt.rows << B2H_EFFORT_BITS));
     }
   }
   B2H_CLK_ADD(9, te);

@@ -183,6 +183,11 @@ class RolloutCollector:
         self._gae = gae
         if batch.tdtype != torch.float32:
             raise ValueError("the device-resident rollout runs on the float32 build (dtype='f32')")
+        if policy.p.obs_dim != batch.obs_dim or policy.p.act_dim != batch.nu:
+            raise ValueError(f"policy shape ({policy.p.obs_dim} -> {policy.p.act_dim}) does not match the env batch "
+                             f"(obs {batch.obs_dim}, actions {batch.nu})")
+        if policy.packed is None and batch.obs_dim % 16:
+            raise ValueError("the round-1 MLP kernel needs obs_dim % 16 == 0; use MlpPolicy(kernel='v2')")
         E, dev, f32 = batch.n_envs, batch.device, torch.float32
         z = lambda *shape, dt=f32: torch.zeros(*shape, device=dev, dtype=dt)
         self._obs = z(n_steps + 1, E, batch.obs_dim)            # slot t: observation before step t; slot T: carry-over

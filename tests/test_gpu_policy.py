@@ -211,3 +211,24 @@ def test_rollout_collector_timeout_bootstrap():
     raw_return = float(col.rewards[:2].sum())                                        # the truncating step's env reward is 0.0
     assert ep[2] == n and ep[1] == 3 * n and abs(ep[0] - raw_return) < 1e-3 * max(1.0, abs(raw_return))
     b.close(); fast.b.close()
+
+
+def test_rollout_on_the_53_column_observation():
+    """obs_mode='qpos_qvel' (the README / north-star "joint position / velocity" observation, 53 columns): the packed-weight
+    MLP pads K itself, so the in-library rollout loop runs on it; buffers equal the op-by-op loop."""
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams, RolloutCollector
+    cols = []
+    for _ in range(2):
+        b = HumanoidBatch(96, frame_skip=3, duration=0.2, reward_type="stand", seed=3, obs_mode="qpos_qvel")
+        cols.append(RolloutCollector(b, MlpPolicy(MlpPolicyParams(obs_dim=53, seed=2), seed=4), n_steps=16))
+    cols[0].collect()
+    cols[1].collect_eager()
+    torch.cuda.synchronize()
+    cols[0].check_error()
+    _same_buffers(cols[0], cols[1])
+    assert cols[0].obs.shape == (16, 96, 53) and float(cols[0].stats[2]) == 96
+    with pytest.raises(ValueError):
+        RolloutCollector(cols[0].b, MlpPolicy(MlpPolicyParams(obs_dim=352, seed=2)), n_steps=4)
+    for c in cols:
+        c.b.close()

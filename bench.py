@@ -58,7 +58,9 @@ def parse():
                     "NCCL gradient all-reduce), 16384 envs/GPU unless --n-envs is given; --steps / --warmup count ITERATIONS")
     ap.add_argument("--ppo-batch", type=int, default=16384, help="PPO minibatch size per GPU")
     ap.add_argument("--ppo-epochs", type=int, default=4)
-    ap.add_argument("--ppo-tf32", action="store_true", help="run the update's library GEMMs on the tf32 tensor cores")
+    ap.add_argument("--ppo-tf32", action="store_true", help="update GEMMs in a single tf32 pass (default: fp32-faithful)")
+    ap.add_argument("--ppo-impl", choices=["native", "torch"], default="native",
+                    help="native: the update kernels of csrc/b2h_ppo.cu; torch: autograd + library GEMMs (the round-2 baseline)")
     ap.add_argument("--no-stagger", action="store_true", help="keep the batch's episodes synchronised (SURVEY 8d C3 as written); the "
                     "timed window then depends on --warmup / --steps")
     return ap.parse_args()
@@ -485,7 +487,7 @@ def run_ppo(args):
     E, T = args.n_envs, 64
     K, W = max(1, args.steps), max(1, args.warmup)
     b = HumanoidBatch(E, frame_skip=FRAME_SKIP, duration=DURATION, reward_type=REWARD, dtype="f32", device=local, seed=1234, env_id_offset=rank * E)
-    tr = PPOTrainer(b, n_steps=T, batch_size=args.ppo_batch, n_epochs=args.ppo_epochs, lr=3e-4, seed=3, update_tf32=args.ppo_tf32)
+    tr = PPOTrainer(b, n_steps=T, batch_size=args.ppo_batch, n_epochs=args.ppo_epochs, lr=3e-4, seed=3, update_tf32=args.ppo_tf32, update_impl=args.ppo_impl)
     tr.col.cuda_graph = True
     tr.time_allreduce = world > 1
     for _ in range(W):
@@ -514,7 +516,9 @@ def run_ppo(args):
                "config": {"workload": f"full PPO `stand` training, {E} envs/GPU x {world} GPU, n_steps {T} (BASELINE config 4)", "n_envs_per_gpu": E,
                           "n_steps": T, "minibatch_per_gpu": args.ppo_batch, "epochs": args.ppo_epochs, "minibatches_per_iteration": n_mb,
                           "gradient_allreduce": "one flat 1.27 MB NCCL all-reduce per minibatch" if world > 1 else "none (1 GPU)",
-                          "update": "PyTorch autograd + library GEMMs (" + ("tf32" if args.ppo_tf32 else "fp32") + "), CUDA-graphed; NOT a hand-written kernel"},
+                          "update": ("hand-written kernels (csrc/b2h_ppo.cu): tcgen05 GEMMs, " + ("single tf32 pass" if args.ppo_tf32 else "tf32 hi/lo split = fp32-faithful")
+                                     + ", loss / clip / Adam kernels") if args.ppo_impl == "native" else
+                                    ("PyTorch autograd + library GEMMs (" + ("tf32" if args.ppo_tf32 else "fp32") + "), CUDA-graphed; NOT a hand-written kernel")},
                "split_ms_per_iteration": {"rollout_incl_gae": roll / K, "update_incl_allreduce": upd / K, "allreduce": ar / K,
                                           "allreduce_calls": n_ar // max(1, K), "wall": wall_ms / K},
                "rollout_value": world * E * FRAME_SKIP * T * K / (roll * 1e-3),

@@ -323,6 +323,59 @@ typedef struct B2HRollout {
 size_t b2h_sizeof_rollout(void);
 int b2h_rollout_collect(B2HHandle* h, const B2HRollout* r, void* stream);
 
+/* ---- PPO update: SB3 2.3.2 PPO.train as model.learn() runs it after every rollout
+ * (train_sb3.py:208-231, kwargs config.py:17-32) on hand-written kernels (csrc/b2h_ppo.cu): tcgen05 GEMMs for the forward
+ * and backward of both MlpPolicy trunks (fp32-faithful tf32 hi / lo split), the clipped-surrogate / value / entropy loss with
+ * per-minibatch advantage normalisation, grad-norm clipping and Adam.
+ *
+ * The parameters live in ONE flat float vector (so do the gradient and Adam's two moment vectors):
+ *   pi W1 [hidden, obs] b1 W2 [hidden, hidden] b2 W3 [act, hidden] b3 | vf W1 b1 W2 b2 W3 [1, hidden] b3 | log_std [act]
+ * in nn.Linear layout, every tensor starting at a multiple of 4 floats (b2h_ppo_param_layout returns the 13 offsets and the
+ * total length; the padding holds zeros).  The rollout kernels read the same memory, so an update needs no weight copy. */
+typedef struct B2HPpoConfig {
+  int32_t obs_dim, hidden, act_dim;
+  int32_t max_batch;            /* largest minibatch (rows) the workspace is sized for                                  */
+  int32_t precise;              /* 1: tf32 hi / lo split, three MMA passes (fp32-faithful, the reference trains in fp32) */
+  int32_t normalize_advantage;  /* SB3 default True: (adv - mean) / (std + 1e-8) per minibatch                          */
+  float clip_range, ent_coef, vf_coef, max_grad_norm;   /* SB3 defaults 0.2, 0.0, 0.5, 0.5 (config.py:23-24)            */
+  float lr, beta1, beta2, adam_eps;                     /* 3e-4 (config.py:18), 0.9, 0.999, 1e-5 (SB3's Adam eps)       */
+} B2HPpoConfig;
+typedef struct B2HPpo B2HPpo;
+size_t b2h_sizeof_ppo_config(void);
+int64_t b2h_ppo_param_layout(int obs_dim, int hidden, int act_dim, int64_t offsets[13]);
+int b2h_ppo_create(const B2HPpoConfig* cfg, B2HPpo** out);
+void b2h_ppo_destroy(B2HPpo* h);
+const char* b2h_ppo_last_error(void);
+/* Gradient of the PPO loss on one minibatch into grad_dev (flat, overwritten).  The rollout buffer is given flattened:
+ * obs [n, obs_dim], actions [n, act_dim] (raw, unclipped), old_log_probs / advantages / returns [n]; the minibatch is rows
+ * idx_dev[0 .. n_rows) (int64, e.g. a slice of torch.randperm) or, with idx_dev == NULL, rows row_start .. row_start + n_rows.
+ * Statistics of the minibatch (b2h_ppo_stats): [0] policy loss, [1] value loss, [2] clip fraction, [3] approx. KL. */
+int b2h_ppo_minibatch_grad(B2HPpo* h, const float* obs_dev, const float* actions_dev, const float* old_log_probs_dev,
+                           const float* advantages_dev, const float* returns_dev, const int64_t* idx_dev, int64_t row_start, int n_rows,
+                           const float* params_dev, float* grad_dev, void* stream);
+/* clip_grad_norm_(max_grad_norm) + one Adam step (step = 1, 2, ...: the bias corrections) on the flat vectors.  grad_scale
+ * multiplies the gradient first: 1 / world_size after a sum all-reduce over ranks (between the two calls).
+ * Statistics [5] receives the gradient norm before clipping. */
+int b2h_ppo_apply(B2HPpo* h, float* params_dev, float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t step, float grad_scale,
+                  void* stream);
+/* PPO.train for one rank: n_epochs passes over perm_dev [n_epochs, n_samples] (each row a permutation of the buffer rows) in
+ * minibatches of batch_size, gradient + apply per minibatch, nothing returns to the host in between. */
+int b2h_ppo_train(B2HPpo* h, const float* obs_dev, const float* actions_dev, const float* old_log_probs_dev, const float* advantages_dev,
+                  const float* returns_dev, const int64_t* perm_dev, int64_t n_samples, int n_epochs, int batch_size, float* params_dev,
+                  float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t* step_inout, void* stream);
+/* Statistics of the last minibatch (8 doubles) and the tensor pipeline's timeout flag; synchronises the stream. */
+int b2h_ppo_stats(B2HPpo* h, double stats_host[8], int* error_host, void* stream);
+const double* b2h_ppo_stats_dev(const B2HPpo* h);
+const int* b2h_ppo_error_dev(const B2HPpo* h);
+/* The GEMM of the update on its own (tests, measurement): C[m, n] (+)= A . B^T (+ bias, ReLU, . (mask > 0)) with fp32 operands
+ * on the tcgen05 tensor cores.  a_kstrided = 0: A is [m, k] row-major (lda >= k); 1: A is [k, m] row-major (lda >= m); B
+ * likewise with n.  transpose_c: the result is written as C[n, m] (ldc >= m).  split_k = 1: one CTA per tile; > 1 (or 0 =
+ * fill the SMs once): the contraction is split over CTAs and partial tiles are ADDED to C with red.global.add, as they are
+ * when accumulate != 0 — the caller zeroes C.  bias_dev [n], mask_dev [m, ldmask] may be NULL. */
+int b2h_gemm(const float* a_dev, int lda, int a_kstrided, const float* b_dev, int ldb, int b_kstrided, float* c_dev, int ldc, int transpose_c,
+             const float* bias_dev, const float* mask_dev, int ldmask, int m, int n, int k, int relu, int precise, int split_k, int accumulate,
+             int* error_flag_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

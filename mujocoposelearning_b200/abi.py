@@ -69,6 +69,15 @@ class B2HRollout(C.Structure):
     ]
 
 
+class B2HPpoConfig(C.Structure):
+    """include/b2h.h B2HPpoConfig: shapes and hyper-parameters of the PPO update kernels (SB3 defaults, config.py:17-32)."""
+    _fields_ = [
+        ("obs_dim", i32), ("hidden", i32), ("act_dim", i32), ("max_batch", i32), ("precise", i32), ("normalize_advantage", i32),
+        ("clip_range", C.c_float), ("ent_coef", C.c_float), ("vf_coef", C.c_float), ("max_grad_norm", C.c_float),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+    ]
+
+
 KNEELING_DEFAULTS = (1.282, 0.85, float(np.pi / 6), 0.1, 0.3, 0.3, 0.2, 0.1, 0.1)  # reward_functions.py:71-81
 KNEELING_KEYS = ("target_height", "min_height", "max_roll_pitch", "com_radius", "energy_weight", "posture_weight",
                  "com_weight", "foot_weight", "alive_weight")

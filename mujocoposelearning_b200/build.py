@@ -11,7 +11,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 # B2H_LIB / B2H_NVCC_EXTRA: tuning builds (e.g. -DB2H_WARPS=14 -DB2H_NROW_S=48) side by side with the default library
 LIB = Path(os.environ["B2H_LIB"]).resolve() if os.environ.get("B2H_LIB") else PKG / "libb2h.so"
-SOURCES = ["b2h_api.cu", "b2h_mlp.cu"]
+SOURCES = ["b2h_api.cu", "b2h_mlp.cu", "b2h_ppo.cu"]
 # -prec-div/-prec-sqrt/-ftz only touch the fp32 build (MUFU reciprocal / rsqrt + one multiply instead of the IEEE
 # sequences with their slow-path calls); the fp64 validation build is unaffected.  fp32 parity bounds hold (tests -m gpu).
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",

@@ -1,0 +1,783 @@
+// b2h_ppo.cu — the PPO update on the device with hand-written kernels, sm_100a.
+//
+// What it replaces: SB3 2.3.2 PPO.train as the reference drives it (train_sb3.py:208-231, kwargs config.py:17-32): per
+// minibatch the forward of the two MlpPolicy trunks (obs -> 256 -> 256 -> 21 / 1, ReLU: main.py:99-105), the clipped
+// surrogate + value MSE (+ entropy bonus) with per-minibatch advantage normalisation, the backward pass, grad-norm clipping
+// and Adam.  The reference runs this through PyTorch autograd on the CPU; round 1-2 here ran it through autograd + library
+// GEMMs.  Now every step of a minibatch is a kernel of this file:
+//
+//   gather_kernel        minibatch rows of the rollout buffer -> contiguous operands
+//   gemm_kernel          C = A . B^T on the tcgen05 tensor cores, fp32-faithful (tf32 hi / lo split, hi*hi + hi*lo + lo*hi,
+//                        accumulator in TMEM).  One kernel serves the three GEMM shapes of the update because each operand
+//                        is staged into the canonical K-major core-matrix layout by the producer warps, which read either
+//                        [rows, K] (K contiguous) or [K, rows] (K strided) row-major memory:
+//                          forward           Y  = X  W^T + b (ReLU)        A: X [B, in]   K contiguous, B: W [out, in] K contiguous
+//                          input gradient    dX = dY W . (X > 0)           A: dY [B, out] K contiguous, B: W [out, in] K strided
+//                          weight gradient   dW = dY^T X                   A: dY [B, out] K strided,    B: X [B, in]   K strided
+//                        the weight gradients contract over the minibatch rows: split over CTAs (grid.z), partial tiles added
+//                        with red.global.add.  Both networks ride in one launch (two problems per grid).
+//   ppo_loss_kernel      advantage moments, log-probability, ratio, clipped surrogate, value loss, their gradients with respect
+//                        to the action mean / value / log_std, head bias gradients, loss statistics
+//   colsum_kernel        hidden-layer bias gradients
+//   sumsq_kernel + adam_kernel   global grad-norm clip (max_grad_norm) and torch.optim.Adam's update rule on the flat
+//                        parameter vector (the caller may all-reduce the flat gradient between b2h_ppo_minibatch_grad and
+//                        b2h_ppo_apply: one NCCL call on 1.27 MB)
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include <algorithm>
+#include <string>
+
+#include "../../include/b2h.h"
+
+namespace {
+
+thread_local std::string g_err_ppo;
+
+// ------------------------------------------------------------------------------------------------------------------ GEMM
+constexpr int GM = 128;          // rows of C per CTA (UMMA M)
+constexpr int GN = 256;          // columns of C per CTA (UMMA N <= 256, multiple of 16)
+constexpr int GK = 32;           // K columns per chunk (four MMA K-steps)
+constexpr int GNS = 2;           // operand stages
+constexpr int GTHREADS = 256;
+constexpr int GPROD = GTHREADS - 32;                            // producer threads: warps 1..7
+constexpr int GA_PART = GM * GK, GB_PART = GN * GK;             // floats of the hi (or lo) part of a chunk
+constexpr int GSTAGE = 2 * GA_PART + 2 * GB_PART;               // floats: A hi | A lo | B hi | B lo  (96 KB)
+constexpr int GITEMS = ((GM + GN) * (GK / 4) + GPROD - 1) / GPROD;   // 16-byte items per producer per chunk (14)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// shared-memory matrix descriptor, no swizzle, K-major: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 << 46
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46);
+}
+// instruction descriptor kind::tf32: D fp32 (bit 4), A / B tf32 (2 at bits 7 and 10), both K-major, N >> 3 at 17, M >> 4 at 24
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_wait(uint32_t mbar, uint32_t parity) {
+  for (int spin = 0; spin < (1 << 22); spin++) {   // bounded: a lost arrive must not hang the GPU
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t mbar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}\n" ::"r"(mbar) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
+struct GemmProblem {
+  const float *A, *B, *bias, *mask;
+  float* C;
+  int lda, ldb, ldc, ldmask;
+  int M, N, K;
+  int a_kstrided, b_kstrided;   // 0: the operand is [rows, K] row-major (K contiguous); 1: [K, rows] row-major
+  int relu;                     // epilogue: max(x, 0) (after the bias)
+  int atomic;                   // epilogue: C += x (split-K partial sums, accumulation into an existing C)
+  int transpose_c;              // epilogue: the tile is written as C[col * ldc + row]
+};
+struct GemmArgs {
+  GemmProblem p[2];
+  int nsplit, k_per_split, precise;
+  int* error;
+};
+
+struct Chunk { float4 v[GITEMS]; };
+
+// Item g of an operand with `rows` rows -> (row r, 16-byte K group k4 of the chunk).
+//   K contiguous: eight consecutive threads take eight consecutive rows of one K group (one 128-byte core matrix per
+//   quarter-warp on the shared side, 64 contiguous bytes of each of 8 rows per warp on the global side).
+//   K strided: consecutive threads take consecutive rows of one K group (the four K values of an item are four loads, each
+//   coalesced over the warp; the shared side is 32 consecutive 16-byte units).
+__device__ __forceinline__ void item_kc(int g, int& r, int& k4) { r = (g & 7) | ((g >> 6) << 3); k4 = (g >> 3) & 7; }
+// g / rows by a multiply: magic = ceil(2^32 / rows) is exact for g < 2^32 / rows (here g < 2048, rows <= 256)
+__device__ __forceinline__ void item_ks(int g, int rows, uint32_t magic, int& r, int& k4) { k4 = (int)__umulhi((uint32_t)g, magic); r = g - k4 * rows; }
+
+__device__ __forceinline__ float4 load_item(const float* __restrict__ base, int ld, bool kstrided, bool vec, int row, int row_lim, int k,
+                                            int kend) {
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (row >= row_lim || k >= kend) return v;
+  if (!kstrided) {
+    const float* src = base + (size_t)row * ld + k;
+    if (vec && k + 3 < kend) return __ldg(reinterpret_cast<const float4*>(src));
+    v.x = __ldg(src);
+    if (k + 1 < kend) v.y = __ldg(src + 1);
+    if (k + 2 < kend) v.z = __ldg(src + 2);
+    if (k + 3 < kend) v.w = __ldg(src + 3);
+  } else {
+    const float* src = base + (size_t)k * ld + row;
+    v.x = __ldg(src);
+    if (k + 1 < kend) v.y = __ldg(src + ld);
+    if (k + 2 < kend) v.z = __ldg(src + 2 * (size_t)ld);
+    if (k + 3 < kend) v.w = __ldg(src + 3 * (size_t)ld);
+  }
+  return v;
+}
+
+__device__ __forceinline__ void load_chunk(Chunk& c, int pt, const GemmProblem& P, int row0, int col0, int nw, uint32_t magic, int k0, int kend) {
+  constexpr int NA = GM * (GK / 4);
+  const int nitems = NA + nw * (GK / 4);
+  const bool veca = (P.lda & 3) == 0 && ((uintptr_t)P.A & 15) == 0, vecb = (P.ldb & 3) == 0 && ((uintptr_t)P.B & 15) == 0;
+#pragma unroll
+  for (int i = 0; i < GITEMS; i++) {
+    const int f = pt + i * GPROD;
+    int r, k4;
+    if (f < NA) {
+      if (P.a_kstrided) { k4 = f >> 7; r = f & (GM - 1); } else item_kc(f, r, k4);
+      c.v[i] = load_item(P.A, P.lda, P.a_kstrided != 0, veca, row0 + r, P.M, k0 + 4 * k4, kend);
+    } else if (f < nitems) {
+      if (P.b_kstrided) item_ks(f - NA, nw, magic, r, k4); else item_kc(f - NA, r, k4);
+      c.v[i] = load_item(P.B, P.ldb, P.b_kstrided != 0, vecb, col0 + r, P.N, k0 + 4 * k4, kend);
+    } else {
+      c.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+}
+// tf32 hi = the value rounded to 10 mantissa bits (exact in the tensor core's operand format), lo = the exact remainder
+__device__ __forceinline__ void split1(float x, float& hi, float& lo) {
+  hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+  lo = x - hi;
+}
+__device__ __forceinline__ void store_chunk(const Chunk& c, int pt, const GemmProblem& P, float* A_hi, float* B_hi, int nw, uint32_t magic, bool precise) {
+  constexpr int NA = GM * (GK / 4);
+  const int nitems = NA + nw * (GK / 4);
+#pragma unroll
+  for (int i = 0; i < GITEMS; i++) {
+    const int f = pt + i * GPROD;
+    if (f >= nitems) continue;
+    const bool isA = f < NA;
+    int r, k4;
+    if (isA) { if (P.a_kstrided) { k4 = f >> 7; r = f & (GM - 1); } else item_kc(f, r, k4); }
+    else     { if (P.b_kstrided) item_ks(f - NA, nw, magic, r, k4); else item_kc(f - NA, r, k4); }
+    const int groups = (isA ? GM : nw) >> 3;
+    const float4 v = c.v[i];
+    float4 hi, lo;
+    split1(v.x, hi.x, lo.x); split1(v.y, hi.y, lo.y); split1(v.z, hi.z, lo.z); split1(v.w, hi.w, lo.w);
+    const int off = ((k4 * groups + (r >> 3)) * 32) + (r & 7) * 4;   // floats; a core matrix is 8 rows x 16 bytes
+    float* dst = isA ? A_hi : B_hi;
+    *reinterpret_cast<float4*>(dst + off) = hi;
+    if (precise) *reinterpret_cast<float4*>(dst + (isA ? GA_PART : GB_PART) + off) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(GTHREADS, 1) gemm_kernel(GemmArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  float* stage0 = reinterpret_cast<float*>(smem);
+  __shared__ __align__(8) unsigned long long bar_storage[2 * GNS + 1];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int prob = blockIdx.z / a.nsplit, split = blockIdx.z - prob * a.nsplit;
+  const GemmProblem P = prob ? a.p[1] : a.p[0];
+  const int row0 = blockIdx.x * GM, col0 = blockIdx.y * GN;
+  if (row0 >= P.M || col0 >= P.N) return;                       // the two problems of a launch share the larger tile grid
+  const int nw = min(GN, ((P.N - col0) + 15) & ~15);            // UMMA N of this tile (rows of B beyond N are zero-filled)
+  const int k_begin = split * a.k_per_split, k_end = min(P.K, k_begin + a.k_per_split);
+  const int nchunk = (k_end - k_begin + GK - 1) / GK;
+  if (nchunk <= 0) return;
+  const bool precise = a.precise != 0;
+  uint32_t full[GNS], empty[GNS];
+#pragma unroll
+  for (int s = 0; s < GNS; s++) { full[s] = smem_u32(&bar_storage[s]); empty[s] = smem_u32(&bar_storage[GNS + s]); }
+  const uint32_t accbar = smem_u32(&bar_storage[2 * GNS]);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < GNS; s++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(full[s]), "r"(GPROD));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(empty[s]));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(accbar));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  bool ok = true;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---- MMA issuer
+      const uint32_t idesc = umma_idesc_tf32(GM, nw);
+      const uint32_t lboA = (GM / 8) * 128, lboB = (uint32_t)(nw / 8) * 128;
+      for (int c = 0; c < nchunk && ok; c++) {
+        const int s = c % GNS, use = c / GNS;
+        ok = mbar_wait(full[s], use & 1);
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t A_hi = smem_u32(stage0 + s * GSTAGE), A_lo = A_hi + GA_PART * 4, B_hi = A_lo + GA_PART * 4, B_lo = B_hi + GB_PART * 4;
+#pragma unroll
+        for (int ks = 0; ks < GK / 8; ks++) {
+          const uint64_t ah = umma_desc(A_hi + ks * 2 * lboA, lboA, 128), bh = umma_desc(B_hi + ks * 2 * lboB, lboB, 128);
+          umma_tf32(tmem, ah, bh, idesc, (c | ks) != 0);
+          if (precise) {
+            const uint64_t al = umma_desc(A_lo + ks * 2 * lboA, lboA, 128), bl = umma_desc(B_lo + ks * 2 * lboB, lboB, 128);
+            umma_tf32(tmem, ah, bl, idesc, 1);
+            umma_tf32(tmem, al, bh, idesc, 1);
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(empty[s]) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(accbar) : "memory");
+    }
+    __syncwarp();
+  } else {               // ---- producers: both operands, global -> registers -> hi / lo -> core-matrix layout
+    const int pt = threadIdx.x - 32;
+    const uint32_t magic = (uint32_t)((0x100000000ULL + (uint32_t)nw - 1) / (uint32_t)nw);
+    Chunk cur, nxt;
+    load_chunk(cur, pt, P, row0, col0, nw, magic, k_begin, k_end);
+    for (int c = 0; c < nchunk && ok; c++) {
+      if (c + 1 < nchunk) load_chunk(nxt, pt, P, row0, col0, nw, magic, k_begin + (c + 1) * GK, k_end);
+      const int s = c % GNS, use = c / GNS;
+      if (use > 0) ok = mbar_wait(empty[s], (use - 1) & 1);
+      if (!ok) break;
+      float* A_hi = stage0 + s * GSTAGE;
+      store_chunk(cur, pt, P, A_hi, A_hi + 2 * GA_PART, nw, magic, precise);
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      mbar_arrive(full[s]);
+      cur = nxt;
+    }
+  }
+  // ---- epilogue (warps 4-7: TMEM lane quadrant = warp % 4, thread = row of the tile)
+  if (warp >= 4 && ok) {
+    ok = mbar_wait(accbar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const int quad = warp & 3;
+    const int grow = row0 + (threadIdx.x - 128);
+    const bool rowok = grow < P.M;
+    const bool first = split == 0;
+    if (ok) {
+      for (int c0 = 0; c0 < nw; c0 += 16) {
+        uint32_t v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        const int colb = col0 + c0;
+        if (!rowok || colb >= P.N) continue;
+        float x[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) x[q] = __uint_as_float(v[q]);
+        const bool full16 = colb + 16 <= P.N;
+        if (P.bias && first) {
+#pragma unroll
+          for (int q = 0; q < 16; q++) if (full16 || colb + q < P.N) x[q] += __ldg(P.bias + colb + q);
+        }
+        if (P.relu) {
+#pragma unroll
+          for (int q = 0; q < 16; q++) x[q] = fmaxf(x[q], 0.f);
+        }
+        if (P.mask) {
+          const float* mrow = P.mask + (size_t)grow * P.ldmask + colb;
+          if (full16 && (P.ldmask & 3) == 0 && ((uintptr_t)P.mask & 15) == 0) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const float4 m = __ldg(reinterpret_cast<const float4*>(mrow) + q);
+              x[4 * q + 0] = m.x > 0.f ? x[4 * q + 0] : 0.f; x[4 * q + 1] = m.y > 0.f ? x[4 * q + 1] : 0.f;
+              x[4 * q + 2] = m.z > 0.f ? x[4 * q + 2] : 0.f; x[4 * q + 3] = m.w > 0.f ? x[4 * q + 3] : 0.f;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; q++) if (colb + q < P.N) x[q] = __ldg(mrow + q) > 0.f ? x[q] : 0.f;
+          }
+        }
+        if (P.transpose_c) {
+#pragma unroll
+          for (int q = 0; q < 16; q++)
+            if (colb + q < P.N) {
+              float* dst = P.C + (size_t)(colb + q) * P.ldc + grow;
+              if (P.atomic) atomicAdd(dst, x[q]); else *dst = x[q];
+            }
+        } else {
+          float* crow = P.C + (size_t)grow * P.ldc + colb;
+          const bool vec = full16 && (P.ldc & 3) == 0 && ((uintptr_t)P.C & 15) == 0;
+          if (vec) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              if (P.atomic) red_add_v4(crow + 4 * q, x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+              else *reinterpret_cast<float4*>(crow + 4 * q) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 16; q++)
+              if (colb + q < P.N) { if (P.atomic) atomicAdd(crow + q, x[q]); else crow[q] = x[q]; }
+          }
+        }
+      }
+    }
+  }
+  if (!ok) atomicExch(a.error, 1);
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem) : "memory");
+}
+
+int g_sm_count = 0;
+
+// Launch one or two problems of the same tile-grid class.  split_k <= 0: chosen so that the launch fills the SMs once.
+int launch_gemm(const GemmProblem* probs, int nprob, int precise, int split_k, int* error_dev, cudaStream_t stream) {
+  static bool attr_set = false;
+  const size_t smem = (size_t)GNS * GSTAGE * sizeof(float);
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+    attr_set = true;
+  }
+  GemmArgs a;
+  int mt = 0, nt = 0, kmax = 0;
+  for (int i = 0; i < nprob; i++) {
+    const GemmProblem& p = probs[i];
+    if (!p.A || !p.B || !p.C || p.M <= 0 || p.N <= 0 || p.K <= 0) { g_err_ppo = "gemm: bad argument"; return B2H_EINVAL; }
+    a.p[i] = p;
+    mt = std::max(mt, (p.M + GM - 1) / GM);
+    nt = std::max(nt, (p.N + GN - 1) / GN);
+    kmax = std::max(kmax, p.K);
+  }
+  if (nprob == 1) a.p[1] = a.p[0];
+  const int chunks = (kmax + GK - 1) / GK;
+  if (split_k <= 0) split_k = std::max(1, std::min(chunks, g_sm_count / std::max(1, mt * nt * nprob)));
+  split_k = std::min(split_k, chunks);
+  for (int i = 0; i < nprob; i++)
+    if (split_k > 1 && (!probs[i].atomic || probs[i].relu || probs[i].mask)) { g_err_ppo = "gemm: split-K needs an accumulating linear epilogue"; return B2H_EINVAL; }
+  a.k_per_split = ((chunks + split_k - 1) / split_k) * GK;
+  a.nsplit = (kmax + a.k_per_split - 1) / a.k_per_split;
+  a.precise = precise;
+  a.error = error_dev;
+  dim3 grid(mt, nt, nprob * a.nsplit);
+  gemm_kernel<<<grid, GTHREADS, smem, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
+}
+
+// --------------------------------------------------------------------------------------------------------- small kernels
+struct GatherArgs {
+  const float *obs, *actions, *old_logp, *adv, *ret;   // flattened rollout buffer [n, ...]
+  const int64_t* idx;                                   // minibatch rows (null: rows row_start ... row_start + n_rows)
+  long long row_start;
+  float *X, *act, *olp, *a, *r;                         // contiguous minibatch
+  double* scratch;                                      // zeroed here: [0..3] loss statistics, [4] gradient sum of squares
+  int n_rows, obs_dim, act_dim;
+};
+__global__ void __launch_bounds__(256) gather_kernel(GatherArgs g) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x < 8) g.scratch[threadIdx.x] = 0.0;
+  if (warp >= g.n_rows) return;
+  const long long src = g.idx ? (long long)g.idx[warp] : g.row_start + warp;
+  const float* xs = g.obs + (size_t)src * g.obs_dim;
+  float* xd = g.X + (size_t)warp * g.obs_dim;
+  if ((g.obs_dim & 3) == 0) {
+    for (int i = lane; i < g.obs_dim / 4; i += 32) reinterpret_cast<float4*>(xd)[i] = __ldg(reinterpret_cast<const float4*>(xs) + i);
+  } else {
+    for (int i = lane; i < g.obs_dim; i += 32) xd[i] = __ldg(xs + i);
+  }
+  for (int i = lane; i < g.act_dim; i += 32) g.act[(size_t)warp * g.act_dim + i] = __ldg(g.actions + (size_t)src * g.act_dim + i);
+  if (lane == 0) { g.olp[warp] = __ldg(g.old_logp + src); g.a[warp] = __ldg(g.adv + src); g.r[warp] = __ldg(g.ret + src); }
+}
+
+constexpr int OUT_LD = 32;      // row stride of the head outputs / their gradients (act_dim <= 32, zero padded)
+constexpr int MAX_ACT = 32;
+
+struct LossArgs {
+  const float *mean, *value;          // [n, OUT_LD] head outputs of the policy / value network (value: column 0)
+  const float *act, *olp, *adv, *ret, *log_std;
+  float *dmean, *dvalue;              // [n, OUT_LD] gradients of the loss with respect to the head outputs
+  float *g_b3_pi, *g_b3_vf, *g_log_std;
+  double* stats;                      // [0] policy loss, [1] value loss, [2] clip fraction (sums over the minibatch / n), [3] approx kl
+  int n, act_dim;
+  float clip, ent_coef, vf_coef;
+  int normalize;
+};
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_sum_f(float v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Every CTA computes the advantage moments of the whole minibatch itself (n floats from L2: cheaper than another launch and
+// bit-identical in every CTA), then one thread per sample.
+__global__ void __launch_bounds__(256) ppo_loss_kernel(LossArgs L) {
+  __shared__ double red[8];
+  __shared__ float fred[8][2 * MAX_ACT + 1];
+  __shared__ double s_mean, s_std;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double amean = 0.0, astd = 1.0;
+  if (L.normalize && L.n > 1) {   // (adv - mean) / (std + 1e-8), torch.std: unbiased
+    double s = 0.0;
+    for (int i = tid; i < L.n; i += 256) s += (double)__ldg(L.adv + i);
+    s = warp_sum_d(s);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t += red[w]; s_mean = t / L.n; }
+    __syncthreads();
+    amean = s_mean;
+    double q = 0.0;
+    for (int i = tid; i < L.n; i += 256) { const double d = (double)__ldg(L.adv + i) - amean; q += d * d; }
+    q = warp_sum_d(q);
+    if (lane == 0) red[warp] = q;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t += red[w]; s_std = sqrt(t / (L.n - 1)); }
+    __syncthreads();
+    astd = s_std;
+  }
+  const int i = blockIdx.x * 256 + tid;
+  const bool live = i < L.n;
+  float pl = 0.f, vl = 0.f, cf = 0.f, kl = 0.f, dv = 0.f;
+  float dm[MAX_ACT], dls[MAX_ACT];
+#pragma unroll
+  for (int j = 0; j < MAX_ACT; j++) { dm[j] = 0.f; dls[j] = 0.f; }
+  const float inv_n = 1.f / (float)L.n;
+  if (live) {
+    const float a = L.normalize && L.n > 1 ? (float)(((double)L.adv[i] - amean)) / ((float)astd + 1e-8f) : L.adv[i];
+    float logp = 0.f;
+    float z[MAX_ACT], istd[MAX_ACT];
+#pragma unroll
+    for (int j = 0; j < MAX_ACT; j++) {
+      z[j] = 0.f; istd[j] = 0.f;
+      if (j < L.act_dim) {
+        const float ls = __ldg(L.log_std + j);
+        istd[j] = __expf(-ls);
+        z[j] = (L.act[(size_t)i * L.act_dim + j] - L.mean[(size_t)i * OUT_LD + j]) * istd[j];
+        logp += -0.5f * z[j] * z[j] - ls - 0.9189385332046727f;
+      }
+    }
+    const float lr = logp - L.olp[i];
+    const float ratio = expf(lr);
+    const float s1 = a * ratio, s2 = a * fminf(fmaxf(ratio, 1.f - L.clip), 1.f + L.clip);
+    pl = -fminf(s1, s2);
+    const bool inside = ratio >= 1.f - L.clip && ratio <= 1.f + L.clip;
+    // d(-min(s1, s2)) / d logp: s1 carries a * ratio; s2 carries it only inside the clip range (ties split evenly, same total)
+    const float glp = (inside || s1 < s2) ? -a * ratio * inv_n : 0.f;
+    cf = fabsf(ratio - 1.f) > L.clip ? 1.f : 0.f;
+    kl = (ratio - 1.f) - lr;
+    const float v = L.value[(size_t)i * OUT_LD], diff = v - L.ret[i];
+    vl = diff * diff;
+    dv = L.vf_coef * 2.f * diff * inv_n;
+#pragma unroll
+    for (int j = 0; j < MAX_ACT; j++)
+      if (j < L.act_dim) { dm[j] = glp * z[j] * istd[j]; dls[j] = glp * (z[j] * z[j] - 1.f); }
+    float4* drow = reinterpret_cast<float4*>(L.dmean + (size_t)i * OUT_LD);
+#pragma unroll
+    for (int q = 0; q < OUT_LD / 4; q++) drow[q] = make_float4(dm[4 * q], dm[4 * q + 1], dm[4 * q + 2], dm[4 * q + 3]);
+    float4* vrow = reinterpret_cast<float4*>(L.dvalue + (size_t)i * OUT_LD);
+    vrow[0] = make_float4(dv, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 1; q < OUT_LD / 4; q++) vrow[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // block reductions: head bias gradients (column sums of dmean / dvalue), log_std gradient, statistics
+#pragma unroll
+  for (int j = 0; j < MAX_ACT; j++) {
+    if (j < L.act_dim) {
+      const float s = warp_sum_f(dm[j]), t = warp_sum_f(dls[j]);
+      if (lane == 0) { fred[warp][j] = s; fred[warp][MAX_ACT + j] = t; }
+    }
+  }
+  {
+    const float s = warp_sum_f(dv);
+    if (lane == 0) fred[warp][2 * MAX_ACT] = s;
+  }
+  __syncthreads();
+  if (tid < 2 * MAX_ACT + 1) {
+    const int j = tid < MAX_ACT ? tid : tid - MAX_ACT;
+    if (tid == 2 * MAX_ACT || j < L.act_dim) {
+      float s = 0.f;
+      for (int w = 0; w < 8; w++) s += fred[w][tid];
+      if (tid == 2 * MAX_ACT) atomicAdd(L.g_b3_vf, s);
+      else if (tid < MAX_ACT) atomicAdd(L.g_b3_pi + j, s);
+      else atomicAdd(L.g_log_std + j, s - (blockIdx.x == 0 ? L.ent_coef : 0.f));   // entropy = sum(log_std) + const; loss has -ent_coef * entropy
+    }
+  }
+  __syncthreads();
+  const double st[4] = {(double)pl, (double)vl, (double)cf, (double)kl};
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const double s = warp_sum_d(st[k]);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t += red[w]; atomicAdd(L.stats + k, t / L.n); }
+    __syncthreads();
+  }
+}
+
+struct ColsumArgs { const float* src[4]; float* dst[4]; int n, width, rows_per_cta; };
+__global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs c) {
+  const float* __restrict__ s = c.src[blockIdx.y];
+  const int r0 = blockIdx.x * c.rows_per_cta, r1 = min(c.n, r0 + c.rows_per_cta);
+  for (int col = threadIdx.x; col < c.width; col += 256) {
+    float acc0 = 0.f, acc1 = 0.f;
+    int r = r0;
+    for (; r + 1 < r1; r += 2) { acc0 += __ldg(s + (size_t)r * c.width + col); acc1 += __ldg(s + (size_t)(r + 1) * c.width + col); }
+    if (r < r1) acc0 += __ldg(s + (size_t)r * c.width + col);
+    atomicAdd(c.dst[blockIdx.y] + col, acc0 + acc1);
+  }
+}
+
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, double* out) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) { const double v = g[i]; s += v * v; }
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t += red[w]; atomicAdd(out, t); }
+}
+
+struct AdamArgs {
+  float *p, *g, *m, *v;
+  long long n;
+  const double* sumsq;     // sum of squares of g (before grad_scale)
+  double* norm_out;        // receives the gradient norm (after grad_scale, before clipping)
+  float grad_scale;        // 1 / world size when g holds a sum over ranks
+  float max_norm, lr, beta1, beta2, eps;
+  float bc1, bc2_sqrt;     // 1 - beta1^t, sqrt(1 - beta2^t)
+};
+// torch.nn.utils.clip_grad_norm_ (coef = max_norm / (norm + 1e-6), clamped to 1) followed by torch.optim.Adam's update rule
+__global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
+  const float norm = (float)sqrt(*a.sumsq) * a.grad_scale;
+  const float coef = a.max_norm > 0.f ? fminf(a.max_norm / (norm + 1e-6f), 1.f) : 1.f;
+  const float gs = a.grad_scale * coef;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.norm_out) *a.norm_out = (double)norm;
+  const float step_size = a.lr / a.bc1;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n; i += (long long)gridDim.x * 256) {
+    const float g = a.g[i] * gs;
+    const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
+    const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
+    a.m[i] = m; a.v[i] = v;
+    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
+    a.p[i] -= step_size * (m / denom);
+  }
+}
+
+int al4(long long x) { return (int)((x + 3) & ~3LL); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------------------- C-ABI
+struct B2HPpo {
+  B2HPpoConfig cfg;
+  int64_t off[13];           // flat offsets: pi W1 b1 W2 b2 W3 b3, vf W1 .. b3, log_std
+  int64_t nflat;
+  int device;
+  // workspace (device)
+  float *X, *act, *olp, *adv, *ret;
+  float *h1[2], *h2[2], *out[2], *dout[2], *dh2[2], *dh1[2];
+  double* scratch;           // [8]: 0..3 statistics, 4 gradient sum of squares, 5 gradient norm
+  int* error;                // tensor pipeline timeout flag
+};
+
+extern "C" {
+
+const char* b2h_ppo_last_error(void) { return g_err_ppo.c_str(); }
+size_t b2h_sizeof_ppo_config(void) { return sizeof(B2HPpoConfig); }
+
+int64_t b2h_ppo_param_layout(int obs_dim, int hidden, int act_dim, int64_t offsets[13]) {
+  const long long sizes[13] = {(long long)hidden * obs_dim, hidden, (long long)hidden * hidden, hidden, (long long)act_dim * hidden, act_dim,
+                               (long long)hidden * obs_dim, hidden, (long long)hidden * hidden, hidden, hidden, 1, act_dim};
+  long long o = 0;
+  for (int i = 0; i < 13; i++) {
+    if (offsets) offsets[i] = o;
+    o = al4(o + sizes[i]);
+  }
+  return o;
+}
+
+int b2h_gemm(const float* a_dev, int lda, int a_kstrided, const float* b_dev, int ldb, int b_kstrided, float* c_dev, int ldc, int transpose_c,
+             const float* bias_dev, const float* mask_dev, int ldmask, int m, int n, int k, int relu, int precise, int split_k, int accumulate,
+             int* error_flag_dev, void* stream) {
+  if (!a_dev || !b_dev || !c_dev || !error_flag_dev || m <= 0 || n <= 0 || k <= 0 || split_k < 0) { g_err_ppo = "b2h_gemm: bad argument"; return B2H_EINVAL; }
+  if ((a_kstrided ? lda < m : lda < k) || (b_kstrided ? ldb < n : ldb < k) || (transpose_c ? ldc < m : ldc < n) || (mask_dev && ldmask < n)) {
+    g_err_ppo = "b2h_gemm: leading dimension too small";
+    return B2H_EINVAL;
+  }
+  GemmProblem p;
+  p.A = a_dev; p.B = b_dev; p.bias = bias_dev; p.mask = mask_dev; p.C = c_dev; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldmask = ldmask;
+  p.M = m; p.N = n; p.K = k; p.a_kstrided = a_kstrided; p.b_kstrided = b_kstrided; p.relu = relu; p.transpose_c = transpose_c;
+  p.atomic = (accumulate || split_k != 1) ? 1 : 0;
+  return launch_gemm(&p, 1, precise, split_k, error_flag_dev, (cudaStream_t)stream);
+}
+
+int b2h_ppo_create(const B2HPpoConfig* cfg, B2HPpo** out) {
+  if (!cfg || !out) { g_err_ppo = "null argument"; return B2H_EINVAL; }
+  if (cfg->obs_dim <= 0 || cfg->hidden <= 0 || cfg->hidden % 4 || cfg->act_dim <= 0 || cfg->act_dim > MAX_ACT || cfg->max_batch <= 0) {
+    g_err_ppo = "b2h_ppo_create: need hidden % 4 == 0, 0 < act_dim <= 32, max_batch > 0";
+    return B2H_EINVAL;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { g_err_ppo = "no CUDA device (this library has no CPU path)"; return B2H_ECUDA; }
+  B2HPpo* h = new B2HPpo();
+  h->cfg = *cfg;
+  h->nflat = b2h_ppo_param_layout(cfg->obs_dim, cfg->hidden, cfg->act_dim, h->off);
+  cudaGetDevice(&h->device);
+  const size_t B = (size_t)cfg->max_batch, H = (size_t)cfg->hidden;
+  const size_t floats = B * cfg->obs_dim + B * cfg->act_dim + 3 * B + 2 * (4 * B * H + 2 * B * OUT_LD) + 512;
+  float* base = nullptr;
+  if (cudaMalloc(&base, floats * sizeof(float) + 8 * sizeof(double) + 64) != cudaSuccess) {
+    g_err_ppo = "b2h_ppo_create: out of device memory";
+    delete h;
+    return B2H_ENOMEM;
+  }
+  cudaMemset(base, 0, floats * sizeof(float) + 8 * sizeof(double) + 64);
+  float* p = base;
+  auto take = [&](size_t n) { float* r = p; p += (n + 3) & ~(size_t)3; return r; };
+  h->scratch = reinterpret_cast<double*>(take(16));
+  h->error = reinterpret_cast<int*>(take(4));
+  h->X = take(B * cfg->obs_dim); h->act = take(B * cfg->act_dim); h->olp = take(B); h->adv = take(B); h->ret = take(B);
+  for (int n = 0; n < 2; n++) {
+    h->h1[n] = take(B * H); h->h2[n] = take(B * H); h->dh2[n] = take(B * H); h->dh1[n] = take(B * H);
+    h->out[n] = take(B * OUT_LD); h->dout[n] = take(B * OUT_LD);
+  }
+  *out = h;
+  return B2H_OK;
+}
+
+void b2h_ppo_destroy(B2HPpo* h) {
+  if (!h) return;
+  cudaFree(h->scratch);   // the first allocation of the block
+  delete h;
+}
+
+int b2h_ppo_minibatch_grad(B2HPpo* h, const float* obs_dev, const float* actions_dev, const float* old_log_probs_dev,
+                           const float* advantages_dev, const float* returns_dev, const int64_t* idx_dev, int64_t row_start, int n_rows,
+                           const float* params_dev, float* grad_dev, void* stream_) {
+  if (!h || !obs_dev || !actions_dev || !old_log_probs_dev || !advantages_dev || !returns_dev || !params_dev || !grad_dev) {
+    g_err_ppo = "null argument";
+    return B2H_EINVAL;
+  }
+  if (n_rows <= 0 || n_rows > h->cfg.max_batch) { g_err_ppo = "b2h_ppo_minibatch_grad: n_rows outside (0, max_batch]"; return B2H_EINVAL; }
+  cudaStream_t s = (cudaStream_t)stream_;
+  const B2HPpoConfig& c = h->cfg;
+  const int H = c.hidden, D = c.obs_dim, A = c.act_dim, n = n_rows;
+  if (cudaMemsetAsync(grad_dev, 0, (size_t)h->nflat * sizeof(float), s) != cudaSuccess) { g_err_ppo = "memset failed"; return B2H_ECUDA; }
+  GatherArgs g;
+  g.obs = obs_dev; g.actions = actions_dev; g.old_logp = old_log_probs_dev; g.adv = advantages_dev; g.ret = returns_dev; g.idx = idx_dev;
+  g.row_start = row_start; g.X = h->X; g.act = h->act; g.olp = h->olp; g.a = h->adv; g.r = h->ret; g.scratch = h->scratch;
+  g.n_rows = n; g.obs_dim = D; g.act_dim = A;
+  gather_kernel<<<(n * 32 + 255) / 256, 256, 0, s>>>(g);
+
+  const float* P = params_dev;
+  float* G = grad_dev;
+  const int64_t* o = h->off;
+  const int nout[2] = {A, 1};
+  auto prob = [](const float* Am, int lda, int ak, const float* Bm, int ldb, int bk, float* C, int ldc, int M, int N, int K) {
+    GemmProblem p;
+    p.A = Am; p.B = Bm; p.C = C; p.bias = nullptr; p.mask = nullptr; p.lda = lda; p.ldb = ldb; p.ldc = ldc; p.ldmask = 0; p.M = M; p.N = N; p.K = K;
+    p.a_kstrided = ak; p.b_kstrided = bk; p.relu = 0; p.atomic = 0; p.transpose_c = 0;
+    return p;
+  };
+  GemmProblem pr[2];
+  int rc;
+  // ---- forward: h1 = relu(X W1^T + b1), h2 = relu(h1 W2^T + b2), out = h2 W3^T + b3
+  for (int k = 0; k < 2; k++) { pr[k] = prob(h->X, D, 0, P + o[6 * k + 0], D, 0, h->h1[k], H, n, H, D); pr[k].bias = P + o[6 * k + 1]; pr[k].relu = 1; }
+  if ((rc = launch_gemm(pr, 2, c.precise, 1, h->error, s)) < 0) return rc;
+  for (int k = 0; k < 2; k++) { pr[k] = prob(h->h1[k], H, 0, P + o[6 * k + 2], H, 0, h->h2[k], H, n, H, H); pr[k].bias = P + o[6 * k + 3]; pr[k].relu = 1; }
+  if ((rc = launch_gemm(pr, 2, c.precise, 1, h->error, s)) < 0) return rc;
+  for (int k = 0; k < 2; k++) { pr[k] = prob(h->h2[k], H, 0, P + o[6 * k + 4], H, 0, h->out[k], OUT_LD, n, nout[k], H); pr[k].bias = P + o[6 * k + 5]; }
+  if ((rc = launch_gemm(pr, 2, c.precise, 1, h->error, s)) < 0) return rc;
+  // ---- loss and its gradient with respect to the head outputs
+  LossArgs L;
+  L.mean = h->out[0]; L.value = h->out[1]; L.act = h->act; L.olp = h->olp; L.adv = h->adv; L.ret = h->ret; L.log_std = P + o[12];
+  L.dmean = h->dout[0]; L.dvalue = h->dout[1]; L.g_b3_pi = G + o[5]; L.g_b3_vf = G + o[11]; L.g_log_std = G + o[12]; L.stats = h->scratch;
+  L.n = n; L.act_dim = A; L.clip = c.clip_range; L.ent_coef = c.ent_coef; L.vf_coef = c.vf_coef; L.normalize = c.normalize_advantage;
+  ppo_loss_kernel<<<(n + 255) / 256, 256, 0, s>>>(L);
+  // ---- backward.  Head: dW3 = dout^T h2 (computed transposed: the 256 hidden features ride on the M side), dh2 = dout W3 . (h2 > 0)
+  for (int k = 0; k < 2; k++) {
+    pr[k] = prob(h->h2[k], H, 1, h->dout[k], OUT_LD, 1, G + o[6 * k + 4], H, H, nout[k], n);
+    pr[k].atomic = 1; pr[k].transpose_c = 1;
+  }
+  if ((rc = launch_gemm(pr, 2, c.precise, 0, h->error, s)) < 0) return rc;
+  for (int k = 0; k < 2; k++) { pr[k] = prob(h->dout[k], OUT_LD, 0, P + o[6 * k + 4], H, 1, h->dh2[k], H, n, H, nout[k]); pr[k].mask = h->h2[k]; pr[k].ldmask = H; }
+  if ((rc = launch_gemm(pr, 2, c.precise, 1, h->error, s)) < 0) return rc;
+  // layer 2: dW2 = dh2^T h1, dh1 = dh2 W2 . (h1 > 0)
+  for (int k = 0; k < 2; k++) { pr[k] = prob(h->dh2[k], H, 1, h->h1[k], H, 1, G + o[6 * k + 2], H, H, H, n); pr[k].atomic = 1; }
+  if ((rc = launch_gemm(pr, 2, c.precise, 0, h->error, s)) < 0) return rc;
+  for (int k = 0; k < 2; k++) { pr[k] = prob(h->dh2[k], H, 0, P + o[6 * k + 2], H, 1, h->dh1[k], H, n, H, H); pr[k].mask = h->h1[k]; pr[k].ldmask = H; }
+  if ((rc = launch_gemm(pr, 2, c.precise, 1, h->error, s)) < 0) return rc;
+  // layer 1: dW1 = dh1^T X
+  for (int k = 0; k < 2; k++) { pr[k] = prob(h->dh1[k], H, 1, h->X, D, 1, G + o[6 * k + 0], D, H, D, n); pr[k].atomic = 1; }
+  if ((rc = launch_gemm(pr, 2, c.precise, 0, h->error, s)) < 0) return rc;
+  // hidden-layer biases
+  ColsumArgs cs;
+  cs.src[0] = h->dh2[0]; cs.dst[0] = G + o[3]; cs.src[1] = h->dh1[0]; cs.dst[1] = G + o[1];
+  cs.src[2] = h->dh2[1]; cs.dst[2] = G + o[9]; cs.src[3] = h->dh1[1]; cs.dst[3] = G + o[7];
+  cs.n = n; cs.width = H; cs.rows_per_cta = 128;
+  colsum_kernel<<<dim3((n + 127) / 128, 4), 256, 0, s>>>(cs);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
+}
+
+int b2h_ppo_apply(B2HPpo* h, float* params_dev, float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t step, float grad_scale,
+                  void* stream_) {
+  if (!h || !params_dev || !grad_dev || !exp_avg_dev || !exp_avg_sq_dev || step < 1) { g_err_ppo = "b2h_ppo_apply: bad argument"; return B2H_EINVAL; }
+  cudaStream_t s = (cudaStream_t)stream_;
+  const B2HPpoConfig& c = h->cfg;
+  if (cudaMemsetAsync(h->scratch + 4, 0, sizeof(double), s) != cudaSuccess) { g_err_ppo = "memset failed"; return B2H_ECUDA; }
+  sumsq_kernel<<<64, 256, 0, s>>>(grad_dev, h->nflat, h->scratch + 4);
+  AdamArgs a;
+  a.p = params_dev; a.g = grad_dev; a.m = exp_avg_dev; a.v = exp_avg_sq_dev; a.n = h->nflat; a.sumsq = h->scratch + 4; a.norm_out = h->scratch + 5;
+  a.grad_scale = grad_scale; a.max_norm = c.max_grad_norm; a.lr = c.lr; a.beta1 = c.beta1; a.beta2 = c.beta2; a.eps = c.adam_eps;
+  a.bc1 = (float)(1.0 - pow((double)c.beta1, (double)step));
+  a.bc2_sqrt = (float)sqrt(1.0 - pow((double)c.beta2, (double)step));
+  adam_kernel<<<(int)std::min<int64_t>((h->nflat + 255) / 256, 592), 256, 0, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
+}
+
+int b2h_ppo_train(B2HPpo* h, const float* obs_dev, const float* actions_dev, const float* old_log_probs_dev, const float* advantages_dev,
+                  const float* returns_dev, const int64_t* perm_dev, int64_t n_samples, int n_epochs, int batch_size, float* params_dev,
+                  float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t* step_inout, void* stream) {
+  if (!h || !perm_dev || !step_inout || n_samples <= 0 || n_epochs <= 0 || batch_size <= 0) { g_err_ppo = "b2h_ppo_train: bad argument"; return B2H_EINVAL; }
+  for (int e = 0; e < n_epochs; e++)
+    for (int64_t i = 0; i < n_samples; i += batch_size) {
+      const int n = (int)std::min<int64_t>(batch_size, n_samples - i);
+      int rc = b2h_ppo_minibatch_grad(h, obs_dev, actions_dev, old_log_probs_dev, advantages_dev, returns_dev, perm_dev + (size_t)e * n_samples + i,
+                                      0, n, params_dev, grad_dev, stream);
+      if (rc < 0) return rc;
+      rc = b2h_ppo_apply(h, params_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, ++*step_inout, 1.f, stream);
+      if (rc < 0) return rc;
+    }
+  return B2H_OK;
+}
+
+int b2h_ppo_stats(B2HPpo* h, double stats_host[8], int* error_host, void* stream) {
+  if (!h || !stats_host) { g_err_ppo = "null argument"; return B2H_EINVAL; }
+  cudaStream_t s = (cudaStream_t)stream;
+  if (cudaMemcpyAsync(stats_host, h->scratch, 8 * sizeof(double), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+      (error_host && cudaMemcpyAsync(error_host, h->error, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess) ||
+      cudaStreamSynchronize(s) != cudaSuccess) {
+    g_err_ppo = cudaGetErrorString(cudaGetLastError());
+    return B2H_ECUDA;
+  }
+  return B2H_OK;
+}
+
+const double* b2h_ppo_stats_dev(const B2HPpo* h) { return h ? h->scratch : nullptr; }
+const int* b2h_ppo_error_dev(const B2HPpo* h) { return h ? h->error : nullptr; }
+
+}  // extern "C"

@@ -49,6 +49,19 @@ SIGNATURES = {
     "b2h_policy_forward_packed": (C.c_int, [vp, vp, vp, vp, vp, vp, C.c_int, C.c_int, vp, vp]),
     "b2h_sizeof_rollout": (C.c_size_t, []),
     "b2h_rollout_collect": (C.c_int, [vp, C.POINTER(abi.B2HRollout), vp]),
+    "b2h_sizeof_ppo_config": (C.c_size_t, []),
+    "b2h_ppo_param_layout": (C.c_int64, [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int64)]),
+    "b2h_ppo_create": (C.c_int, [C.POINTER(abi.B2HPpoConfig), C.POINTER(vp)]),
+    "b2h_ppo_destroy": (None, [vp]),
+    "b2h_ppo_last_error": (C.c_char_p, []),
+    "b2h_ppo_minibatch_grad": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp, vp]),
+    "b2h_ppo_apply": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, C.c_float, vp]),
+    "b2h_ppo_train": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int64), vp]),
+    "b2h_ppo_stats": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int), vp]),
+    "b2h_ppo_stats_dev": (vp, [vp]),
+    "b2h_ppo_error_dev": (vp, [vp]),
+    "b2h_gemm": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
+                           C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
 }
 
 
@@ -69,7 +82,7 @@ def load():
             fn = getattr(L, name)
             fn.restype, fn.argtypes = res, args
         if (L.b2h_sizeof_model() != C.sizeof(abi.B2HModel) or L.b2h_sizeof_config() != C.sizeof(abi.B2HConfig)
-                or L.b2h_sizeof_rollout() != C.sizeof(abi.B2HRollout)):
+                or L.b2h_sizeof_rollout() != C.sizeof(abi.B2HRollout) or L.b2h_sizeof_ppo_config() != C.sizeof(abi.B2HPpoConfig)):
             raise B2HError("struct layout mismatch between abi.py and libb2h.so")
         _lib = L
     return _lib

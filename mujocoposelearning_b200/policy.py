@@ -21,34 +21,54 @@ def _p(t):
     return C.c_void_p(t.data_ptr())
 
 
+def param_layout(obs_dim, hidden, act_dim):
+    """Offsets (floats) of the 13 parameter tensors in the flat vector and its length: pi W1 b1 W2 b2 W3 b3, vf W1 .. b3,
+    log_std, every tensor starting at a multiple of 4 floats (the layout of include/b2h.h ``b2h_ppo_param_layout``)."""
+    shapes = [(hidden, obs_dim), (hidden,), (hidden, hidden), (hidden,), (act_dim, hidden), (act_dim,),
+              (hidden, obs_dim), (hidden,), (hidden, hidden), (hidden,), (1, hidden), (1,), (act_dim,)]
+    offs, o = [], 0
+    for sh in shapes:
+        offs.append(o)
+        o = (o + math.prod(sh) + 3) & ~3
+    return shapes, offs, o
+
+
 class MlpPolicyParams:
+    """All parameters are views of ONE flat float32 vector ``flat`` (the update kernels and Adam work on it; the rollout
+    kernels read the views' memory directly, so an in-place update needs no copy)."""
+
+    def _alloc(self, obs_dim, hidden, act_dim, device):
+        self.obs_dim, self.act_dim, self.hidden, self.device = int(obs_dim), int(act_dim), int(hidden), torch.device(device)
+        shapes, offs, n = param_layout(self.obs_dim, self.hidden, self.act_dim)
+        self.flat = torch.zeros(n, device=self.device, dtype=torch.float32)
+        views = [self.flat[o:o + math.prod(sh)].view(sh) for sh, o in zip(shapes, offs)]
+        self.pi, self.vf, self.log_std = views[0:6], views[6:12], views[12]
+        self.offsets = offs
+
     def __init__(self, obs_dim=352, act_dim=21, hidden=256, device="cuda", seed=0):
         g = torch.Generator().manual_seed(seed)
+        self._alloc(obs_dim, hidden, act_dim, device)
 
-        def ortho(out_f, in_f, gain):
-            w = torch.empty(out_f, in_f)
+        def ortho(dst, gain):
+            w = torch.empty(*dst.shape)
             torch.nn.init.orthogonal_(w, gain=gain, generator=g)
-            return w.to(device).contiguous()
-        z = lambda n: torch.zeros(n, device=device)
+            dst.copy_(w)
         s2 = math.sqrt(2.0)
-        self.obs_dim, self.act_dim, self.hidden, self.device = obs_dim, act_dim, hidden, torch.device(device)
-        self.pi = [ortho(hidden, obs_dim, s2), z(hidden), ortho(hidden, hidden, s2), z(hidden), ortho(act_dim, hidden, 0.01), z(act_dim)]
-        self.vf = [ortho(hidden, obs_dim, s2), z(hidden), ortho(hidden, hidden, s2), z(hidden), ortho(1, hidden, 1.0), z(1)]
-        self.log_std = torch.zeros(act_dim, device=device)
+        for net, head_gain in ((self.pi, 0.01), (self.vf, 1.0)):      # zero biases, log_std 0
+            ortho(net[0], s2); ortho(net[2], s2); ortho(net[4], head_gain)
 
     @classmethod
     def from_sb3_state_dict(cls, sd, device="cuda"):
         """``sd = PPO.load(...).policy.state_dict()`` (keys of SB3 ActorCriticPolicy)."""
-        w = lambda k: sd[k].detach().to(device, torch.float32).contiguous()
+        keys = ["mlp_extractor.policy_net.0.weight", "mlp_extractor.policy_net.0.bias", "mlp_extractor.policy_net.2.weight",
+                "mlp_extractor.policy_net.2.bias", "action_net.weight", "action_net.bias",
+                "mlp_extractor.value_net.0.weight", "mlp_extractor.value_net.0.bias", "mlp_extractor.value_net.2.weight",
+                "mlp_extractor.value_net.2.bias", "value_net.weight", "value_net.bias", "log_std"]
         self = cls.__new__(cls)
-        self.pi = [w("mlp_extractor.policy_net.0.weight"), w("mlp_extractor.policy_net.0.bias"), w("mlp_extractor.policy_net.2.weight"),
-                   w("mlp_extractor.policy_net.2.bias"), w("action_net.weight"), w("action_net.bias")]
-        self.vf = [w("mlp_extractor.value_net.0.weight"), w("mlp_extractor.value_net.0.bias"), w("mlp_extractor.value_net.2.weight"),
-                   w("mlp_extractor.value_net.2.bias"), w("value_net.weight"), w("value_net.bias")]
-        self.log_std = w("log_std")
-        self.hidden, self.obs_dim = self.pi[0].shape
-        self.act_dim = self.pi[4].shape[0]
-        self.device = torch.device(device)
+        hidden, obs_dim = sd[keys[0]].shape
+        self._alloc(obs_dim, hidden, sd[keys[4]].shape[0], device)
+        for dst, k in zip(self.pi + self.vf + [self.log_std], keys):
+            dst.copy_(sd[k].detach().to(torch.float32).reshape(dst.shape))
         return self
 
     def n_params(self):

@@ -5,24 +5,102 @@ random permutation of the T*E samples, minibatches, per-minibatch advantage norm
 (clip 0.2), value MSE x vf_coef 0.5, entropy bonus, grad-norm clip 0.5, Adam(eps 1e-5).  With several GPUs every rank
 holds a replica of the 318 k parameters and gradients are averaged with one NCCL all-reduce (1.27 MB) per minibatch.
 
-The rollout (policy forward, sampling, physics, GAE) runs on the hand-written kernels; this update step is plain
-PyTorch autograd + library GEMMs for now — it is outside the round-1 hot path and is stated as such in DESIGN.md.
-The kernels read the very tensors Adam updates in place (shared storage), so no weight copies are needed.
+``update_impl="native"`` (default): every step of a minibatch runs on the hand-written kernels of ``csrc/b2h_ppo.cu``
+(``b2h_ppo_minibatch_grad`` / ``b2h_ppo_apply`` / ``b2h_ppo_train``): tcgen05 GEMMs for the forward and backward of both
+trunks (fp32-faithful tf32 hi / lo split), the loss kernel, grad-norm clip and Adam on the flat parameter vector.  On one
+rank the whole ``PPO.train`` is ONE foreign call; with several ranks the flat gradient is all-reduced between the two calls.
+``update_impl="torch"`` is the same update written with PyTorch autograd + library GEMMs (round 1-2; the tests check the
+kernels against it).  The rollout kernels read the very memory the update writes, so no weight copies are needed.
 """
 from __future__ import annotations
 
+import ctypes as C
 import math
 
 import torch
 import torch.distributed as dist
 import torch.nn.functional as F
 
+from . import abi
+from .lib import load
 from .policy import MlpPolicy, MlpPolicyParams, RolloutCollector
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+class PpoKernels:
+    """ctypes face of the update kernels (include/b2h.h ``b2h_ppo_*``) for one parameter set on one device."""
+
+    def __init__(self, params: MlpPolicyParams, max_batch, lr=3e-4, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5,
+                 precise=True, normalize_advantage=True, betas=(0.9, 0.999), adam_eps=1e-5):
+        self.lib, self.p = load(), params
+        offs = (C.c_int64 * 13)()
+        n = self.lib.b2h_ppo_param_layout(params.obs_dim, params.hidden, params.act_dim, offs)
+        if n != params.flat.numel() or list(offs) != list(params.offsets):
+            raise RuntimeError("parameter layout of policy.py and libb2h.so disagree")
+        c = abi.B2HPpoConfig()
+        c.obs_dim, c.hidden, c.act_dim, c.max_batch = params.obs_dim, params.hidden, params.act_dim, int(max_batch)
+        c.precise, c.normalize_advantage = int(bool(precise)), int(bool(normalize_advantage))
+        c.clip_range, c.ent_coef, c.vf_coef, c.max_grad_norm = clip_range, ent_coef, vf_coef, max_grad_norm
+        c.lr, c.beta1, c.beta2, c.adam_eps = lr, betas[0], betas[1], adam_eps
+        self.cfg = c
+        h = C.c_void_p()
+        with torch.cuda.device(params.device):
+            self._check(self.lib.b2h_ppo_create(C.byref(c), C.byref(h)))
+        self.h = h
+        dev = params.device
+        self.grad = torch.zeros_like(params.flat)
+        self.exp_avg, self.exp_avg_sq = torch.zeros_like(params.flat), torch.zeros_like(params.flat)
+        self.step = 0
+        self.device = dev
+
+    def _check(self, rc):
+        if rc < 0:
+            raise RuntimeError(f"b2h_ppo: {self.lib.b2h_ppo_last_error().decode()} (rc {rc})")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.lib.b2h_ppo_destroy(self.h)
+            self.h = None
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def minibatch_grad(self, obs, actions, old_logp, adv, ret, idx=None, row_start=0, n_rows=None):
+        """Flat gradient of the PPO loss on rows ``idx`` (int64 tensor) or ``row_start .. row_start + n_rows`` -> ``self.grad``."""
+        n_rows = int(idx.numel()) if idx is not None else int(n_rows if n_rows is not None else obs.shape[0] - row_start)
+        self._check(self.lib.b2h_ppo_minibatch_grad(self.h, _p(obs), _p(actions), _p(old_logp), _p(adv), _p(ret), _p(idx) if idx is not None else None,
+                                                    int(row_start), n_rows, _p(self.p.flat), _p(self.grad), self._stream()))
+        return self.grad
+
+    def apply(self, grad_scale=1.0):
+        self.step += 1
+        self._check(self.lib.b2h_ppo_apply(self.h, _p(self.p.flat), _p(self.grad), _p(self.exp_avg), _p(self.exp_avg_sq), self.step,
+                                           float(grad_scale), self._stream()))
+
+    def train(self, obs, actions, old_logp, adv, ret, perm, batch_size):
+        """``perm`` int64 [n_epochs, n]: the whole PPO.train of one rank in one foreign call."""
+        step = C.c_int64(self.step)
+        self._check(self.lib.b2h_ppo_train(self.h, _p(obs), _p(actions), _p(old_logp), _p(adv), _p(ret), _p(perm), int(perm.shape[1]),
+                                           int(perm.shape[0]), int(batch_size), _p(self.p.flat), _p(self.grad), _p(self.exp_avg),
+                                           _p(self.exp_avg_sq), C.byref(step), self._stream()))
+        self.step = step.value
+
+    def stats(self):
+        """Statistics of the last minibatch (synchronises): policy_loss, value_loss, clip_fraction, approx_kl, grad_norm."""
+        out, err = (C.c_double * 8)(), C.c_int(0)
+        self._check(self.lib.b2h_ppo_stats(self.h, out, C.byref(err), self._stream()))
+        if err.value:
+            raise RuntimeError("tcgen05 GEMM pipeline timed out during the PPO update (mbarrier wait exceeded its bound)")
+        return dict(policy_loss=out[0], value_loss=out[1], clip_fraction=out[2], approx_kl=out[3], grad_norm=out[5])
 
 
 class PPOTrainer:
     def __init__(self, batch, params: MlpPolicyParams | None = None, n_steps=64, batch_size=16384, n_epochs=4, lr=3e-4, gamma=0.99,
-                 gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, seed=0, precise=True, update_tf32=False, cuda_graph=True):
+                 gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, seed=0, precise=True, update_tf32=False, cuda_graph=True,
+                 update_impl="native"):
         self.b = batch
         self.params = params or MlpPolicyParams(batch.obs_dim, batch.nu, 256, batch.device, seed)
         rank = dist.get_rank() if dist.is_initialized() else 0
@@ -30,11 +108,25 @@ class PPOTrainer:
         self.policy = MlpPolicy(self.params, precise=precise, seed=seed + 1, row_offset=rank * batch.n_envs)
         self.col = RolloutCollector(batch, self.policy, n_steps, gamma, gae_lambda)
         self.tensors = self.params.pi + self.params.vf + [self.params.log_std]
+        if update_impl not in ("native", "torch"):
+            raise ValueError(f"unknown update_impl {update_impl!r}")
+        self.update_impl = update_impl
+        if self.world > 1:                       # identical replicas: broadcast rank 0's initialisation
+            dist.broadcast(self.params.flat, 0)
+        self.batch_size, self.n_epochs, self.clip, self.ent_coef, self.vf_coef, self.max_grad_norm = batch_size, n_epochs, clip_range, ent_coef, vf_coef, max_grad_norm
+        self.gen = torch.Generator(device=batch.device).manual_seed(seed + 17 + rank)
+        self.iterations = 0
+        self.update_tf32 = bool(update_tf32)   # torch impl: library GEMMs on the tf32 tensor cores; native impl: a single tf32 pass
+        self.time_allreduce = False            # bench: CUDA events around every gradient all-reduce (adds two event records each)
+        self._ar_events = []
+        self.kernels = None
+        if update_impl == "native":
+            self.kernels = PpoKernels(self.params, batch_size, lr=lr, clip_range=clip_range, ent_coef=ent_coef, vf_coef=vf_coef,
+                                      max_grad_norm=max_grad_norm, precise=not update_tf32)
+            self.flat_grad = self.kernels.grad
+            return
         for t in self.tensors:
             t.requires_grad_(True)
-        if self.world > 1:                       # identical replicas: broadcast rank 0's initialisation
-            for t in self.tensors:
-                dist.broadcast(t.data, 0)
         # one flat gradient buffer: every tensor's .grad is a view of it, so the all-reduce, the norm clip and the
         # zeroing are single calls on 1.27 MB instead of 13 small ones; Adam runs as one fused multi-tensor kernel
         self.flat_grad = torch.zeros(sum(t.numel() for t in self.tensors), device=batch.device, dtype=torch.float32)
@@ -48,12 +140,6 @@ class PPOTrainer:
         # and [clip, Adam] - replayed per minibatch around the (eager) NCCL all-reduce of the flat gradient.
         self.cuda_graph = bool(cuda_graph)
         self._graphs = None
-        self.batch_size, self.n_epochs, self.clip, self.ent_coef, self.vf_coef, self.max_grad_norm = batch_size, n_epochs, clip_range, ent_coef, vf_coef, max_grad_norm
-        self.gen = torch.Generator(device=batch.device).manual_seed(seed + 17 + rank)
-        self.iterations = 0
-        self.update_tf32 = bool(update_tf32)   # library GEMMs of the update on the tf32 tensor cores (default: fp32 like the reference)
-        self.time_allreduce = False            # bench: CUDA events around every gradient all-reduce (adds two event records each)
-        self._ar_events = []
 
     def _evaluate(self, obs, actions):
         p = self.params
@@ -68,8 +154,33 @@ class PPOTrainer:
         entropy = (0.5 + 0.5 * math.log(2 * math.pi) + p.log_std).sum()
         return value, logp, entropy
 
+    def _update_native(self):
+        c, k = self.col, self.kernels
+        n = c.T * self.b.n_envs
+        obs, actions = c.obs[:c.T].reshape(n, -1), c.actions.reshape(n, -1)
+        old_logp, adv, ret = c.log_probs.reshape(n), c.advantages.reshape(n), c.returns.reshape(n)
+        perm = torch.stack([torch.randperm(n, device=obs.device, generator=self.gen) for _ in range(self.n_epochs)])
+        if self.world == 1:
+            k.train(obs, actions, old_logp, adv, ret, perm, self.batch_size)
+        else:
+            for e in range(self.n_epochs):
+                for i in range(0, n, self.batch_size):
+                    k.minibatch_grad(obs, actions, old_logp, adv, ret, idx=perm[e, i:i + self.batch_size])
+                    if self.time_allreduce:
+                        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        e0.record()
+                    dist.all_reduce(k.grad)      # one flat NCCL all-reduce over NVLink; the mean is taken inside the Adam kernel
+                    if self.time_allreduce:
+                        e1.record()
+                        self._ar_events.append((e0, e1))
+                    k.apply(grad_scale=1.0 / self.world)
+        st = k.stats()
+        return {key: torch.tensor(st[key], device=obs.device) for key in ("policy_loss", "value_loss", "clip_fraction")}
+
     def update(self):
         """One PPO.train() over the current rollout buffer; returns the last minibatch's loss terms."""
+        if self.update_impl == "native":
+            return self._update_native()
         prev_tf32 = torch.backends.cuda.matmul.allow_tf32
         torch.backends.cuda.matmul.allow_tf32 = self.update_tf32
         try:

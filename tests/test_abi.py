@@ -73,3 +73,19 @@ def test_launch_shape_rule(lib):
     w, r = C.c_int(), C.c_int()
     assert lib.b2h_choose_launch_shape(4096, 148, 8 * 1024, 0, C.byref(w), C.byref(r)) < 0   # scratch does not fit
     assert lib.b2h_choose_launch_shape(0, 148, 232448, 0, C.byref(w), C.byref(r)) < 0
+
+
+def test_ppo_parameter_layout_matches_python(lib):
+    """The flat parameter vector of the PPO update kernels (b2h_ppo_param_layout) is the one policy.py allocates."""
+    from mujocoposelearning_b200 import abi
+    from mujocoposelearning_b200.policy import param_layout
+    assert lib.b2h_sizeof_ppo_config() == C.sizeof(abi.B2HPpoConfig)
+    for dims in ((352, 256, 21), (53, 64, 21), (40, 128, 3)):
+        offs = (C.c_int64 * 13)()
+        n = lib.b2h_ppo_param_layout(*dims, offs)
+        shapes, want, total = param_layout(*dims)
+        assert list(offs) == want and n == total and all(o % 4 == 0 for o in want)
+    assert 317995 <= param_layout(352, 256, 21)[2] < 317995 + 13 * 4      # SURVEY 8e: 317 995 parameters (+ alignment padding)
+    cfg = abi.B2HPpoConfig()
+    h = C.c_void_p()
+    assert lib.b2h_ppo_create(C.byref(cfg), C.byref(h)) == abi.EINVAL      # zero shapes are refused before any device work

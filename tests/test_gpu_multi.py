@@ -24,7 +24,7 @@ def _worker(rank, world, port, q):
     from mujocoposelearning_b200.ppo import PPOTrainer
     n, T = 128, 8
     b = HumanoidBatch(n, frame_skip=3, duration=10.0, reward_type="stand", device=rank, seed=2, env_id_offset=rank * n)
-    tr = PPOTrainer(b, n_steps=T, batch_size=n * T, n_epochs=1, lr=3e-4, seed=5, cuda_graph=False)
+    tr = PPOTrainer(b, n_steps=T, batch_size=n * T, n_epochs=1, lr=3e-4, seed=5)      # update_impl native: b2h_ppo_* kernels around the all-reduce
     with torch.no_grad():
         tr.col.collect()
     before = [t.detach().clone() for t in tr.tensors]
@@ -60,7 +60,7 @@ def _worker(rank, world, port, q):
         opt.step()
         err = max(float((g - w).abs().max()) for g, w in zip(tr.tensors, ref))
         moved = max(float((g - w).abs().max()) for g, w in zip(tr.tensors, before))
-        ok = err < 2e-6 and moved > 1e-5
+        ok = err < 4e-6 and moved > 1e-5
     q.put((rank, ok, err))
     dist.barrier()
     b.close()

@@ -93,7 +93,8 @@ def test_rollout_collector_buffers_and_gae():
 
 
 def test_ppo_iteration_updates_policy_and_stats():
-    """collect_rollouts + PPO.train mechanics (the update itself is PyTorch autograd; 'next' row 8f-1)."""
+    """collect_rollouts + PPO.train mechanics (the update runs on the kernels of csrc/b2h_ppo.cu; their numerics are checked
+    in tests/test_gpu_ppo_kernels.py)."""
     from mujocoposelearning_b200.batch import HumanoidBatch
     from mujocoposelearning_b200.ppo import PPOTrainer
     b = HumanoidBatch(512, frame_skip=3, duration=0.2, reward_type="stand", seed=4)       # 13-step episodes
@@ -111,45 +112,6 @@ def test_ppo_iteration_updates_policy_and_stats():
     assert float((m1 - mref.detach()).abs().max()) < 1e-4
     s2 = tr.iterate()
     assert s2["timesteps"] == 2 * 26 * 512 and float(s2["value_loss"]) == float(s2["value_loss"])
-
-
-def test_ppo_minibatch_update_matches_sb3_recipe():
-    """One epoch of PPOTrainer.update (flat gradient buffer, fused Adam) against the SB3 2.3.2 PPO.train recipe written
-    with stock PyTorch pieces (clip_grad_norm_, unfused Adam) on the same rollout and the same permutation."""
-    import math
-    import torch.nn.functional as F
-    from mujocoposelearning_b200.batch import HumanoidBatch
-    from mujocoposelearning_b200.ppo import PPOTrainer
-    b = HumanoidBatch(256, frame_skip=3, duration=10.0, reward_type="stand", seed=2)
-    tr = PPOTrainer(b, n_steps=16, batch_size=1024, n_epochs=1, lr=3e-4, seed=5)
-    with torch.no_grad():
-        tr.col.collect()
-    ref = [t.detach().clone().requires_grad_(True) for t in tr.tensors]
-    opt = torch.optim.Adam(ref, lr=3e-4, eps=1e-5)
-    gstate = tr.gen.get_state()
-    tr.update()
-    c, n = tr.col, 16 * 256
-    obs, actions = c.obs.reshape(n, -1), c.actions.reshape(n, -1)
-    old_logp, adv, ret = c.log_probs.reshape(n), c.advantages.reshape(n), c.returns.reshape(n)
-    gen = torch.Generator(device="cuda")
-    gen.set_state(gstate)
-    perm = torch.randperm(n, device="cuda", generator=gen)
-    net = lambda w, x: F.linear(F.relu(F.linear(F.relu(F.linear(x, w[0], w[1])), w[2], w[3])), w[4], w[5])
-    for i in range(0, n, 1024):
-        idx = perm[i:i + 1024]
-        a = adv[idx]
-        a = (a - a.mean()) / (a.std() + 1e-8)
-        mean, value, log_std = net(ref[0:6], obs[idx]), net(ref[6:12], obs[idx]).squeeze(1), ref[12]
-        logp = (-0.5 * ((actions[idx] - mean) / log_std.exp()) ** 2 - log_std - 0.5 * math.log(2 * math.pi)).sum(1)
-        ratio = torch.exp(logp - old_logp[idx])
-        loss = -torch.min(a * ratio, a * torch.clamp(ratio, 0.8, 1.2)).mean() + 0.5 * F.mse_loss(ret[idx], value)
-        opt.zero_grad()
-        loss.backward()
-        torch.nn.utils.clip_grad_norm_(ref, 0.5)
-        opt.step()
-    for got, want in zip(tr.tensors, ref):
-        assert float((got - want).abs().max()) < 2e-6
-    b.close()
 
 
 def _twin_collectors(n, n_steps, duration, seed, **kw):

@@ -339,6 +339,9 @@ typedef struct B2HPpoConfig {
   int32_t normalize_advantage;  /* SB3 default True: (adv - mean) / (std + 1e-8) per minibatch                          */
   float clip_range, ent_coef, vf_coef, max_grad_norm;   /* SB3 defaults 0.2, 0.0, 0.5, 0.5 (config.py:23-24)            */
   float lr, beta1, beta2, adam_eps;                     /* 3e-4 (config.py:18), 0.9, 0.999, 1e-5 (SB3's Adam eps)       */
+  int32_t staged_operands;      /* 0 (default): operands kept pre-split in core-matrix order and streamed by TMA; 1: the
+                                   first version of the GEMM, producer warps stage plain row-major operands (kept for A/B
+                                   measurements and for hidden widths that are not a multiple of 32)                     */
 } B2HPpoConfig;
 typedef struct B2HPpo B2HPpo;
 size_t b2h_sizeof_ppo_config(void);
@@ -375,6 +378,13 @@ const int* b2h_ppo_error_dev(const B2HPpo* h);
 int b2h_gemm(const float* a_dev, int lda, int a_kstrided, const float* b_dev, int ldb, int b_kstrided, float* c_dev, int ldc, int transpose_c,
              const float* bias_dev, const float* mask_dev, int ldmask, int m, int n, int k, int relu, int precise, int split_k, int accumulate,
              int* error_flag_dev, void* stream);
+
+/* The TMA-fed GEMM of the update on its own (tests, measurement): the plain row-major operands are first packed into the
+ * pre-split core-matrix format the update keeps its activations in (temporary device buffers; the call synchronises).
+ * a_mn = 0: A is [m, k] (contraction over its columns, K-major use); 1: A is [k, m] (contraction over its rows, MN-major
+ * use); B likewise with n.  split_k = 1 stores C; 0 (fill the SMs) or > 1 adds partial tiles into C (the caller zeroes it). */
+int b2h_gemm_tma(const float* a_dev, int a_mn, const float* b_dev, int b_mn, float* c_dev, int ldc, int transpose_c, const float* bias_dev,
+                 int m, int n, int k, int precise, int split_k, int* error_flag_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -74,7 +74,7 @@ class B2HPpoConfig(C.Structure):
     _fields_ = [
         ("obs_dim", i32), ("hidden", i32), ("act_dim", i32), ("max_batch", i32), ("precise", i32), ("normalize_advantage", i32),
         ("clip_range", C.c_float), ("ent_coef", C.c_float), ("vf_coef", C.c_float), ("max_grad_norm", C.c_float),
-        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float),
+        ("lr", C.c_float), ("beta1", C.c_float), ("beta2", C.c_float), ("adam_eps", C.c_float), ("staged_operands", i32),
     ]
 
 

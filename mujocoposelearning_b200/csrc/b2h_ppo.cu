@@ -22,6 +22,7 @@
 //   sumsq_kernel + adam_kernel   global grad-norm clip (max_grad_norm) and torch.optim.Adam's update rule on the flat
 //                        parameter vector (the caller may all-reduce the flat gradient between b2h_ppo_minibatch_grad and
 //                        b2h_ppo_apply: one NCCL call on 1.27 MB)
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -402,7 +403,9 @@ constexpr int MAX_ACT = 32;
 struct LossArgs {
   const float *mean, *value;          // [n, OUT_LD] head outputs of the policy / value network (value: column 0)
   const float *act, *olp, *adv, *ret, *log_std;
-  float *dmean, *dvalue;              // [n, OUT_LD] gradients of the loss with respect to the head outputs
+  float *dmean, *dvalue;              // [n, OUT_LD] gradients of the loss with respect to the head outputs (row-major; staged GEMM)
+  float *dt_hi[2], *dt_lo[2];         // the same as split planes [rows padded to 128][32] for the TMA GEMM (dmean null then)
+  int rows_pad;
   float *g_b3_pi, *g_b3_vf, *g_log_std;
   double* stats;                      // [0] policy loss, [1] value loss, [2] clip fraction (sums over the minibatch / n), [3] approx kl
   int n, act_dim;
@@ -481,13 +484,29 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(LossArgs L) {
 #pragma unroll
     for (int j = 0; j < MAX_ACT; j++)
       if (j < L.act_dim) { dm[j] = glp * z[j] * istd[j]; dls[j] = glp * (z[j] * z[j] - 1.f); }
-    float4* drow = reinterpret_cast<float4*>(L.dmean + (size_t)i * OUT_LD);
+    if (L.dmean) {
+      float4* drow = reinterpret_cast<float4*>(L.dmean + (size_t)i * OUT_LD);
 #pragma unroll
-    for (int q = 0; q < OUT_LD / 4; q++) drow[q] = make_float4(dm[4 * q], dm[4 * q + 1], dm[4 * q + 2], dm[4 * q + 3]);
-    float4* vrow = reinterpret_cast<float4*>(L.dvalue + (size_t)i * OUT_LD);
-    vrow[0] = make_float4(dv, 0.f, 0.f, 0.f);
+      for (int q = 0; q < OUT_LD / 4; q++) drow[q] = make_float4(dm[4 * q], dm[4 * q + 1], dm[4 * q + 2], dm[4 * q + 3]);
+      float4* vrow = reinterpret_cast<float4*>(L.dvalue + (size_t)i * OUT_LD);
+      vrow[0] = make_float4(dv, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int q = 1; q < OUT_LD / 4; q++) vrow[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int q = 1; q < OUT_LD / 4; q++) vrow[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  if (!L.dmean && i < L.rows_pad) {   // split planes [rows_pad][32]; rows between n and the tile boundary are zeros (they enter the weight-gradient sums)
+    const size_t off = (size_t)i * OUT_LD;
+#pragma unroll
+    for (int q = 0; q < OUT_LD / 4; q++) {
+      float4 hi, lo;
+      split1(dm[4 * q], hi.x, lo.x); split1(dm[4 * q + 1], hi.y, lo.y); split1(dm[4 * q + 2], hi.z, lo.z); split1(dm[4 * q + 3], hi.w, lo.w);
+      *reinterpret_cast<float4*>(L.dt_hi[0] + off + 4 * q) = hi;
+      *reinterpret_cast<float4*>(L.dt_lo[0] + off + 4 * q) = lo;
+      float4 vh = make_float4(0.f, 0.f, 0.f, 0.f), vl = vh;
+      if (q == 0) split1(dv, vh.x, vl.x);
+      *reinterpret_cast<float4*>(L.dt_hi[1] + off + 4 * q) = vh;
+      *reinterpret_cast<float4*>(L.dt_lo[1] + off + 4 * q) = vl;
+    }
   }
   // block reductions: head bias gradients (column sums of dmean / dvalue), log_std gradient, statistics
 #pragma unroll
@@ -575,6 +594,8 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
 
 int al4(long long x) { return (int)((x + 3) & ~3LL); }
 
+#include "b2h_ppo_tma.cuh"
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------------------- C-ABI
@@ -588,7 +609,218 @@ struct B2HPpo {
   float *h1[2], *h2[2], *out[2], *dout[2], *dh2[2], *dh1[2];
   double* scratch;           // [8]: 0..3 statistics, 4 gradient sum of squares, 5 gradient norm
   int* error;                // tensor pipeline timeout flag
+  // TMA path (b2h_ppo_tma.cuh): every GEMM operand as two row-major planes (tf32 hi / lo), rows padded to 128, columns to 32
+  bool tma;
+  float* tbase;
+  struct TMat { float *hi, *lo; int ld, rows_pad; };
+  TMat tX, th1[2], th2[2], tdh2[2], tdh1[2], tdout[2], tW1[2], tW2[2], tW3[2];
+  TMaps maps[8];             // fwd1 fwd2 fwd3 dW3 dh2 dW2 dh1 dW1, each [network][A hi, A lo, B hi, B lo]
+  int nw_obs;                // N tile of the first-layer weight gradient (obs_dim split into equal tiles <= 256)
 };
+
+namespace {
+
+int roundup(int x, int m) { return (x + m - 1) / m * m; }
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                             const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// K-major use of a plane: 2-D map {columns, rows}, box {32 columns, `rows` rows}, 128-byte swizzle
+bool encode_k(EncodeFn encode, CUtensorMap* m, float* plane, int ld, int rows_pad, int rows) {
+  const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows_pad};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  const cuuint32_t box[2] = {32, (cuuint32_t)rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// MN-major use: 3-D map {32 columns of a group, rows, column groups}, box {32, 32 rows, `cols` / 32 groups}, 128-byte swizzle
+// with 32-byte atoms (what tcgen05's SWIZZLE_128B_BASE32B reads)
+bool encode_mn(EncodeFn encode, CUtensorMap* m, float* plane, int ld, int rows_pad, int cols) {
+  const cuuint64_t dims[3] = {32, (cuuint64_t)rows_pad, (cuuint64_t)(ld / 32)};
+  const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
+  const cuuint32_t box[3] = {32, 32, (cuuint32_t)(cols / 32)};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, plane, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// operand maps of one GEMM: `rows` = 128 for A, the N tile for B
+bool operand_maps(EncodeFn enc, CUtensorMap* hi_lo, const B2HPpo::TMat& t, int mn, int rows) {
+  if (mn) return encode_mn(enc, hi_lo + 0, t.hi, t.ld, t.rows_pad, rows) && encode_mn(enc, hi_lo + 1, t.lo, t.ld, t.rows_pad, rows);
+  return encode_k(enc, hi_lo + 0, t.hi, t.ld, t.rows_pad, rows) && encode_k(enc, hi_lo + 1, t.lo, t.ld, t.rows_pad, rows);
+}
+
+int setup_tma(B2HPpo* h) {
+  const B2HPpoConfig& c = h->cfg;
+  const int H = c.hidden, D = c.obs_dim;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+    g_err_ppo = "cuTensorMapEncodeTiled is not available from this driver";
+    return B2H_ECUDA;
+  }
+  EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
+  const int Bp = roundup(c.max_batch, 128), Hp = roundup(H, 128), Dp = roundup(D, 32);
+  const int tiles_obs = (Dp + 255) / 256;
+  h->nw_obs = roundup((Dp + tiles_obs - 1) / tiles_obs, 32);       // MN-major tiles come in groups of 32 columns
+  size_t total = 0;
+  auto plan = [&](B2HPpo::TMat& t, int rows_pad, int cols_pad) { t.rows_pad = rows_pad; t.ld = cols_pad; total += 2 * (size_t)rows_pad * cols_pad; };
+  plan(h->tX, Bp, std::max(Dp, h->nw_obs * tiles_obs));
+  for (int n = 0; n < 2; n++) {
+    plan(h->th1[n], Bp, Hp); plan(h->th2[n], Bp, Hp); plan(h->tdh2[n], Bp, Hp); plan(h->tdh1[n], Bp, Hp); plan(h->tdout[n], Bp, OUT_LD);
+    plan(h->tW1[n], roundup(H, 128), Dp); plan(h->tW2[n], roundup(H, 128), Hp); plan(h->tW3[n], 128, Hp);
+  }
+  if (cudaMalloc(&h->tbase, total * sizeof(float)) != cudaSuccess) { g_err_ppo = "b2h_ppo_create: out of device memory (T-format workspace)"; return B2H_ENOMEM; }
+  cudaMemset(h->tbase, 0, total * sizeof(float));
+  float* p = h->tbase;
+  auto place = [&](B2HPpo::TMat& t) { const size_t n = (size_t)t.rows_pad * t.ld; t.hi = p; t.lo = p + n; p += 2 * n; };
+  place(h->tX);
+  for (int n = 0; n < 2; n++) {
+    place(h->th1[n]); place(h->th2[n]); place(h->tdh2[n]); place(h->tdh1[n]); place(h->tdout[n]);
+    place(h->tW1[n]); place(h->tW2[n]); place(h->tW3[n]);
+  }
+  bool ok = true;
+  for (int n = 0; n < 2 && ok; n++) {
+    CUtensorMap(*m)[4] = nullptr;
+    auto gemm_maps = [&](int g, const B2HPpo::TMat& A, int a_mn, const B2HPpo::TMat& Bm, int b_mn, int nw) {
+      m = &h->maps[g].m[n];
+      return operand_maps(enc, &(*m)[0], A, a_mn, 128) && operand_maps(enc, &(*m)[2], Bm, b_mn, nw);
+    };
+    ok = ok && gemm_maps(0, h->tX, 0, h->tW1[n], 0, H);                 // fwd1  h1 = relu(X W1^T + b1)
+    ok = ok && gemm_maps(1, h->th1[n], 0, h->tW2[n], 0, H);             // fwd2  h2 = relu(h1 W2^T + b2)
+    ok = ok && gemm_maps(2, h->th2[n], 0, h->tW3[n], 0, 32);            // fwd3  out = h2 W3^T + b3
+    ok = ok && gemm_maps(3, h->th2[n], 1, h->tdout[n], 1, 32);          // dW3^T = h2^T dout
+    ok = ok && gemm_maps(4, h->tdout[n], 0, h->tW3[n], 1, H);           // dh2 = dout W3 . (h2 > 0)
+    ok = ok && gemm_maps(5, h->tdh2[n], 1, h->th1[n], 1, H);            // dW2 = dh2^T h1
+    ok = ok && gemm_maps(6, h->tdh2[n], 0, h->tW2[n], 1, H);            // dh1 = dh2 W2 . (h1 > 0)
+    ok = ok && gemm_maps(7, h->tdh1[n], 1, h->tX, 1, h->nw_obs);        // dW1 = dh1^T X
+  }
+  if (!ok) { g_err_ppo = "cuTensorMapEncodeTiled failed"; return B2H_ECUDA; }
+  cudaError_t e = cudaFuncSetAttribute(gemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TNS * T_STAGE * sizeof(float)));
+  if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
+}
+
+int launch_gemm_t(const B2HPpo* h, int g, TProblem* pr, int precise, bool split, cudaStream_t s) {
+  if (g_sm_count <= 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  TArgs a;
+  a.p[0] = pr[0]; a.p[1] = pr[1];
+  const int tiles = pr[0].m_tiles * pr[0].n_tiles * 2, chunks = pr[0].chunks;
+  int nsplit = split ? std::max(1, std::min(chunks, g_sm_count / std::max(1, tiles))) : 1;
+  a.chunks_per_split = (chunks + nsplit - 1) / nsplit;
+  a.nsplit = (chunks + a.chunks_per_split - 1) / a.chunks_per_split;
+  a.precise = precise;
+  a.error = h->error;
+  gemm_t_kernel<<<dim3(pr[0].m_tiles, pr[0].n_tiles, 2 * a.nsplit), 256, TNS * T_STAGE * sizeof(float), s>>>(h->maps[g], a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
+}
+
+int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const float* old_logp, const float* adv, const float* ret,
+                       const int64_t* idx, int64_t row_start, int n, const float* P, float* G, cudaStream_t s) {
+  const B2HPpoConfig& c = h->cfg;
+  const int H = c.hidden, D = c.obs_dim, A = c.act_dim;
+  const int64_t* o = h->off;
+  const int rows_pad = roundup(n, 128), m_tiles_b = rows_pad / 128, kchunks_b = roundup(n, 32) / 32;
+  const int nout[2] = {A, 1};
+  // weights -> T-format (they change with every Adam step; 0.3 M floats)
+  PackTJobs pj;
+  int max_items = 0;
+  for (int k = 0; k < 2; k++) {
+    const B2HPpo::TMat* t[3] = {&h->tW1[k], &h->tW2[k], &h->tW3[k]};
+    const int R[3] = {H, H, nout[k]}, F[3] = {D, H, H};
+    for (int l = 0; l < 3; l++) {
+      PackTJob& j = pj.j[3 * k + l];
+      j.W = P + o[6 * k + 2 * l]; j.hi = t[l]->hi; j.lo = t[l]->lo; j.R = R[l]; j.F = F[l]; j.rows_pad = t[l]->rows_pad; j.ld = t[l]->ld;
+      max_items = std::max(max_items, j.rows_pad * j.ld / 4);
+    }
+  }
+  pack_t_kernel<<<dim3((max_items + 255) / 256, 6), 256, 0, s>>>(pj);
+  GatherTArgs g;
+  g.obs = obs; g.actions = actions; g.old_logp = old_logp; g.adv = adv; g.ret = ret; g.idx = idx; g.row_start = row_start;
+  g.x_hi = h->tX.hi; g.x_lo = h->tX.lo; g.act = h->act; g.olp = h->olp; g.a = h->adv; g.r = h->ret; g.scratch = h->scratch;
+  g.n_rows = n; g.rows_pad = rows_pad; g.obs_dim = D; g.ld = h->tX.ld; g.act_dim = A;
+  gather_t_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, s>>>(g);
+
+  auto base = [&](int a_mn, int b_mn, int m_tiles, int n_tiles, int nw, int chunks) {
+    TProblem p;
+    p.a_mn = a_mn; p.b_mn = b_mn; p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.nw = nw; p.chunks = chunks; p.M = 0; p.N = 0; p.epi = 0;
+    p.c_hi = p.c_lo = nullptr; p.c_ld = 0; p.C = nullptr; p.ldc = 0; p.transpose_c = 0; p.bias = nullptr; p.relu = 0; p.mask_hi = nullptr; p.mask_ld = 0;
+    return p;
+  };
+  TProblem pr[2];
+  int rc;
+  const int kc_obs = roundup(D, 32) / 32, kc_h = roundup(H, 32) / 32, h_tiles = roundup(H, 128) / 128;
+  // ---- forward
+  for (int k = 0; k < 2; k++) {
+    pr[k] = base(0, 0, m_tiles_b, 1, H, kc_obs);
+    pr[k].c_hi = h->th1[k].hi; pr[k].c_lo = h->th1[k].lo; pr[k].c_ld = h->th1[k].ld; pr[k].bias = P + o[6 * k + 1]; pr[k].relu = 1; pr[k].N = H;
+  }
+  if ((rc = launch_gemm_t(h, 0, pr, c.precise, false, s)) < 0) return rc;
+  for (int k = 0; k < 2; k++) {
+    pr[k] = base(0, 0, m_tiles_b, 1, H, kc_h);
+    pr[k].c_hi = h->th2[k].hi; pr[k].c_lo = h->th2[k].lo; pr[k].c_ld = h->th2[k].ld; pr[k].bias = P + o[6 * k + 3]; pr[k].relu = 1; pr[k].N = H;
+  }
+  if ((rc = launch_gemm_t(h, 1, pr, c.precise, false, s)) < 0) return rc;
+  for (int k = 0; k < 2; k++) {
+    pr[k] = base(0, 0, m_tiles_b, 1, 32, kc_h);
+    pr[k].epi = 1; pr[k].C = h->out[k]; pr[k].ldc = OUT_LD; pr[k].M = n; pr[k].N = nout[k]; pr[k].bias = P + o[6 * k + 5];
+  }
+  if ((rc = launch_gemm_t(h, 2, pr, c.precise, false, s)) < 0) return rc;
+  // ---- loss
+  LossArgs L;
+  L.mean = h->out[0]; L.value = h->out[1]; L.act = h->act; L.olp = h->olp; L.adv = h->adv; L.ret = h->ret; L.log_std = P + o[12];
+  L.dmean = nullptr; L.dvalue = nullptr; L.rows_pad = rows_pad;
+  for (int k = 0; k < 2; k++) { L.dt_hi[k] = h->tdout[k].hi; L.dt_lo[k] = h->tdout[k].lo; }
+  L.g_b3_pi = G + o[5]; L.g_b3_vf = G + o[11]; L.g_log_std = G + o[12]; L.stats = h->scratch;
+  L.n = n; L.act_dim = A; L.clip = c.clip_range; L.ent_coef = c.ent_coef; L.vf_coef = c.vf_coef; L.normalize = c.normalize_advantage;
+  ppo_loss_kernel<<<(rows_pad + 255) / 256, 256, 0, s>>>(L);
+  // ---- backward
+  for (int k = 0; k < 2; k++) {   // dW3^T [H, nout] = h2^T dout, written transposed into the [nout, H] gradient
+    pr[k] = base(1, 1, h_tiles, 1, 32, kchunks_b);
+    pr[k].epi = 2; pr[k].C = G + o[6 * k + 4]; pr[k].ldc = H; pr[k].transpose_c = 1; pr[k].M = H; pr[k].N = nout[k];
+  }
+  if ((rc = launch_gemm_t(h, 3, pr, c.precise, true, s)) < 0) return rc;
+  for (int k = 0; k < 2; k++) {   // dh2 = dout W3 . (h2 > 0)
+    pr[k] = base(0, 1, m_tiles_b, 1, H, 1);
+    pr[k].c_hi = h->tdh2[k].hi; pr[k].c_lo = h->tdh2[k].lo; pr[k].c_ld = h->tdh2[k].ld; pr[k].mask_hi = h->th2[k].hi; pr[k].mask_ld = h->th2[k].ld; pr[k].N = H;
+  }
+  if ((rc = launch_gemm_t(h, 4, pr, c.precise, false, s)) < 0) return rc;
+  for (int k = 0; k < 2; k++) {   // dW2 = dh2^T h1
+    pr[k] = base(1, 1, h_tiles, 1, H, kchunks_b);
+    pr[k].epi = 2; pr[k].C = G + o[6 * k + 2]; pr[k].ldc = H; pr[k].M = H; pr[k].N = H;
+  }
+  if ((rc = launch_gemm_t(h, 5, pr, c.precise, true, s)) < 0) return rc;
+  for (int k = 0; k < 2; k++) {   // dh1 = dh2 W2 . (h1 > 0)
+    pr[k] = base(0, 1, m_tiles_b, 1, H, kc_h);
+    pr[k].c_hi = h->tdh1[k].hi; pr[k].c_lo = h->tdh1[k].lo; pr[k].c_ld = h->tdh1[k].ld; pr[k].mask_hi = h->th1[k].hi; pr[k].mask_ld = h->th1[k].ld; pr[k].N = H;
+  }
+  if ((rc = launch_gemm_t(h, 6, pr, c.precise, false, s)) < 0) return rc;
+  const int obs_tiles = (roundup(D, 32) + 255) / 256;
+  for (int k = 0; k < 2; k++) {   // dW1 = dh1^T X
+    pr[k] = base(1, 1, h_tiles, obs_tiles, h->nw_obs, kchunks_b);
+    pr[k].epi = 2; pr[k].C = G + o[6 * k + 0]; pr[k].ldc = D; pr[k].M = H; pr[k].N = D;
+  }
+  if ((rc = launch_gemm_t(h, 7, pr, c.precise, true, s)) < 0) return rc;
+  ColsumTArgs cs;
+  const B2HPpo::TMat* src[4] = {&h->tdh2[0], &h->tdh1[0], &h->tdh2[1], &h->tdh1[1]};
+  float* dst[4] = {G + o[3], G + o[1], G + o[9], G + o[7]};
+  for (int i = 0; i < 4; i++) { cs.hi[i] = src[i]->hi; cs.lo[i] = src[i]->lo; cs.dst[i] = dst[i]; }
+  cs.rows = n; cs.ld = h->tdh2[0].ld; cs.width = H; cs.rows_per_cta = 128;
+  colsum_t_kernel<<<dim3((n + 127) / 128, 4), 256, 0, s>>>(cs);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -621,6 +853,61 @@ int b2h_gemm(const float* a_dev, int lda, int a_kstrided, const float* b_dev, in
   return launch_gemm(&p, 1, precise, split_k, error_flag_dev, (cudaStream_t)stream);
 }
 
+// Test / measurement entry of the TMA-fed GEMM: plain row-major operands are packed into T-format here (device work + two
+// temporary allocations; synchronises), then C (+)= A . B^T runs through gemm_t_kernel.
+int b2h_gemm_tma(const float* a_dev, int a_mn, const float* b_dev, int b_mn, float* c_dev, int ldc, int transpose_c, const float* bias_dev,
+                 int m, int n, int k, int precise, int split_k, int* error_flag_dev, void* stream) {
+  if (!a_dev || !b_dev || !c_dev || !error_flag_dev || m <= 0 || n <= 0 || k <= 0) { g_err_ppo = "b2h_gemm_tma: bad argument"; return B2H_EINVAL; }
+  cudaStream_t s = (cudaStream_t)stream;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+    g_err_ppo = "cuTensorMapEncodeTiled is not available from this driver";
+    return B2H_ECUDA;
+  }
+  EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
+  const int n_tiles = (roundup(n, 32) + 255) / 256, nw = roundup((roundup(n, 32) + n_tiles - 1) / n_tiles, 32);
+  // A is [m, k] (K-major use) or [k, m] (MN-major use); likewise B with n
+  const int ar = a_mn ? k : m, ac = a_mn ? m : k, br = b_mn ? k : n, bc = b_mn ? n : k;
+  B2HPpo::TMat ta, tb;
+  ta.rows_pad = roundup(ar, 128); ta.ld = roundup(std::max(ac, a_mn ? 128 : 32), 32);
+  tb.rows_pad = roundup(br, 256); tb.ld = roundup(std::max(bc, b_mn ? nw * n_tiles : 32), 32);
+  const size_t na = (size_t)ta.rows_pad * ta.ld, nb = (size_t)tb.rows_pad * tb.ld;
+  float* buf = nullptr;
+  if (cudaMalloc(&buf, 2 * (na + nb) * sizeof(float)) != cudaSuccess) { g_err_ppo = "out of device memory"; return B2H_ENOMEM; }
+  ta.hi = buf; ta.lo = buf + na; tb.hi = buf + 2 * na; tb.lo = tb.hi + nb;
+  PackTJobs pj;
+  pj.j[0] = PackTJob{a_dev, ta.hi, ta.lo, ar, ac, ta.rows_pad, ta.ld};
+  pj.j[1] = PackTJob{b_dev, tb.hi, tb.lo, br, bc, tb.rows_pad, tb.ld};
+  const int items = (int)std::max(na, nb) / 4;
+  pack_t_kernel<<<dim3((items + 255) / 256, 2), 256, 0, s>>>(pj);
+  B2HPpo hh;
+  bool ok = operand_maps(enc, &hh.maps[0].m[0][0], ta, a_mn, 128) && operand_maps(enc, &hh.maps[0].m[0][2], tb, b_mn, nw);
+  hh.maps[0].m[1][0] = hh.maps[0].m[0][0]; hh.maps[0].m[1][1] = hh.maps[0].m[0][1]; hh.maps[0].m[1][2] = hh.maps[0].m[0][2]; hh.maps[0].m[1][3] = hh.maps[0].m[0][3];
+  int rc = B2H_OK;
+  if (!ok) { g_err_ppo = "cuTensorMapEncodeTiled failed"; rc = B2H_ECUDA; }
+  if (rc == B2H_OK && cudaFuncSetAttribute(gemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TNS * T_STAGE * sizeof(float))) != cudaSuccess) {
+    g_err_ppo = "cudaFuncSetAttribute failed"; rc = B2H_ECUDA;
+  }
+  if (rc == B2H_OK) {
+    TProblem p;
+    p.a_mn = a_mn; p.b_mn = b_mn; p.m_tiles = (m + 127) / 128; p.n_tiles = n_tiles; p.nw = nw; p.chunks = (k + TK - 1) / TK; p.M = m; p.N = n;
+    p.epi = split_k == 1 ? 1 : 2; p.c_hi = p.c_lo = nullptr; p.c_ld = 0; p.C = c_dev; p.ldc = ldc; p.transpose_c = transpose_c; p.bias = bias_dev; p.relu = 0;
+    p.mask_hi = nullptr; p.mask_ld = 0;
+    TArgs a;
+    a.p[0] = p; a.p[1] = p;
+    int nsplit = split_k == 1 ? 1 : (split_k > 1 ? std::min(split_k, p.chunks) : std::max(1, std::min(p.chunks, 148 / (p.m_tiles * p.n_tiles))));
+    a.chunks_per_split = (p.chunks + nsplit - 1) / nsplit;
+    a.nsplit = (p.chunks + a.chunks_per_split - 1) / a.chunks_per_split;
+    a.precise = precise; a.error = error_flag_dev;
+    gemm_t_kernel<<<dim3(p.m_tiles, p.n_tiles, a.nsplit), 256, TNS * T_STAGE * sizeof(float), s>>>(hh.maps[0], a);
+    if (cudaGetLastError() != cudaSuccess) { g_err_ppo = "launch failed"; rc = B2H_ECUDA; }
+  }
+  if (cudaStreamSynchronize(s) != cudaSuccess && rc == B2H_OK) { g_err_ppo = cudaGetErrorString(cudaGetLastError()); rc = B2H_ECUDA; }
+  cudaFree(buf);
+  return rc;
+}
+
 int b2h_ppo_create(const B2HPpoConfig* cfg, B2HPpo** out) {
   if (!cfg || !out) { g_err_ppo = "null argument"; return B2H_EINVAL; }
   if (cfg->obs_dim <= 0 || cfg->hidden <= 0 || cfg->hidden % 4 || cfg->act_dim <= 0 || cfg->act_dim > MAX_ACT || cfg->max_batch <= 0) {
@@ -651,6 +938,12 @@ int b2h_ppo_create(const B2HPpoConfig* cfg, B2HPpo** out) {
     h->h1[n] = take(B * H); h->h2[n] = take(B * H); h->dh2[n] = take(B * H); h->dh1[n] = take(B * H);
     h->out[n] = take(B * OUT_LD); h->dout[n] = take(B * OUT_LD);
   }
+  h->tbase = nullptr;
+  h->tma = !cfg->staged_operands && cfg->hidden % 32 == 0 && cfg->hidden <= 256;
+  if (h->tma) {
+    const int rc = setup_tma(h);
+    if (rc < 0) { b2h_ppo_destroy(h); return rc; }
+  }
   *out = h;
   return B2H_OK;
 }
@@ -658,6 +951,7 @@ int b2h_ppo_create(const B2HPpoConfig* cfg, B2HPpo** out) {
 void b2h_ppo_destroy(B2HPpo* h) {
   if (!h) return;
   cudaFree(h->scratch);   // the first allocation of the block
+  if (h->tbase) cudaFree(h->tbase);
   delete h;
 }
 
@@ -673,6 +967,8 @@ int b2h_ppo_minibatch_grad(B2HPpo* h, const float* obs_dev, const float* actions
   const B2HPpoConfig& c = h->cfg;
   const int H = c.hidden, D = c.obs_dim, A = c.act_dim, n = n_rows;
   if (cudaMemsetAsync(grad_dev, 0, (size_t)h->nflat * sizeof(float), s) != cudaSuccess) { g_err_ppo = "memset failed"; return B2H_ECUDA; }
+  if (h->tma)
+    return minibatch_grad_tma(h, obs_dev, actions_dev, old_log_probs_dev, advantages_dev, returns_dev, idx_dev, row_start, n, params_dev, grad_dev, s);
   GatherArgs g;
   g.obs = obs_dev; g.actions = actions_dev; g.old_logp = old_log_probs_dev; g.adv = advantages_dev; g.ret = returns_dev; g.idx = idx_dev;
   g.row_start = row_start; g.X = h->X; g.act = h->act; g.olp = h->olp; g.a = h->adv; g.r = h->ret; g.scratch = h->scratch;
@@ -701,7 +997,7 @@ int b2h_ppo_minibatch_grad(B2HPpo* h, const float* obs_dev, const float* actions
   // ---- loss and its gradient with respect to the head outputs
   LossArgs L;
   L.mean = h->out[0]; L.value = h->out[1]; L.act = h->act; L.olp = h->olp; L.adv = h->adv; L.ret = h->ret; L.log_std = P + o[12];
-  L.dmean = h->dout[0]; L.dvalue = h->dout[1]; L.g_b3_pi = G + o[5]; L.g_b3_vf = G + o[11]; L.g_log_std = G + o[12]; L.stats = h->scratch;
+  L.dmean = h->dout[0]; L.dvalue = h->dout[1]; L.rows_pad = 0; L.dt_hi[0] = L.dt_hi[1] = L.dt_lo[0] = L.dt_lo[1] = nullptr; L.g_b3_pi = G + o[5]; L.g_b3_vf = G + o[11]; L.g_log_std = G + o[12]; L.stats = h->scratch;
   L.n = n; L.act_dim = A; L.clip = c.clip_range; L.ent_coef = c.ent_coef; L.vf_coef = c.vf_coef; L.normalize = c.normalize_advantage;
   ppo_loss_kernel<<<(n + 255) / 256, 256, 0, s>>>(L);
   // ---- backward.  Head: dW3 = dout^T h2 (computed transposed: the 256 hidden features ride on the M side), dh2 = dout W3 . (h2 > 0)

@@ -1,0 +1,319 @@
+// b2h_ppo_tma.cuh — the TMA-fed GEMM of the PPO update and the operand format it reads (included by b2h_ppo.cu).
+//
+// The staged kernel of b2h_ppo.cu (gemm_kernel) spends its time in seven producer warps that pull fp32 operands through
+// registers, split them into tf32 hi / lo and scatter them into the tensor cores' core-matrix order: ~8000 warp
+// instructions per K chunk, tensor pipe 16-20 % active (profiles/r02_ppo_gemm_staged.txt).  Here no thread touches an operand:
+//
+//   * every matrix a GEMM of the update reads is kept in HBM already split: two row-major planes (hi, lo), rows padded to
+//     128 and columns to 32.  The kernels that PRODUCE those matrices write them that way (the gather of the minibatch, the
+//     GEMM epilogues, the loss kernel, the weight split after Adam), so the split costs no extra pass;
+//   * the same planes serve both roles a matrix plays in the update.  As a K-major operand (contraction over its columns:
+//     forward, input gradient) a K chunk is a 2-D TMA box {32 columns, 128 or N rows} with the 128-byte swizzle, read by
+//     tcgen05.mma through a SWIZZLE_128B descriptor.  As an MN-major operand (contraction over its rows: weight gradients, W
+//     in the input gradient) a K chunk is a 3-D box {32 columns, 32 rows, M or N / 32 column groups} with the 32-byte-atom
+//     128-byte swizzle -- the one layout tcgen05 accepts for MN-major tf32 (SWIZZLE_128B_BASE32B) -- and the instruction
+//     descriptor's major bits are set.  Nothing is ever transposed in memory; tile tails are zero-filled by the TMA unit;
+//   * roles: warp 0 issues tcgen05.mma (hi*hi + hi*lo + lo*hi), warp 1 issues the TMA loads (mbarrier expect_tx), warps
+//     4-7 run the epilogue out of TMEM -- bias / ReLU / ReLU-mask, then either the next GEMM's operand planes (split into
+//     hi / lo on the way out), a plain row-major tile (head outputs), or red.global.add into the flat gradient (weight
+//     gradients, split over the SMs along the minibatch).
+#pragma once
+
+constexpr int TK = 32;                       // K per chunk: 32 columns (K-major: one 128-byte swizzle row) or 32 rows (MN-major)
+constexpr int TNS = 2;                       // stages
+constexpr int T_A_PART = 128 * TK;           // floats of one plane of an A chunk (16 KB)
+constexpr int T_B_PART = 256 * TK;           // ... of a B chunk at the widest N (32 KB)
+constexpr int T_STAGE = 2 * T_A_PART + 2 * T_B_PART;   // A hi | A lo | B hi | B lo: 96 KB
+
+struct alignas(64) TMaps { CUtensorMap m[2][4]; };      // [problem][A hi, A lo, B hi, B lo]
+
+struct TProblem {
+  int a_mn, b_mn;            // operand use: 0 = K-major (contraction over the matrix's columns), 1 = MN-major (over its rows)
+  int m_tiles, n_tiles;      // tiles of 128 rows / nw columns
+  int nw;                    // UMMA N of a tile (multiple of 16, <= 256)
+  int chunks;                // K chunks of 32
+  int M, N;                  // valid rows / columns of the result (plain epilogues)
+  int epi;                   // 0: result as operand planes (hi / lo), 1: plain row-major store, 2: red.global.add (weight gradient)
+  float *c_hi, *c_lo;        // epi 0: result planes
+  int c_ld;                  //        their row stride (padded columns)
+  float* C;                  // epi 1 / 2
+  int ldc, transpose_c;
+  const float* bias;         // [N] or null
+  int relu;
+  const float* mask_hi;      // epi 0: hi plane of the activation whose sign gates the result (ReLU backward), or null
+  int mask_ld;
+};
+struct TArgs {
+  TProblem p[2];
+  int nsplit, chunks_per_split, precise;
+  int* error;
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+// shared-memory matrix descriptor with a swizzled layout: layout type at bits 61-63 (2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B)
+__device__ __forceinline__ uint64_t umma_desc_sw(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {
+  return umma_desc(saddr, lbo, sbo) | ((uint64_t)layout_type << 61);
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+// instruction descriptor kind::tf32 with the operands' major bits (15: A, 16: B; 1 = MN-major)
+__device__ __forceinline__ uint32_t umma_idesc_tf32_major(int m, int n, int a_mn, int b_mn) {
+  return umma_idesc_tf32(m, n) | ((uint32_t)(a_mn != 0) << 15) | ((uint32_t)(b_mn != 0) << 16);
+}
+
+__global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ TMaps maps, TArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem_t[];
+  float* stage0 = reinterpret_cast<float*>(smem_t);
+  __shared__ __align__(8) unsigned long long bar_storage[2 * TNS + 1];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int prob = blockIdx.z / a.nsplit, split = blockIdx.z - prob * a.nsplit;
+  const TProblem P = prob ? a.p[1] : a.p[0];
+  if ((int)blockIdx.x >= P.m_tiles || (int)blockIdx.y >= P.n_tiles) return;
+  const int row0 = blockIdx.x * 128, col0 = blockIdx.y * P.nw;
+  const int c_begin = split * a.chunks_per_split, c_end = min(P.chunks, c_begin + a.chunks_per_split);
+  const int nchunk = c_end - c_begin;
+  if (nchunk <= 0) return;
+  const bool precise = a.precise != 0;
+  const int nw = P.nw;
+  uint32_t full[TNS], empty[TNS];
+#pragma unroll
+  for (int s = 0; s < TNS; s++) { full[s] = smem_u32(&bar_storage[s]); empty[s] = smem_u32(&bar_storage[TNS + s]); }
+  const uint32_t accbar = smem_u32(&bar_storage[2 * TNS]);
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < TNS; s++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(full[s]));    // the TMA thread's arrive.expect_tx + the bytes
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(empty[s]));   // tcgen05.commit
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(accbar));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  const uint32_t tmem = tmem_base_s;
+  bool ok = true;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ---- MMA issuer
+      const uint32_t idesc = umma_idesc_tf32_major(128, nw, P.a_mn, P.b_mn);
+      // K-major (SWIZZLE_128B): rows of 128 bytes, 8-row swizzle atoms 1024 B apart (SBO), LBO unused (1); a K step of 8 tf32
+      // is 32 bytes further along the row.  MN-major (SWIZZLE_128B_BASE32B): per group of 32 columns, 32 K rows of 128 bytes;
+      // atoms of 4 K rows 512 B apart (SBO), column groups 4096 B apart (LBO); a K step of 8 = two atoms = 1024 B.
+      const uint32_t lboA = P.a_mn ? 4096u : 16u, sboA = P.a_mn ? 512u : 1024u, stepA = P.a_mn ? 1024u : 32u, ltA = P.a_mn ? 1u : 2u;
+      const uint32_t lboB = P.b_mn ? 4096u : 16u, sboB = P.b_mn ? 512u : 1024u, stepB = P.b_mn ? 1024u : 32u, ltB = P.b_mn ? 1u : 2u;
+      for (int c = 0; c < nchunk && ok; c++) {
+        const int s = c % TNS, use = c / TNS;
+        ok = mbar_wait(full[s], use & 1);
+        if (!ok) break;
+        asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+        const uint32_t A_hi = smem_u32(stage0 + s * T_STAGE), A_lo = A_hi + T_A_PART * 4, B_hi = A_lo + T_A_PART * 4, B_lo = B_hi + T_B_PART * 4;
+#pragma unroll
+        for (int ks = 0; ks < TK / 8; ks++) {
+          const uint64_t ah = umma_desc_sw(A_hi + ks * stepA, lboA, sboA, ltA), bh = umma_desc_sw(B_hi + ks * stepB, lboB, sboB, ltB);
+          umma_tf32(tmem, ah, bh, idesc, (c | ks) != 0);
+          if (precise) {
+            const uint64_t al = umma_desc_sw(A_lo + ks * stepA, lboA, sboA, ltA), bl = umma_desc_sw(B_lo + ks * stepB, lboB, sboB, ltB);
+            umma_tf32(tmem, ah, bl, idesc, 1);
+            umma_tf32(tmem, al, bh, idesc, 1);
+          }
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(empty[s]) : "memory");
+      }
+      asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(accbar) : "memory");
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {   // ---- TMA producer
+      const CUtensorMap* mp = maps.m[prob ? 1 : 0];
+      const uint32_t bytes = (uint32_t)(128 * TK * 4 + nw * TK * 4) * (precise ? 2u : 1u);
+      for (int c = 0; c < nchunk && ok; c++) {
+        const int s = c % TNS, use = c / TNS, kc = c_begin + c;
+        if (use > 0) ok = mbar_wait(empty[s], (use - 1) & 1);
+        if (!ok) break;
+        const uint32_t A_hi = smem_u32(stage0 + s * T_STAGE), A_lo = A_hi + T_A_PART * 4, B_hi = A_lo + T_A_PART * 4, B_lo = B_hi + T_B_PART * 4;
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(full[s]), "r"(bytes) : "memory");
+        // K-major: 2-D box at {first column of the chunk, first row of the tile}; MN-major: 3-D box at {0, first row of the
+        // chunk, first column group of the tile}
+        if (P.a_mn) { tma_load_3d(A_hi, mp + 0, 0, kc * TK, row0 / 32, full[s]); if (precise) tma_load_3d(A_lo, mp + 1, 0, kc * TK, row0 / 32, full[s]); }
+        else        { tma_load_2d(A_hi, mp + 0, kc * TK, row0, full[s]);        if (precise) tma_load_2d(A_lo, mp + 1, kc * TK, row0, full[s]); }
+        if (P.b_mn) { tma_load_3d(B_hi, mp + 2, 0, kc * TK, col0 / 32, full[s]); if (precise) tma_load_3d(B_lo, mp + 3, 0, kc * TK, col0 / 32, full[s]); }
+        else        { tma_load_2d(B_hi, mp + 2, kc * TK, col0, full[s]);        if (precise) tma_load_2d(B_lo, mp + 3, kc * TK, col0, full[s]); }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4) {   // ---- epilogue: TMEM lane quadrant = warp % 4, thread = row of the tile
+    ok = mbar_wait(accbar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+    const int quad = warp & 3;
+    const int grow = row0 + (threadIdx.x - 128);
+    const bool first = split == 0;
+    if (ok) {
+      for (int c0 = 0; c0 < nw; c0 += 16) {
+        uint32_t v[16];
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+              "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            : "r"(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        const int colb = col0 + c0;
+        float x[16];
+#pragma unroll
+        for (int q = 0; q < 16; q++) x[q] = __uint_as_float(v[q]);
+        if (P.epi == 0) {           // ---- the next GEMM's operand: bias, ReLU / mask, split into the hi / lo planes
+          if (colb >= P.c_ld) continue;
+          if (P.bias) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) x[q] += colb + q < P.N ? __ldg(P.bias + colb + q) : 0.f;
+          }
+          if (P.relu) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) x[q] = fmaxf(x[q], 0.f);
+          }
+          if (P.mask_hi) {
+            const float4* mrow = reinterpret_cast<const float4*>(P.mask_hi + (size_t)grow * P.mask_ld + colb);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const float4 m = __ldg(mrow + q);
+              x[4 * q + 0] = m.x > 0.f ? x[4 * q + 0] : 0.f; x[4 * q + 1] = m.y > 0.f ? x[4 * q + 1] : 0.f;
+              x[4 * q + 2] = m.z > 0.f ? x[4 * q + 2] : 0.f; x[4 * q + 3] = m.w > 0.f ? x[4 * q + 3] : 0.f;
+            }
+          }
+          const size_t off = (size_t)grow * P.c_ld + colb;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            float4 hi, lo;
+            split1(x[4 * q + 0], hi.x, lo.x); split1(x[4 * q + 1], hi.y, lo.y); split1(x[4 * q + 2], hi.z, lo.z); split1(x[4 * q + 3], hi.w, lo.w);
+            *reinterpret_cast<float4*>(P.c_hi + off + 4 * q) = hi;
+            *reinterpret_cast<float4*>(P.c_lo + off + 4 * q) = lo;
+          }
+        } else {
+          if (grow >= P.M || colb >= P.N) continue;
+          if (P.bias && first) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) x[q] += colb + q < P.N ? __ldg(P.bias + colb + q) : 0.f;
+          }
+          if (P.transpose_c) {
+#pragma unroll
+            for (int q = 0; q < 16; q++)
+              if (colb + q < P.N) {
+                float* dst = P.C + (size_t)(colb + q) * P.ldc + grow;
+                if (P.epi == 2) atomicAdd(dst, x[q]); else *dst = x[q];
+              }
+          } else {
+            float* crow = P.C + (size_t)grow * P.ldc + colb;
+            if (colb + 16 <= P.N && (P.ldc & 3) == 0 && ((uintptr_t)P.C & 15) == 0) {
+#pragma unroll
+              for (int q = 0; q < 4; q++) {
+                if (P.epi == 2) red_add_v4(crow + 4 * q, x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+                else *reinterpret_cast<float4*>(crow + 4 * q) = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 16; q++)
+                if (colb + q < P.N) { if (P.epi == 2) atomicAdd(crow + q, x[q]); else crow[q] = x[q]; }
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!ok) atomicExch(a.error, 1);
+  asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ producers of operand planes
+struct GatherTArgs {
+  const float *obs, *actions, *old_logp, *adv, *ret;
+  const int64_t* idx;
+  long long row_start;
+  float *x_hi, *x_lo;        // [rows padded to 128][ld]: the minibatch observations, split
+  float *act, *olp, *a, *r;  // plain minibatch vectors
+  double* scratch;
+  int n_rows, rows_pad, obs_dim, ld, act_dim;
+};
+// One warp per row.  Rows beyond the minibatch and columns beyond obs_dim are zeros (they enter the weight-gradient sums).
+__global__ void __launch_bounds__(256) gather_t_kernel(GatherTArgs g) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x < 8) g.scratch[threadIdx.x] = 0.0;
+  if (row >= g.rows_pad) return;
+  const bool live = row < g.n_rows;
+  const long long src = live ? (g.idx ? (long long)g.idx[row] : g.row_start + row) : 0;
+  const float* xs = g.obs + (size_t)src * g.obs_dim;
+  const bool vec = (g.obs_dim & 3) == 0;
+  for (int col = lane * 4; col < g.ld; col += 128) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      if (vec && col + 3 < g.obs_dim) v = __ldg(reinterpret_cast<const float4*>(xs + col));
+      else {
+        if (col + 0 < g.obs_dim) v.x = __ldg(xs + col + 0);
+        if (col + 1 < g.obs_dim) v.y = __ldg(xs + col + 1);
+        if (col + 2 < g.obs_dim) v.z = __ldg(xs + col + 2);
+        if (col + 3 < g.obs_dim) v.w = __ldg(xs + col + 3);
+      }
+    }
+    float4 hi, lo;
+    split1(v.x, hi.x, lo.x); split1(v.y, hi.y, lo.y); split1(v.z, hi.z, lo.z); split1(v.w, hi.w, lo.w);
+    *reinterpret_cast<float4*>(g.x_hi + (size_t)row * g.ld + col) = hi;
+    *reinterpret_cast<float4*>(g.x_lo + (size_t)row * g.ld + col) = lo;
+  }
+  if (live) {
+    for (int i = lane; i < g.act_dim; i += 32) g.act[(size_t)row * g.act_dim + i] = __ldg(g.actions + (size_t)src * g.act_dim + i);
+    if (lane == 0) { g.olp[row] = __ldg(g.old_logp + src); g.a[row] = __ldg(g.adv + src); g.r[row] = __ldg(g.ret + src); }
+  }
+}
+
+// Weights W [R, F] (nn.Linear layout, inside the flat parameter vector) -> split planes [rows_pad][ld], zero padded
+struct PackTJob { const float* W; float *hi, *lo; int R, F, rows_pad, ld; };
+struct PackTJobs { PackTJob j[6]; };
+__global__ void __launch_bounds__(256) pack_t_kernel(PackTJobs jobs) {
+  const PackTJob jb = jobs.j[blockIdx.y];
+  const int ld4 = jb.ld / 4, total = jb.rows_pad * ld4;   // float4 items
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int row = i / ld4, col = (i - row * ld4) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < jb.R) {
+      const float* src = jb.W + (size_t)row * jb.F + col;
+      if (col + 0 < jb.F) v.x = src[0];
+      if (col + 1 < jb.F) v.y = src[1];
+      if (col + 2 < jb.F) v.z = src[2];
+      if (col + 3 < jb.F) v.w = src[3];
+    }
+    float4 hi, lo;
+    split1(v.x, hi.x, lo.x); split1(v.y, hi.y, lo.y); split1(v.z, hi.z, lo.z); split1(v.w, hi.w, lo.w);
+    *reinterpret_cast<float4*>(jb.hi + (size_t)row * jb.ld + col) = hi;
+    *reinterpret_cast<float4*>(jb.lo + (size_t)row * jb.ld + col) = lo;
+  }
+}
+
+// Column sums of split matrices (hidden-layer bias gradients): thread = column, a slab of rows per CTA
+struct ColsumTArgs { const float *hi[4], *lo[4]; float* dst[4]; int rows, ld, width, rows_per_cta; };
+__global__ void __launch_bounds__(256) colsum_t_kernel(ColsumTArgs c) {
+  const float* __restrict__ hi = c.hi[blockIdx.y];
+  const float* __restrict__ lo = c.lo[blockIdx.y];
+  const int r0 = blockIdx.x * c.rows_per_cta, r1 = min(c.rows, r0 + c.rows_per_cta);
+  for (int col = threadIdx.x; col < c.width; col += 256) {
+    float a0 = 0.f, a1 = 0.f;
+    int r = r0;
+    for (; r + 1 < r1; r += 2) {
+      a0 += __ldg(hi + (size_t)r * c.ld + col) + __ldg(lo + (size_t)r * c.ld + col);
+      a1 += __ldg(hi + (size_t)(r + 1) * c.ld + col) + __ldg(lo + (size_t)(r + 1) * c.ld + col);
+    }
+    if (r < r1) a0 += __ldg(hi + (size_t)r * c.ld + col) + __ldg(lo + (size_t)r * c.ld + col);
+    atomicAdd(c.dst[blockIdx.y] + col, a0 + a1);
+  }
+}

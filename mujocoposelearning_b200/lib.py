@@ -60,6 +60,7 @@ SIGNATURES = {
     "b2h_ppo_stats": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int), vp]),
     "b2h_ppo_stats_dev": (vp, [vp]),
     "b2h_ppo_error_dev": (vp, [vp]),
+    "b2h_gemm_tma": (C.c_int, [vp, C.c_int, vp, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
     "b2h_gemm": (C.c_int, [vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp, vp, C.c_int, C.c_int, C.c_int, C.c_int,
                            C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]),
 }

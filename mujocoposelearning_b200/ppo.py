@@ -34,7 +34,7 @@ class PpoKernels:
     """ctypes face of the update kernels (include/b2h.h ``b2h_ppo_*``) for one parameter set on one device."""
 
     def __init__(self, params: MlpPolicyParams, max_batch, lr=3e-4, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5,
-                 precise=True, normalize_advantage=True, betas=(0.9, 0.999), adam_eps=1e-5):
+                 precise=True, normalize_advantage=True, betas=(0.9, 0.999), adam_eps=1e-5, staged_operands=False):
         self.lib, self.p = load(), params
         offs = (C.c_int64 * 13)()
         n = self.lib.b2h_ppo_param_layout(params.obs_dim, params.hidden, params.act_dim, offs)
@@ -45,6 +45,7 @@ class PpoKernels:
         c.precise, c.normalize_advantage = int(bool(precise)), int(bool(normalize_advantage))
         c.clip_range, c.ent_coef, c.vf_coef, c.max_grad_norm = clip_range, ent_coef, vf_coef, max_grad_norm
         c.lr, c.beta1, c.beta2, c.adam_eps = lr, betas[0], betas[1], adam_eps
+        c.staged_operands = int(bool(staged_operands))
         self.cfg = c
         h = C.c_void_p()
         with torch.cuda.device(params.device):

@@ -614,7 +614,8 @@ struct B2HPpo {
   float* tbase;
   struct TMat { float *hi, *lo; int ld, rows_pad; };
   TMat tX, th1[2], th2[2], tdh2[2], tdh1[2], tdout[2], tW1[2], tW2[2], tW3[2];
-  TMaps maps[8];             // fwd1 fwd2 fwd3 dW3 dh2 dW2 dh1 dW1, each [network][A hi, A lo, B hi, B lo]
+  TMaps maps[8];             // fwd1 fwd2 fwd3 dW3 dh2 dW2 dh1 dW1, each [network][A hi, A lo, B hi, B lo, C hi, C lo]
+  uint32_t *bits1[2], *bits2[2];   // sign bits of h1 / h2 (one bit per element, [rows][8] words): the ReLU masks of the backward pass
   int nw_obs;                // N tile of the first-layer weight gradient (obs_dim split into equal tiles <= 256)
 };
 
@@ -671,7 +672,8 @@ int setup_tma(B2HPpo* h) {
     plan(h->th1[n], Bp, Hp); plan(h->th2[n], Bp, Hp); plan(h->tdh2[n], Bp, Hp); plan(h->tdh1[n], Bp, Hp); plan(h->tdout[n], Bp, OUT_LD);
     plan(h->tW1[n], roundup(H, 128), Dp); plan(h->tW2[n], roundup(H, 128), Hp); plan(h->tW3[n], 128, Hp);
   }
-  if (cudaMalloc(&h->tbase, total * sizeof(float)) != cudaSuccess) { g_err_ppo = "b2h_ppo_create: out of device memory (T-format workspace)"; return B2H_ENOMEM; }
+  total += 4 * (size_t)Bp * 8;                                      // the four sign-bit arrays
+  if (cudaMalloc(&h->tbase, total * sizeof(float)) != cudaSuccess) { g_err_ppo = "b2h_ppo_create: out of device memory (operand planes)"; return B2H_ENOMEM; }
   cudaMemset(h->tbase, 0, total * sizeof(float));
   float* p = h->tbase;
   auto place = [&](B2HPpo::TMat& t) { const size_t n = (size_t)t.rows_pad * t.ld; t.hi = p; t.lo = p + n; p += 2 * n; };
@@ -680,21 +682,23 @@ int setup_tma(B2HPpo* h) {
     place(h->th1[n]); place(h->th2[n]); place(h->tdh2[n]); place(h->tdh1[n]); place(h->tdout[n]);
     place(h->tW1[n]); place(h->tW2[n]); place(h->tW3[n]);
   }
+  for (int n = 0; n < 2; n++) { h->bits1[n] = reinterpret_cast<uint32_t*>(p); p += (size_t)Bp * 8; h->bits2[n] = reinterpret_cast<uint32_t*>(p); p += (size_t)Bp * 8; }
   bool ok = true;
   for (int n = 0; n < 2 && ok; n++) {
-    CUtensorMap(*m)[4] = nullptr;
-    auto gemm_maps = [&](int g, const B2HPpo::TMat& A, int a_mn, const B2HPpo::TMat& Bm, int b_mn, int nw) {
+    CUtensorMap(*m)[6] = nullptr;
+    auto gemm_maps = [&](int g, const B2HPpo::TMat& A, int a_mn, const B2HPpo::TMat& Bm, int b_mn, int nw, const B2HPpo::TMat* Cm) {
       m = &h->maps[g].m[n];
-      return operand_maps(enc, &(*m)[0], A, a_mn, 128) && operand_maps(enc, &(*m)[2], Bm, b_mn, nw);
+      // results that are operands of later GEMMs leave through TMA stores of {32 columns, 128 rows} swizzled boxes
+      return operand_maps(enc, &(*m)[0], A, a_mn, 128) && operand_maps(enc, &(*m)[2], Bm, b_mn, nw) && (!Cm || operand_maps(enc, &(*m)[4], *Cm, 0, 128));
     };
-    ok = ok && gemm_maps(0, h->tX, 0, h->tW1[n], 0, H);                 // fwd1  h1 = relu(X W1^T + b1)
-    ok = ok && gemm_maps(1, h->th1[n], 0, h->tW2[n], 0, H);             // fwd2  h2 = relu(h1 W2^T + b2)
-    ok = ok && gemm_maps(2, h->th2[n], 0, h->tW3[n], 0, 32);            // fwd3  out = h2 W3^T + b3
-    ok = ok && gemm_maps(3, h->th2[n], 1, h->tdout[n], 1, 32);          // dW3^T = h2^T dout
-    ok = ok && gemm_maps(4, h->tdout[n], 0, h->tW3[n], 1, H);           // dh2 = dout W3 . (h2 > 0)
-    ok = ok && gemm_maps(5, h->tdh2[n], 1, h->th1[n], 1, H);            // dW2 = dh2^T h1
-    ok = ok && gemm_maps(6, h->tdh2[n], 0, h->tW2[n], 1, H);            // dh1 = dh2 W2 . (h1 > 0)
-    ok = ok && gemm_maps(7, h->tdh1[n], 1, h->tX, 1, h->nw_obs);        // dW1 = dh1^T X
+    ok = ok && gemm_maps(0, h->tX, 0, h->tW1[n], 0, H, &h->th1[n]);           // fwd1  h1 = relu(X W1^T + b1)
+    ok = ok && gemm_maps(1, h->th1[n], 0, h->tW2[n], 0, H, &h->th2[n]);       // fwd2  h2 = relu(h1 W2^T + b2)
+    ok = ok && gemm_maps(2, h->th2[n], 0, h->tW3[n], 0, 32, nullptr);         // fwd3  out = h2 W3^T + b3
+    ok = ok && gemm_maps(3, h->th2[n], 1, h->tdout[n], 1, 32, nullptr);       // dW3^T = h2^T dout
+    ok = ok && gemm_maps(4, h->tdout[n], 0, h->tW3[n], 1, H, &h->tdh2[n]);    // dh2 = dout W3 . (h2 > 0)
+    ok = ok && gemm_maps(5, h->tdh2[n], 1, h->th1[n], 1, H, nullptr);         // dW2 = dh2^T h1
+    ok = ok && gemm_maps(6, h->tdh2[n], 0, h->tW2[n], 1, H, &h->tdh1[n]);     // dh1 = dh2 W2 . (h1 > 0)
+    ok = ok && gemm_maps(7, h->tdh1[n], 1, h->tX, 1, h->nw_obs, nullptr);     // dW1 = dh1^T X
   }
   if (!ok) { g_err_ppo = "cuTensorMapEncodeTiled failed"; return B2H_ECUDA; }
   cudaError_t e = cudaFuncSetAttribute(gemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TNS * T_STAGE * sizeof(float)));
@@ -752,7 +756,7 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
   auto base = [&](int a_mn, int b_mn, int m_tiles, int n_tiles, int nw, int chunks) {
     TProblem p;
     p.a_mn = a_mn; p.b_mn = b_mn; p.m_tiles = m_tiles; p.n_tiles = n_tiles; p.nw = nw; p.chunks = chunks; p.M = 0; p.N = 0; p.epi = 0;
-    p.c_hi = p.c_lo = nullptr; p.c_ld = 0; p.C = nullptr; p.ldc = 0; p.transpose_c = 0; p.bias = nullptr; p.relu = 0; p.mask_hi = nullptr; p.mask_ld = 0;
+    p.c_hi = p.c_lo = nullptr; p.c_ld = 0; p.C = nullptr; p.ldc = 0; p.transpose_c = 0; p.bias = nullptr; p.relu = 0; p.bits_in = nullptr; p.bits_out = nullptr; p.colsum = nullptr;
     return p;
   };
   TProblem pr[2];
@@ -761,12 +765,12 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
   // ---- forward
   for (int k = 0; k < 2; k++) {
     pr[k] = base(0, 0, m_tiles_b, 1, H, kc_obs);
-    pr[k].c_hi = h->th1[k].hi; pr[k].c_lo = h->th1[k].lo; pr[k].c_ld = h->th1[k].ld; pr[k].bias = P + o[6 * k + 1]; pr[k].relu = 1; pr[k].N = H;
+    pr[k].c_hi = h->th1[k].hi; pr[k].c_lo = h->th1[k].lo; pr[k].c_ld = h->th1[k].ld; pr[k].bias = P + o[6 * k + 1]; pr[k].relu = 1; pr[k].N = H; pr[k].bits_out = h->bits1[k];
   }
   if ((rc = launch_gemm_t(h, 0, pr, c.precise, false, s)) < 0) return rc;
   for (int k = 0; k < 2; k++) {
     pr[k] = base(0, 0, m_tiles_b, 1, H, kc_h);
-    pr[k].c_hi = h->th2[k].hi; pr[k].c_lo = h->th2[k].lo; pr[k].c_ld = h->th2[k].ld; pr[k].bias = P + o[6 * k + 3]; pr[k].relu = 1; pr[k].N = H;
+    pr[k].c_hi = h->th2[k].hi; pr[k].c_lo = h->th2[k].lo; pr[k].c_ld = h->th2[k].ld; pr[k].bias = P + o[6 * k + 3]; pr[k].relu = 1; pr[k].N = H; pr[k].bits_out = h->bits2[k];
   }
   if ((rc = launch_gemm_t(h, 1, pr, c.precise, false, s)) < 0) return rc;
   for (int k = 0; k < 2; k++) {
@@ -790,7 +794,7 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
   if ((rc = launch_gemm_t(h, 3, pr, c.precise, true, s)) < 0) return rc;
   for (int k = 0; k < 2; k++) {   // dh2 = dout W3 . (h2 > 0)
     pr[k] = base(0, 1, m_tiles_b, 1, H, 1);
-    pr[k].c_hi = h->tdh2[k].hi; pr[k].c_lo = h->tdh2[k].lo; pr[k].c_ld = h->tdh2[k].ld; pr[k].mask_hi = h->th2[k].hi; pr[k].mask_ld = h->th2[k].ld; pr[k].N = H;
+    pr[k].c_hi = h->tdh2[k].hi; pr[k].c_lo = h->tdh2[k].lo; pr[k].c_ld = h->tdh2[k].ld; pr[k].bits_in = h->bits2[k]; pr[k].colsum = G + o[6 * k + 3]; pr[k].N = H;
   }
   if ((rc = launch_gemm_t(h, 4, pr, c.precise, false, s)) < 0) return rc;
   for (int k = 0; k < 2; k++) {   // dW2 = dh2^T h1
@@ -800,7 +804,7 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
   if ((rc = launch_gemm_t(h, 5, pr, c.precise, true, s)) < 0) return rc;
   for (int k = 0; k < 2; k++) {   // dh1 = dh2 W2 . (h1 > 0)
     pr[k] = base(0, 1, m_tiles_b, 1, H, kc_h);
-    pr[k].c_hi = h->tdh1[k].hi; pr[k].c_lo = h->tdh1[k].lo; pr[k].c_ld = h->tdh1[k].ld; pr[k].mask_hi = h->th1[k].hi; pr[k].mask_ld = h->th1[k].ld; pr[k].N = H;
+    pr[k].c_hi = h->tdh1[k].hi; pr[k].c_lo = h->tdh1[k].lo; pr[k].c_ld = h->tdh1[k].ld; pr[k].bits_in = h->bits1[k]; pr[k].colsum = G + o[6 * k + 1]; pr[k].N = H;
   }
   if ((rc = launch_gemm_t(h, 6, pr, c.precise, false, s)) < 0) return rc;
   const int obs_tiles = (roundup(D, 32) + 255) / 256;
@@ -809,12 +813,6 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
     pr[k].epi = 2; pr[k].C = G + o[6 * k + 0]; pr[k].ldc = D; pr[k].M = H; pr[k].N = D;
   }
   if ((rc = launch_gemm_t(h, 7, pr, c.precise, true, s)) < 0) return rc;
-  ColsumTArgs cs;
-  const B2HPpo::TMat* src[4] = {&h->tdh2[0], &h->tdh1[0], &h->tdh2[1], &h->tdh1[1]};
-  float* dst[4] = {G + o[3], G + o[1], G + o[9], G + o[7]};
-  for (int i = 0; i < 4; i++) { cs.hi[i] = src[i]->hi; cs.lo[i] = src[i]->lo; cs.dst[i] = dst[i]; }
-  cs.rows = n; cs.ld = h->tdh2[0].ld; cs.width = H; cs.rows_per_cta = 128;
-  colsum_t_kernel<<<dim3((n + 127) / 128, 4), 256, 0, s>>>(cs);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
   return B2H_OK;
@@ -883,7 +881,8 @@ int b2h_gemm_tma(const float* a_dev, int a_mn, const float* b_dev, int b_mn, flo
   pack_t_kernel<<<dim3((items + 255) / 256, 2), 256, 0, s>>>(pj);
   B2HPpo hh;
   bool ok = operand_maps(enc, &hh.maps[0].m[0][0], ta, a_mn, 128) && operand_maps(enc, &hh.maps[0].m[0][2], tb, b_mn, nw);
-  hh.maps[0].m[1][0] = hh.maps[0].m[0][0]; hh.maps[0].m[1][1] = hh.maps[0].m[0][1]; hh.maps[0].m[1][2] = hh.maps[0].m[0][2]; hh.maps[0].m[1][3] = hh.maps[0].m[0][3];
+  for (int i = 0; i < 4; i++) hh.maps[0].m[1][i] = hh.maps[0].m[0][i];
+  for (int i = 4; i < 6; i++) { hh.maps[0].m[0][i] = hh.maps[0].m[0][0]; hh.maps[0].m[1][i] = hh.maps[0].m[0][0]; }
   int rc = B2H_OK;
   if (!ok) { g_err_ppo = "cuTensorMapEncodeTiled failed"; rc = B2H_ECUDA; }
   if (rc == B2H_OK && cudaFuncSetAttribute(gemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TNS * T_STAGE * sizeof(float))) != cudaSuccess) {
@@ -893,7 +892,7 @@ int b2h_gemm_tma(const float* a_dev, int a_mn, const float* b_dev, int b_mn, flo
     TProblem p;
     p.a_mn = a_mn; p.b_mn = b_mn; p.m_tiles = (m + 127) / 128; p.n_tiles = n_tiles; p.nw = nw; p.chunks = (k + TK - 1) / TK; p.M = m; p.N = n;
     p.epi = split_k == 1 ? 1 : 2; p.c_hi = p.c_lo = nullptr; p.c_ld = 0; p.C = c_dev; p.ldc = ldc; p.transpose_c = transpose_c; p.bias = bias_dev; p.relu = 0;
-    p.mask_hi = nullptr; p.mask_ld = 0;
+    p.bits_in = nullptr; p.bits_out = nullptr; p.colsum = nullptr;
     TArgs a;
     a.p[0] = p; a.p[1] = p;
     int nsplit = split_k == 1 ? 1 : (split_k > 1 ? std::min(split_k, p.chunks) : std::max(1, std::min(p.chunks, 148 / (p.m_tiles * p.n_tiles))));

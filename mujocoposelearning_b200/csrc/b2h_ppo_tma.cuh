@@ -25,7 +25,7 @@ constexpr int T_A_PART = 128 * TK;           // floats of one plane of an A chun
 constexpr int T_B_PART = 256 * TK;           // ... of a B chunk at the widest N (32 KB)
 constexpr int T_STAGE = 2 * T_A_PART + 2 * T_B_PART;   // A hi | A lo | B hi | B lo: 96 KB
 
-struct alignas(64) TMaps { CUtensorMap m[2][4]; };      // [problem][A hi, A lo, B hi, B lo]
+struct alignas(64) TMaps { CUtensorMap m[2][6]; };      // [problem][A hi, A lo, B hi, B lo, C hi, C lo (operand-plane results)]
 
 struct TProblem {
   int a_mn, b_mn;            // operand use: 0 = K-major (contraction over the matrix's columns), 1 = MN-major (over its rows)
@@ -40,8 +40,9 @@ struct TProblem {
   int ldc, transpose_c;
   const float* bias;         // [N] or null
   int relu;
-  const float* mask_hi;      // epi 0: hi plane of the activation whose sign gates the result (ReLU backward), or null
-  int mask_ld;
+  const uint32_t* bits_in;   // epi 0: sign bits of the activation that gates the result (ReLU backward): [rows][8] words, or null
+  uint32_t* bits_out;        // epi 0: sign bits of this result (x > 0) for the backward pass, or null
+  float* colsum;             // epi 0: column sums of the result are added here (bias gradient), or null
 };
 struct TArgs {
   TProblem p[2];
@@ -152,14 +153,112 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp >= 4) {   // ---- epilogue: TMEM lane quadrant = warp % 4, thread = row of the tile
-    ok = mbar_wait(accbar, 0);
+  }
+  {   // ---- epilogue on all eight warps: TMEM lane quadrant = warp % 4 (thread = row of the tile), the two warps of a
+      // quadrant take alternate groups of columns
+    ok = mbar_wait(accbar, 0) && ok;
+    __syncwarp();
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const int quad = warp & 3;
-    const int grow = row0 + (threadIdx.x - 128);
+    const int quad = warp & 3, half = warp >> 2;
+    const int r = quad * 32 + lane;
+    const int grow = row0 + r;
     const bool first = split == 0;
-    if (ok) {
-      for (int c0 = 0; c0 < nw; c0 += 16) {
+    if (ok && P.epi == 0) {
+      // ---- the result is the next GEMM's operand: bias, ReLU / ReLU mask, split into hi / lo, staged in the (now idle)
+      // operand ring as 128-byte swizzled rows and written with TMA stores, 32 columns at a time; the column sums of the
+      // tile (bias gradient) are taken from the staged copy, the ReLU pattern travels as one bit per element
+      constexpr int NB = (TNS * T_STAGE) / (2 * T_A_PART);          // staging buffers of 32 columns x 128 rows x (hi + lo)
+      static_assert(NB % 2 == 0, "a buffer must come back to the same half");
+      const CUtensorMap* cmap = maps.m[prob ? 1 : 0] + 4;
+      uint32_t in_bits[8], out_bits[4];
+      if (P.bits_in) {
+        const uint4* bp = reinterpret_cast<const uint4*>(P.bits_in + (size_t)grow * 8);
+        const uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
+        in_bits[0] = b0.x; in_bits[1] = b0.y; in_bits[2] = b0.z; in_bits[3] = b0.w; in_bits[4] = b1.x; in_bits[5] = b1.y; in_bits[6] = b1.z; in_bits[7] = b1.w;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; g++) out_bits[g] = 0u;
+#pragma unroll
+      for (int gp = 0; gp < 4; gp++) {
+        if (gp * 64 >= nw) break;                                  // uniform over the CTA: both halves keep the barrier count
+        const int g = 2 * gp + half;
+        const bool active = g * 32 < nw;
+        uint32_t v[32];
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++)
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+              : "=r"(v[16 * hh + 0]), "=r"(v[16 * hh + 1]), "=r"(v[16 * hh + 2]), "=r"(v[16 * hh + 3]), "=r"(v[16 * hh + 4]), "=r"(v[16 * hh + 5]),
+                "=r"(v[16 * hh + 6]), "=r"(v[16 * hh + 7]), "=r"(v[16 * hh + 8]), "=r"(v[16 * hh + 9]), "=r"(v[16 * hh + 10]), "=r"(v[16 * hh + 11]),
+                "=r"(v[16 * hh + 12]), "=r"(v[16 * hh + 13]), "=r"(v[16 * hh + 14]), "=r"(v[16 * hh + 15])
+              : "r"(tmem + ((uint32_t)(quad * 32) << 16) + (uint32_t)(g * 32 + 16 * hh)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+        const int colb = col0 + g * 32;
+        float x[32];
+        uint32_t word = 0u;
+        if (P.bias && active) {                                    // N is a multiple of 32 for operand-plane results
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + colb) + q);
+            v[4 * q + 0] = __float_as_uint(__uint_as_float(v[4 * q + 0]) + b4.x); v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + b4.y);
+            v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + b4.z); v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + b4.w);
+          }
+        }
+        const uint32_t gate = P.bits_in ? (half ? in_bits[2 * gp + 1] : in_bits[2 * gp]) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int q = 0; q < 32; q++) {
+          float y = __uint_as_float(v[q]);
+          if (P.relu) y = fmaxf(y, 0.f);
+          y = (gate >> q) & 1u ? y : 0.f;
+          word |= (y > 0.f ? 1u : 0u) << q;
+          x[q] = y;
+        }
+        out_bits[gp] = word;
+        const int b = g % NB;
+        float* s_hi = stage0 + b * (2 * T_A_PART);
+        float* s_lo = s_hi + T_A_PART;
+        if (gp * 2 >= NB) {       // the TMA store that read this buffer NB groups ago (same half) must have finished reading it
+          if (r == 0) asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(NB / 2 - 1) : "memory");
+          asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        }
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          if (!active) break;
+          float4 hi, lo;
+          split1(x[4 * q + 0], hi.x, lo.x); split1(x[4 * q + 1], hi.y, lo.y); split1(x[4 * q + 2], hi.z, lo.z); split1(x[4 * q + 3], hi.w, lo.w);
+          const int off = r * 32 + ((q ^ (r & 7)) << 2);             // 128-byte swizzle: 16-byte chunk index ^ (row % 8)
+          *reinterpret_cast<float4*>(s_hi + off) = hi;
+          *reinterpret_cast<float4*>(s_lo + off) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+        asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        if (r == 0 && active) {
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n"
+                       ::"l"(cmap + 0), "r"(colb), "r"(row0), "r"(smem_u32(s_hi)) : "memory");
+          asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n"
+                       ::"l"(cmap + 1), "r"(colb), "r"(row0), "r"(smem_u32(s_lo)) : "memory");
+          asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
+        }
+        if (P.colsum && active) { // thread = (column of the group, quarter of the rows)
+          const int col = r & 31, rq = r >> 5;
+          float acc = 0.f;
+#pragma unroll 8
+          for (int i = 0; i < 32; i++) {
+            const int rr = rq * 32 + i;
+            const int off = rr * 32 + ((((col >> 2) ^ (rr & 7)) << 2) | (col & 3));
+            acc += s_hi[off] + s_lo[off];
+          }
+          if (colb + col < P.N) atomicAdd(P.colsum + colb + col, acc);
+        }
+      }
+      if (P.bits_out) {           // each half owns the words of its groups (even / odd)
+        uint32_t* bp = P.bits_out + (size_t)grow * 8;
+#pragma unroll
+        for (int gp = 0; gp < 4; gp++) bp[2 * gp + half] = out_bits[gp];
+      }
+      if (r == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // shared memory stays valid until the stores have read it
+    } else if (ok) {
+      for (int c0 = half * 16; c0 < nw; c0 += 32) {
         uint32_t v[16];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -171,34 +270,6 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
         float x[16];
 #pragma unroll
         for (int q = 0; q < 16; q++) x[q] = __uint_as_float(v[q]);
-        if (P.epi == 0) {           // ---- the next GEMM's operand: bias, ReLU / mask, split into the hi / lo planes
-          if (colb >= P.c_ld) continue;
-          if (P.bias) {
-#pragma unroll
-            for (int q = 0; q < 16; q++) x[q] += colb + q < P.N ? __ldg(P.bias + colb + q) : 0.f;
-          }
-          if (P.relu) {
-#pragma unroll
-            for (int q = 0; q < 16; q++) x[q] = fmaxf(x[q], 0.f);
-          }
-          if (P.mask_hi) {
-            const float4* mrow = reinterpret_cast<const float4*>(P.mask_hi + (size_t)grow * P.mask_ld + colb);
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const float4 m = __ldg(mrow + q);
-              x[4 * q + 0] = m.x > 0.f ? x[4 * q + 0] : 0.f; x[4 * q + 1] = m.y > 0.f ? x[4 * q + 1] : 0.f;
-              x[4 * q + 2] = m.z > 0.f ? x[4 * q + 2] : 0.f; x[4 * q + 3] = m.w > 0.f ? x[4 * q + 3] : 0.f;
-            }
-          }
-          const size_t off = (size_t)grow * P.c_ld + colb;
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            float4 hi, lo;
-            split1(x[4 * q + 0], hi.x, lo.x); split1(x[4 * q + 1], hi.y, lo.y); split1(x[4 * q + 2], hi.z, lo.z); split1(x[4 * q + 3], hi.w, lo.w);
-            *reinterpret_cast<float4*>(P.c_hi + off + 4 * q) = hi;
-            *reinterpret_cast<float4*>(P.c_lo + off + 4 * q) = lo;
-          }
-        } else {
           if (grow >= P.M || colb >= P.N) continue;
           if (P.bias && first) {
 #pragma unroll
@@ -225,7 +296,6 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
                 if (colb + q < P.N) { if (P.epi == 2) atomicAdd(crow + q, x[q]); else crow[q] = x[q]; }
             }
           }
-        }
       }
     }
   }
@@ -297,23 +367,5 @@ __global__ void __launch_bounds__(256) pack_t_kernel(PackTJobs jobs) {
     split1(v.x, hi.x, lo.x); split1(v.y, hi.y, lo.y); split1(v.z, hi.z, lo.z); split1(v.w, hi.w, lo.w);
     *reinterpret_cast<float4*>(jb.hi + (size_t)row * jb.ld + col) = hi;
     *reinterpret_cast<float4*>(jb.lo + (size_t)row * jb.ld + col) = lo;
-  }
-}
-
-// Column sums of split matrices (hidden-layer bias gradients): thread = column, a slab of rows per CTA
-struct ColsumTArgs { const float *hi[4], *lo[4]; float* dst[4]; int rows, ld, width, rows_per_cta; };
-__global__ void __launch_bounds__(256) colsum_t_kernel(ColsumTArgs c) {
-  const float* __restrict__ hi = c.hi[blockIdx.y];
-  const float* __restrict__ lo = c.lo[blockIdx.y];
-  const int r0 = blockIdx.x * c.rows_per_cta, r1 = min(c.rows, r0 + c.rows_per_cta);
-  for (int col = threadIdx.x; col < c.width; col += 256) {
-    float a0 = 0.f, a1 = 0.f;
-    int r = r0;
-    for (; r + 1 < r1; r += 2) {
-      a0 += __ldg(hi + (size_t)r * c.ld + col) + __ldg(lo + (size_t)r * c.ld + col);
-      a1 += __ldg(hi + (size_t)(r + 1) * c.ld + col) + __ldg(lo + (size_t)(r + 1) * c.ld + col);
-    }
-    if (r < r1) a0 += __ldg(hi + (size_t)r * c.ld + col) + __ldg(lo + (size_t)r * c.ld + col);
-    atomicAdd(c.dst[blockIdx.y] + col, a0 + a1);
   }
 }

@@ -20,7 +20,8 @@
 #pragma once
 
 constexpr int TK = 32;                       // K per chunk: 32 columns (K-major: one 128-byte swizzle row) or 32 rows (MN-major)
-constexpr int TNS = 2;                       // stages
+constexpr int TNS = 2;                       // stages at the widest N; narrower tiles get more (the ring is always 192 KB)
+constexpr int TNS_MAX = 6;
 constexpr int T_A_PART = 128 * TK;           // floats of one plane of an A chunk (16 KB)
 constexpr int T_B_PART = 256 * TK;           // ... of a B chunk at the widest N (32 KB)
 constexpr int T_STAGE = 2 * T_A_PART + 2 * T_B_PART;   // A hi | A lo | B hi | B lo: 96 KB
@@ -70,7 +71,7 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32_major(int m, int n, int a_mn
 __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ TMaps maps, TArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_t[];
   float* stage0 = reinterpret_cast<float*>(smem_t);
-  __shared__ __align__(8) unsigned long long bar_storage[2 * TNS + 1];
+  __shared__ __align__(8) unsigned long long bar_storage[2 * TNS_MAX + 1];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.z / a.nsplit, split = blockIdx.z - prob * a.nsplit;
@@ -82,15 +83,16 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
   if (nchunk <= 0) return;
   const bool precise = a.precise != 0;
   const int nw = P.nw;
-  uint32_t full[TNS], empty[TNS];
-#pragma unroll
-  for (int s = 0; s < TNS; s++) { full[s] = smem_u32(&bar_storage[s]); empty[s] = smem_u32(&bar_storage[TNS + s]); }
-  const uint32_t accbar = smem_u32(&bar_storage[2 * TNS]);
+  // a stage holds A hi | A lo | B hi | B lo of one K chunk; its size follows the N tile, the ring always fills the 192 KB
+  const int b_part = nw * TK;                                       // floats of one plane of a B chunk (a multiple of 1 KB: nw % 8 == 0)
+  const int stage_floats = 2 * T_A_PART + 2 * ((b_part + 255) & ~255);
+  const int ns = min(TNS_MAX, (TNS * T_STAGE) / stage_floats);
+  const uint32_t full0 = smem_u32(&bar_storage[0]), empty0 = smem_u32(&bar_storage[TNS_MAX]);
+  const uint32_t accbar = smem_u32(&bar_storage[2 * TNS_MAX]);
   if (threadIdx.x == 0) {
-#pragma unroll
-    for (int s = 0; s < TNS; s++) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(full[s]));    // the TMA thread's arrive.expect_tx + the bytes
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(empty[s]));   // tcgen05.commit
+    for (int s = 0; s < ns; s++) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(full0 + 8 * s));    // the TMA thread's arrive.expect_tx + the bytes
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(empty0 + 8 * s));   // tcgen05.commit
     }
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(accbar));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -113,12 +115,13 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
       // atoms of 4 K rows 512 B apart (SBO), column groups 4096 B apart (LBO); a K step of 8 = two atoms = 1024 B.
       const uint32_t lboA = P.a_mn ? 4096u : 16u, sboA = P.a_mn ? 512u : 1024u, stepA = P.a_mn ? 1024u : 32u, ltA = P.a_mn ? 1u : 2u;
       const uint32_t lboB = P.b_mn ? 4096u : 16u, sboB = P.b_mn ? 512u : 1024u, stepB = P.b_mn ? 1024u : 32u, ltB = P.b_mn ? 1u : 2u;
+      int s = 0, use = 0;
       for (int c = 0; c < nchunk && ok; c++) {
-        const int s = c % TNS, use = c / TNS;
-        ok = mbar_wait(full[s], use & 1);
+        ok = mbar_wait(full0 + 8 * s, use & 1);
         if (!ok) break;
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-        const uint32_t A_hi = smem_u32(stage0 + s * T_STAGE), A_lo = A_hi + T_A_PART * 4, B_hi = A_lo + T_A_PART * 4, B_lo = B_hi + T_B_PART * 4;
+        const uint32_t A_hi = smem_u32(stage0 + s * stage_floats), A_lo = A_hi + T_A_PART * 4, B_hi = A_lo + T_A_PART * 4,
+                       B_lo = B_hi + (uint32_t)(stage_floats - 2 * T_A_PART) * 2;
 #pragma unroll
         for (int ks = 0; ks < TK / 8; ks++) {
           const uint64_t ah = umma_desc_sw(A_hi + ks * stepA, lboA, sboA, ltA), bh = umma_desc_sw(B_hi + ks * stepB, lboB, sboB, ltB);
@@ -129,7 +132,8 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
             umma_tf32(tmem, al, bh, idesc, 1);
           }
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(empty[s]) : "memory");
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(empty0 + 8 * s) : "memory");
+        if (++s == ns) { s = 0; use++; }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(accbar) : "memory");
     }
@@ -138,18 +142,22 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
     if (lane == 0) {   // ---- TMA producer
       const CUtensorMap* mp = maps.m[prob ? 1 : 0];
       const uint32_t bytes = (uint32_t)(128 * TK * 4 + nw * TK * 4) * (precise ? 2u : 1u);
+      int s = 0, use = 0;
       for (int c = 0; c < nchunk && ok; c++) {
-        const int s = c % TNS, use = c / TNS, kc = c_begin + c;
-        if (use > 0) ok = mbar_wait(empty[s], (use - 1) & 1);
+        const int kc = c_begin + c;
+        const uint32_t fullb = full0 + 8 * s;
+        if (use > 0) ok = mbar_wait(empty0 + 8 * s, (use - 1) & 1);
         if (!ok) break;
-        const uint32_t A_hi = smem_u32(stage0 + s * T_STAGE), A_lo = A_hi + T_A_PART * 4, B_hi = A_lo + T_A_PART * 4, B_lo = B_hi + T_B_PART * 4;
-        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(full[s]), "r"(bytes) : "memory");
+        const uint32_t A_hi = smem_u32(stage0 + s * stage_floats), A_lo = A_hi + T_A_PART * 4, B_hi = A_lo + T_A_PART * 4,
+                       B_lo = B_hi + (uint32_t)(stage_floats - 2 * T_A_PART) * 2;
+        asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}\n" ::"r"(fullb), "r"(bytes) : "memory");
         // K-major: 2-D box at {first column of the chunk, first row of the tile}; MN-major: 3-D box at {0, first row of the
         // chunk, first column group of the tile}
-        if (P.a_mn) { tma_load_3d(A_hi, mp + 0, 0, kc * TK, row0 / 32, full[s]); if (precise) tma_load_3d(A_lo, mp + 1, 0, kc * TK, row0 / 32, full[s]); }
-        else        { tma_load_2d(A_hi, mp + 0, kc * TK, row0, full[s]);        if (precise) tma_load_2d(A_lo, mp + 1, kc * TK, row0, full[s]); }
-        if (P.b_mn) { tma_load_3d(B_hi, mp + 2, 0, kc * TK, col0 / 32, full[s]); if (precise) tma_load_3d(B_lo, mp + 3, 0, kc * TK, col0 / 32, full[s]); }
-        else        { tma_load_2d(B_hi, mp + 2, kc * TK, col0, full[s]);        if (precise) tma_load_2d(B_lo, mp + 3, kc * TK, col0, full[s]); }
+        if (P.a_mn) { tma_load_3d(A_hi, mp + 0, 0, kc * TK, row0 / 32, fullb); if (precise) tma_load_3d(A_lo, mp + 1, 0, kc * TK, row0 / 32, fullb); }
+        else        { tma_load_2d(A_hi, mp + 0, kc * TK, row0, fullb);        if (precise) tma_load_2d(A_lo, mp + 1, kc * TK, row0, fullb); }
+        if (P.b_mn) { tma_load_3d(B_hi, mp + 2, 0, kc * TK, col0 / 32, fullb); if (precise) tma_load_3d(B_lo, mp + 3, 0, kc * TK, col0 / 32, fullb); }
+        else        { tma_load_2d(B_hi, mp + 2, kc * TK, col0, fullb);        if (precise) tma_load_2d(B_lo, mp + 3, kc * TK, col0, fullb); }
+        if (++s == ns) { s = 0; use++; }
       }
     }
     __syncwarp();

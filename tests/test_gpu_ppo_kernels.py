@@ -76,6 +76,36 @@ def test_tcgen05_gemm_modes(case, precise, tol):
         assert torch.equal(out[:, n:], torch.zeros_like(out[:, n:]))
 
 
+@pytest.mark.parametrize("a_mn", [0, 1])
+@pytest.mark.parametrize("b_mn", [0, 1])
+@pytest.mark.parametrize("m,n,k,split", [(128, 32, 32, 1), (128, 64, 64, 1), (256, 256, 96, 1), (256, 352, 200, 1), (300, 21, 1000, 0), (256, 352, 4096, 0)])
+def test_tma_gemm_operand_majors(m, n, k, split, a_mn, b_mn):
+    """The TMA-fed GEMM (b2h_gemm_tma) in each combination of operand majors: K-major operands arrive through SWIZZLE_128B
+    boxes, MN-major ones (contraction over the rows of a row-major matrix: the weight gradients) through 32-byte-atom
+    swizzled boxes + SWIZZLE_128B_BASE32B descriptors.  Ragged M / N / K are zero-filled by the TMA unit; split = 0 spreads
+    the contraction over the SMs and adds the partial tiles with red.global.add."""
+    from mujocoposelearning_b200.lib import load
+    lib = load()
+    g = torch.Generator(device="cuda").manual_seed(m + 3 * n + 7 * k + a_mn + 2 * b_mn)
+    rnd = lambda *s: torch.randn(*s, device="cuda", generator=g)
+    A = rnd(k, m) if a_mn else rnd(m, k)
+    B = rnd(k, n) if b_mn else rnd(n, k)
+    bias = rnd(n) if split == 1 else None
+    ref = (A.double().t() if a_mn else A.double()) @ (B.double() if b_mn else B.double().t())
+    if bias is not None:
+        ref = ref + bias.double()
+    out = torch.zeros(m, n, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    for precise, tol in ((1, 2e-5), (0, 2e-3)):
+        out.zero_()
+        assert lib.b2h_gemm_tma(p(A), a_mn, p(B), b_mn, p(out), n, 0, p(bias), m, n, k, precise, split, p(err), None) == 0, lib.b2h_ppo_last_error()
+        torch.cuda.synchronize()
+        assert int(err.item()) == 0
+        e = float((out.double() - ref).abs().max())
+        assert e < tol * max(1.0, float(ref.abs().max())), (precise, e)
+
+
 def _problem(n, obs_dim=352, hidden=256, act_dim=21, seed=0):
     from mujocoposelearning_b200.policy import MlpPolicyParams
     g = torch.Generator(device="cuda").manual_seed(seed)

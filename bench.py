@@ -59,6 +59,8 @@ def parse():
     ap.add_argument("--ppo-batch", type=int, default=16384, help="PPO minibatch size per GPU")
     ap.add_argument("--ppo-epochs", type=int, default=4)
     ap.add_argument("--ppo-tf32", action="store_true", help="update GEMMs in a single tf32 pass (default: fp32-faithful)")
+    ap.add_argument("--ppo-allreduce", choices=["p2p", "nccl"], default="p2p",
+                    help="gradient all-reduce of the native update: p2p = summed by peer loads over NVLink inside the update kernels; nccl = one flat NCCL call")
     ap.add_argument("--ppo-impl", choices=["native", "torch"], default="native",
                     help="native: the update kernels of csrc/b2h_ppo.cu; torch: autograd + library GEMMs (the round-2 baseline)")
     ap.add_argument("--no-stagger", action="store_true", help="keep the batch's episodes synchronised (SURVEY 8d C3 as written); the "
@@ -487,7 +489,7 @@ def run_ppo(args):
     E, T = args.n_envs, 64
     K, W = max(1, args.steps), max(1, args.warmup)
     b = HumanoidBatch(E, frame_skip=FRAME_SKIP, duration=DURATION, reward_type=REWARD, dtype="f32", device=local, seed=1234, env_id_offset=rank * E)
-    tr = PPOTrainer(b, n_steps=T, batch_size=args.ppo_batch, n_epochs=args.ppo_epochs, lr=3e-4, seed=3, update_tf32=args.ppo_tf32, update_impl=args.ppo_impl)
+    tr = PPOTrainer(b, n_steps=T, batch_size=args.ppo_batch, n_epochs=args.ppo_epochs, lr=3e-4, seed=3, update_tf32=args.ppo_tf32, update_impl=args.ppo_impl, allreduce=args.ppo_allreduce)
     tr.col.cuda_graph = True
     tr.time_allreduce = world > 1
     for _ in range(W):
@@ -515,7 +517,10 @@ def run_ppo(args):
                "steps": K, "warmup": W, "ms_per_step": wall_ms / K, "higher_is_better": True, "scaling": "weak", "dtype": "f32", "data": "synthetic",
                "config": {"workload": f"full PPO `stand` training, {E} envs/GPU x {world} GPU, n_steps {T} (BASELINE config 4)", "n_envs_per_gpu": E,
                           "n_steps": T, "minibatch_per_gpu": args.ppo_batch, "epochs": args.ppo_epochs, "minibatches_per_iteration": n_mb,
-                          "gradient_allreduce": "one flat 1.27 MB NCCL all-reduce per minibatch" if world > 1 else "none (1 GPU)",
+                          "gradient_allreduce": "none (1 GPU)" if world == 1 else
+                                                ("peer loads over NVLink inside the update kernels (flag barrier + rank-ordered sum + sum of squares in one kernel); the `allreduce` "
+                                                 "time below is that kernel + clip + Adam" if (args.ppo_impl == "native" and args.ppo_allreduce == "p2p")
+                                                 else "one flat 1.27 MB NCCL all-reduce per minibatch"),
                           "update": ("hand-written kernels (csrc/b2h_ppo.cu): tcgen05 GEMMs, " + ("single tf32 pass" if args.ppo_tf32 else "tf32 hi/lo split = fp32-faithful")
                                      + ", loss / clip / Adam kernels") if args.ppo_impl == "native" else
                                     ("PyTorch autograd + library GEMMs (" + ("tf32" if args.ppo_tf32 else "fp32") + "), CUDA-graphed; NOT a hand-written kernel")},

@@ -362,10 +362,23 @@ int b2h_ppo_minibatch_grad(B2HPpo* h, const float* obs_dev, const float* actions
 int b2h_ppo_apply(B2HPpo* h, float* params_dev, float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t step, float grad_scale,
                   void* stream);
 /* PPO.train for one rank: n_epochs passes over perm_dev [n_epochs, n_samples] (each row a permutation of the buffer rows) in
- * minibatches of batch_size, gradient + apply per minibatch, nothing returns to the host in between. */
+ * minibatches of batch_size, gradient + apply per minibatch, nothing returns to the host in between.  After
+ * b2h_ppo_p2p_attach (several ranks) every rank makes this same call and the gradients are summed over the ranks by peer
+ * loads inside it (all ranks must use the same n_samples / batch_size / n_epochs). */
 int b2h_ppo_train(B2HPpo* h, const float* obs_dev, const float* actions_dev, const float* old_log_probs_dev, const float* advantages_dev,
                   const float* returns_dev, const int64_t* perm_dev, int64_t n_samples, int n_epochs, int batch_size, float* params_dev,
                   float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t* step_inout, void* stream);
+/* Gradient all-reduce over NVLink peer memory instead of a library collective (one node, one process per GPU).  Each rank
+ * exports the allocation that holds its flat gradient (b2h_ppo_p2p_export fills a 64-byte cudaIpcMemHandle_t), the ranks
+ * exchange the handles (e.g. torch.distributed.all_gather_object) and attach the peers' buffers.  Per minibatch the gradient
+ * is then computed INTO b2h_ppo_p2p_grad(h) (the copy alternates) and b2h_ppo_apply_p2p runs: flag barrier across the ranks,
+ * sum of all ranks' gradients by peer loads in rank order (bit-identical on every rank) fused with the sum of squares,
+ * clip + Adam on the mean.  Waits are bounded: a rank that never arrives raises the error flag (b2h_ppo_stats) instead of
+ * hanging the GPU. */
+int b2h_ppo_p2p_export(B2HPpo* h, void* ipc_handle_out64);
+int b2h_ppo_p2p_attach(B2HPpo* h, int rank, int world, const void* ipc_handles);
+float* b2h_ppo_p2p_grad(B2HPpo* h);
+int b2h_ppo_apply_p2p(B2HPpo* h, float* params_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t step, void* stream);
 /* Statistics of the last minibatch (8 doubles) and the tensor pipeline's timeout flag; synchronises the stream. */
 int b2h_ppo_stats(B2HPpo* h, double stats_host[8], int* error_host, void* stream);
 const double* b2h_ppo_stats_dev(const B2HPpo* h);

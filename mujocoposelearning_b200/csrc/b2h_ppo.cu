@@ -26,6 +26,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include <algorithm>
 #include <string>
@@ -592,6 +593,84 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
   }
 }
 
+// ---- gradient all-reduce over NVLink peer memory, fused with the sum of squares of the reduced gradient --------------------
+// Every rank keeps its flat gradient in a buffer the other ranks of the node have mapped (CUDA IPC).  One kernel per minibatch:
+//   1. tell every peer "my gradient of epoch e is complete" (st.release.sys into the peer's flag row), wait until all peers
+//      have said so (ld.acquire.sys on the local flag row);
+//   2. each thread sums its float4 slice over the ranks IN RANK ORDER (peer loads through NVLink / NVSwitch), so every rank
+//      computes bit-identical sums: the replicas cannot drift;
+//   3. the reduced gradient goes to a local buffer and its sum of squares (the grad-norm clip needs it) to the accumulator.
+// The gradient buffers alternate between two copies (epoch parity): a rank overwrites copy e % 2 again at epoch e + 2, i.e. after
+// it has passed the barrier of epoch e + 1, which every peer only signals after its reduction of epoch e has finished -- no
+// second barrier is needed.  Waits are bounded; on a timeout the error flag is raised and the kernel carries on.
+constexpr int P2P_MAX_RANKS = 16;
+struct P2PArgs {
+  const float* grad[P2P_MAX_RANKS];     // this epoch's gradient copy on every rank (index = rank; own entry is local memory)
+  uint32_t* flags[P2P_MAX_RANKS];       // flag rows [P2P_MAX_RANKS] on every rank
+  float* reduced;                       // local: sum over ranks
+  double* sumsq;
+  int* error;
+  long long n4;                         // float4 elements
+  int rank, world;
+  uint32_t epoch;
+};
+__global__ void __launch_bounds__(256) p2p_reduce_kernel(P2PArgs a) {
+  __shared__ double red[8];
+  if (threadIdx.x < a.world) {
+    const int j = threadIdx.x;
+    if (blockIdx.x == 0) {
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(a.flags[j] + a.rank), "r"(a.epoch) : "memory");
+    }
+    const uint32_t* mine = a.flags[a.rank] + j;
+    bool seen = false;
+    for (int spin = 0; spin < (1 << 22) && !seen; spin++) {
+      uint32_t v;
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
+      seen = (int32_t)(v - a.epoch) >= 0;
+      if (!seen) __nanosleep(64);
+    }
+    if (!seen) atomicExch(a.error, 2);
+  }
+  __syncthreads();
+  double s = 0.0;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n4; i += (long long)gridDim.x * 256) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j0 = 0; j0 < a.world; j0 += 8) {   // eight peer loads in flight (one asm block: ptxas must not interleave the sums), then the sum in rank order
+      float4 w[8];
+      // ld.volatile: the peers' buffers change between launches, nothing may come from a non-coherent cache; entries beyond
+      // `world` alias this rank's own buffer and are dropped below
+      asm volatile(
+          "ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%32];\n\t"
+          "ld.volatile.global.v4.f32 {%4, %5, %6, %7}, [%33];\n\t"
+          "ld.volatile.global.v4.f32 {%8, %9, %10, %11}, [%34];\n\t"
+          "ld.volatile.global.v4.f32 {%12, %13, %14, %15}, [%35];\n\t"
+          "ld.volatile.global.v4.f32 {%16, %17, %18, %19}, [%36];\n\t"
+          "ld.volatile.global.v4.f32 {%20, %21, %22, %23}, [%37];\n\t"
+          "ld.volatile.global.v4.f32 {%24, %25, %26, %27}, [%38];\n\t"
+          "ld.volatile.global.v4.f32 {%28, %29, %30, %31}, [%39];\n"
+          : "=f"(w[0].x), "=f"(w[0].y), "=f"(w[0].z), "=f"(w[0].w), "=f"(w[1].x), "=f"(w[1].y), "=f"(w[1].z), "=f"(w[1].w),
+            "=f"(w[2].x), "=f"(w[2].y), "=f"(w[2].z), "=f"(w[2].w), "=f"(w[3].x), "=f"(w[3].y), "=f"(w[3].z), "=f"(w[3].w),
+            "=f"(w[4].x), "=f"(w[4].y), "=f"(w[4].z), "=f"(w[4].w), "=f"(w[5].x), "=f"(w[5].y), "=f"(w[5].z), "=f"(w[5].w),
+            "=f"(w[6].x), "=f"(w[6].y), "=f"(w[6].z), "=f"(w[6].w), "=f"(w[7].x), "=f"(w[7].y), "=f"(w[7].z), "=f"(w[7].w)
+          : "l"(reinterpret_cast<const float4*>(a.grad[j0 + 0]) + i), "l"(reinterpret_cast<const float4*>(a.grad[j0 + 1]) + i),
+            "l"(reinterpret_cast<const float4*>(a.grad[j0 + 2]) + i), "l"(reinterpret_cast<const float4*>(a.grad[j0 + 3]) + i),
+            "l"(reinterpret_cast<const float4*>(a.grad[j0 + 4]) + i), "l"(reinterpret_cast<const float4*>(a.grad[j0 + 5]) + i),
+            "l"(reinterpret_cast<const float4*>(a.grad[j0 + 6]) + i), "l"(reinterpret_cast<const float4*>(a.grad[j0 + 7]) + i)
+          : "memory");
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j0 + j < a.world) { acc.x += w[j].x; acc.y += w[j].y; acc.z += w[j].z; acc.w += w[j].w; }
+    }
+    reinterpret_cast<float4*>(a.reduced)[i] = acc;
+    s += (double)acc.x * acc.x + (double)acc.y * acc.y + (double)acc.z * acc.z + (double)acc.w * acc.w;
+  }
+  s = warp_sum_d(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t += red[w]; atomicAdd(a.sumsq, t); }
+}
+
 int al4(long long x) { return (int)((x + 3) & ~3LL); }
 
 #include "b2h_ppo_tma.cuh"
@@ -617,6 +696,12 @@ struct B2HPpo {
   TMaps maps[8];             // fwd1 fwd2 fwd3 dW3 dh2 dW2 dh1 dW1, each [network][A hi, A lo, B hi, B lo, C hi, C lo]
   uint32_t *bits1[2], *bits2[2];   // sign bits of h1 / h2 (one bit per element, [rows][8] words): the ReLU masks of the backward pass
   int nw_obs;                // N tile of the first-layer weight gradient (obs_dim split into equal tiles <= 256)
+  // peer-memory gradient reduction: [grad copy 0 | grad copy 1 | reduced | flags] in one IPC-exported allocation
+  float* comm;
+  size_t comm_floats;
+  int rank, world;
+  uint32_t epoch;
+  void* peer_base[P2P_MAX_RANKS];
 };
 
 namespace {
@@ -937,6 +1022,8 @@ int b2h_ppo_create(const B2HPpoConfig* cfg, B2HPpo** out) {
     h->h1[n] = take(B * H); h->h2[n] = take(B * H); h->dh2[n] = take(B * H); h->dh1[n] = take(B * H);
     h->out[n] = take(B * OUT_LD); h->dout[n] = take(B * OUT_LD);
   }
+  h->comm = nullptr; h->comm_floats = 0; h->rank = 0; h->world = 1; h->epoch = 0;
+  for (int i = 0; i < P2P_MAX_RANKS; i++) h->peer_base[i] = nullptr;
   h->tbase = nullptr;
   h->tma = !cfg->staged_operands && cfg->hidden % 32 == 0 && cfg->hidden <= 256;
   if (h->tma) {
@@ -951,6 +1038,9 @@ void b2h_ppo_destroy(B2HPpo* h) {
   if (!h) return;
   cudaFree(h->scratch);   // the first allocation of the block
   if (h->tbase) cudaFree(h->tbase);
+  for (int i = 0; i < P2P_MAX_RANKS; i++)
+    if (h->peer_base[i] && i != h->rank) cudaIpcCloseMemHandle(h->peer_base[i]);
+  if (h->comm) cudaFree(h->comm);
   delete h;
 }
 
@@ -1044,17 +1134,79 @@ int b2h_ppo_apply(B2HPpo* h, float* params_dev, float* grad_dev, float* exp_avg_
   return B2H_OK;
 }
 
+// ---- peer-memory gradient reduction (one node, one process per GPU)
+int b2h_ppo_p2p_export(B2HPpo* h, void* ipc_handle_out64) {
+  if (!h || !ipc_handle_out64) { g_err_ppo = "null argument"; return B2H_EINVAL; }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  if (!h->comm) {
+    h->comm_floats = 3 * (size_t)h->nflat + 64;
+    if (cudaMalloc(&h->comm, h->comm_floats * sizeof(float)) != cudaSuccess) { g_err_ppo = "out of device memory (gradient exchange buffers)"; return B2H_ENOMEM; }
+    cudaMemset(h->comm, 0, h->comm_floats * sizeof(float));
+    cudaDeviceSynchronize();
+  }
+  cudaIpcMemHandle_t hd;
+  cudaError_t e = cudaIpcGetMemHandle(&hd, h->comm);
+  if (e != cudaSuccess) { g_err_ppo = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e); return B2H_ECUDA; }
+  memcpy(ipc_handle_out64, &hd, 64);
+  return B2H_OK;
+}
+
+int b2h_ppo_p2p_attach(B2HPpo* h, int rank, int world, const void* ipc_handles) {
+  if (!h || !ipc_handles || !h->comm || world < 1 || world > P2P_MAX_RANKS || rank < 0 || rank >= world) { g_err_ppo = "b2h_ppo_p2p_attach: bad argument (export first)"; return B2H_EINVAL; }
+  h->rank = rank; h->world = world;
+  for (int j = 0; j < world; j++) {
+    if (j == rank) { h->peer_base[j] = h->comm; continue; }
+    cudaIpcMemHandle_t hd;
+    memcpy(&hd, static_cast<const char*>(ipc_handles) + 64 * j, 64);
+    cudaError_t e = cudaIpcOpenMemHandle(&h->peer_base[j], hd, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { g_err_ppo = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e); h->peer_base[j] = nullptr; return B2H_ECUDA; }
+  }
+  return B2H_OK;
+}
+
+float* b2h_ppo_p2p_grad(B2HPpo* h) { return h && h->comm ? h->comm + (size_t)((h->epoch + 1) & 1) * h->nflat : nullptr; }
+
+int b2h_ppo_apply_p2p(B2HPpo* h, float* params_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t step, void* stream_) {
+  if (!h || !h->comm || !h->peer_base[h->world - 1] || !params_dev || !exp_avg_dev || !exp_avg_sq_dev || step < 1) { g_err_ppo = "b2h_ppo_apply_p2p: not attached / bad argument"; return B2H_EINVAL; }
+  cudaStream_t s = (cudaStream_t)stream_;
+  const B2HPpoConfig& c = h->cfg;
+  h->epoch++;
+  if (cudaMemsetAsync(h->scratch + 4, 0, sizeof(double), s) != cudaSuccess) { g_err_ppo = "memset failed"; return B2H_ECUDA; }
+  P2PArgs p;
+  const size_t copy = (size_t)(h->epoch & 1) * h->nflat;
+  for (int j = 0; j < h->world; j++) {
+    float* base = static_cast<float*>(h->peer_base[j]);
+    p.grad[j] = base + copy;
+    p.flags[j] = reinterpret_cast<uint32_t*>(base + 3 * (size_t)h->nflat);
+  }
+  for (int j = h->world; j < P2P_MAX_RANKS; j++) { p.grad[j] = p.grad[h->rank]; p.flags[j] = p.flags[h->rank]; }
+  p.reduced = h->comm + 2 * (size_t)h->nflat; p.sumsq = h->scratch + 4; p.error = h->error; p.n4 = h->nflat / 4; p.rank = h->rank; p.world = h->world; p.epoch = h->epoch;
+  p2p_reduce_kernel<<<g_sm_count > 0 ? g_sm_count : 148, 256, 0, s>>>(p);
+  AdamArgs a;
+  a.p = params_dev; a.g = p.reduced; a.m = exp_avg_dev; a.v = exp_avg_sq_dev; a.n = h->nflat; a.sumsq = h->scratch + 4; a.norm_out = h->scratch + 5;
+  a.grad_scale = 1.f / (float)h->world; a.max_norm = c.max_grad_norm; a.lr = c.lr; a.beta1 = c.beta1; a.beta2 = c.beta2; a.eps = c.adam_eps;
+  a.bc1 = (float)(1.0 - pow((double)c.beta1, (double)step));
+  a.bc2_sqrt = (float)sqrt(1.0 - pow((double)c.beta2, (double)step));
+  adam_kernel<<<(int)std::min<int64_t>((h->nflat + 255) / 256, 592), 256, 0, s>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
+  return B2H_OK;
+}
+
 int b2h_ppo_train(B2HPpo* h, const float* obs_dev, const float* actions_dev, const float* old_log_probs_dev, const float* advantages_dev,
                   const float* returns_dev, const int64_t* perm_dev, int64_t n_samples, int n_epochs, int batch_size, float* params_dev,
                   float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t* step_inout, void* stream) {
   if (!h || !perm_dev || !step_inout || n_samples <= 0 || n_epochs <= 0 || batch_size <= 0) { g_err_ppo = "b2h_ppo_train: bad argument"; return B2H_EINVAL; }
+  const bool p2p = h->comm && h->world > 1 && h->peer_base[h->world - 1];     // attached: gradients summed over the ranks by peer loads
   for (int e = 0; e < n_epochs; e++)
     for (int64_t i = 0; i < n_samples; i += batch_size) {
       const int n = (int)std::min<int64_t>(batch_size, n_samples - i);
+      float* g = p2p ? b2h_ppo_p2p_grad(h) : grad_dev;
       int rc = b2h_ppo_minibatch_grad(h, obs_dev, actions_dev, old_log_probs_dev, advantages_dev, returns_dev, perm_dev + (size_t)e * n_samples + i,
-                                      0, n, params_dev, grad_dev, stream);
+                                      0, n, params_dev, g, stream);
       if (rc < 0) return rc;
-      rc = b2h_ppo_apply(h, params_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, ++*step_inout, 1.f, stream);
+      rc = p2p ? b2h_ppo_apply_p2p(h, params_dev, exp_avg_dev, exp_avg_sq_dev, ++*step_inout, stream)
+               : b2h_ppo_apply(h, params_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, ++*step_inout, 1.f, stream);
       if (rc < 0) return rc;
     }
   return B2H_OK;

@@ -57,6 +57,10 @@ SIGNATURES = {
     "b2h_ppo_minibatch_grad": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, vp, vp, vp]),
     "b2h_ppo_apply": (C.c_int, [vp, vp, vp, vp, vp, C.c_int64, C.c_float, vp]),
     "b2h_ppo_train": (C.c_int, [vp, vp, vp, vp, vp, vp, vp, C.c_int64, C.c_int, C.c_int, vp, vp, vp, vp, C.POINTER(C.c_int64), vp]),
+    "b2h_ppo_p2p_export": (C.c_int, [vp, vp]),
+    "b2h_ppo_p2p_attach": (C.c_int, [vp, C.c_int, C.c_int, vp]),
+    "b2h_ppo_p2p_grad": (vp, [vp]),
+    "b2h_ppo_apply_p2p": (C.c_int, [vp, vp, vp, vp, C.c_int64, vp]),
     "b2h_ppo_stats": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_int), vp]),
     "b2h_ppo_stats_dev": (vp, [vp]),
     "b2h_ppo_error_dev": (vp, [vp]),

@@ -56,6 +56,7 @@ class PpoKernels:
         self.exp_avg, self.exp_avg_sq = torch.zeros_like(params.flat), torch.zeros_like(params.flat)
         self.step = 0
         self.device = dev
+        self.p2p = False
 
     def _check(self, rc):
         if rc < 0:
@@ -75,6 +76,31 @@ class PpoKernels:
         self._check(self.lib.b2h_ppo_minibatch_grad(self.h, _p(obs), _p(actions), _p(old_logp), _p(adv), _p(ret), _p(idx) if idx is not None else None,
                                                     int(row_start), n_rows, _p(self.p.flat), _p(self.grad), self._stream()))
         return self.grad
+
+    def enable_p2p(self):
+        """Map every rank's gradient buffer into this process (CUDA IPC; one node) so that ``apply_p2p`` can reduce the
+        gradients with peer loads over NVLink instead of a library all-reduce."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        mine = (C.c_char * 64)()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.b2h_ppo_p2p_export(self.h, mine))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(mine.raw))
+            blob = (C.c_char * (64 * world)).from_buffer_copy(b"".join(handles))
+            self._check(self.lib.b2h_ppo_p2p_attach(self.h, rank, world, blob))
+        dist.barrier()                                         # nobody starts reducing before every rank has attached
+        self.p2p = True
+
+    def minibatch_grad_p2p(self, obs, actions, old_logp, adv, ret, idx):
+        """As ``minibatch_grad``, into this epoch's copy of the peer-visible gradient buffer."""
+        g = C.c_void_p(self.lib.b2h_ppo_p2p_grad(self.h))
+        self._check(self.lib.b2h_ppo_minibatch_grad(self.h, _p(obs), _p(actions), _p(old_logp), _p(adv), _p(ret), _p(idx), 0, int(idx.numel()),
+                                                    _p(self.p.flat), g, self._stream()))
+
+    def apply_p2p(self):
+        """Flag barrier over the ranks, sum of all ranks' gradients by peer loads (bit-identical everywhere), clip + Adam on the mean."""
+        self.step += 1
+        self._check(self.lib.b2h_ppo_apply_p2p(self.h, _p(self.p.flat), _p(self.exp_avg), _p(self.exp_avg_sq), self.step, self._stream()))
 
     def apply(self, grad_scale=1.0):
         self.step += 1
@@ -101,7 +127,7 @@ class PpoKernels:
 class PPOTrainer:
     def __init__(self, batch, params: MlpPolicyParams | None = None, n_steps=64, batch_size=16384, n_epochs=4, lr=3e-4, gamma=0.99,
                  gae_lambda=0.95, clip_range=0.2, ent_coef=0.0, vf_coef=0.5, max_grad_norm=0.5, seed=0, precise=True, update_tf32=False, cuda_graph=True,
-                 update_impl="native"):
+                 update_impl="native", allreduce="p2p"):
         self.b = batch
         self.params = params or MlpPolicyParams(batch.obs_dim, batch.nu, 256, batch.device, seed)
         rank = dist.get_rank() if dist.is_initialized() else 0
@@ -125,6 +151,10 @@ class PPOTrainer:
             self.kernels = PpoKernels(self.params, batch_size, lr=lr, clip_range=clip_range, ent_coef=ent_coef, vf_coef=vf_coef,
                                       max_grad_norm=max_grad_norm, precise=not update_tf32)
             self.flat_grad = self.kernels.grad
+            if allreduce not in ("p2p", "nccl"):
+                raise ValueError(f"unknown allreduce {allreduce!r}")
+            if self.world > 1 and allreduce == "p2p":          # gradients summed by peer loads over NVLink (csrc/b2h_ppo.cu)
+                self.kernels.enable_p2p()
             return
         for t in self.tensors:
             t.requires_grad_(True)
@@ -161,11 +191,21 @@ class PPOTrainer:
         obs, actions = c.obs[:c.T].reshape(n, -1), c.actions.reshape(n, -1)
         old_logp, adv, ret = c.log_probs.reshape(n), c.advantages.reshape(n), c.returns.reshape(n)
         perm = torch.stack([torch.randperm(n, device=obs.device, generator=self.gen) for _ in range(self.n_epochs)])
-        if self.world == 1:
-            k.train(obs, actions, old_logp, adv, ret, perm, self.batch_size)
+        if self.world == 1 or (k.p2p and not self.time_allreduce):
+            k.train(obs, actions, old_logp, adv, ret, perm, self.batch_size)      # one foreign call; with p2p the ranks meet inside the kernels
         else:
             for e in range(self.n_epochs):
                 for i in range(0, n, self.batch_size):
+                    if k.p2p:
+                        k.minibatch_grad_p2p(obs, actions, old_logp, adv, ret, perm[e, i:i + self.batch_size])
+                        if self.time_allreduce:                # here: barrier + peer-load reduction + clip + Adam
+                            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                            e0.record()
+                        k.apply_p2p()
+                        if self.time_allreduce:
+                            e1.record()
+                            self._ar_events.append((e0, e1))
+                        continue
                     k.minibatch_grad(obs, actions, old_logp, adv, ret, idx=perm[e, i:i + self.batch_size])
                     if self.time_allreduce:
                         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

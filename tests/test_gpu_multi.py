@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 torch = pytest.importorskip("torch")
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, allreduce):
     import torch.distributed as dist
     import torch.nn.functional as F
     os.environ.update(RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -24,7 +24,8 @@ def _worker(rank, world, port, q):
     from mujocoposelearning_b200.ppo import PPOTrainer
     n, T = 128, 8
     b = HumanoidBatch(n, frame_skip=3, duration=10.0, reward_type="stand", device=rank, seed=2, env_id_offset=rank * n)
-    tr = PPOTrainer(b, n_steps=T, batch_size=n * T, n_epochs=1, lr=3e-4, seed=5)      # update_impl native: b2h_ppo_* kernels around the all-reduce
+    tr = PPOTrainer(b, n_steps=T, batch_size=n * T, n_epochs=1, lr=3e-4, seed=5, allreduce=allreduce)   # update_impl native: b2h_ppo_* kernels
+    assert tr.kernels.p2p == (allreduce == "p2p")
     with torch.no_grad():
         tr.col.collect()
     before = [t.detach().clone() for t in tr.tensors]
@@ -67,13 +68,16 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("allreduce", ["p2p", "nccl"])
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_rank_nccl_update_equals_single_process_mean_gradient():
+def test_two_rank_update_equals_single_process_mean_gradient(allreduce):
+    """allreduce='p2p': the gradients are summed by peer loads over NVLink inside the update kernels (CUDA IPC buffers, flag
+    barrier); 'nccl': one flat NCCL all-reduce between b2h_ppo_minibatch_grad and b2h_ppo_apply."""
     import torch.multiprocessing as mp
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, allreduce)) for r in range(2)]
     for p in procs:
         p.start()
     out = sorted(q.get(timeout=300) for _ in range(2))

@@ -364,6 +364,25 @@ def run_b200(args):
     ceg[1].record()
     torch.cuda.synchronize()
     col_eager_ms = ceg[0].elapsed_time(ceg[1])
+    # ---- the row after the path (section 8 f-1): one minibatch of SB3's PPO.train on the buffers just collected, on the update
+    # kernels of csrc/b2h_ppo.cu (forward + backward of both trunks on TMA-fed tcgen05 GEMMs, loss, clip, Adam); rank-0 time
+    from mujocoposelearning_b200.ppo import PpoKernels
+    n_buf = T_ROLL * E
+    mb = min(16384, n_buf)
+    pk = PpoKernels(pol.p, max_batch=mb)
+    saved_flat = pol.p.flat.clone()
+    buf = (col.obs.reshape(n_buf, -1), col.actions.reshape(n_buf, -1), col.log_probs.reshape(n_buf), col.advantages.reshape(n_buf), col.returns.reshape(n_buf))
+    perm = torch.randperm(n_buf, device=dev).reshape(1, n_buf)
+    n_mb = n_buf // mb
+    pk.train(*buf, perm, mb)                         # warm-up epoch
+    uev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    uev[0].record()
+    pk.train(*buf, perm, mb)
+    uev[1].record()
+    torch.cuda.synchronize()
+    ppo_stats = pk.stats()                           # raises if the tensor pipeline timed out
+    upd_ms = uev[0].elapsed_time(uev[1]) / n_mb
+    pol.p.flat.copy_(saved_flat)                     # the following legs run the policy they started with
     # ---- the same rollout with the 53-column observation (qpos[2:] | qvel; SURVEY 8d C3 asks for both), rank-0 time
     b53 = HumanoidBatch(E, frame_skip=FRAME_SKIP, duration=DURATION, reward_type=REWARD, dtype=args.dtype, device=local,
                         seed=1234, env_id_offset=rank * E, obs_mode="qpos_qvel")
@@ -455,6 +474,10 @@ def run_b200(args):
                              "op_by_op_python_loop": {"value": world * E * FRAME_SKIP * T_ROLL / (col_eager_ms * 1e-3), "ms_per_step": col_eager_ms / T_ROLL},
                              "what": "b2h_rollout_collect: policy/value MLP + sampling + env step + buffer record for 64 steps, last values and GAE, "
                                      "one CUDA graph per rollout (SB3 collect_rollouts + compute_returns_and_advantage); rank-0 time"},
+        "ppo_update": {"ms_per_minibatch": upd_ms, "minibatch": mb, "minibatches": n_mb, "gemm_flop_per_minibatch": 6.0 * mb * 2 * (batch.obs_dim * 256 + 256 * 256 + 256 * 11),
+                       "value_loss": ppo_stats["value_loss"], "grad_norm": ppo_stats["grad_norm"],
+                       "what": "SB3 PPO.train minibatch on the hand-written update kernels (b2h_ppo_train): forward + backward of both 352-256-256 trunks "
+                               "on TMA-fed tcgen05 GEMMs (tf32 hi/lo split, fp32-faithful), loss, grad-norm clip, Adam; rank-0 time, `bench.py --ppo` times whole iterations"},
         "obs_qpos_qvel": {"value": world * E * FRAME_SKIP / (ms53 * 1e-3), "unit": UNIT, "ms_per_step": ms53, "steps": K53,
                           "what": "same rollout, 53-column observation (control steps W..W+steps of the first episode); rank-0 time"},
         "launch": batch.launch_info(), "step_ms_min_med_max": [float(step_ms.min()), float(np.median(step_ms)), float(step_ms.max())],

@@ -696,6 +696,8 @@ struct B2HPpo {
   TMaps maps[8];             // fwd1 fwd2 fwd3 dW3 dh2 dW2 dh1 dW1, each [network][A hi, A lo, B hi, B lo, C hi, C lo]
   uint32_t *bits1[2], *bits2[2];   // sign bits of h1 / h2 (one bit per element, [rows][8] words): the ReLU masks of the backward pass
   int nw_obs;                // N tile of the first-layer weight gradient (obs_dim split into equal tiles <= 256)
+  cudaStream_t side;         // the weight-gradient GEMMs of the head and of layer 2 run here, beside the input-gradient chain
+  cudaEvent_t ev_fork[2], ev_join;
   // peer-memory gradient reduction: [grad copy 0 | grad copy 1 | reduced | flags] in one IPC-exported allocation
   float* comm;
   size_t comm_floats;
@@ -788,6 +790,11 @@ int setup_tma(B2HPpo* h) {
   if (!ok) { g_err_ppo = "cuTensorMapEncodeTiled failed"; return B2H_ECUDA; }
   cudaError_t e = cudaFuncSetAttribute(gemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TNS * T_STAGE * sizeof(float)));
   if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
+  if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_fork[0], cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_fork[1], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+    g_err_ppo = "stream / event creation failed";
+    return B2H_ECUDA;
+  }
   return B2H_OK;
 }
 
@@ -876,7 +883,11 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
     pr[k] = base(1, 1, h_tiles, 1, 32, kchunks_b);
     pr[k].epi = 2; pr[k].C = G + o[6 * k + 4]; pr[k].ldc = H; pr[k].transpose_c = 1; pr[k].M = H; pr[k].N = nout[k];
   }
-  if ((rc = launch_gemm_t(h, 3, pr, c.precise, true, s)) < 0) return rc;
+  // the weight gradients of the head and of layer 2 only feed the flat gradient: they run on a side stream beside the
+  // input-gradient chain (dh2 -> dh1 -> dW1) and fill the SMs its partial waves leave idle
+  cudaStream_t s2 = h->side;
+  if (cudaEventRecord(h->ev_fork[0], s) != cudaSuccess || cudaStreamWaitEvent(s2, h->ev_fork[0], 0) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
+  if ((rc = launch_gemm_t(h, 3, pr, c.precise, true, s2)) < 0) return rc;
   for (int k = 0; k < 2; k++) {   // dh2 = dout W3 . (h2 > 0)
     pr[k] = base(0, 1, m_tiles_b, 1, H, 1);
     pr[k].c_hi = h->tdh2[k].hi; pr[k].c_lo = h->tdh2[k].lo; pr[k].c_ld = h->tdh2[k].ld; pr[k].bits_in = h->bits2[k]; pr[k].colsum = G + o[6 * k + 3]; pr[k].N = H;
@@ -886,7 +897,9 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
     pr[k] = base(1, 1, h_tiles, 1, H, kchunks_b);
     pr[k].epi = 2; pr[k].C = G + o[6 * k + 2]; pr[k].ldc = H; pr[k].M = H; pr[k].N = H;
   }
-  if ((rc = launch_gemm_t(h, 5, pr, c.precise, true, s)) < 0) return rc;
+  if (cudaEventRecord(h->ev_fork[1], s) != cudaSuccess || cudaStreamWaitEvent(s2, h->ev_fork[1], 0) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
+  if ((rc = launch_gemm_t(h, 5, pr, c.precise, true, s2)) < 0) return rc;
+  if (cudaEventRecord(h->ev_join, s2) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
   for (int k = 0; k < 2; k++) {   // dh1 = dh2 W2 . (h1 > 0)
     pr[k] = base(0, 1, m_tiles_b, 1, H, kc_h);
     pr[k].c_hi = h->tdh1[k].hi; pr[k].c_lo = h->tdh1[k].lo; pr[k].c_ld = h->tdh1[k].ld; pr[k].bits_in = h->bits1[k]; pr[k].colsum = G + o[6 * k + 1]; pr[k].N = H;
@@ -898,6 +911,7 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
     pr[k].epi = 2; pr[k].C = G + o[6 * k + 0]; pr[k].ldc = D; pr[k].M = H; pr[k].N = D;
   }
   if ((rc = launch_gemm_t(h, 7, pr, c.precise, true, s)) < 0) return rc;
+  if (cudaStreamWaitEvent(s, h->ev_join, 0) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
   return B2H_OK;
@@ -1023,6 +1037,7 @@ int b2h_ppo_create(const B2HPpoConfig* cfg, B2HPpo** out) {
     h->out[n] = take(B * OUT_LD); h->dout[n] = take(B * OUT_LD);
   }
   h->comm = nullptr; h->comm_floats = 0; h->rank = 0; h->world = 1; h->epoch = 0;
+  h->side = nullptr; h->ev_fork[0] = h->ev_fork[1] = h->ev_join = nullptr;
   for (int i = 0; i < P2P_MAX_RANKS; i++) h->peer_base[i] = nullptr;
   h->tbase = nullptr;
   h->tma = !cfg->staged_operands && cfg->hidden % 32 == 0 && cfg->hidden <= 256;
@@ -1038,6 +1053,8 @@ void b2h_ppo_destroy(B2HPpo* h) {
   if (!h) return;
   cudaFree(h->scratch);   // the first allocation of the block
   if (h->tbase) cudaFree(h->tbase);
+  if (h->ev_join) { cudaEventDestroy(h->ev_fork[0]); cudaEventDestroy(h->ev_fork[1]); cudaEventDestroy(h->ev_join); }
+  if (h->side) cudaStreamDestroy(h->side);
   for (int i = 0; i < P2P_MAX_RANKS; i++)
     if (h->peer_base[i] && i != h->rank) cudaIpcCloseMemHandle(h->peer_base[i]);
   if (h->comm) cudaFree(h->comm);

@@ -146,7 +146,8 @@ def test_minibatch_gradient_matches_autograd(n, obs_dim, hidden, act_dim, staged
         views = p.pi + p.vf + [p.log_std]
         with torch.no_grad():
             old_logp = _torch_loss(views, obs, actions, torch.zeros(n, device="cuda"), adv, ret)[4]
-            old_logp = old_logp + torch.randn(n, device="cuda") * 0.15        # ratios spread around 1: some clipped, some not
+            gn = torch.Generator(device="cuda").manual_seed(n + 1)
+            old_logp = old_logp + torch.randn(n, device="cuda", generator=gn) * 0.15   # ratios spread around 1: some clipped, some not
         # the reference gradient in float64 (the truth both fp32 implementations approximate)
         ref = [t.detach().double().requires_grad_(True) for t in views]
         loss, pl, vl, cf, _ = _torch_loss(ref, obs.double(), actions.double(), old_logp.double(), adv.double(), ret.double(), ent_coef=0.01)

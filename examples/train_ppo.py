@@ -30,7 +30,8 @@ def main():
     ap.add_argument("--batch-size", type=int, default=16384)
     ap.add_argument("--epochs", type=int, default=4)
     ap.add_argument("--ent-coef", type=float, default=0.0)
-    ap.add_argument("--update-tf32", action="store_true", help="run the update's library GEMMs on the tf32 tensor cores")
+    ap.add_argument("--update-tf32", action="store_true", help="update GEMMs in a single tf32 pass (default: fp32-faithful hi / lo split)")
+    ap.add_argument("--update-impl", choices=["native", "torch"], default="native", help="native: the kernels of csrc/b2h_ppo.cu; torch: autograd + library GEMMs")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -40,7 +41,8 @@ def main():
     from mujocoposelearning_b200.ppo import PPOTrainer
     b = HumanoidBatch(args.n_envs, frame_skip=args.frame_skip, duration=args.duration, reward_type=args.reward, device=local, seed=0,
                       env_id_offset=rank * args.n_envs)
-    tr = PPOTrainer(b, n_steps=args.n_steps, batch_size=args.batch_size, n_epochs=args.epochs, lr=args.lr, ent_coef=args.ent_coef, update_tf32=args.update_tf32)
+    tr = PPOTrainer(b, n_steps=args.n_steps, batch_size=args.batch_size, n_epochs=args.epochs, lr=args.lr, ent_coef=args.ent_coef, update_tf32=args.update_tf32,
+                    update_impl=args.update_impl)
     for it in range(args.iters):
         torch.cuda.synchronize(); t0 = time.perf_counter()
         with torch.no_grad():

@@ -19,9 +19,10 @@
 //   ppo_loss_kernel      advantage moments, log-probability, ratio, clipped surrogate, value loss, their gradients with respect
 //                        to the action mean / value / log_std, head bias gradients, loss statistics
 //   colsum_kernel        hidden-layer bias gradients
-//   sumsq_kernel + adam_kernel   global grad-norm clip (max_grad_norm) and torch.optim.Adam's update rule on the flat
-//                        parameter vector (the caller may all-reduce the flat gradient between b2h_ppo_minibatch_grad and
-//                        b2h_ppo_apply: one NCCL call on 1.27 MB)
+//   apply_kernel         one launch: [sum of the ranks' gradients by peer loads over NVLink] -> sum of squares -> grid barrier ->
+//                        grad-norm clip (max_grad_norm) + torch.optim.Adam's update rule on the flat parameter vector (or the
+//                        caller all-reduces the flat gradient itself between b2h_ppo_minibatch_grad and b2h_ppo_apply)
+//   b2h_ppo_tma.cuh      the TMA-fed form of the GEMM (operands kept pre-split by their producers) that the update runs on
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -425,31 +426,35 @@ __device__ __forceinline__ float warp_sum_f(float v) {
 
 // Every CTA computes the advantage moments of the whole minibatch itself (n floats from L2: cheaper than another launch and
 // bit-identical in every CTA), then one thread per sample.
-__global__ void __launch_bounds__(256) ppo_loss_kernel(LossArgs L) {
-  __shared__ double red[8];
-  __shared__ float fred[8][2 * MAX_ACT + 1];
+constexpr int LOSS_NT = 128, LOSS_NW = LOSS_NT / 32;
+__global__ void __launch_bounds__(LOSS_NT) ppo_loss_kernel(LossArgs L) {
+  __shared__ double red[2 * LOSS_NW];
+  __shared__ float fred[LOSS_NW][2 * MAX_ACT + 1];
   __shared__ double s_mean, s_std;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double amean = 0.0, astd = 1.0;
-  if (L.normalize && L.n > 1) {   // (adv - mean) / (std + 1e-8), torch.std: unbiased
-    double s = 0.0;
-    for (int i = tid; i < L.n; i += 256) s += (double)__ldg(L.adv + i);
-    s = warp_sum_d(s);
-    if (lane == 0) red[warp] = s;
+  if (L.normalize && L.n > 1) {   // (adv - mean) / (std + 1e-8), torch.std: unbiased.  One pass: sums of x and x^2 in double
+    double s = 0.0, q = 0.0;
+    const int n4 = (((uintptr_t)L.adv & 15) == 0) ? L.n / 4 : 0;
+    for (int i = tid; i < n4; i += LOSS_NT) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(L.adv) + i);
+      s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+      q += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+    }
+    for (int i = 4 * n4 + tid; i < L.n; i += LOSS_NT) { const double v = (double)__ldg(L.adv + i); s += v; q += v * v; }
+    s = warp_sum_d(s); q = warp_sum_d(q);
+    if (lane == 0) { red[warp] = s; red[LOSS_NW + warp] = q; }
     __syncthreads();
-    if (tid == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t += red[w]; s_mean = t / L.n; }
+    if (tid == 0) {
+      double ts = 0.0, tq = 0.0;
+      for (int w = 0; w < LOSS_NW; w++) { ts += red[w]; tq += red[LOSS_NW + w]; }
+      const double m = ts / L.n;
+      s_mean = m; s_std = sqrt(fmax(tq - ts * m, 0.0) / (L.n - 1));
+    }
     __syncthreads();
-    amean = s_mean;
-    double q = 0.0;
-    for (int i = tid; i < L.n; i += 256) { const double d = (double)__ldg(L.adv + i) - amean; q += d * d; }
-    q = warp_sum_d(q);
-    if (lane == 0) red[warp] = q;
-    __syncthreads();
-    if (tid == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t += red[w]; s_std = sqrt(t / (L.n - 1)); }
-    __syncthreads();
-    astd = s_std;
+    amean = s_mean; astd = s_std;
   }
-  const int i = blockIdx.x * 256 + tid;
+  const int i = blockIdx.x * LOSS_NT + tid;
   const bool live = i < L.n;
   float pl = 0.f, vl = 0.f, cf = 0.f, kl = 0.f, dv = 0.f;
   float dm[MAX_ACT], dls[MAX_ACT];
@@ -526,7 +531,7 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(LossArgs L) {
     const int j = tid < MAX_ACT ? tid : tid - MAX_ACT;
     if (tid == 2 * MAX_ACT || j < L.act_dim) {
       float s = 0.f;
-      for (int w = 0; w < 8; w++) s += fred[w][tid];
+      for (int w = 0; w < LOSS_NW; w++) s += fred[w][tid];
       if (tid == 2 * MAX_ACT) atomicAdd(L.g_b3_vf, s);
       else if (tid < MAX_ACT) atomicAdd(L.g_b3_pi + j, s);
       else atomicAdd(L.g_log_std + j, s - (blockIdx.x == 0 ? L.ent_coef : 0.f));   // entropy = sum(log_std) + const; loss has -ent_coef * entropy
@@ -539,7 +544,7 @@ __global__ void __launch_bounds__(256) ppo_loss_kernel(LossArgs L) {
     const double s = warp_sum_d(st[k]);
     if (lane == 0) red[warp] = s;
     __syncthreads();
-    if (tid == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t += red[w]; atomicAdd(L.stats + k, t / L.n); }
+    if (tid == 0) { double t = 0.0; for (int w = 0; w < LOSS_NW; w++) t += red[w]; atomicAdd(L.stats + k, t / L.n); }
     __syncthreads();
   }
 }
@@ -557,42 +562,6 @@ __global__ void __launch_bounds__(256) colsum_kernel(ColsumArgs c) {
   }
 }
 
-__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, double* out) {
-  __shared__ double red[8];
-  double s = 0.0;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) { const double v = g[i]; s += v * v; }
-  s = warp_sum_d(s);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-  __syncthreads();
-  if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t += red[w]; atomicAdd(out, t); }
-}
-
-struct AdamArgs {
-  float *p, *g, *m, *v;
-  long long n;
-  const double* sumsq;     // sum of squares of g (before grad_scale)
-  double* norm_out;        // receives the gradient norm (after grad_scale, before clipping)
-  float grad_scale;        // 1 / world size when g holds a sum over ranks
-  float max_norm, lr, beta1, beta2, eps;
-  float bc1, bc2_sqrt;     // 1 - beta1^t, sqrt(1 - beta2^t)
-};
-// torch.nn.utils.clip_grad_norm_ (coef = max_norm / (norm + 1e-6), clamped to 1) followed by torch.optim.Adam's update rule
-__global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
-  const float norm = (float)sqrt(*a.sumsq) * a.grad_scale;
-  const float coef = a.max_norm > 0.f ? fminf(a.max_norm / (norm + 1e-6f), 1.f) : 1.f;
-  const float gs = a.grad_scale * coef;
-  if (blockIdx.x == 0 && threadIdx.x == 0 && a.norm_out) *a.norm_out = (double)norm;
-  const float step_size = a.lr / a.bc1;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n; i += (long long)gridDim.x * 256) {
-    const float g = a.g[i] * gs;
-    const float m = a.beta1 * a.m[i] + (1.f - a.beta1) * g;
-    const float v = a.beta2 * a.v[i] + (1.f - a.beta2) * g * g;
-    a.m[i] = m; a.v[i] = v;
-    const float denom = sqrtf(v) / a.bc2_sqrt + a.eps;
-    a.p[i] -= step_size * (m / denom);
-  }
-}
-
 // ---- gradient all-reduce over NVLink peer memory, fused with the sum of squares of the reduced gradient --------------------
 // Every rank keeps its flat gradient in a buffer the other ranks of the node have mapped (CUDA IPC).  One kernel per minibatch:
 //   1. tell every peer "my gradient of epoch e is complete" (st.release.sys into the peer's flag row), wait until all peers
@@ -604,71 +573,123 @@ __global__ void __launch_bounds__(256) adam_kernel(AdamArgs a) {
 // it has passed the barrier of epoch e + 1, which every peer only signals after its reduction of epoch e has finished -- no
 // second barrier is needed.  Waits are bounded; on a timeout the error flag is raised and the kernel carries on.
 constexpr int P2P_MAX_RANKS = 16;
-struct P2PArgs {
+struct ApplyArgs {
+  // clip + Adam
+  float *p, *g, *m, *v;                 // parameters, gradient (world > 1: receives the sum over the ranks), Adam moments
+  long long n;
+  double* sumsq;                        // accumulator (zeroed by the caller): sum of squares of g (before grad_scale)
+  double* norm_out;                     // receives the gradient norm (after grad_scale, before clipping)
+  unsigned* arrived;                    // grid barrier counter (zeroed by the caller)
+  int* error;
+  float grad_scale;                     // 1 / world size when g holds a sum over ranks
+  float max_norm, lr, beta1, beta2, eps;
+  float bc1, bc2_sqrt;                  // 1 - beta1^t, sqrt(1 - beta2^t)
+  // cross-rank sum (world > 1)
   const float* grad[P2P_MAX_RANKS];     // this epoch's gradient copy on every rank (index = rank; own entry is local memory)
   uint32_t* flags[P2P_MAX_RANKS];       // flag rows [P2P_MAX_RANKS] on every rank
-  float* reduced;                       // local: sum over ranks
-  double* sumsq;
-  int* error;
-  long long n4;                         // float4 elements
   int rank, world;
   uint32_t epoch;
 };
-__global__ void __launch_bounds__(256) p2p_reduce_kernel(P2PArgs a) {
+// One launch: [cross-rank gradient sum] -> sum of squares -> grid barrier -> torch.nn.utils.clip_grad_norm_ (coef = max_norm /
+// (norm + 1e-6), clamped to 1) + torch.optim.Adam's update rule.  The grid is one CTA per SM (all co-resident), every thread
+// owns the same slice in both phases.
+__global__ void __launch_bounds__(256) apply_kernel(ApplyArgs a) {
   __shared__ double red[8];
-  if (threadIdx.x < a.world) {
-    const int j = threadIdx.x;
-    if (blockIdx.x == 0) {
-      __threadfence_system();
-      asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(a.flags[j] + a.rank), "r"(a.epoch) : "memory");
+  __shared__ float s_coef;
+  const long long n4 = a.n / 4;         // the flat vectors are padded to a multiple of 4 floats
+  if (a.world > 1) {
+    if (threadIdx.x < a.world) {
+      const int j = threadIdx.x;
+      if (blockIdx.x == 0) {
+        __threadfence_system();
+        asm volatile("st.release.sys.global.u32 [%0], %1;\n" ::"l"(a.flags[j] + a.rank), "r"(a.epoch) : "memory");
+      }
+      const uint32_t* mine = a.flags[a.rank] + j;
+      bool seen = false;
+      for (int spin = 0; spin < (1 << 22) && !seen; spin++) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
+        seen = (int32_t)(v - a.epoch) >= 0;
+        if (!seen) __nanosleep(64);
+      }
+      if (!seen) atomicExch(a.error, 2);
     }
-    const uint32_t* mine = a.flags[a.rank] + j;
-    bool seen = false;
-    for (int spin = 0; spin < (1 << 22) && !seen; spin++) {
-      uint32_t v;
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];\n" : "=r"(v) : "l"(mine) : "memory");
-      seen = (int32_t)(v - a.epoch) >= 0;
-      if (!seen) __nanosleep(64);
-    }
-    if (!seen) atomicExch(a.error, 2);
+    __syncthreads();
   }
-  __syncthreads();
   double s = 0.0;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < a.n4; i += (long long)gridDim.x * 256) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j0 = 0; j0 < a.world; j0 += 8) {   // eight peer loads in flight (one asm block: ptxas must not interleave the sums), then the sum in rank order
-      float4 w[8];
-      // ld.volatile: the peers' buffers change between launches, nothing may come from a non-coherent cache; entries beyond
-      // `world` alias this rank's own buffer and are dropped below
-      asm volatile(
-          "ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%32];\n\t"
-          "ld.volatile.global.v4.f32 {%4, %5, %6, %7}, [%33];\n\t"
-          "ld.volatile.global.v4.f32 {%8, %9, %10, %11}, [%34];\n\t"
-          "ld.volatile.global.v4.f32 {%12, %13, %14, %15}, [%35];\n\t"
-          "ld.volatile.global.v4.f32 {%16, %17, %18, %19}, [%36];\n\t"
-          "ld.volatile.global.v4.f32 {%20, %21, %22, %23}, [%37];\n\t"
-          "ld.volatile.global.v4.f32 {%24, %25, %26, %27}, [%38];\n\t"
-          "ld.volatile.global.v4.f32 {%28, %29, %30, %31}, [%39];\n"
-          : "=f"(w[0].x), "=f"(w[0].y), "=f"(w[0].z), "=f"(w[0].w), "=f"(w[1].x), "=f"(w[1].y), "=f"(w[1].z), "=f"(w[1].w),
-            "=f"(w[2].x), "=f"(w[2].y), "=f"(w[2].z), "=f"(w[2].w), "=f"(w[3].x), "=f"(w[3].y), "=f"(w[3].z), "=f"(w[3].w),
-            "=f"(w[4].x), "=f"(w[4].y), "=f"(w[4].z), "=f"(w[4].w), "=f"(w[5].x), "=f"(w[5].y), "=f"(w[5].z), "=f"(w[5].w),
-            "=f"(w[6].x), "=f"(w[6].y), "=f"(w[6].z), "=f"(w[6].w), "=f"(w[7].x), "=f"(w[7].y), "=f"(w[7].z), "=f"(w[7].w)
-          : "l"(reinterpret_cast<const float4*>(a.grad[j0 + 0]) + i), "l"(reinterpret_cast<const float4*>(a.grad[j0 + 1]) + i),
-            "l"(reinterpret_cast<const float4*>(a.grad[j0 + 2]) + i), "l"(reinterpret_cast<const float4*>(a.grad[j0 + 3]) + i),
-            "l"(reinterpret_cast<const float4*>(a.grad[j0 + 4]) + i), "l"(reinterpret_cast<const float4*>(a.grad[j0 + 5]) + i),
-            "l"(reinterpret_cast<const float4*>(a.grad[j0 + 6]) + i), "l"(reinterpret_cast<const float4*>(a.grad[j0 + 7]) + i)
-          : "memory");
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 acc;
+    if (a.world > 1) {
+      acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int j0 = 0; j0 < a.world; j0 += 8) {   // eight peer loads in flight (one asm block: ptxas must not interleave the sums), then the sum in rank order
+        float4 w[8];
+        // ld.volatile: the peers' buffers change between launches, nothing may come from a non-coherent cache; entries beyond
+        // `world` alias this rank's own buffer and are dropped below
+        asm volatile(
+            "ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%32];\n\t"
+            "ld.volatile.global.v4.f32 {%4, %5, %6, %7}, [%33];\n\t"
+            "ld.volatile.global.v4.f32 {%8, %9, %10, %11}, [%34];\n\t"
+            "ld.volatile.global.v4.f32 {%12, %13, %14, %15}, [%35];\n\t"
+            "ld.volatile.global.v4.f32 {%16, %17, %18, %19}, [%36];\n\t"
+            "ld.volatile.global.v4.f32 {%20, %21, %22, %23}, [%37];\n\t"
+            "ld.volatile.global.v4.f32 {%24, %25, %26, %27}, [%38];\n\t"
+            "ld.volatile.global.v4.f32 {%28, %29, %30, %31}, [%39];\n"
+            : "=f"(w[0].x), "=f"(w[0].y), "=f"(w[0].z), "=f"(w[0].w), "=f"(w[1].x), "=f"(w[1].y), "=f"(w[1].z), "=f"(w[1].w),
+              "=f"(w[2].x), "=f"(w[2].y), "=f"(w[2].z), "=f"(w[2].w), "=f"(w[3].x), "=f"(w[3].y), "=f"(w[3].z), "=f"(w[3].w),
+              "=f"(w[4].x), "=f"(w[4].y), "=f"(w[4].z), "=f"(w[4].w), "=f"(w[5].x), "=f"(w[5].y), "=f"(w[5].z), "=f"(w[5].w),
+              "=f"(w[6].x), "=f"(w[6].y), "=f"(w[6].z), "=f"(w[6].w), "=f"(w[7].x), "=f"(w[7].y), "=f"(w[7].z), "=f"(w[7].w)
+            : "l"(reinterpret_cast<const float4*>(a.grad[j0 + 0]) + i), "l"(reinterpret_cast<const float4*>(a.grad[j0 + 1]) + i),
+              "l"(reinterpret_cast<const float4*>(a.grad[j0 + 2]) + i), "l"(reinterpret_cast<const float4*>(a.grad[j0 + 3]) + i),
+              "l"(reinterpret_cast<const float4*>(a.grad[j0 + 4]) + i), "l"(reinterpret_cast<const float4*>(a.grad[j0 + 5]) + i),
+              "l"(reinterpret_cast<const float4*>(a.grad[j0 + 6]) + i), "l"(reinterpret_cast<const float4*>(a.grad[j0 + 7]) + i)
+            : "memory");
 #pragma unroll
-      for (int j = 0; j < 8; j++)
-        if (j0 + j < a.world) { acc.x += w[j].x; acc.y += w[j].y; acc.z += w[j].z; acc.w += w[j].w; }
+        for (int j = 0; j < 8; j++)
+          if (j0 + j < a.world) { acc.x += w[j].x; acc.y += w[j].y; acc.z += w[j].z; acc.w += w[j].w; }
+      }
+      reinterpret_cast<float4*>(a.g)[i] = acc;
+    } else {
+      acc = reinterpret_cast<const float4*>(a.g)[i];
     }
-    reinterpret_cast<float4*>(a.reduced)[i] = acc;
     s += (double)acc.x * acc.x + (double)acc.y * acc.y + (double)acc.z * acc.z + (double)acc.w * acc.w;
   }
   s = warp_sum_d(s);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 8; w++) t += red[w]; atomicAdd(a.sumsq, t); }
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += red[w];
+    atomicAdd(a.sumsq, t);
+    __threadfence();
+    atomicAdd(a.arrived, 1u);
+    bool all = false;
+    for (int spin = 0; spin < (1 << 24) && !all; spin++) {   // grid barrier: one CTA per SM, all co-resident; bounded all the same
+      unsigned v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(a.arrived) : "memory");
+      all = v >= gridDim.x;
+    }
+    if (!all) atomicExch(a.error, 3);
+    double total;
+    asm volatile("ld.volatile.global.f64 %0, [%1];\n" : "=d"(total) : "l"(a.sumsq) : "memory");
+    const float norm = (float)sqrt(total) * a.grad_scale;
+    s_coef = a.max_norm > 0.f ? fminf(a.max_norm / (norm + 1e-6f), 1.f) : 1.f;
+    if (blockIdx.x == 0 && a.norm_out) *a.norm_out = (double)norm;
+  }
+  __syncthreads();
+  const float gs = a.grad_scale * s_coef;
+  const float step_size = a.lr / a.bc1;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    const float4 g4 = reinterpret_cast<const float4*>(a.g)[i];
+    float4 m4 = reinterpret_cast<float4*>(a.m)[i], v4 = reinterpret_cast<float4*>(a.v)[i], p4 = reinterpret_cast<float4*>(a.p)[i];
+    auto upd = [&](float g, float& m, float& v, float& p) {
+      g *= gs;
+      m = a.beta1 * m + (1.f - a.beta1) * g;
+      v = a.beta2 * v + (1.f - a.beta2) * g * g;
+      p -= step_size * (m / (sqrtf(v) / a.bc2_sqrt + a.eps));
+    };
+    upd(g4.x, m4.x, v4.x, p4.x); upd(g4.y, m4.y, v4.y, p4.y); upd(g4.z, m4.z, v4.z, p4.z); upd(g4.w, m4.w, v4.w, p4.w);
+    reinterpret_cast<float4*>(a.m)[i] = m4; reinterpret_cast<float4*>(a.v)[i] = v4; reinterpret_cast<float4*>(a.p)[i] = p4;
+  }
 }
 
 int al4(long long x) { return (int)((x + 3) & ~3LL); }
@@ -877,7 +898,7 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
   for (int k = 0; k < 2; k++) { L.dt_hi[k] = h->tdout[k].hi; L.dt_lo[k] = h->tdout[k].lo; }
   L.g_b3_pi = G + o[5]; L.g_b3_vf = G + o[11]; L.g_log_std = G + o[12]; L.stats = h->scratch;
   L.n = n; L.act_dim = A; L.clip = c.clip_range; L.ent_coef = c.ent_coef; L.vf_coef = c.vf_coef; L.normalize = c.normalize_advantage;
-  ppo_loss_kernel<<<(rows_pad + 255) / 256, 256, 0, s>>>(L);
+  ppo_loss_kernel<<<(rows_pad + LOSS_NT - 1) / LOSS_NT, LOSS_NT, 0, s>>>(L);
   // ---- backward
   for (int k = 0; k < 2; k++) {   // dW3^T [H, nout] = h2^T dout, written transposed into the [nout, H] gradient
     pr[k] = base(1, 1, h_tiles, 1, 32, kchunks_b);
@@ -1105,7 +1126,7 @@ int b2h_ppo_minibatch_grad(B2HPpo* h, const float* obs_dev, const float* actions
   L.mean = h->out[0]; L.value = h->out[1]; L.act = h->act; L.olp = h->olp; L.adv = h->adv; L.ret = h->ret; L.log_std = P + o[12];
   L.dmean = h->dout[0]; L.dvalue = h->dout[1]; L.rows_pad = 0; L.dt_hi[0] = L.dt_hi[1] = L.dt_lo[0] = L.dt_lo[1] = nullptr; L.g_b3_pi = G + o[5]; L.g_b3_vf = G + o[11]; L.g_log_std = G + o[12]; L.stats = h->scratch;
   L.n = n; L.act_dim = A; L.clip = c.clip_range; L.ent_coef = c.ent_coef; L.vf_coef = c.vf_coef; L.normalize = c.normalize_advantage;
-  ppo_loss_kernel<<<(n + 255) / 256, 256, 0, s>>>(L);
+  ppo_loss_kernel<<<(n + LOSS_NT - 1) / LOSS_NT, LOSS_NT, 0, s>>>(L);
   // ---- backward.  Head: dW3 = dout^T h2 (computed transposed: the 256 hidden features ride on the M side), dh2 = dout W3 . (h2 > 0)
   for (int k = 0; k < 2; k++) {
     pr[k] = prob(h->h2[k], H, 1, h->dout[k], OUT_LD, 1, G + o[6 * k + 4], H, H, nout[k], n);
@@ -1133,22 +1154,36 @@ int b2h_ppo_minibatch_grad(B2HPpo* h, const float* obs_dev, const float* actions
   return B2H_OK;
 }
 
-int b2h_ppo_apply(B2HPpo* h, float* params_dev, float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t step, float grad_scale,
-                  void* stream_) {
-  if (!h || !params_dev || !grad_dev || !exp_avg_dev || !exp_avg_sq_dev || step < 1) { g_err_ppo = "b2h_ppo_apply: bad argument"; return B2H_EINVAL; }
-  cudaStream_t s = (cudaStream_t)stream_;
+namespace {
+int launch_apply(B2HPpo* h, ApplyArgs& a, int64_t step, cudaStream_t s) {
   const B2HPpoConfig& c = h->cfg;
-  if (cudaMemsetAsync(h->scratch + 4, 0, sizeof(double), s) != cudaSuccess) { g_err_ppo = "memset failed"; return B2H_ECUDA; }
-  sumsq_kernel<<<64, 256, 0, s>>>(grad_dev, h->nflat, h->scratch + 4);
-  AdamArgs a;
-  a.p = params_dev; a.g = grad_dev; a.m = exp_avg_dev; a.v = exp_avg_sq_dev; a.n = h->nflat; a.sumsq = h->scratch + 4; a.norm_out = h->scratch + 5;
-  a.grad_scale = grad_scale; a.max_norm = c.max_grad_norm; a.lr = c.lr; a.beta1 = c.beta1; a.beta2 = c.beta2; a.eps = c.adam_eps;
+  if (g_sm_count <= 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sm_count <= 0) g_sm_count = 148;
+  }
+  if (cudaMemsetAsync(h->scratch + 4, 0, 3 * sizeof(double), s) != cudaSuccess) { g_err_ppo = "memset failed"; return B2H_ECUDA; }
+  a.n = h->nflat; a.sumsq = h->scratch + 4; a.norm_out = h->scratch + 5; a.arrived = reinterpret_cast<unsigned*>(h->scratch + 6); a.error = h->error;
+  a.max_norm = c.max_grad_norm; a.lr = c.lr; a.beta1 = c.beta1; a.beta2 = c.beta2; a.eps = c.adam_eps;
   a.bc1 = (float)(1.0 - pow((double)c.beta1, (double)step));
   a.bc2_sqrt = (float)sqrt(1.0 - pow((double)c.beta2, (double)step));
-  adam_kernel<<<(int)std::min<int64_t>((h->nflat + 255) / 256, 592), 256, 0, s>>>(a);
+  const int blocks = (int)std::max<long long>(1, std::min<long long>(g_sm_count, (h->nflat / 4 + 255) / 256));
+  apply_kernel<<<blocks, 256, 0, s>>>(a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
   return B2H_OK;
+}
+}  // namespace
+
+int b2h_ppo_apply(B2HPpo* h, float* params_dev, float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t step, float grad_scale,
+                  void* stream_) {
+  if (!h || !params_dev || !grad_dev || !exp_avg_dev || !exp_avg_sq_dev || step < 1) { g_err_ppo = "b2h_ppo_apply: bad argument"; return B2H_EINVAL; }
+  ApplyArgs a;
+  a.p = params_dev; a.g = grad_dev; a.m = exp_avg_dev; a.v = exp_avg_sq_dev; a.grad_scale = grad_scale;
+  a.rank = 0; a.world = 1; a.epoch = 0;
+  for (int j = 0; j < P2P_MAX_RANKS; j++) { a.grad[j] = grad_dev; a.flags[j] = nullptr; }
+  return launch_apply(h, a, step, (cudaStream_t)stream_);
 }
 
 // ---- peer-memory gradient reduction (one node, one process per GPU)
@@ -1185,29 +1220,18 @@ float* b2h_ppo_p2p_grad(B2HPpo* h) { return h && h->comm ? h->comm + (size_t)((h
 
 int b2h_ppo_apply_p2p(B2HPpo* h, float* params_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t step, void* stream_) {
   if (!h || !h->comm || !h->peer_base[h->world - 1] || !params_dev || !exp_avg_dev || !exp_avg_sq_dev || step < 1) { g_err_ppo = "b2h_ppo_apply_p2p: not attached / bad argument"; return B2H_EINVAL; }
-  cudaStream_t s = (cudaStream_t)stream_;
-  const B2HPpoConfig& c = h->cfg;
   h->epoch++;
-  if (cudaMemsetAsync(h->scratch + 4, 0, sizeof(double), s) != cudaSuccess) { g_err_ppo = "memset failed"; return B2H_ECUDA; }
-  P2PArgs p;
+  ApplyArgs a;
   const size_t copy = (size_t)(h->epoch & 1) * h->nflat;
   for (int j = 0; j < h->world; j++) {
     float* base = static_cast<float*>(h->peer_base[j]);
-    p.grad[j] = base + copy;
-    p.flags[j] = reinterpret_cast<uint32_t*>(base + 3 * (size_t)h->nflat);
+    a.grad[j] = base + copy;
+    a.flags[j] = reinterpret_cast<uint32_t*>(base + 3 * (size_t)h->nflat);
   }
-  for (int j = h->world; j < P2P_MAX_RANKS; j++) { p.grad[j] = p.grad[h->rank]; p.flags[j] = p.flags[h->rank]; }
-  p.reduced = h->comm + 2 * (size_t)h->nflat; p.sumsq = h->scratch + 4; p.error = h->error; p.n4 = h->nflat / 4; p.rank = h->rank; p.world = h->world; p.epoch = h->epoch;
-  p2p_reduce_kernel<<<g_sm_count > 0 ? g_sm_count : 148, 256, 0, s>>>(p);
-  AdamArgs a;
-  a.p = params_dev; a.g = p.reduced; a.m = exp_avg_dev; a.v = exp_avg_sq_dev; a.n = h->nflat; a.sumsq = h->scratch + 4; a.norm_out = h->scratch + 5;
-  a.grad_scale = 1.f / (float)h->world; a.max_norm = c.max_grad_norm; a.lr = c.lr; a.beta1 = c.beta1; a.beta2 = c.beta2; a.eps = c.adam_eps;
-  a.bc1 = (float)(1.0 - pow((double)c.beta1, (double)step));
-  a.bc2_sqrt = (float)sqrt(1.0 - pow((double)c.beta2, (double)step));
-  adam_kernel<<<(int)std::min<int64_t>((h->nflat + 255) / 256, 592), 256, 0, s>>>(a);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
-  return B2H_OK;
+  for (int j = h->world; j < P2P_MAX_RANKS; j++) { a.grad[j] = a.grad[h->rank]; a.flags[j] = a.flags[h->rank]; }
+  a.p = params_dev; a.g = h->comm + 2 * (size_t)h->nflat; a.m = exp_avg_dev; a.v = exp_avg_sq_dev; a.grad_scale = 1.f / (float)h->world;
+  a.rank = h->rank; a.world = h->world; a.epoch = h->epoch;
+  return launch_apply(h, a, step, (cudaStream_t)stream_);
 }
 
 int b2h_ppo_train(B2HPpo* h, const float* obs_dev, const float* actions_dev, const float* old_log_probs_dev, const float* advantages_dev,

@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -717,6 +718,7 @@ struct B2HPpo {
   TMaps maps[8];             // fwd1 fwd2 fwd3 dW3 dh2 dW2 dh1 dW1, each [network][A hi, A lo, B hi, B lo, C hi, C lo]
   uint32_t *bits1[2], *bits2[2];   // sign bits of h1 / h2 (one bit per element, [rows][8] words): the ReLU masks of the backward pass
   int nw_obs;                // N tile of the first-layer weight gradient (obs_dim split into equal tiles <= 256)
+  int cluster[8];            // per GEMM: 2 = pairs of CTAs share every B chunk through TMA multicast (its B maps hold half boxes)
   cudaStream_t side;         // the weight-gradient GEMMs of the head and of layer 2 run here, beside the input-gradient chain
   cudaEvent_t ev_fork[2], ev_join;
   // peer-memory gradient reduction: [grad copy 0 | grad copy 1 | reduced | flags] in one IPC-exported allocation
@@ -770,7 +772,7 @@ int setup_tma(B2HPpo* h) {
     return B2H_ECUDA;
   }
   EncodeFn enc = reinterpret_cast<EncodeFn>(fn);
-  const int Bp = roundup(c.max_batch, 128), Hp = roundup(H, 128), Dp = roundup(D, 32);
+  const int Bp = roundup(c.max_batch, 256), Hp = roundup(H, 128), Dp = roundup(D, 32);   // row tiles come in pairs (clusters of two)
   const int tiles_obs = (Dp + 255) / 256;
   h->nw_obs = roundup((Dp + tiles_obs - 1) / tiles_obs, 32);       // MN-major tiles come in groups of 32 columns
   size_t total = 0;
@@ -796,8 +798,18 @@ int setup_tma(B2HPpo* h) {
     CUtensorMap(*m)[6] = nullptr;
     auto gemm_maps = [&](int g, const B2HPpo::TMat& A, int a_mn, const B2HPpo::TMat& Bm, int b_mn, int nw, const B2HPpo::TMat* Cm) {
       m = &h->maps[g].m[n];
+      // M tiles in pairs that share the B tile (batch rows are padded to 256; the weight gradients have H / 128 tiles): each CTA of
+      // a pair loads half of every B chunk and multicasts it, so the B maps hold half boxes
+      // Measured (B200, minibatch 16384): 0.315 ms with the pairs against 0.305 ms without -- what bounds the main loops is
+      // each SM's own ingest (96 KB per K chunk per 0.78 us of MMA = 63 B/clk), which multicast does not lower, not the
+      // aggregate L2 traffic it halves; the pairing adds a cross-CTA hand-off per stage.  So it is off unless B2H_PPO_CLUSTER=1
+      // (the test entry b2h_gemm_tma keeps exercising the multicast path).
+      const bool batch_rows_on_m = !a_mn;
+      static const bool want = getenv("B2H_PPO_CLUSTER") && atoi(getenv("B2H_PPO_CLUSTER")) != 0;
+      h->cluster[g] = (want && nw % 64 == 0 && (batch_rows_on_m || (roundup(H, 128) / 128) % 2 == 0)) ? 2 : 1;
       // results that are operands of later GEMMs leave through TMA stores of {32 columns, 128 rows} swizzled boxes
-      return operand_maps(enc, &(*m)[0], A, a_mn, 128) && operand_maps(enc, &(*m)[2], Bm, b_mn, nw) && (!Cm || operand_maps(enc, &(*m)[4], *Cm, 0, 128));
+      return operand_maps(enc, &(*m)[0], A, a_mn, 128) && operand_maps(enc, &(*m)[2], Bm, b_mn, nw / h->cluster[g]) &&
+             (!Cm || operand_maps(enc, &(*m)[4], *Cm, 0, 128));
     };
     ok = ok && gemm_maps(0, h->tX, 0, h->tW1[n], 0, H, &h->th1[n]);           // fwd1  h1 = relu(X W1^T + b1)
     ok = ok && gemm_maps(1, h->th1[n], 0, h->tW2[n], 0, H, &h->th2[n]);       // fwd2  h2 = relu(h1 W2^T + b2)
@@ -834,8 +846,16 @@ int launch_gemm_t(const B2HPpo* h, int g, TProblem* pr, int precise, bool split,
   a.nsplit = (chunks + a.chunks_per_split - 1) / a.chunks_per_split;
   a.precise = precise;
   a.error = h->error;
-  gemm_t_kernel<<<dim3(pr[0].m_tiles, pr[0].n_tiles, 2 * a.nsplit), 256, TNS * T_STAGE * sizeof(float), s>>>(h->maps[g], a);
-  cudaError_t e = cudaGetLastError();
+  a.cluster = h->cluster[g];
+  if (a.cluster > 1 && pr[0].m_tiles % 2) { g_err_ppo = "internal: odd number of M tiles in a clustered GEMM"; return B2H_EINVAL; }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(pr[0].m_tiles, pr[0].n_tiles, 2 * a.nsplit); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = TNS * T_STAGE * sizeof(float); cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = a.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_t_kernel, h->maps[g], a);
+  if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
   return B2H_OK;
 }
@@ -845,7 +865,7 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
   const B2HPpoConfig& c = h->cfg;
   const int H = c.hidden, D = c.obs_dim, A = c.act_dim;
   const int64_t* o = h->off;
-  const int rows_pad = roundup(n, 128), m_tiles_b = rows_pad / 128, kchunks_b = roundup(n, 32) / 32;
+  const int rows_pad = roundup(n, 256), m_tiles_b = rows_pad / 128, kchunks_b = roundup(n, 32) / 32;
   const int nout[2] = {A, 1};
   // weights -> T-format (they change with every Adam step; 0.3 M floats)
   PackTJobs pj;
@@ -1000,7 +1020,8 @@ int b2h_gemm_tma(const float* a_dev, int a_mn, const float* b_dev, int b_mn, flo
   const int items = (int)std::max(na, nb) / 4;
   pack_t_kernel<<<dim3((items + 255) / 256, 2), 256, 0, s>>>(pj);
   B2HPpo hh;
-  bool ok = operand_maps(enc, &hh.maps[0].m[0][0], ta, a_mn, 128) && operand_maps(enc, &hh.maps[0].m[0][2], tb, b_mn, nw);
+  const int cluster = (nw % 64 == 0 && ((m + 127) / 128) % 2 == 0) ? 2 : 1;   // pairs of M tiles share the B chunks (TMA multicast)
+  bool ok = operand_maps(enc, &hh.maps[0].m[0][0], ta, a_mn, 128) && operand_maps(enc, &hh.maps[0].m[0][2], tb, b_mn, nw / cluster);
   for (int i = 0; i < 4; i++) hh.maps[0].m[1][i] = hh.maps[0].m[0][i];
   for (int i = 4; i < 6; i++) { hh.maps[0].m[0][i] = hh.maps[0].m[0][0]; hh.maps[0].m[1][i] = hh.maps[0].m[0][0]; }
   int rc = B2H_OK;
@@ -1018,9 +1039,15 @@ int b2h_gemm_tma(const float* a_dev, int a_mn, const float* b_dev, int b_mn, flo
     int nsplit = split_k == 1 ? 1 : (split_k > 1 ? std::min(split_k, p.chunks) : std::max(1, std::min(p.chunks, 148 / (p.m_tiles * p.n_tiles))));
     a.chunks_per_split = (p.chunks + nsplit - 1) / nsplit;
     a.nsplit = (p.chunks + a.chunks_per_split - 1) / a.chunks_per_split;
-    a.precise = precise; a.error = error_flag_dev;
-    gemm_t_kernel<<<dim3(p.m_tiles, p.n_tiles, a.nsplit), 256, TNS * T_STAGE * sizeof(float), s>>>(hh.maps[0], a);
-    if (cudaGetLastError() != cudaSuccess) { g_err_ppo = "launch failed"; rc = B2H_ECUDA; }
+    a.precise = precise; a.error = error_flag_dev; a.cluster = cluster;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(p.m_tiles, p.n_tiles, a.nsplit); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = TNS * T_STAGE * sizeof(float); cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_t_kernel, hh.maps[0], a);
+    if (le != cudaSuccess || cudaGetLastError() != cudaSuccess) { g_err_ppo = std::string("launch failed: ") + cudaGetErrorString(le); rc = B2H_ECUDA; }
   }
   if (cudaStreamSynchronize(s) != cudaSuccess && rc == B2H_OK) { g_err_ppo = cudaGetErrorString(cudaGetLastError()); rc = B2H_ECUDA; }
   cudaFree(buf);

@@ -48,6 +48,7 @@ struct TProblem {
 struct TArgs {
   TProblem p[2];
   int nsplit, chunks_per_split, precise;
+  int cluster;               // 1, or 2: pairs of CTAs along the M tiles share every B chunk (each loads half of it and multicasts)
   int* error;
 };
 
@@ -62,6 +63,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw(uint32_t saddr, uint32_t lbo, u
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];\n"
                ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar) : "memory");
+}
+// the same loads delivered to every CTA of the cluster named in `mask` (same shared-memory offset, same mbarrier offset in each)
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3}], [%4], %5;\n"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;\n"
+               ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
 // instruction descriptor kind::tf32 with the operands' major bits (15: A, 16: B; 1 = MN-major)
 __device__ __forceinline__ uint32_t umma_idesc_tf32_major(int m, int n, int a_mn, int b_mn) {
@@ -89,10 +102,17 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
   const int ns = min(TNS_MAX, (TNS * T_STAGE) / stage_floats);
   const uint32_t full0 = smem_u32(&bar_storage[0]), empty0 = smem_u32(&bar_storage[TNS_MAX]);
   const uint32_t accbar = smem_u32(&bar_storage[2 * TNS_MAX]);
+  // Cluster of two CTAs along the M tiles (same B tile): each loads half of every B chunk and multicasts it to both, so a B
+  // chunk crosses L2 -> SM once per pair.  A stage is then only free when BOTH CTAs' MMAs have read it: the commits are
+  // multicast to the pair's empty barriers (count 2).  Both CTAs of a pair take the same early returns (same y / z, m_tiles even).
+  const int csize = a.cluster;
+  uint32_t crank = 0;
+  if (csize > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(crank));
+  const uint16_t cmask = (uint16_t)((1u << csize) - 1u);
   if (threadIdx.x == 0) {
     for (int s = 0; s < ns; s++) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(full0 + 8 * s));    // the TMA thread's arrive.expect_tx + the bytes
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(empty0 + 8 * s));   // tcgen05.commit
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(empty0 + 8 * s), "r"(csize));   // tcgen05.commit of every CTA of the cluster
     }
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(accbar));
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -104,6 +124,7 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
+  if (csize > 1) cluster_sync_all();   // the peer's barriers are initialised before anything of ours can reach them
   const uint32_t tmem = tmem_base_s;
   bool ok = true;
 
@@ -132,7 +153,11 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
             umma_tf32(tmem, al, bh, idesc, 1);
           }
         }
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(empty0 + 8 * s) : "memory");
+        if (csize > 1)
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+                       ::"r"(empty0 + 8 * s), "h"(cmask) : "memory");
+        else
+          asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(empty0 + 8 * s) : "memory");
         if (++s == ns) { s = 0; use++; }
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(accbar) : "memory");
@@ -155,8 +180,18 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
         // chunk, first column group of the tile}
         if (P.a_mn) { tma_load_3d(A_hi, mp + 0, 0, kc * TK, row0 / 32, fullb); if (precise) tma_load_3d(A_lo, mp + 1, 0, kc * TK, row0 / 32, fullb); }
         else        { tma_load_2d(A_hi, mp + 0, kc * TK, row0, fullb);        if (precise) tma_load_2d(A_lo, mp + 1, kc * TK, row0, fullb); }
-        if (P.b_mn) { tma_load_3d(B_hi, mp + 2, 0, kc * TK, col0 / 32, fullb); if (precise) tma_load_3d(B_lo, mp + 3, 0, kc * TK, col0 / 32, fullb); }
-        else        { tma_load_2d(B_hi, mp + 2, kc * TK, col0, fullb);        if (precise) tma_load_2d(B_lo, mp + 3, kc * TK, col0, fullb); }
+        if (csize > 1) {   // this CTA's half of the B chunk, delivered to both CTAs of the pair (the half-box maps are built for it)
+          if (P.b_mn) {
+            const uint32_t off = crank * (uint32_t)(nw / 64) * 4096u;
+            tma_load_3d_mc(B_hi + off, mp + 2, 0, kc * TK, col0 / 32 + (int)crank * (nw / 64), fullb, cmask);
+            if (precise) tma_load_3d_mc(B_lo + off, mp + 3, 0, kc * TK, col0 / 32 + (int)crank * (nw / 64), fullb, cmask);
+          } else {
+            const uint32_t off = crank * (uint32_t)(nw / 2) * 128u;
+            tma_load_2d_mc(B_hi + off, mp + 2, kc * TK, col0 + (int)crank * (nw / 2), fullb, cmask);
+            if (precise) tma_load_2d_mc(B_lo + off, mp + 3, kc * TK, col0 + (int)crank * (nw / 2), fullb, cmask);
+          }
+        } else if (P.b_mn) { tma_load_3d(B_hi, mp + 2, 0, kc * TK, col0 / 32, fullb); if (precise) tma_load_3d(B_lo, mp + 3, 0, kc * TK, col0 / 32, fullb); }
+        else               { tma_load_2d(B_hi, mp + 2, kc * TK, col0, fullb);        if (precise) tma_load_2d(B_lo, mp + 3, kc * TK, col0, fullb); }
         if (++s == ns) { s = 0; use++; }
       }
     }
@@ -312,6 +347,7 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem) : "memory");
+  if (csize > 1) cluster_sync_all();   // nobody leaves while the peer's commits / multicasts may still target its shared memory
 }
 
 // ------------------------------------------------------------------------------------------------ producers of operand planes

@@ -831,6 +831,9 @@ int setup_tma(B2HPpo* h) {
   return B2H_OK;
 }
 
+#ifdef B2H_GEMM_CLK
+long long* g_clkbuf = nullptr;
+#endif
 int launch_gemm_t(const B2HPpo* h, int g, TProblem* pr, int precise, bool split, cudaStream_t s) {
   if (g_sm_count <= 0) {
     int dev = 0;
@@ -841,15 +844,24 @@ int launch_gemm_t(const B2HPpo* h, int g, TProblem* pr, int precise, bool split,
   TArgs a;
   a.p[0] = pr[0]; a.p[1] = pr[1];
   const int tiles = pr[0].m_tiles * pr[0].n_tiles * 2, chunks = pr[0].chunks;
-  int nsplit = split ? std::max(1, std::min(chunks, g_sm_count / std::max(1, tiles))) : 1;
+  int nsplit = split ? std::max(1, std::min(chunks, g_sm_count * T_CTAS / std::max(1, tiles))) : 1;
   a.chunks_per_split = (chunks + nsplit - 1) / nsplit;
   a.nsplit = (chunks + a.chunks_per_split - 1) / a.chunks_per_split;
   a.precise = precise;
   a.error = h->error;
+  a.clk = nullptr;
+#ifdef B2H_GEMM_CLK
+  {   // measurement build: one buffer of time stamps per GEMM of the minibatch (g), read back by tools/gemm_clocks.py
+    static long long* clkbuf = nullptr;
+    if (!clkbuf) { cudaMalloc(&clkbuf, 8 * 8 * 4096 * sizeof(long long)); cudaMemset(clkbuf, 0, 8 * 8 * 4096 * sizeof(long long)); }
+    a.clk = clkbuf + (size_t)g * 8 * 4096;
+    g_clkbuf = clkbuf;
+  }
+#endif
   a.cluster = h->cluster[g];
   if (a.cluster > 1 && pr[0].m_tiles % 2) { g_err_ppo = "internal: odd number of M tiles in a clustered GEMM"; return B2H_EINVAL; }
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(pr[0].m_tiles, pr[0].n_tiles, 2 * a.nsplit); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = TNS * T_STAGE * sizeof(float); cfg.stream = s;
+  cfg.gridDim = dim3(pr[0].m_tiles, pr[0].n_tiles, 2 * a.nsplit); cfg.blockDim = dim3(T_THREADS); cfg.dynamicSmemBytes = TNS * T_STAGE * sizeof(float); cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = a.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -1039,9 +1051,9 @@ int b2h_gemm_tma(const float* a_dev, int a_mn, const float* b_dev, int b_mn, flo
     int nsplit = split_k == 1 ? 1 : (split_k > 1 ? std::min(split_k, p.chunks) : std::max(1, std::min(p.chunks, 148 / (p.m_tiles * p.n_tiles))));
     a.chunks_per_split = (p.chunks + nsplit - 1) / nsplit;
     a.nsplit = (p.chunks + a.chunks_per_split - 1) / a.chunks_per_split;
-    a.precise = precise; a.error = error_flag_dev; a.cluster = cluster;
+    a.precise = precise; a.error = error_flag_dev; a.cluster = cluster; a.clk = nullptr;
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(p.m_tiles, p.n_tiles, a.nsplit); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = TNS * T_STAGE * sizeof(float); cfg.stream = s;
+    cfg.gridDim = dim3(p.m_tiles, p.n_tiles, a.nsplit); cfg.blockDim = dim3(T_THREADS); cfg.dynamicSmemBytes = TNS * T_STAGE * sizeof(float); cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
@@ -1292,6 +1304,13 @@ int b2h_ppo_stats(B2HPpo* h, double stats_host[8], int* error_host, void* stream
   return B2H_OK;
 }
 
+#ifdef B2H_GEMM_CLK
+int b2h_ppo_gemm_clocks(long long* out_host) {   // [8 GEMMs][4096 CTAs][8 stamps]
+  if (!g_clkbuf) return B2H_EINVAL;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(out_host, g_clkbuf, 8 * 8 * 4096 * sizeof(long long), cudaMemcpyDeviceToHost) == cudaSuccess ? B2H_OK : B2H_ECUDA;
+}
+#endif
 const double* b2h_ppo_stats_dev(const B2HPpo* h) { return h ? h->scratch : nullptr; }
 const int* b2h_ppo_error_dev(const B2HPpo* h) { return h ? h->error : nullptr; }
 

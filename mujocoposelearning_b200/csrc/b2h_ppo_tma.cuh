@@ -20,7 +20,14 @@
 #pragma once
 
 constexpr int TK = 32;                       // K per chunk: 32 columns (K-major: one 128-byte swizzle row) or 32 rows (MN-major)
-constexpr int TNS = 2;                       // stages at the widest N; narrower tiles get more (the ring is always 192 KB)
+#ifndef B2H_GEMM_CTAS
+#define B2H_GEMM_CTAS 2
+#endif
+// CTAs per SM: 1 = a 192 KB ring (two stages at N = 256), 16 warps; 2 = two CTAs of 96 KB (one stage at N = 256) and 8 warps
+// each share an SM and its 512 TMEM columns, so that one's prologue / epilogue runs under the other's main loop and the 256
+// tiles of a forward GEMM are one wave (measured: 0.305 -> 0.295 ms per minibatch; the default)
+constexpr int T_CTAS = B2H_GEMM_CTAS;
+constexpr int TNS = T_CTAS == 1 ? 2 : 1;     // stages at the widest N; narrower tiles get more
 constexpr int TNS_MAX = 6;
 constexpr int T_A_PART = 128 * TK;           // floats of one plane of an A chunk (16 KB)
 constexpr int T_B_PART = 256 * TK;           // ... of a B chunk at the widest N (32 KB)
@@ -45,7 +52,13 @@ struct TProblem {
   uint32_t* bits_out;        // epi 0: sign bits of this result (x > 0) for the backward pass, or null
   float* colsum;             // epi 0: column sums of the result are added here (bias gradient), or null
 };
+#ifdef B2H_GEMM_CLK
+#define GCLK(i) do { if (threadIdx.x == (i == 4 || i == 5 ? 64 : 0)) a.clk[(size_t)(blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z)) * 8 + (i)] = clock64(); } while (0)
+#else
+#define GCLK(i) do { } while (0)
+#endif
 struct TArgs {
+  long long* clk;            // B2H_GEMM_CLK builds: eight time stamps per CTA
   TProblem p[2];
   int nsplit, chunks_per_split, precise;
   int cluster;               // 1, or 2: pairs of CTAs along the M tiles share every B chunk (each loads half of it and multicasts)
@@ -73,6 +86,15 @@ __device__ __forceinline__ void tma_load_3d_mc(uint32_t dst, const CUtensorMap* 
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%2, %3, %4}], [%5], %6;\n"
                ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar), "h"(mask) : "memory");
 }
+// named barrier of an epilogue part (128 threads); immediate ids, so that the kernel claims only the barriers it uses (two
+// CTAs share an SM's sixteen)
+template <int NPART>
+__device__ __forceinline__ void part_barrier(int part) {
+  if (part == 0) asm volatile("bar.sync 1, 128;\n" ::: "memory");
+  else if (part == 1) asm volatile("bar.sync 2, 128;\n" ::: "memory");
+  else if (NPART > 2 && part == 2) asm volatile("bar.sync 3, 128;\n" ::: "memory");
+  else if (NPART > 2) asm volatile("bar.sync 4, 128;\n" ::: "memory");
+}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;\n" ::: "memory");
 }
@@ -81,7 +103,9 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32_major(int m, int n, int a_mn
   return umma_idesc_tf32(m, n) | ((uint32_t)(a_mn != 0) << 15) | ((uint32_t)(b_mn != 0) << 16);
 }
 
-__global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ TMaps maps, TArgs a) {
+constexpr int T_THREADS = T_CTAS == 1 ? 512 : 256;   // two roles during the main loop, then epilogue parts of four warps each
+constexpr int T_NPART = T_THREADS / 128, T_ROUNDS = 8 / T_NPART;
+__global__ void __launch_bounds__(T_THREADS, T_CTAS) gemm_t_kernel(const __grid_constant__ TMaps maps, TArgs a) {
   extern __shared__ __align__(1024) unsigned char smem_t[];
   float* stage0 = reinterpret_cast<float*>(smem_t);
   __shared__ __align__(8) unsigned long long bar_storage[2 * TNS_MAX + 1];
@@ -89,6 +113,7 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int prob = blockIdx.z / a.nsplit, split = blockIdx.z - prob * a.nsplit;
   const TProblem P = prob ? a.p[1] : a.p[0];
+  GCLK(0);
   if ((int)blockIdx.x >= P.m_tiles || (int)blockIdx.y >= P.n_tiles) return;
   const int row0 = blockIdx.x * 128, col0 = blockIdx.y * P.nw;
   const int c_begin = split * a.chunks_per_split, c_end = min(P.chunks, c_begin + a.chunks_per_split);
@@ -127,6 +152,7 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
   if (csize > 1) cluster_sync_all();   // the peer's barriers are initialised before anything of ours can reach them
   const uint32_t tmem = tmem_base_s;
   bool ok = true;
+  GCLK(1);
 
   if (warp == 0) {
     if (lane == 0) {   // ---- MMA issuer
@@ -140,6 +166,7 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
       for (int c = 0; c < nchunk && ok; c++) {
         ok = mbar_wait(full0 + 8 * s, use & 1);
         if (!ok) break;
+        if (c == 0) GCLK(2);
         asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
         const uint32_t A_hi = smem_u32(stage0 + s * stage_floats), A_lo = A_hi + T_A_PART * 4, B_hi = A_lo + T_A_PART * 4,
                        B_lo = B_hi + (uint32_t)(stage_floats - 2 * T_A_PART) * 2;
@@ -197,12 +224,13 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
     }
     __syncwarp();
   }
-  {   // ---- epilogue on all eight warps: TMEM lane quadrant = warp % 4 (thread = row of the tile), the two warps of a
-      // quadrant take alternate groups of columns
+  {   // ---- epilogue on all warps: TMEM lane quadrant = warp % 4 (thread = row of the tile); the four warps with the
+      // same warp / 4 form a PART that owns every fourth group of 32 columns and synchronises only with itself
     ok = mbar_wait(accbar, 0) && ok;
     __syncwarp();
+    GCLK(4);
     asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
-    const int quad = warp & 3, half = warp >> 2;
+    const int quad = warp & 3, part = warp >> 2;
     const int r = quad * 32 + lane;
     const int grow = row0 + r;
     const bool first = split == 0;
@@ -210,22 +238,23 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
       // ---- the result is the next GEMM's operand: bias, ReLU / ReLU mask, split into hi / lo, staged in the (now idle)
       // operand ring as 128-byte swizzled rows and written with TMA stores, 32 columns at a time; the column sums of the
       // tile (bias gradient) are taken from the staged copy, the ReLU pattern travels as one bit per element
-      constexpr int NB = (TNS * T_STAGE) / (2 * T_A_PART);          // staging buffers of 32 columns x 128 rows x (hi + lo)
-      static_assert(NB % 2 == 0, "a buffer must come back to the same half");
+      // staging buffers of 32 columns x 128 rows x (hi + lo) = 32 KB in the idle operand ring (six fit): parts 0 and 1 use
+      // buffers {0, 4} and {1, 5} for their two groups, parts 2 and 3 reuse buffer 2 / 3 once the first store has read it
+      static_assert((TNS * T_STAGE) / (2 * T_A_PART) >= (T_NPART == 4 ? 6 : 2), "staging buffers");
       const CUtensorMap* cmap = maps.m[prob ? 1 : 0] + 4;
-      uint32_t in_bits[8], out_bits[4];
+      uint32_t in_bits[8], out_bits[T_ROUNDS];
       if (P.bits_in) {
         const uint4* bp = reinterpret_cast<const uint4*>(P.bits_in + (size_t)grow * 8);
         const uint4 b0 = __ldg(bp), b1 = __ldg(bp + 1);
         in_bits[0] = b0.x; in_bits[1] = b0.y; in_bits[2] = b0.z; in_bits[3] = b0.w; in_bits[4] = b1.x; in_bits[5] = b1.y; in_bits[6] = b1.z; in_bits[7] = b1.w;
       }
 #pragma unroll
-      for (int g = 0; g < 4; g++) out_bits[g] = 0u;
+      for (int gp = 0; gp < T_ROUNDS; gp++) out_bits[gp] = 0u;
 #pragma unroll
-      for (int gp = 0; gp < 4; gp++) {
-        if (gp * 64 >= nw) break;                                  // uniform over the CTA: both halves keep the barrier count
-        const int g = 2 * gp + half;
+      for (int gp = 0; gp < T_ROUNDS; gp++) {
+        const int g = T_NPART * gp + part;
         const bool active = g * 32 < nw;
+        if (!active) break;                                        // uniform over the part
         uint32_t v[32];
 #pragma unroll
         for (int hh = 0; hh < 2; hh++)
@@ -239,7 +268,7 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
         const int colb = col0 + g * 32;
         float x[32];
         uint32_t word = 0u;
-        if (P.bias && active) {                                    // N is a multiple of 32 for operand-plane results
+        if (P.bias) {                                              // N is a multiple of 32 for operand-plane results
 #pragma unroll
           for (int q = 0; q < 8; q++) {
             const float4 b4 = __ldg(reinterpret_cast<const float4*>(P.bias + colb) + q);
@@ -247,7 +276,15 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
             v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + b4.z); v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + b4.w);
           }
         }
-        const uint32_t gate = P.bits_in ? (half ? in_bits[2 * gp + 1] : in_bits[2 * gp]) : 0xFFFFFFFFu;
+        uint32_t gate = 0xFFFFFFFFu;
+        if (P.bits_in) {
+          if constexpr (T_NPART == 4) {
+            const uint32_t lo2 = part & 1 ? in_bits[4 * gp + 1] : in_bits[4 * gp], hi2 = part & 1 ? in_bits[4 * gp + 3] : in_bits[4 * gp + 2];
+            gate = part & 2 ? hi2 : lo2;
+          } else {
+            gate = part & 1 ? in_bits[2 * gp + 1] : in_bits[2 * gp];
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 32; q++) {
           float y = __uint_as_float(v[q]);
@@ -257,16 +294,16 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
           x[q] = y;
         }
         out_bits[gp] = word;
-        const int b = g % NB;
+        // four parts, six buffers: parts 0 / 1 use {0, 4} / {1, 5}, parts 2 / 3 reuse 2 / 3; two parts: one buffer each, reused every round
+        const int b = T_NPART == 4 ? (part < 2 ? part + 4 * gp : part) : part;
         float* s_hi = stage0 + b * (2 * T_A_PART);
         float* s_lo = s_hi + T_A_PART;
-        if (gp * 2 >= NB) {       // the TMA store that read this buffer NB groups ago (same half) must have finished reading it
-          if (r == 0) asm volatile("cp.async.bulk.wait_group.read %0;\n" ::"n"(NB / 2 - 1) : "memory");
-          asm volatile("bar.sync 1, 256;\n" ::: "memory");
+        if (T_NPART == 4 ? (gp == 1 && part >= 2) : gp >= 1) {   // the TMA store of this part's previous group must have finished reading the buffer
+          if (r == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
+          part_barrier<T_NPART>(part);
         }
 #pragma unroll
         for (int q = 0; q < 8; q++) {
-          if (!active) break;
           float4 hi, lo;
           split1(x[4 * q + 0], hi.x, lo.x); split1(x[4 * q + 1], hi.y, lo.y); split1(x[4 * q + 2], hi.z, lo.z); split1(x[4 * q + 3], hi.w, lo.w);
           const int off = r * 32 + ((q ^ (r & 7)) << 2);             // 128-byte swizzle: 16-byte chunk index ^ (row % 8)
@@ -274,15 +311,15 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
           *reinterpret_cast<float4*>(s_lo + off) = lo;
         }
         asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-        asm volatile("bar.sync 1, 256;\n" ::: "memory");
-        if (r == 0 && active) {
+        part_barrier<T_NPART>(part);
+        if (r == 0) {
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n"
                        ::"l"(cmap + 0), "r"(colb), "r"(row0), "r"(smem_u32(s_hi)) : "memory");
           asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];\n"
                        ::"l"(cmap + 1), "r"(colb), "r"(row0), "r"(smem_u32(s_lo)) : "memory");
           asm volatile("cp.async.bulk.commit_group;\n" ::: "memory");
         }
-        if (P.colsum && active) { // thread = (column of the group, quarter of the rows)
+        if (P.colsum) {           // thread = (column of the group, quarter of the rows)
           const int col = r & 31, rq = r >> 5;
           float acc = 0.f;
 #pragma unroll 8
@@ -294,14 +331,16 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
           if (colb + col < P.N) atomicAdd(P.colsum + colb + col, acc);
         }
       }
-      if (P.bits_out) {           // each half owns the words of its groups (even / odd)
+      if (P.bits_out) {           // each part owns the words of its groups
         uint32_t* bp = P.bits_out + (size_t)grow * 8;
 #pragma unroll
-        for (int gp = 0; gp < 4; gp++) bp[2 * gp + half] = out_bits[gp];
+        for (int gp = 0; gp < T_ROUNDS; gp++)
+          if ((T_NPART * gp + part) * 32 < nw) bp[T_NPART * gp + part] = out_bits[gp];
       }
+      GCLK(5);
       if (r == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");   // shared memory stays valid until the stores have read it
     } else if (ok) {
-      for (int c0 = half * 16; c0 < nw; c0 += 32) {
+      for (int c0 = part * 16; c0 < nw; c0 += 16 * T_NPART) {
         uint32_t v[16];
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -345,6 +384,7 @@ __global__ void __launch_bounds__(256, 1) gemm_t_kernel(const __grid_constant__ 
   if (!ok) atomicExch(a.error, 1);
   asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory");
   __syncthreads();
+  GCLK(6);
   asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory");
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem) : "memory");
   if (csize > 1) cluster_sync_all();   // nobody leaves while the peer's commits / multicasts may still target its shared memory

@@ -71,6 +71,17 @@ class MlpPolicyParams:
             dst.copy_(sd[k].detach().to(torch.float32).reshape(dst.shape))
         return self
 
+    SB3_KEYS = ["mlp_extractor.policy_net.0.weight", "mlp_extractor.policy_net.0.bias", "mlp_extractor.policy_net.2.weight",
+                "mlp_extractor.policy_net.2.bias", "action_net.weight", "action_net.bias",
+                "mlp_extractor.value_net.0.weight", "mlp_extractor.value_net.0.bias", "mlp_extractor.value_net.2.weight",
+                "mlp_extractor.value_net.2.bias", "value_net.weight", "value_net.bias", "log_std"]
+
+    def to_sb3_state_dict(self):
+        """The inverse of ``from_sb3_state_dict``: tensors under the keys of SB3's ActorCriticPolicy (``policy.load_state_dict``
+        of a ``PPO("MlpPolicy", ..., policy_kwargs=dict(activation_fn=nn.ReLU, net_arch=dict(pi=[h, h], vf=[h, h])))``), so that
+        a policy trained here runs in the reference's ``generate_trajectories.py`` / ``model.predict``."""
+        return {k: t.detach().clone().cpu() for k, t in zip(self.SB3_KEYS, self.pi + self.vf + [self.log_std])}
+
     def n_params(self):
         return sum(t.numel() for t in self.pi + self.vf) + self.log_std.numel()
 

@@ -324,6 +324,28 @@ class PPOTrainer:
                 stats = dict(policy_loss=pl, value_loss=vl, clip_fraction=cf)
         return {k: v.clone() for k, v in stats.items()}
 
+    def state_dict(self):
+        """Everything ``model.save`` keeps for resuming (train_sb3.py:234): parameters, Adam moments and step, counters."""
+        if self.kernels is not None:
+            opt = dict(exp_avg=self.kernels.exp_avg.clone(), exp_avg_sq=self.kernels.exp_avg_sq.clone(), step=self.kernels.step)
+        else:
+            opt = self.opt.state_dict()
+        return dict(flat=self.params.flat.detach().clone(), optimizer=opt, iterations=self.iterations, num_timesteps=self.col.num_timesteps,
+                    update_impl=self.update_impl, generator=self.gen.get_state())
+
+    def load_state_dict(self, sd):
+        if sd["update_impl"] != self.update_impl:
+            raise ValueError(f"checkpoint was written by update_impl={sd['update_impl']!r}")
+        with torch.no_grad():
+            self.params.flat.copy_(sd["flat"])
+        if self.kernels is not None:
+            self.kernels.exp_avg.copy_(sd["optimizer"]["exp_avg"]); self.kernels.exp_avg_sq.copy_(sd["optimizer"]["exp_avg_sq"])
+            self.kernels.step = int(sd["optimizer"]["step"])
+        else:
+            self.opt.load_state_dict(sd["optimizer"])
+        self.iterations, self.col.num_timesteps = int(sd["iterations"]), int(sd["num_timesteps"])
+        self.gen.set_state(sd["generator"])
+
     def allreduce_ms(self):
         """Device time spent in the gradient all-reduces since the last call (needs ``time_allreduce``; synchronises)."""
         torch.cuda.synchronize(self.b.device)

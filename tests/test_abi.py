@@ -89,3 +89,18 @@ def test_ppo_parameter_layout_matches_python(lib):
     cfg = abi.B2HPpoConfig()
     h = C.c_void_p()
     assert lib.b2h_ppo_create(C.byref(cfg), C.byref(h)) == abi.EINVAL      # zero shapes are refused before any device work
+
+
+def test_policy_parameters_round_trip_through_the_sb3_state_dict():
+    """MlpPolicyParams <-> the keys of SB3's ActorCriticPolicy (what PPO.load(...).policy.state_dict() holds): a policy trained
+    here loads into the reference's tooling and back; all tensors are views of one flat vector."""
+    import torch
+    from mujocoposelearning_b200.policy import MlpPolicyParams
+    p = MlpPolicyParams(obs_dim=53, act_dim=21, hidden=64, device="cpu", seed=3)
+    p.log_std.copy_(torch.linspace(-1, 0, 21))
+    sd = p.to_sb3_state_dict()
+    assert sd["mlp_extractor.policy_net.0.weight"].shape == (64, 53) and sd["action_net.weight"].shape == (21, 64) and sd["value_net.weight"].shape == (1, 64)
+    q = MlpPolicyParams.from_sb3_state_dict(sd, device="cpu")
+    assert torch.equal(q.flat, p.flat) and q.offsets == p.offsets
+    q.flat.zero_()
+    assert all(float(t.abs().sum()) == 0 for t in q.pi + q.vf + [q.log_std])      # views, not copies

@@ -114,6 +114,27 @@ def test_ppo_iteration_updates_policy_and_stats():
     assert s2["timesteps"] == 2 * 26 * 512 and float(s2["value_loss"]) == float(s2["value_loss"])
 
 
+def test_trainer_checkpoint_round_trip():
+    """PPOTrainer.state_dict / load_state_dict (what model.save / PPO.load keep, train_sb3.py:234): parameters, Adam moments,
+    step and the minibatch RNG survive; a resumed trainer makes the same update on the same rollout buffers."""
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    from mujocoposelearning_b200.ppo import PPOTrainer
+    mk = lambda: PPOTrainer(HumanoidBatch(128, frame_skip=3, duration=10.0, reward_type="stand", seed=4), n_steps=8, batch_size=512, n_epochs=2, seed=3)
+    a = mk()
+    a.iterate()
+    sd = a.state_dict()
+    b = mk()
+    b.load_state_dict(sd)
+    assert torch.equal(a.params.flat, b.params.flat) and b.kernels.step == a.kernels.step == 4 and b.iterations == 1
+    for name in ("obs", "actions", "log_probs", "advantages", "returns"):        # the same rollout in both buffers
+        getattr(b.col, name).copy_(getattr(a.col, name))
+    a.update(); b.update()
+    torch.cuda.synchronize()
+    assert float((a.params.flat - b.params.flat).abs().max()) < 1e-6              # red.global.add order is the only difference
+    assert torch.equal(a.kernels.exp_avg != 0, b.kernels.exp_avg != 0)
+    a.b.close(); b.b.close()
+
+
 def _twin_collectors(n, n_steps, duration, seed, **kw):
     from mujocoposelearning_b200.batch import HumanoidBatch
     from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams, RolloutCollector

@@ -379,7 +379,9 @@ int b2h_ppo_p2p_export(B2HPpo* h, void* ipc_handle_out64);
 int b2h_ppo_p2p_attach(B2HPpo* h, int rank, int world, const void* ipc_handles);
 float* b2h_ppo_p2p_grad(B2HPpo* h);
 int b2h_ppo_apply_p2p(B2HPpo* h, float* params_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t step, void* stream);
-/* Statistics of the last minibatch (8 doubles) and the tensor pipeline's timeout flag; synchronises the stream. */
+/* Statistics of the last minibatch (8 doubles) and the error flag (0 = fine; 1 = a tensor / TMA pipeline wait exceeded its bound,
+ * 2 = a peer rank never signalled its gradient, 3 = the apply kernel's grid barrier timed out: all waits in the kernels are bounded,
+ * a failure raises this flag instead of hanging the GPU); synchronises the stream. */
 int b2h_ppo_stats(B2HPpo* h, double stats_host[8], int* error_host, void* stream);
 const double* b2h_ppo_stats_dev(const B2HPpo* h);
 const int* b2h_ppo_error_dev(const B2HPpo* h);

@@ -120,7 +120,9 @@ class PpoKernels:
         out, err = (C.c_double * 8)(), C.c_int(0)
         self._check(self.lib.b2h_ppo_stats(self.h, out, C.byref(err), self._stream()))
         if err.value:
-            raise RuntimeError("tcgen05 GEMM pipeline timed out during the PPO update (mbarrier wait exceeded its bound)")
+            what = {1: "a tcgen05 / TMA pipeline wait exceeded its bound", 2: "a peer rank never signalled its gradient (cross-rank flag barrier timed out)",
+                    3: "the grid barrier of the apply kernel timed out"}.get(err.value, f"error flag {err.value}")
+            raise RuntimeError(f"PPO update kernels: {what}; the update that raised this flag is not to be trusted")
         return dict(policy_loss=out[0], value_loss=out[1], clip_fraction=out[2], approx_kl=out[3], grad_norm=out[5])
 
 

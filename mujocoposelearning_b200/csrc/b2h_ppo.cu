@@ -411,6 +411,7 @@ struct LossArgs {
   int rows_pad;
   float *g_b3_pi, *g_b3_vf, *g_log_std;
   double* stats;                      // [0] policy loss, [1] value loss, [2] clip fraction (sums over the minibatch / n), [3] approx kl
+  const double* moments;              // advantage mean and unbiased std of the minibatch (adv_moments_kernel)
   int n, act_dim;
   float clip, ent_coef, vf_coef;
   int normalize;
@@ -420,133 +421,124 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float warp_sum_f(float v) {
-  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+
+// Advantage moments of the minibatch, once: mean and torch.std (unbiased) in double -> moments[0], moments[1].  One CTA; it
+// runs on the side stream while the forward GEMMs run (the loss kernel is the first to need it).
+__global__ void __launch_bounds__(1024) adv_moments_kernel(const float* __restrict__ adv, int n, double* moments) {
+  __shared__ double red[64];
+  double s = 0.0, q = 0.0;
+  const int n4 = (((uintptr_t)adv & 15) == 0) ? n / 4 : 0;
+  for (int i = threadIdx.x; i < n4; i += 1024) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(adv) + i);
+    s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+    q += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+  }
+  for (int i = 4 * n4 + threadIdx.x; i < n; i += 1024) { const double v = (double)__ldg(adv + i); s += v; q += v * v; }
+  s = warp_sum_d(s); q = warp_sum_d(q);
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = s; red[32 + (threadIdx.x >> 5)] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double ts = 0.0, tq = 0.0;
+    for (int w = 0; w < 32; w++) { ts += red[w]; tq += red[32 + w]; }
+    const double m = ts / n;
+    moments[0] = m;
+    moments[1] = n > 1 ? sqrt(fmax(tq - ts * m, 0.0) / (n - 1)) : 1.0;
+  }
 }
 
-// Every CTA computes the advantage moments of the whole minibatch itself (n floats from L2: cheaper than another launch and
-// bit-identical in every CTA), then one thread per sample.
-constexpr int LOSS_NT = 128, LOSS_NW = LOSS_NT / 32;
+// Eight lanes per sample, four action dimensions per lane (one float4 of the head output): coalesced reads of the means and
+// writes of the gradient planes, three shuffles for the log-probability, nine values per thread to reduce for the head-bias /
+// log_std gradients.  Lane 0 of a sample carries the value-network terms and the statistics.
+constexpr int LOSS_NT = 256, LOSS_ROWS = LOSS_NT / 8;
 __global__ void __launch_bounds__(LOSS_NT) ppo_loss_kernel(LossArgs L) {
-  __shared__ double red[2 * LOSS_NW];
-  __shared__ float fred[LOSS_NW][2 * MAX_ACT + 1];
-  __shared__ double s_mean, s_std;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  double amean = 0.0, astd = 1.0;
-  if (L.normalize && L.n > 1) {   // (adv - mean) / (std + 1e-8), torch.std: unbiased.  One pass: sums of x and x^2 in double
-    double s = 0.0, q = 0.0;
-    const int n4 = (((uintptr_t)L.adv & 15) == 0) ? L.n / 4 : 0;
-    for (int i = tid; i < n4; i += LOSS_NT) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(L.adv) + i);
-      s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
-      q += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
-    }
-    for (int i = 4 * n4 + tid; i < L.n; i += LOSS_NT) { const double v = (double)__ldg(L.adv + i); s += v; q += v * v; }
-    s = warp_sum_d(s); q = warp_sum_d(q);
-    if (lane == 0) { red[warp] = s; red[LOSS_NW + warp] = q; }
-    __syncthreads();
-    if (tid == 0) {
-      double ts = 0.0, tq = 0.0;
-      for (int w = 0; w < LOSS_NW; w++) { ts += red[w]; tq += red[LOSS_NW + w]; }
-      const double m = ts / L.n;
-      s_mean = m; s_std = sqrt(fmax(tq - ts * m, 0.0) / (L.n - 1));
-    }
-    __syncthreads();
-    amean = s_mean; astd = s_std;
-  }
-  const int i = blockIdx.x * LOSS_NT + tid;
+  __shared__ float fred[LOSS_NT / 32][8][9];
+  __shared__ double dred[LOSS_NT / 32][4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, l8 = tid & 7;
+  const int i = blockIdx.x * LOSS_ROWS + (tid >> 3);
   const bool live = i < L.n;
-  float pl = 0.f, vl = 0.f, cf = 0.f, kl = 0.f, dv = 0.f;
-  float dm[MAX_ACT], dls[MAX_ACT];
+  const int j0 = 4 * l8;
+  float ls[4], istd[4], z[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < MAX_ACT; j++) { dm[j] = 0.f; dls[j] = 0.f; }
-  const float inv_n = 1.f / (float)L.n;
+  for (int q = 0; q < 4; q++) { ls[q] = j0 + q < L.act_dim ? __ldg(L.log_std + j0 + q) : 0.f; istd[q] = __expf(-ls[q]); }
+  float part = 0.f;
   if (live) {
-    const float a = L.normalize && L.n > 1 ? (float)(((double)L.adv[i] - amean)) / ((float)astd + 1e-8f) : L.adv[i];
-    float logp = 0.f;
-    float z[MAX_ACT], istd[MAX_ACT];
+    const float4 m4 = *reinterpret_cast<const float4*>(L.mean + (size_t)i * OUT_LD + j0);
+    const float mu[4] = {m4.x, m4.y, m4.z, m4.w};
 #pragma unroll
-    for (int j = 0; j < MAX_ACT; j++) {
-      z[j] = 0.f; istd[j] = 0.f;
-      if (j < L.act_dim) {
-        const float ls = __ldg(L.log_std + j);
-        istd[j] = __expf(-ls);
-        z[j] = (L.act[(size_t)i * L.act_dim + j] - L.mean[(size_t)i * OUT_LD + j]) * istd[j];
-        logp += -0.5f * z[j] * z[j] - ls - 0.9189385332046727f;
+    for (int q = 0; q < 4; q++)
+      if (j0 + q < L.act_dim) {
+        z[q] = (L.act[(size_t)i * L.act_dim + j0 + q] - mu[q]) * istd[q];
+        part += -0.5f * z[q] * z[q] - ls[q] - 0.9189385332046727f;
       }
-    }
+  }
+  part += __shfl_xor_sync(0xffffffffu, part, 1); part += __shfl_xor_sync(0xffffffffu, part, 2); part += __shfl_xor_sync(0xffffffffu, part, 4);
+  const float logp = part;
+  float pl = 0.f, vl = 0.f, cf = 0.f, kl = 0.f, dv = 0.f, glp = 0.f;
+  if (live) {
+    const float inv_n = 1.f / (float)L.n;
+    float a = L.adv[i];
+    if (L.normalize && L.n > 1) a = (float)((double)a - L.moments[0]) / ((float)L.moments[1] + 1e-8f);   // (adv - mean) / (std + 1e-8)
     const float lr = logp - L.olp[i];
     const float ratio = expf(lr);
     const float s1 = a * ratio, s2 = a * fminf(fmaxf(ratio, 1.f - L.clip), 1.f + L.clip);
-    pl = -fminf(s1, s2);
     const bool inside = ratio >= 1.f - L.clip && ratio <= 1.f + L.clip;
     // d(-min(s1, s2)) / d logp: s1 carries a * ratio; s2 carries it only inside the clip range (ties split evenly, same total)
-    const float glp = (inside || s1 < s2) ? -a * ratio * inv_n : 0.f;
-    cf = fabsf(ratio - 1.f) > L.clip ? 1.f : 0.f;
-    kl = (ratio - 1.f) - lr;
-    const float v = L.value[(size_t)i * OUT_LD], diff = v - L.ret[i];
-    vl = diff * diff;
-    dv = L.vf_coef * 2.f * diff * inv_n;
-#pragma unroll
-    for (int j = 0; j < MAX_ACT; j++)
-      if (j < L.act_dim) { dm[j] = glp * z[j] * istd[j]; dls[j] = glp * (z[j] * z[j] - 1.f); }
-    if (L.dmean) {
-      float4* drow = reinterpret_cast<float4*>(L.dmean + (size_t)i * OUT_LD);
-#pragma unroll
-      for (int q = 0; q < OUT_LD / 4; q++) drow[q] = make_float4(dm[4 * q], dm[4 * q + 1], dm[4 * q + 2], dm[4 * q + 3]);
-      float4* vrow = reinterpret_cast<float4*>(L.dvalue + (size_t)i * OUT_LD);
-      vrow[0] = make_float4(dv, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int q = 1; q < OUT_LD / 4; q++) vrow[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    glp = (inside || s1 < s2) ? -a * ratio * inv_n : 0.f;
+    if (l8 == 0) {
+      pl = -fminf(s1, s2);
+      cf = fabsf(ratio - 1.f) > L.clip ? 1.f : 0.f;
+      kl = (ratio - 1.f) - lr;
+      const float diff = L.value[(size_t)i * OUT_LD] - L.ret[i];
+      vl = diff * diff;
+      dv = L.vf_coef * 2.f * diff * inv_n;
     }
   }
-  if (!L.dmean && i < L.rows_pad) {   // split planes [rows_pad][32]; rows between n and the tile boundary are zeros (they enter the weight-gradient sums)
-    const size_t off = (size_t)i * OUT_LD;
+  float dm[4], dls[4];
 #pragma unroll
-    for (int q = 0; q < OUT_LD / 4; q++) {
-      float4 hi, lo;
-      split1(dm[4 * q], hi.x, lo.x); split1(dm[4 * q + 1], hi.y, lo.y); split1(dm[4 * q + 2], hi.z, lo.z); split1(dm[4 * q + 3], hi.w, lo.w);
-      *reinterpret_cast<float4*>(L.dt_hi[0] + off + 4 * q) = hi;
-      *reinterpret_cast<float4*>(L.dt_lo[0] + off + 4 * q) = lo;
-      float4 vh = make_float4(0.f, 0.f, 0.f, 0.f), vl = vh;
-      if (q == 0) split1(dv, vh.x, vl.x);
-      *reinterpret_cast<float4*>(L.dt_hi[1] + off + 4 * q) = vh;
-      *reinterpret_cast<float4*>(L.dt_lo[1] + off + 4 * q) = vl;
-    }
+  for (int q = 0; q < 4; q++) {
+    const bool on = live && j0 + q < L.act_dim;
+    dm[q] = on ? glp * z[q] * istd[q] : 0.f;
+    dls[q] = on ? glp * (z[q] * z[q] - 1.f) : 0.f;
   }
-  // block reductions: head bias gradients (column sums of dmean / dvalue), log_std gradient, statistics
+  // gradients with respect to the head outputs: rows beyond the minibatch (up to the tile boundary) are zeros
+  if (L.dmean) {
+    if (live) {
+      *reinterpret_cast<float4*>(L.dmean + (size_t)i * OUT_LD + j0) = make_float4(dm[0], dm[1], dm[2], dm[3]);
+      *reinterpret_cast<float4*>(L.dvalue + (size_t)i * OUT_LD + j0) = make_float4(l8 == 0 ? dv : 0.f, 0.f, 0.f, 0.f);
+    }
+  } else if (i < L.rows_pad) {
+    const size_t off = (size_t)i * OUT_LD + j0;
+    float4 hi, lo;
+    split1(dm[0], hi.x, lo.x); split1(dm[1], hi.y, lo.y); split1(dm[2], hi.z, lo.z); split1(dm[3], hi.w, lo.w);
+    *reinterpret_cast<float4*>(L.dt_hi[0] + off) = hi;
+    *reinterpret_cast<float4*>(L.dt_lo[0] + off) = lo;
+    float4 vh = make_float4(0.f, 0.f, 0.f, 0.f), vlo = vh;
+    if (l8 == 0) split1(dv, vh.x, vlo.x);
+    *reinterpret_cast<float4*>(L.dt_hi[1] + off) = vh;
+    *reinterpret_cast<float4*>(L.dt_lo[1] + off) = vlo;
+  }
+  // ---- reductions.  Column sums: the four samples of a warp that share a lane position (xor 8, 16), then over the warps
+  float red9[9] = {dm[0], dm[1], dm[2], dm[3], dls[0], dls[1], dls[2], dls[3], dv};
 #pragma unroll
-  for (int j = 0; j < MAX_ACT; j++) {
-    if (j < L.act_dim) {
-      const float s = warp_sum_f(dm[j]), t = warp_sum_f(dls[j]);
-      if (lane == 0) { fred[warp][j] = s; fred[warp][MAX_ACT + j] = t; }
-    }
+  for (int k = 0; k < 9; k++) { red9[k] += __shfl_xor_sync(0xffffffffu, red9[k], 8); red9[k] += __shfl_xor_sync(0xffffffffu, red9[k], 16); }
+  if (lane < 8) {
+#pragma unroll
+    for (int k = 0; k < 9; k++) fred[warp][lane][k] = red9[k];
   }
-  {
-    const float s = warp_sum_f(dv);
-    if (lane == 0) fred[warp][2 * MAX_ACT] = s;
-  }
+  const double st[4] = {warp_sum_d((double)pl), warp_sum_d((double)vl), warp_sum_d((double)cf), warp_sum_d((double)kl)};
+  if (lane == 0) { dred[warp][0] = st[0]; dred[warp][1] = st[1]; dred[warp][2] = st[2]; dred[warp][3] = st[3]; }
   __syncthreads();
-  if (tid < 2 * MAX_ACT + 1) {
-    const int j = tid < MAX_ACT ? tid : tid - MAX_ACT;
-    if (tid == 2 * MAX_ACT || j < L.act_dim) {
-      float s = 0.f;
-      for (int w = 0; w < LOSS_NW; w++) s += fred[w][tid];
-      if (tid == 2 * MAX_ACT) atomicAdd(L.g_b3_vf, s);
-      else if (tid < MAX_ACT) atomicAdd(L.g_b3_pi + j, s);
-      else atomicAdd(L.g_log_std + j, s - (blockIdx.x == 0 ? L.ent_coef : 0.f));   // entropy = sum(log_std) + const; loss has -ent_coef * entropy
-    }
-  }
-  __syncthreads();
-  const double st[4] = {(double)pl, (double)vl, (double)cf, (double)kl};
-#pragma unroll
-  for (int k = 0; k < 4; k++) {
-    const double s = warp_sum_d(st[k]);
-    if (lane == 0) red[warp] = s;
-    __syncthreads();
-    if (tid == 0) { double t = 0.0; for (int w = 0; w < LOSS_NW; w++) t += red[w]; atomicAdd(L.stats + k, t / L.n); }
-    __syncthreads();
+  if (tid < 72) {               // (lane position, value): 8 x 9
+    const int lp = tid / 9, k = tid - 9 * lp;
+    float t = 0.f;
+    for (int w = 0; w < LOSS_NT / 32; w++) t += fred[w][lp][k];
+    if (k < 4) { if (4 * lp + k < L.act_dim) atomicAdd(L.g_b3_pi + 4 * lp + k, t); }
+    else if (k < 8) { if (4 * lp + k - 4 < L.act_dim) atomicAdd(L.g_log_std + 4 * lp + k - 4, t - (blockIdx.x == 0 ? L.ent_coef : 0.f)); }   // entropy = sum(log_std) + const
+    else if (lp == 0) atomicAdd(L.g_b3_vf, t);
+  } else if (tid >= 96 && tid < 100) {
+    double t = 0.0;
+    for (int w = 0; w < LOSS_NT / 32; w++) t += dred[w][tid - 96];
+    atomicAdd(L.stats + (tid - 96), t / L.n);
   }
 }
 
@@ -720,7 +712,8 @@ struct B2HPpo {
   int nw_obs;                // N tile of the first-layer weight gradient (obs_dim split into equal tiles <= 256)
   int cluster[8];            // per GEMM: 2 = pairs of CTAs share every B chunk through TMA multicast (its B maps hold half boxes)
   cudaStream_t side;         // the weight-gradient GEMMs of the head and of layer 2 run here, beside the input-gradient chain
-  cudaEvent_t ev_fork[2], ev_join;
+  cudaEvent_t ev_fork[2], ev_join, ev_moments;
+  double* moments;           // advantage mean / std of the minibatch (device)
   // peer-memory gradient reduction: [grad copy 0 | grad copy 1 | reduced | flags] in one IPC-exported allocation
   float* comm;
   size_t comm_floats;
@@ -824,7 +817,8 @@ int setup_tma(B2HPpo* h) {
   cudaError_t e = cudaFuncSetAttribute(gemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TNS * T_STAGE * sizeof(float)));
   if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
   if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_fork[0], cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_fork[1], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_fork[1], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_moments, cudaEventDisableTiming) != cudaSuccess) {
     g_err_ppo = "stream / event creation failed";
     return B2H_ECUDA;
   }
@@ -897,6 +891,10 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
   g.x_hi = h->tX.hi; g.x_lo = h->tX.lo; g.act = h->act; g.olp = h->olp; g.a = h->adv; g.r = h->ret; g.scratch = h->scratch;
   g.n_rows = n; g.rows_pad = rows_pad; g.obs_dim = D; g.ld = h->tX.ld; g.act_dim = A;
   gather_t_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, s>>>(g);
+  // the advantage moments of the minibatch: one small CTA on the side stream, under the forward GEMMs
+  if (cudaEventRecord(h->ev_fork[0], s) != cudaSuccess || cudaStreamWaitEvent(h->side, h->ev_fork[0], 0) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
+  adv_moments_kernel<<<1, 1024, 0, h->side>>>(h->adv, n, h->moments);
+  if (cudaEventRecord(h->ev_moments, h->side) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
 
   auto base = [&](int a_mn, int b_mn, int m_tiles, int n_tiles, int nw, int chunks) {
     TProblem p;
@@ -930,7 +928,9 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
   for (int k = 0; k < 2; k++) { L.dt_hi[k] = h->tdout[k].hi; L.dt_lo[k] = h->tdout[k].lo; }
   L.g_b3_pi = G + o[5]; L.g_b3_vf = G + o[11]; L.g_log_std = G + o[12]; L.stats = h->scratch;
   L.n = n; L.act_dim = A; L.clip = c.clip_range; L.ent_coef = c.ent_coef; L.vf_coef = c.vf_coef; L.normalize = c.normalize_advantage;
-  ppo_loss_kernel<<<(rows_pad + LOSS_NT - 1) / LOSS_NT, LOSS_NT, 0, s>>>(L);
+  L.moments = h->moments;
+  if (cudaStreamWaitEvent(s, h->ev_moments, 0) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
+  ppo_loss_kernel<<<(rows_pad + LOSS_ROWS - 1) / LOSS_ROWS, LOSS_NT, 0, s>>>(L);
   // ---- backward
   for (int k = 0; k < 2; k++) {   // dW3^T [H, nout] = h2^T dout, written transposed into the [nout, H] gradient
     pr[k] = base(1, 1, h_tiles, 1, 32, kchunks_b);
@@ -1089,7 +1089,8 @@ int b2h_ppo_create(const B2HPpoConfig* cfg, B2HPpo** out) {
   cudaMemset(base, 0, floats * sizeof(float) + 8 * sizeof(double) + 64);
   float* p = base;
   auto take = [&](size_t n) { float* r = p; p += (n + 3) & ~(size_t)3; return r; };
-  h->scratch = reinterpret_cast<double*>(take(16));
+  h->scratch = reinterpret_cast<double*>(take(32));
+  h->moments = h->scratch + 8;
   h->error = reinterpret_cast<int*>(take(4));
   h->X = take(B * cfg->obs_dim); h->act = take(B * cfg->act_dim); h->olp = take(B); h->adv = take(B); h->ret = take(B);
   for (int n = 0; n < 2; n++) {
@@ -1097,7 +1098,7 @@ int b2h_ppo_create(const B2HPpoConfig* cfg, B2HPpo** out) {
     h->out[n] = take(B * OUT_LD); h->dout[n] = take(B * OUT_LD);
   }
   h->comm = nullptr; h->comm_floats = 0; h->rank = 0; h->world = 1; h->epoch = 0;
-  h->side = nullptr; h->ev_fork[0] = h->ev_fork[1] = h->ev_join = nullptr;
+  h->side = nullptr; h->ev_fork[0] = h->ev_fork[1] = h->ev_join = h->ev_moments = nullptr;
   for (int i = 0; i < P2P_MAX_RANKS; i++) h->peer_base[i] = nullptr;
   h->tbase = nullptr;
   h->tma = !cfg->staged_operands && cfg->hidden % 32 == 0 && cfg->hidden <= 256;
@@ -1114,6 +1115,7 @@ void b2h_ppo_destroy(B2HPpo* h) {
   cudaFree(h->scratch);   // the first allocation of the block
   if (h->tbase) cudaFree(h->tbase);
   if (h->ev_join) { cudaEventDestroy(h->ev_fork[0]); cudaEventDestroy(h->ev_fork[1]); cudaEventDestroy(h->ev_join); }
+  if (h->ev_moments) cudaEventDestroy(h->ev_moments);
   if (h->side) cudaStreamDestroy(h->side);
   for (int i = 0; i < P2P_MAX_RANKS; i++)
     if (h->peer_base[i] && i != h->rank) cudaIpcCloseMemHandle(h->peer_base[i]);
@@ -1165,7 +1167,9 @@ int b2h_ppo_minibatch_grad(B2HPpo* h, const float* obs_dev, const float* actions
   L.mean = h->out[0]; L.value = h->out[1]; L.act = h->act; L.olp = h->olp; L.adv = h->adv; L.ret = h->ret; L.log_std = P + o[12];
   L.dmean = h->dout[0]; L.dvalue = h->dout[1]; L.rows_pad = 0; L.dt_hi[0] = L.dt_hi[1] = L.dt_lo[0] = L.dt_lo[1] = nullptr; L.g_b3_pi = G + o[5]; L.g_b3_vf = G + o[11]; L.g_log_std = G + o[12]; L.stats = h->scratch;
   L.n = n; L.act_dim = A; L.clip = c.clip_range; L.ent_coef = c.ent_coef; L.vf_coef = c.vf_coef; L.normalize = c.normalize_advantage;
-  ppo_loss_kernel<<<(n + LOSS_NT - 1) / LOSS_NT, LOSS_NT, 0, s>>>(L);
+  L.moments = h->moments;
+  adv_moments_kernel<<<1, 1024, 0, s>>>(h->adv, n, h->moments);
+  ppo_loss_kernel<<<(n + LOSS_ROWS - 1) / LOSS_ROWS, LOSS_NT, 0, s>>>(L);
   // ---- backward.  Head: dW3 = dout^T h2 (computed transposed: the 256 hidden features ride on the M side), dh2 = dout W3 . (h2 > 0)
   for (int k = 0; k < 2; k++) {
     pr[k] = prob(h->h2[k], H, 1, h->dout[k], OUT_LD, 1, G + o[6 * k + 4], H, H, nout[k], n);

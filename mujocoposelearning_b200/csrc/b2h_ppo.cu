@@ -755,6 +755,27 @@ bool operand_maps(EncodeFn enc, CUtensorMap* hi_lo, const B2HPpo::TMat& t, int m
   return encode_k(enc, hi_lo + 0, t.hi, t.ld, t.rows_pad, rows) && encode_k(enc, hi_lo + 1, t.lo, t.ld, t.rows_pad, rows);
 }
 
+cudaError_t gemm_t_attributes() {
+  cudaError_t e = cudaFuncSetAttribute(gemm_t_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(t_ns(1) * T_STAGE * sizeof(float)));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_t_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(t_ns(2) * T_STAGE * sizeof(float)));
+  return e;
+}
+// Which instantiation a GEMM runs.  Measured: sending the narrow N tiles (the heads, N = 32: bound by TMA latency, not bytes) to
+// the one-CTA-per-SM instantiation, whose 192 KB ring holds four stages of their small chunks, is SLOWER (0.294 against 0.285 ms
+// per minibatch): their 256 tiles become 1.7 waves again and cannot share SMs with the 96 KB CTAs of the GEMM on the other stream.
+int ctas_for(int nw) { (void)nw; return T_CTAS_DEFAULT; }
+cudaError_t launch_gemm_t_kernel(int ctas, dim3 grid, int cluster, cudaStream_t s, const TMaps& maps, const TArgs& a) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(t_threads(ctas)); cfg.dynamicSmemBytes = t_ns(ctas) * T_STAGE * sizeof(float); cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaError_t e = ctas == 1 ? cudaLaunchKernelEx(&cfg, gemm_t_kernel<1>, maps, a) : cudaLaunchKernelEx(&cfg, gemm_t_kernel<2>, maps, a);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  return e;
+}
+
 int setup_tma(B2HPpo* h) {
   const B2HPpoConfig& c = h->cfg;
   const int H = c.hidden, D = c.obs_dim;
@@ -814,7 +835,7 @@ int setup_tma(B2HPpo* h) {
     ok = ok && gemm_maps(7, h->tdh1[n], 1, h->tX, 1, h->nw_obs, nullptr);     // dW1 = dh1^T X
   }
   if (!ok) { g_err_ppo = "cuTensorMapEncodeTiled failed"; return B2H_ECUDA; }
-  cudaError_t e = cudaFuncSetAttribute(gemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TNS * T_STAGE * sizeof(float)));
+  cudaError_t e = gemm_t_attributes();
   if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
   if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_fork[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork[1], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
@@ -838,7 +859,8 @@ int launch_gemm_t(const B2HPpo* h, int g, TProblem* pr, int precise, bool split,
   TArgs a;
   a.p[0] = pr[0]; a.p[1] = pr[1];
   const int tiles = pr[0].m_tiles * pr[0].n_tiles * 2, chunks = pr[0].chunks;
-  int nsplit = split ? std::max(1, std::min(chunks, g_sm_count * T_CTAS / std::max(1, tiles))) : 1;
+  const int ctas = ctas_for(pr[0].nw);
+  int nsplit = split ? std::max(1, std::min(chunks, g_sm_count * ctas / std::max(1, tiles))) : 1;
   a.chunks_per_split = (chunks + nsplit - 1) / nsplit;
   a.nsplit = (chunks + a.chunks_per_split - 1) / a.chunks_per_split;
   a.precise = precise;
@@ -854,14 +876,7 @@ int launch_gemm_t(const B2HPpo* h, int g, TProblem* pr, int precise, bool split,
 #endif
   a.cluster = h->cluster[g];
   if (a.cluster > 1 && pr[0].m_tiles % 2) { g_err_ppo = "internal: odd number of M tiles in a clustered GEMM"; return B2H_EINVAL; }
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(pr[0].m_tiles, pr[0].n_tiles, 2 * a.nsplit); cfg.blockDim = dim3(T_THREADS); cfg.dynamicSmemBytes = TNS * T_STAGE * sizeof(float); cfg.stream = s;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = a.cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_t_kernel, h->maps[g], a);
-  if (e == cudaSuccess) e = cudaGetLastError();
+  cudaError_t e = launch_gemm_t_kernel(ctas, dim3(pr[0].m_tiles, pr[0].n_tiles, 2 * a.nsplit), a.cluster, s, h->maps[g], a);
   if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
   return B2H_OK;
 }
@@ -1038,7 +1053,7 @@ int b2h_gemm_tma(const float* a_dev, int a_mn, const float* b_dev, int b_mn, flo
   for (int i = 4; i < 6; i++) { hh.maps[0].m[0][i] = hh.maps[0].m[0][0]; hh.maps[0].m[1][i] = hh.maps[0].m[0][0]; }
   int rc = B2H_OK;
   if (!ok) { g_err_ppo = "cuTensorMapEncodeTiled failed"; rc = B2H_ECUDA; }
-  if (rc == B2H_OK && cudaFuncSetAttribute(gemm_t_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TNS * T_STAGE * sizeof(float))) != cudaSuccess) {
+  if (rc == B2H_OK && gemm_t_attributes() != cudaSuccess) {
     g_err_ppo = "cudaFuncSetAttribute failed"; rc = B2H_ECUDA;
   }
   if (rc == B2H_OK) {
@@ -1052,13 +1067,7 @@ int b2h_gemm_tma(const float* a_dev, int a_mn, const float* b_dev, int b_mn, flo
     a.chunks_per_split = (p.chunks + nsplit - 1) / nsplit;
     a.nsplit = (p.chunks + a.chunks_per_split - 1) / a.chunks_per_split;
     a.precise = precise; a.error = error_flag_dev; a.cluster = cluster; a.clk = nullptr;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(p.m_tiles, p.n_tiles, a.nsplit); cfg.blockDim = dim3(T_THREADS); cfg.dynamicSmemBytes = TNS * T_STAGE * sizeof(float); cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t le = cudaLaunchKernelEx(&cfg, gemm_t_kernel, hh.maps[0], a);
+    cudaError_t le = launch_gemm_t_kernel(ctas_for(nw), dim3(p.m_tiles, p.n_tiles, a.nsplit), cluster, s, hh.maps[0], a);
     if (le != cudaSuccess || cudaGetLastError() != cudaSuccess) { g_err_ppo = std::string("launch failed: ") + cudaGetErrorString(le); rc = B2H_ECUDA; }
   }
   if (cudaStreamSynchronize(s) != cudaSuccess && rc == B2H_OK) { g_err_ppo = cudaGetErrorString(cudaGetLastError()); rc = B2H_ECUDA; }

@@ -26,8 +26,10 @@ constexpr int TK = 32;                       // K per chunk: 32 columns (K-major
 // CTAs per SM: 1 = a 192 KB ring (two stages at N = 256), 16 warps; 2 = two CTAs of 96 KB (one stage at N = 256) and 8 warps
 // each share an SM and its 512 TMEM columns, so that one's prologue / epilogue runs under the other's main loop and the 256
 // tiles of a forward GEMM are one wave (measured: 0.305 -> 0.295 ms per minibatch; the default)
-constexpr int T_CTAS = B2H_GEMM_CTAS;
-constexpr int TNS = T_CTAS == 1 ? 2 : 1;     // stages at the widest N; narrower tiles get more
+constexpr int T_CTAS_DEFAULT = B2H_GEMM_CTAS;
+// per kernel instantiation (template parameter CTAS): stages at the widest N (narrower tiles get more), threads
+__host__ __device__ constexpr int t_ns(int ctas) { return ctas == 1 ? 2 : 1; }
+__host__ __device__ constexpr int t_threads(int ctas) { return ctas == 1 ? 512 : 256; }
 constexpr int TNS_MAX = 6;
 constexpr int T_A_PART = 128 * TK;           // floats of one plane of an A chunk (16 KB)
 constexpr int T_B_PART = 256 * TK;           // ... of a B chunk at the widest N (32 KB)
@@ -103,9 +105,10 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32_major(int m, int n, int a_mn
   return umma_idesc_tf32(m, n) | ((uint32_t)(a_mn != 0) << 15) | ((uint32_t)(b_mn != 0) << 16);
 }
 
-constexpr int T_THREADS = T_CTAS == 1 ? 512 : 256;   // two roles during the main loop, then epilogue parts of four warps each
-constexpr int T_NPART = T_THREADS / 128, T_ROUNDS = 8 / T_NPART;
-__global__ void __launch_bounds__(T_THREADS, T_CTAS) gemm_t_kernel(const __grid_constant__ TMaps maps, TArgs a) {
+template <int CTAS>
+__global__ void __launch_bounds__(t_threads(CTAS), CTAS) gemm_t_kernel(const __grid_constant__ TMaps maps, TArgs a) {
+  constexpr int TNS = t_ns(CTAS), T_THREADS = t_threads(CTAS);   // two roles during the main loop, then epilogue parts of four warps each
+  constexpr int T_NPART = T_THREADS / 128, T_ROUNDS = 8 / T_NPART;
   extern __shared__ __align__(1024) unsigned char smem_t[];
   float* stage0 = reinterpret_cast<float*>(smem_t);
   __shared__ __align__(8) unsigned long long bar_storage[2 * TNS_MAX + 1];

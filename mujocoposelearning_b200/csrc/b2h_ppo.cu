@@ -1088,29 +1088,37 @@ int b2h_ppo_create(const B2HPpoConfig* cfg, B2HPpo** out) {
   h->nflat = b2h_ppo_param_layout(cfg->obs_dim, cfg->hidden, cfg->act_dim, h->off);
   cudaGetDevice(&h->device);
   const size_t B = (size_t)cfg->max_batch, H = (size_t)cfg->hidden;
-  const size_t floats = B * cfg->obs_dim + B * cfg->act_dim + 3 * B + 2 * (4 * B * H + 2 * B * OUT_LD) + 512;
+  h->tma = !cfg->staged_operands && cfg->hidden % 32 == 0 && cfg->hidden <= 256;
+  // plain row-major workspace: the minibatch vectors and head outputs always; the activations only for the staged GEMM (the TMA
+  // path keeps them as operand planes, setup_tma)
+  const size_t staged = h->tma ? 0 : B * cfg->obs_dim + 2 * (4 * B * H + B * OUT_LD);
+  const size_t floats = staged + B * cfg->act_dim + 3 * B + 2 * B * OUT_LD + 1024;
   float* base = nullptr;
-  if (cudaMalloc(&base, floats * sizeof(float) + 8 * sizeof(double) + 64) != cudaSuccess) {
+  if (cudaMalloc(&base, floats * sizeof(float)) != cudaSuccess) {
     g_err_ppo = "b2h_ppo_create: out of device memory";
     delete h;
     return B2H_ENOMEM;
   }
-  cudaMemset(base, 0, floats * sizeof(float) + 8 * sizeof(double) + 64);
+  cudaMemset(base, 0, floats * sizeof(float));
   float* p = base;
   auto take = [&](size_t n) { float* r = p; p += (n + 3) & ~(size_t)3; return r; };
   h->scratch = reinterpret_cast<double*>(take(32));
   h->moments = h->scratch + 8;
   h->error = reinterpret_cast<int*>(take(4));
-  h->X = take(B * cfg->obs_dim); h->act = take(B * cfg->act_dim); h->olp = take(B); h->adv = take(B); h->ret = take(B);
+  h->act = take(B * cfg->act_dim); h->olp = take(B); h->adv = take(B); h->ret = take(B);
+  h->X = nullptr;
   for (int n = 0; n < 2; n++) {
-    h->h1[n] = take(B * H); h->h2[n] = take(B * H); h->dh2[n] = take(B * H); h->dh1[n] = take(B * H);
-    h->out[n] = take(B * OUT_LD); h->dout[n] = take(B * OUT_LD);
+    h->out[n] = take(B * OUT_LD);
+    h->h1[n] = h->h2[n] = h->dh2[n] = h->dh1[n] = h->dout[n] = nullptr;
+  }
+  if (!h->tma) {
+    h->X = take(B * cfg->obs_dim);
+    for (int n = 0; n < 2; n++) { h->h1[n] = take(B * H); h->h2[n] = take(B * H); h->dh2[n] = take(B * H); h->dh1[n] = take(B * H); h->dout[n] = take(B * OUT_LD); }
   }
   h->comm = nullptr; h->comm_floats = 0; h->rank = 0; h->world = 1; h->epoch = 0;
   h->side = nullptr; h->ev_fork[0] = h->ev_fork[1] = h->ev_join = h->ev_moments = nullptr;
   for (int i = 0; i < P2P_MAX_RANKS; i++) h->peer_base[i] = nullptr;
   h->tbase = nullptr;
-  h->tma = !cfg->staged_operands && cfg->hidden % 32 == 0 && cfg->hidden <= 256;
   if (h->tma) {
     const int rc = setup_tma(h);
     if (rc < 0) { b2h_ppo_destroy(h); return rc; }

@@ -730,12 +730,13 @@ typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void
                              const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 // K-major use of a plane: 2-D map {columns, rows}, box {32 columns, `rows` rows}, 128-byte swizzle
-bool encode_k(EncodeFn encode, CUtensorMap* m, float* plane, int ld, int rows_pad, int rows) {
+bool encode_k(EncodeFn encode, CUtensorMap* m, float* plane, int ld, int rows_pad, int rows, int kcols = TK) {
   const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows_pad};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-  const cuuint32_t box[2] = {32, (cuuint32_t)rows};
+  const cuuint32_t box[2] = {(cuuint32_t)kcols, (cuuint32_t)rows};
   const cuuint32_t estr[2] = {1, 1};
-  return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                kcols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // MN-major use: 3-D map {32 columns of a group, rows, column groups}, box {32, 32 rows, `cols` / 32 groups}, 128-byte swizzle
@@ -743,7 +744,7 @@ bool encode_k(EncodeFn encode, CUtensorMap* m, float* plane, int ld, int rows_pa
 bool encode_mn(EncodeFn encode, CUtensorMap* m, float* plane, int ld, int rows_pad, int cols) {
   const cuuint64_t dims[3] = {32, (cuuint64_t)rows_pad, (cuuint64_t)(ld / 32)};
   const cuuint64_t strides[2] = {(cuuint64_t)ld * 4, 128};
-  const cuuint32_t box[3] = {32, 32, (cuuint32_t)(cols / 32)};
+  const cuuint32_t box[3] = {32, (cuuint32_t)TK, (cuuint32_t)(cols / 32)};
   const cuuint32_t estr[3] = {1, 1, 1};
   return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, plane, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -823,7 +824,7 @@ int setup_tma(B2HPpo* h) {
       h->cluster[g] = (want && nw % 64 == 0 && (batch_rows_on_m || (roundup(H, 128) / 128) % 2 == 0)) ? 2 : 1;
       // results that are operands of later GEMMs leave through TMA stores of {32 columns, 128 rows} swizzled boxes
       return operand_maps(enc, &(*m)[0], A, a_mn, 128) && operand_maps(enc, &(*m)[2], Bm, b_mn, nw / h->cluster[g]) &&
-             (!Cm || operand_maps(enc, &(*m)[4], *Cm, 0, 128));
+             (!Cm || (encode_k(enc, &(*m)[4], Cm->hi, Cm->ld, Cm->rows_pad, 128, 32) && encode_k(enc, &(*m)[5], Cm->lo, Cm->ld, Cm->rows_pad, 128, 32)));
     };
     ok = ok && gemm_maps(0, h->tX, 0, h->tW1[n], 0, H, &h->th1[n]);           // fwd1  h1 = relu(X W1^T + b1)
     ok = ok && gemm_maps(1, h->th1[n], 0, h->tW2[n], 0, H, &h->th2[n]);       // fwd2  h2 = relu(h1 W2^T + b2)
@@ -886,7 +887,7 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
   const B2HPpoConfig& c = h->cfg;
   const int H = c.hidden, D = c.obs_dim, A = c.act_dim;
   const int64_t* o = h->off;
-  const int rows_pad = roundup(n, 256), m_tiles_b = rows_pad / 128, kchunks_b = roundup(n, 32) / 32;
+  const int rows_pad = roundup(n, 256), m_tiles_b = rows_pad / 128, kchunks_b = roundup(n, 32) / TK;
   const int nout[2] = {A, 1};
   // weights -> T-format (they change with every Adam step; 0.3 M floats)
   PackTJobs pj;
@@ -919,7 +920,7 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
   };
   TProblem pr[2];
   int rc;
-  const int kc_obs = roundup(D, 32) / 32, kc_h = roundup(H, 32) / 32, h_tiles = roundup(H, 128) / 128;
+  const int kc_obs = roundup(D, 32) / TK, kc_h = roundup(H, 32) / TK, h_tiles = roundup(H, 128) / 128;
   // ---- forward
   for (int k = 0; k < 2; k++) {
     pr[k] = base(0, 0, m_tiles_b, 1, H, kc_obs);
@@ -957,7 +958,7 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
   if (cudaEventRecord(h->ev_fork[0], s) != cudaSuccess || cudaStreamWaitEvent(s2, h->ev_fork[0], 0) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
   if ((rc = launch_gemm_t(h, 3, pr, c.precise, true, s2)) < 0) return rc;
   for (int k = 0; k < 2; k++) {   // dh2 = dout W3 . (h2 > 0)
-    pr[k] = base(0, 1, m_tiles_b, 1, H, 1);
+    pr[k] = base(0, 1, m_tiles_b, 1, H, 32 / TK);
     pr[k].c_hi = h->tdh2[k].hi; pr[k].c_lo = h->tdh2[k].lo; pr[k].c_ld = h->tdh2[k].ld; pr[k].bits_in = h->bits2[k]; pr[k].colsum = G + o[6 * k + 3]; pr[k].N = H;
   }
   if ((rc = launch_gemm_t(h, 4, pr, c.precise, false, s)) < 0) return rc;

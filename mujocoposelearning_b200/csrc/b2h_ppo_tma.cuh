@@ -19,7 +19,13 @@
 //     gradients, split over the SMs along the minibatch).
 #pragma once
 
-constexpr int TK = 32;                       // K per chunk: 32 columns (K-major: one 128-byte swizzle row) or 32 rows (MN-major)
+#ifndef B2H_GEMM_TK
+#define B2H_GEMM_TK 16
+#endif
+constexpr int TK = B2H_GEMM_TK;              // K per chunk: 32 (K-major: one 128-byte swizzle row) or 16 (64-byte swizzle rows: half-size stages, twice as
+                                             // many -- with two CTAs per SM each CTA then has a two-stage ring of its own: 0.284 -> 0.266 ms per minibatch; the default)
+static_assert(TK == 32 || TK == 16, "K chunk");
+constexpr int T_EPI_PART = 128 * 32;         // floats of one plane of an epilogue staging buffer: 128 rows x 32 columns (16 KB)
 #ifndef B2H_GEMM_CTAS
 #define B2H_GEMM_CTAS 2
 #endif
@@ -28,7 +34,7 @@ constexpr int TK = 32;                       // K per chunk: 32 columns (K-major
 // tiles of a forward GEMM are one wave (measured: 0.305 -> 0.295 ms per minibatch; the default)
 constexpr int T_CTAS_DEFAULT = B2H_GEMM_CTAS;
 // per kernel instantiation (template parameter CTAS): stages at the widest N (narrower tiles get more), threads
-__host__ __device__ constexpr int t_ns(int ctas) { return ctas == 1 ? 2 : 1; }
+__host__ __device__ constexpr int t_ns(int ctas) { return (ctas == 1 ? 2 : 1) * (32 / B2H_GEMM_TK); }
 __host__ __device__ constexpr int t_threads(int ctas) { return ctas == 1 ? 512 : 256; }
 constexpr int TNS_MAX = 6;
 constexpr int T_A_PART = 128 * TK;           // floats of one plane of an A chunk (16 KB)
@@ -163,8 +169,10 @@ __global__ void __launch_bounds__(t_threads(CTAS), CTAS) gemm_t_kernel(const __g
       // K-major (SWIZZLE_128B): rows of 128 bytes, 8-row swizzle atoms 1024 B apart (SBO), LBO unused (1); a K step of 8 tf32
       // is 32 bytes further along the row.  MN-major (SWIZZLE_128B_BASE32B): per group of 32 columns, 32 K rows of 128 bytes;
       // atoms of 4 K rows 512 B apart (SBO), column groups 4096 B apart (LBO); a K step of 8 = two atoms = 1024 B.
-      const uint32_t lboA = P.a_mn ? 4096u : 16u, sboA = P.a_mn ? 512u : 1024u, stepA = P.a_mn ? 1024u : 32u, ltA = P.a_mn ? 1u : 2u;
-      const uint32_t lboB = P.b_mn ? 4096u : 16u, sboB = P.b_mn ? 512u : 1024u, stepB = P.b_mn ? 1024u : 32u, ltB = P.b_mn ? 1u : 2u;
+      // (K chunks of 16: the K-major rows are 64 bytes -> SWIZZLE_64B, atoms of 8 rows 512 B apart; MN-major chunks hold 16 rows per column group)
+      constexpr uint32_t kSbo = TK == 32 ? 1024u : 512u, kLt = TK == 32 ? 2u : 4u, mnLbo = (uint32_t)TK * 128u;
+      const uint32_t lboA = P.a_mn ? mnLbo : 16u, sboA = P.a_mn ? 512u : kSbo, stepA = P.a_mn ? 1024u : 32u, ltA = P.a_mn ? 1u : kLt;
+      const uint32_t lboB = P.b_mn ? mnLbo : 16u, sboB = P.b_mn ? 512u : kSbo, stepB = P.b_mn ? 1024u : 32u, ltB = P.b_mn ? 1u : kLt;
       int s = 0, use = 0;
       for (int c = 0; c < nchunk && ok; c++) {
         ok = mbar_wait(full0 + 8 * s, use & 1);
@@ -212,11 +220,11 @@ __global__ void __launch_bounds__(t_threads(CTAS), CTAS) gemm_t_kernel(const __g
         else        { tma_load_2d(A_hi, mp + 0, kc * TK, row0, fullb);        if (precise) tma_load_2d(A_lo, mp + 1, kc * TK, row0, fullb); }
         if (csize > 1) {   // this CTA's half of the B chunk, delivered to both CTAs of the pair (the half-box maps are built for it)
           if (P.b_mn) {
-            const uint32_t off = crank * (uint32_t)(nw / 64) * 4096u;
+            const uint32_t off = crank * (uint32_t)(nw / 64) * (uint32_t)(TK * 128);
             tma_load_3d_mc(B_hi + off, mp + 2, 0, kc * TK, col0 / 32 + (int)crank * (nw / 64), fullb, cmask);
             if (precise) tma_load_3d_mc(B_lo + off, mp + 3, 0, kc * TK, col0 / 32 + (int)crank * (nw / 64), fullb, cmask);
           } else {
-            const uint32_t off = crank * (uint32_t)(nw / 2) * 128u;
+            const uint32_t off = crank * (uint32_t)(nw / 2) * (uint32_t)(TK * 4);
             tma_load_2d_mc(B_hi + off, mp + 2, kc * TK, col0 + (int)crank * (nw / 2), fullb, cmask);
             if (precise) tma_load_2d_mc(B_lo + off, mp + 3, kc * TK, col0 + (int)crank * (nw / 2), fullb, cmask);
           }
@@ -243,7 +251,7 @@ __global__ void __launch_bounds__(t_threads(CTAS), CTAS) gemm_t_kernel(const __g
       // tile (bias gradient) are taken from the staged copy, the ReLU pattern travels as one bit per element
       // staging buffers of 32 columns x 128 rows x (hi + lo) = 32 KB in the idle operand ring (six fit): parts 0 and 1 use
       // buffers {0, 4} and {1, 5} for their two groups, parts 2 and 3 reuse buffer 2 / 3 once the first store has read it
-      static_assert((TNS * T_STAGE) / (2 * T_A_PART) >= (T_NPART == 4 ? 6 : 2), "staging buffers");
+      static_assert((TNS * T_STAGE) / (2 * T_EPI_PART) >= (T_NPART == 4 ? 6 : 2), "staging buffers");
       const CUtensorMap* cmap = maps.m[prob ? 1 : 0] + 4;
       uint32_t in_bits[8], out_bits[T_ROUNDS];
       if (P.bits_in) {
@@ -299,8 +307,8 @@ __global__ void __launch_bounds__(t_threads(CTAS), CTAS) gemm_t_kernel(const __g
         out_bits[gp] = word;
         // four parts, six buffers: parts 0 / 1 use {0, 4} / {1, 5}, parts 2 / 3 reuse 2 / 3; two parts: one buffer each, reused every round
         const int b = T_NPART == 4 ? (part < 2 ? part + 4 * gp : part) : part;
-        float* s_hi = stage0 + b * (2 * T_A_PART);
-        float* s_lo = s_hi + T_A_PART;
+        float* s_hi = stage0 + b * (2 * T_EPI_PART);
+        float* s_lo = s_hi + T_EPI_PART;
         if (T_NPART == 4 ? (gp == 1 && part >= 2) : gp >= 1) {   // the TMA store of this part's previous group must have finished reading the buffer
           if (r == 0) asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory");
           part_barrier<T_NPART>(part);

@@ -861,7 +861,10 @@ int launch_gemm_t(const B2HPpo* h, int g, TProblem* pr, int precise, bool split,
   a.p[0] = pr[0]; a.p[1] = pr[1];
   const int tiles = pr[0].m_tiles * pr[0].n_tiles * 2, chunks = pr[0].chunks;
   const int ctas = ctas_for(pr[0].nw);
-  int nsplit = split ? std::max(1, std::min(chunks, g_sm_count * ctas / std::max(1, tiles))) : 1;
+#ifndef B2H_SPLIT_PER_SM
+#define B2H_SPLIT_PER_SM ctas
+#endif
+  int nsplit = split ? std::max(1, std::min(chunks, g_sm_count * (B2H_SPLIT_PER_SM) / std::max(1, tiles))) : 1;
   a.chunks_per_split = (chunks + nsplit - 1) / nsplit;
   a.nsplit = (chunks + a.chunks_per_split - 1) / a.chunks_per_split;
   a.precise = precise;

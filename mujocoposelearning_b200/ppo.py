@@ -16,6 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 import torch.distributed as dist
@@ -79,17 +80,27 @@ class PpoKernels:
 
     def enable_p2p(self):
         """Map every rank's gradient buffer into this process (CUDA IPC; one node) so that ``apply_p2p`` can reduce the
-        gradients with peer loads over NVLink instead of a library all-reduce."""
+        gradients with peer loads over NVLink instead of a library all-reduce.  Returns False (on every rank, after agreeing
+        on it) when some rank cannot map a peer, e.g. ranks on different nodes or without peer access: the caller then
+        keeps the NCCL all-reduce."""
         rank, world = dist.get_rank(), dist.get_world_size()
         mine = (C.c_char * 64)()
+        ok = True
         with torch.cuda.device(self.device):
-            self._check(self.lib.b2h_ppo_p2p_export(self.h, mine))
+            ok = self.lib.b2h_ppo_p2p_export(self.h, mine) >= 0
             handles = [None] * world
-            dist.all_gather_object(handles, bytes(mine.raw))
-            blob = (C.c_char * (64 * world)).from_buffer_copy(b"".join(handles))
-            self._check(self.lib.b2h_ppo_p2p_attach(self.h, rank, world, blob))
-        dist.barrier()                                         # nobody starts reducing before every rank has attached
-        self.p2p = True
+            dist.all_gather_object(handles, (bytes(mine.raw), os.uname().nodename, ok))
+            ok = all(h[2] for h in handles) and len({h[1] for h in handles}) == 1
+            if ok:
+                blob = (C.c_char * (64 * world)).from_buffer_copy(b"".join(h[0] for h in handles))
+                ok = self.lib.b2h_ppo_p2p_attach(self.h, rank, world, blob) >= 0
+        flag = torch.tensor([1 if ok else 0], device=self.device, dtype=torch.int32)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)              # also the barrier: nobody reduces before every rank has attached
+        self.p2p = bool(int(flag.item()))
+        if not self.p2p and rank == 0:
+            import warnings
+            warnings.warn("peer-memory gradient reduction unavailable (" + self.lib.b2h_ppo_last_error().decode() + "); using the NCCL all-reduce")
+        return self.p2p
 
     def minibatch_grad_p2p(self, obs, actions, old_logp, adv, ret, idx):
         """As ``minibatch_grad``, into this epoch's copy of the peer-visible gradient buffer."""

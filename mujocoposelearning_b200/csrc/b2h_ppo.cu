@@ -736,7 +736,7 @@ bool encode_k(EncodeFn encode, CUtensorMap* m, float* plane, int ld, int rows_pa
   const cuuint32_t box[2] = {(cuuint32_t)kcols, (cuuint32_t)rows};
   const cuuint32_t estr[2] = {1, 1};
   return encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, plane, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                kcols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                kcols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : (kcols == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 // MN-major use: 3-D map {32 columns of a group, rows, column groups}, box {32, 32 rows, `cols` / 32 groups}, 128-byte swizzle

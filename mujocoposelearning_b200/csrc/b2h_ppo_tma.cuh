@@ -23,8 +23,9 @@
 #define B2H_GEMM_TK 16
 #endif
 constexpr int TK = B2H_GEMM_TK;              // K per chunk: 32 (K-major: one 128-byte swizzle row) or 16 (64-byte swizzle rows: half-size stages, twice as
-                                             // many -- with two CTAs per SM each CTA then has a two-stage ring of its own: 0.284 -> 0.266 ms per minibatch; the default)
-static_assert(TK == 32 || TK == 16, "K chunk");
+                                             // many -- with two CTAs per SM each CTA then has a two-stage ring of its own: 0.284 -> 0.266 ms per minibatch; the default) or 8
+                                             // (32-byte swizzle, four stages: measured slower, 0.298 ms)
+static_assert(TK == 32 || TK == 16 || TK == 8, "K chunk");
 constexpr int T_EPI_PART = 128 * 32;         // floats of one plane of an epilogue staging buffer: 128 rows x 32 columns (16 KB)
 #ifndef B2H_GEMM_CTAS
 #define B2H_GEMM_CTAS 2
@@ -36,7 +37,7 @@ constexpr int T_CTAS_DEFAULT = B2H_GEMM_CTAS;
 // per kernel instantiation (template parameter CTAS): stages at the widest N (narrower tiles get more), threads
 __host__ __device__ constexpr int t_ns(int ctas) { return (ctas == 1 ? 2 : 1) * (32 / B2H_GEMM_TK); }
 __host__ __device__ constexpr int t_threads(int ctas) { return ctas == 1 ? 512 : 256; }
-constexpr int TNS_MAX = 6;
+constexpr int TNS_MAX = 8;
 constexpr int T_A_PART = 128 * TK;           // floats of one plane of an A chunk (16 KB)
 constexpr int T_B_PART = 256 * TK;           // ... of a B chunk at the widest N (32 KB)
 constexpr int T_STAGE = 2 * T_A_PART + 2 * T_B_PART;   // A hi | A lo | B hi | B lo: 96 KB
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(t_threads(CTAS), CTAS) gemm_t_kernel(const __g
       // is 32 bytes further along the row.  MN-major (SWIZZLE_128B_BASE32B): per group of 32 columns, 32 K rows of 128 bytes;
       // atoms of 4 K rows 512 B apart (SBO), column groups 4096 B apart (LBO); a K step of 8 = two atoms = 1024 B.
       // (K chunks of 16: the K-major rows are 64 bytes -> SWIZZLE_64B, atoms of 8 rows 512 B apart; MN-major chunks hold 16 rows per column group)
-      constexpr uint32_t kSbo = TK == 32 ? 1024u : 512u, kLt = TK == 32 ? 2u : 4u, mnLbo = (uint32_t)TK * 128u;
+      constexpr uint32_t kSbo = (uint32_t)TK * 32u, kLt = TK == 32 ? 2u : (TK == 16 ? 4u : 6u), mnLbo = (uint32_t)TK * 128u;   // 8 rows of TK floats; SWIZZLE_128B / _64B / _32B
       const uint32_t lboA = P.a_mn ? mnLbo : 16u, sboA = P.a_mn ? 512u : kSbo, stepA = P.a_mn ? 1024u : 32u, ltA = P.a_mn ? 1u : kLt;
       const uint32_t lboB = P.b_mn ? mnLbo : 16u, sboB = P.b_mn ? 512u : kSbo, stepB = P.b_mn ? 1024u : 32u, ltB = P.b_mn ? 1u : kLt;
       int s = 0, use = 0;

@@ -714,6 +714,8 @@ struct B2HPpo {
   cudaStream_t side;         // the weight-gradient GEMMs of the head and of layer 2 run here, beside the input-gradient chain
   cudaEvent_t ev_fork[2], ev_join, ev_moments;
   double* moments;           // advantage mean / std of the minibatch (device)
+  const int64_t* gathered_idx; int gathered_n;   // the minibatch whose rows b2h_ppo_train has already gathered beside the previous apply
+  cudaEvent_t ev_gather;
   // peer-memory gradient reduction: [grad copy 0 | grad copy 1 | reduced | flags] in one IPC-exported allocation
   float* comm;
   size_t comm_floats;
@@ -840,7 +842,7 @@ int setup_tma(B2HPpo* h) {
   if (e != cudaSuccess) { g_err_ppo = cudaGetErrorString(e); return B2H_ECUDA; }
   if (cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_fork[0], cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_fork[1], cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_moments, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_moments, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&h->ev_gather, cudaEventDisableTiming) != cudaSuccess) {
     g_err_ppo = "stream / event creation failed";
     return B2H_ECUDA;
   }
@@ -885,6 +887,26 @@ int launch_gemm_t(const B2HPpo* h, int g, TProblem* pr, int precise, bool split,
   return B2H_OK;
 }
 
+// Minibatch rows -> split observation planes + plain action / log-probability / advantage / return vectors, then the advantage
+// moments (one CTA on the side stream).  `s` is the stream the gather runs on: the caller's, or the side stream when
+// b2h_ppo_train prefetches the next minibatch beside the apply kernel (nothing of the previous minibatch reads these buffers then).
+int gather_stage(B2HPpo* h, const float* obs, const float* actions, const float* old_logp, const float* adv, const float* ret,
+                 const int64_t* idx, int64_t row_start, int n, cudaStream_t s) {
+  const B2HPpoConfig& c = h->cfg;
+  const int rows_pad = roundup(n, 256);
+  GatherTArgs g;
+  g.obs = obs; g.actions = actions; g.old_logp = old_logp; g.adv = adv; g.ret = ret; g.idx = idx; g.row_start = row_start;
+  g.x_hi = h->tX.hi; g.x_lo = h->tX.lo; g.act = h->act; g.olp = h->olp; g.a = h->adv; g.r = h->ret; g.scratch = h->scratch;
+  g.n_rows = n; g.rows_pad = rows_pad; g.obs_dim = c.obs_dim; g.ld = h->tX.ld; g.act_dim = c.act_dim;
+  gather_t_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, s>>>(g);
+  if (s != h->side) {
+    if (cudaEventRecord(h->ev_fork[0], s) != cudaSuccess || cudaStreamWaitEvent(h->side, h->ev_fork[0], 0) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
+  }
+  adv_moments_kernel<<<1, 1024, 0, h->side>>>(h->adv, n, h->moments);
+  if (cudaEventRecord(h->ev_moments, h->side) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
+  return B2H_OK;
+}
+
 int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const float* old_logp, const float* adv, const float* ret,
                        const int64_t* idx, int64_t row_start, int n, const float* P, float* G, cudaStream_t s) {
   const B2HPpoConfig& c = h->cfg;
@@ -905,15 +927,15 @@ int minibatch_grad_tma(B2HPpo* h, const float* obs, const float* actions, const 
     }
   }
   pack_t_kernel<<<dim3((max_items + 255) / 256, 6), 256, 0, s>>>(pj);
-  GatherTArgs g;
-  g.obs = obs; g.actions = actions; g.old_logp = old_logp; g.adv = adv; g.ret = ret; g.idx = idx; g.row_start = row_start;
-  g.x_hi = h->tX.hi; g.x_lo = h->tX.lo; g.act = h->act; g.olp = h->olp; g.a = h->adv; g.r = h->ret; g.scratch = h->scratch;
-  g.n_rows = n; g.rows_pad = rows_pad; g.obs_dim = D; g.ld = h->tX.ld; g.act_dim = A;
-  gather_t_kernel<<<(rows_pad * 32 + 255) / 256, 256, 0, s>>>(g);
-  // the advantage moments of the minibatch: one small CTA on the side stream, under the forward GEMMs
-  if (cudaEventRecord(h->ev_fork[0], s) != cudaSuccess || cudaStreamWaitEvent(h->side, h->ev_fork[0], 0) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
-  adv_moments_kernel<<<1, 1024, 0, h->side>>>(h->adv, n, h->moments);
-  if (cudaEventRecord(h->ev_moments, h->side) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
+  if (cudaMemsetAsync(h->scratch, 0, 4 * sizeof(double), s) != cudaSuccess) { g_err_ppo = "memset failed"; return B2H_ECUDA; }   // the statistics
+  if (h->gathered_idx && h->gathered_idx == idx && h->gathered_n == n) {
+    // b2h_ppo_train gathered this minibatch on the side stream while the previous minibatch's apply ran
+    if (cudaStreamWaitEvent(s, h->ev_gather, 0) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
+  } else {
+    int rc = gather_stage(h, obs, actions, old_logp, adv, ret, idx, row_start, n, s);
+    if (rc < 0) return rc;
+  }
+  h->gathered_idx = nullptr;
 
   auto base = [&](int a_mn, int b_mn, int m_tiles, int n_tiles, int nw, int chunks) {
     TProblem p;
@@ -1120,7 +1142,8 @@ int b2h_ppo_create(const B2HPpoConfig* cfg, B2HPpo** out) {
     for (int n = 0; n < 2; n++) { h->h1[n] = take(B * H); h->h2[n] = take(B * H); h->dh2[n] = take(B * H); h->dh1[n] = take(B * H); h->dout[n] = take(B * OUT_LD); }
   }
   h->comm = nullptr; h->comm_floats = 0; h->rank = 0; h->world = 1; h->epoch = 0;
-  h->side = nullptr; h->ev_fork[0] = h->ev_fork[1] = h->ev_join = h->ev_moments = nullptr;
+  h->side = nullptr; h->ev_fork[0] = h->ev_fork[1] = h->ev_join = h->ev_moments = h->ev_gather = nullptr;
+  h->gathered_idx = nullptr; h->gathered_n = 0;
   for (int i = 0; i < P2P_MAX_RANKS; i++) h->peer_base[i] = nullptr;
   h->tbase = nullptr;
   if (h->tma) {
@@ -1137,6 +1160,7 @@ void b2h_ppo_destroy(B2HPpo* h) {
   if (h->tbase) cudaFree(h->tbase);
   if (h->ev_join) { cudaEventDestroy(h->ev_fork[0]); cudaEventDestroy(h->ev_fork[1]); cudaEventDestroy(h->ev_join); }
   if (h->ev_moments) cudaEventDestroy(h->ev_moments);
+  if (h->ev_gather) cudaEventDestroy(h->ev_gather);
   if (h->side) cudaStreamDestroy(h->side);
   for (int i = 0; i < P2P_MAX_RANKS; i++)
     if (h->peer_base[i] && i != h->rank) cudaIpcCloseMemHandle(h->peer_base[i]);
@@ -1310,6 +1334,21 @@ int b2h_ppo_train(B2HPpo* h, const float* obs_dev, const float* actions_dev, con
       int rc = b2h_ppo_minibatch_grad(h, obs_dev, actions_dev, old_log_probs_dev, advantages_dev, returns_dev, perm_dev + (size_t)e * n_samples + i,
                                       0, n, params_dev, g, stream);
       if (rc < 0) return rc;
+      // the next minibatch's rows are gathered on the side stream while this one's apply kernel runs: after the last GEMM nothing
+      // reads the observation planes or the minibatch vectors any more, and the gather does not depend on the weights
+      int64_t ni = i + batch_size;
+      int ne = e;
+      if (ni >= n_samples) { ni = 0; ne = e + 1; }
+      if (h->tma && ne < n_epochs) {
+        cudaStream_t s = (cudaStream_t)stream;
+        const int nn = (int)std::min<int64_t>(batch_size, n_samples - ni);
+        const int64_t* nidx = perm_dev + (size_t)ne * n_samples + ni;
+        if (cudaEventRecord(h->ev_fork[0], s) != cudaSuccess || cudaStreamWaitEvent(h->side, h->ev_fork[0], 0) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
+        rc = gather_stage(h, obs_dev, actions_dev, old_log_probs_dev, advantages_dev, returns_dev, nidx, 0, nn, h->side);
+        if (rc < 0) return rc;
+        if (cudaEventRecord(h->ev_gather, h->side) != cudaSuccess) { g_err_ppo = "event failed"; return B2H_ECUDA; }
+        h->gathered_idx = nidx; h->gathered_n = nn;
+      }
       rc = p2p ? b2h_ppo_apply_p2p(h, params_dev, exp_avg_dev, exp_avg_sq_dev, ++*step_inout, stream)
                : b2h_ppo_apply(h, params_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, ++*step_inout, 1.f, stream);
       if (rc < 0) return rc;

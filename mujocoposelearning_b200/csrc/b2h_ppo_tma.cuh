@@ -415,7 +415,6 @@ struct GatherTArgs {
 // One warp per row.  Rows beyond the minibatch and columns beyond obs_dim are zeros (they enter the weight-gradient sums).
 __global__ void __launch_bounds__(256) gather_t_kernel(GatherTArgs g) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (blockIdx.x == 0 && threadIdx.x < 8) g.scratch[threadIdx.x] = 0.0;
   if (row >= g.rows_pad) return;
   const bool live = row < g.n_rows;
   const long long src = live ? (g.idx ? (long long)g.idx[row] : g.row_start + row) : 0;

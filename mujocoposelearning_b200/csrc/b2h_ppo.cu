@@ -4,25 +4,30 @@
 // minibatch the forward of the two MlpPolicy trunks (obs -> 256 -> 256 -> 21 / 1, ReLU: main.py:99-105), the clipped
 // surrogate + value MSE (+ entropy bonus) with per-minibatch advantage normalisation, the backward pass, grad-norm clipping
 // and Adam.  The reference runs this through PyTorch autograd on the CPU; round 1-2 here ran it through autograd + library
-// GEMMs.  Now every step of a minibatch is a kernel of this file:
+// GEMMs.  Now every step of a minibatch is a kernel of this file or of b2h_ppo_tma.cuh.
 //
-//   gather_kernel        minibatch rows of the rollout buffer -> contiguous operands
-//   gemm_kernel          C = A . B^T on the tcgen05 tensor cores, fp32-faithful (tf32 hi / lo split, hi*hi + hi*lo + lo*hi,
-//                        accumulator in TMEM).  One kernel serves the three GEMM shapes of the update because each operand
-//                        is staged into the canonical K-major core-matrix layout by the producer warps, which read either
-//                        [rows, K] (K contiguous) or [K, rows] (K strided) row-major memory:
-//                          forward           Y  = X  W^T + b (ReLU)        A: X [B, in]   K contiguous, B: W [out, in] K contiguous
-//                          input gradient    dX = dY W . (X > 0)           A: dY [B, out] K contiguous, B: W [out, in] K strided
-//                          weight gradient   dW = dY^T X                   A: dY [B, out] K strided,    B: X [B, in]   K strided
-//                        the weight gradients contract over the minibatch rows: split over CTAs (grid.z), partial tiles added
-//                        with red.global.add.  Both networks ride in one launch (two problems per grid).
-//   ppo_loss_kernel      advantage moments, log-probability, ratio, clipped surrogate, value loss, their gradients with respect
-//                        to the action mean / value / log_std, head bias gradients, loss statistics
-//   colsum_kernel        hidden-layer bias gradients
+// The path the update runs on (b2h_ppo_tma.cuh):
+//   pack_t_kernel        the weights, split into tf32 hi / lo planes
+//   gather_t_kernel      minibatch rows of the rollout buffer -> split observation planes + plain vectors (b2h_ppo_train gathers
+//                        the next minibatch on a side stream while the previous apply runs); adv_moments_kernel: their advantage moments
+//   gemm_t_kernel        C = A . B^T on the tcgen05 tensor cores, fp32-faithful (hi*hi + hi*lo + lo*hi into TMEM), every operand
+//                        streamed by TMA from planes its producer kernel already split; K-major (SWIZZLE_64B boxes) or MN-major
+//                        (32-byte-atom swizzled 3-D boxes) use of the same planes gives the forward, input-gradient and
+//                        weight-gradient products without a transpose; two CTAs per SM share the TMEM; results that feed later GEMMs
+//                        leave through TMA stores (+ bias-gradient column sums, ReLU sign bits), weight gradients through red.global.add
+//   ppo_loss_kernel      log-probability, ratio, clipped surrogate, value loss, their gradients with respect to the action mean /
+//                        value / log_std, head bias gradients, loss statistics (eight lanes per sample)
 //   apply_kernel         one launch: [sum of the ranks' gradients by peer loads over NVLink] -> sum of squares -> grid barrier ->
 //                        grad-norm clip (max_grad_norm) + torch.optim.Adam's update rule on the flat parameter vector (or the
 //                        caller all-reduces the flat gradient itself between b2h_ppo_minibatch_grad and b2h_ppo_apply)
-//   b2h_ppo_tma.cuh      the TMA-fed form of the GEMM (operands kept pre-split by their producers) that the update runs on
+//
+// The first version of the GEMM stays in this file for A/B measurements, hidden widths that are not a multiple of 32 and the
+// generic b2h_gemm entry (staged_operands = 1):
+//   gather_kernel        minibatch rows -> contiguous row-major operands
+//   gemm_kernel          the same three products with plain row-major fp32 operands: seven producer warps read either [rows, K]
+//                        (K contiguous) or [K, rows] (K strided) memory, split into hi / lo and stage the canonical no-swizzle
+//                        K-major core-matrix layout; split-K partial tiles added with red.global.add
+//   colsum_kernel        hidden-layer bias gradients
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>

@@ -119,6 +119,9 @@ template <> struct Tol<double> { static constexpr double ls_rel = 0.0, cost_rel 
 template <> struct Tol<float> { static constexpr float ls_rel = 2e-5f, cost_rel = 1e-6f, step_rel = 2e-7f; static constexpr bool exact_stop = true; static constexpr int maxiter = 30; };
 
 #define B2H_MINVAL T(1e-15)
+#ifndef B2H_LS_FUSED
+#define B2H_LS_FUSED 0   // 1: bracketing phase of the line search as passes of three independent evaluations (measured)
+#endif
 // the (at most NSLOT) dense-row slots a lane owns, fully unrolled so per-slot registers stay registers
 #define B2H_SLOTS(s) _Pragma("unroll") for (int s = 0; s < NSLOT; s++) if (s < nslot)
 
@@ -1211,7 +1214,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
         if (lsign != T(0)) { q0r[NSLOT] = T(0.5) * lD * lJaref * lJaref; q1r[NSLOT] = lD * lJaref * lJv; q2r[NSLOT] = T(0.5) * lD * lJv * lJv; }
         int lsiter = 0;
         struct Pnt { T alpha, cost, d0, d1; };
-        auto eval = [&](T a) {
+        auto evalp = [&](T a) {
           T s0 = 0, s1 = 0, s2 = 0;
           B2H_SLOTS(s)
             if (lane + 32 * s < nrow && Jaref[s] + a * Jv[s] < T(0)) { s0 += q0r[s]; s1 += q1r[s]; s2 += q2r[s]; }
@@ -1220,9 +1223,9 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
           Pnt p;
           p.alpha = a; p.cost = a * a * s2 + a * s1 + s0; p.d0 = T(2) * a * s2 + s1; p.d1 = T(2) * s2;
           if (p.d1 <= T(0)) p.d1 = B2H_MINVAL;
-          lsiter++;
           return p;
         };
+        auto eval = [&](T a) { lsiter++; return evalp(a); };
         Pnt p0 = eval(T(0));
         gtol = m_max(gtol, Tol<T>::ls_rel * m_abs(p0.d0));
         Pnt p1 = eval(p0.alpha - p0.d0 / p0.d1);
@@ -1246,6 +1249,38 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
           if (!done && (lsiter >= ls_iterations || !p2update)) { alpha = p1.alpha; done = true; }
           if (!done) {
             Pnt p2next = p1;
+#if B2H_LS_FUSED
+            // The bracketing phase as passes of independent evaluations: the midpoint of the NEXT round depends only on the
+            // brackets, not on the two Newton points evaluated after the bracket update, so the three run side by side (their
+            // butterfly sums interleave); a Newton point whose bracket did not move is evaluated again and dropped.  Same
+            // evaluations, same order of the counted ones, same bits.
+            Pnt p1next = evalp(p1.alpha - p1.d0 / p1.d1);
+            Pnt pmid = evalp(T(0.5) * (p1.alpha + p2.alpha));
+            lsiter++;
+            while (lsiter < ls_iterations && !done) {
+              lsiter++;                            // the midpoint is consumed
+              Pnt cand[3] = {p1next, p2next, pmid};
+              T bestcost = 0; int best = -1;
+              for (int i = 0; i < 3; i++)
+                if (m_abs(cand[i].d0) < gtol && (best == -1 || cand[i].cost < bestcost)) { bestcost = cand[i].cost; best = i; }
+              if (best >= 0) { alpha = best == 0 ? cand[0].alpha : best == 1 ? cand[1].alpha : cand[2].alpha; done = true; break; }
+              int b1 = 0, b2 = 0;
+              for (int i = 0; i < 3; i++) {
+                if (p1.d0 < T(0) && cand[i].d0 < T(0) && p1.d0 < cand[i].d0) { p1 = cand[i]; b1 = 1; }
+                else if (p1.d0 > T(0) && cand[i].d0 > T(0) && p1.d0 > cand[i].d0) { p1 = cand[i]; b1 = 1; }
+              }
+              for (int i = 0; i < 3; i++) {
+                if (p2.d0 < T(0) && cand[i].d0 < T(0) && p2.d0 < cand[i].d0) { p2 = cand[i]; b2 = 1; }
+                else if (p2.d0 > T(0) && cand[i].d0 > T(0) && p2.d0 > cand[i].d0) { p2 = cand[i]; b2 = 1; }
+              }
+              if (!b1 && !b2) { alpha = pmid.cost < p0.cost ? pmid.alpha : T(0); done = true; break; }
+              Pnt e1 = evalp(p1.alpha - p1.d0 / p1.d1);
+              Pnt e2 = evalp(p2.alpha - p2.d0 / p2.d1);
+              pmid = evalp(T(0.5) * (p1.alpha + p2.alpha));
+              if (b1) { p1next = e1; lsiter++; }
+              if (b2) { p2next = e2; lsiter++; }
+            }
+#else
             Pnt p1next = eval(p1.alpha - p1.d0 / p1.d1);
             while (lsiter < ls_iterations && !done) {
               Pnt pmid = eval(T(0.5) * (p1.alpha + p2.alpha));
@@ -1267,6 +1302,7 @@ B2H_DEV_NOINLINE int physics_step(const DevModel<T>& m_arg, Scratch<T>& S, T* Js
               if (b2) p2next = eval(p2.alpha - p2.d0 / p2.d1);
               if (!b1 && !b2) { alpha = pmid.cost < p0.cost ? pmid.alpha : T(0); done = true; }
             }
+#endif
             if (!done) {
               if (p1.cost <= p2.cost && p1.cost < p0.cost) alpha = p1.alpha;
               else if (p2.cost <= p1.cost && p2.cost < p0.cost) alpha = p2.alpha;

@@ -30,7 +30,7 @@ def main(path, src_path="mujocoposelearning_b200/csrc/b2h_physics.cuh"):
             cur["rows"].append(r)
     src = open(src_path).read().split("\n")
     marks = []
-    first = next(i for i, l in enumerate(src) if "bool physics_step(" in l)
+    first = next(i for i, l in enumerate(src) if " physics_step(const DevModel" in l)
     marks.append((1, "helpers (inlined math, cholesky, mat_vec)"))
     for key, name in STAGES + SUB:
         for i, l in enumerate(src):

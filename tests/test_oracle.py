@@ -203,3 +203,33 @@ def test_gae_matches_sb3_formula():
         adv[t] = last
     a, ret = orc.gae(r, v, es, lv, dn.astype(np.uint8), gamma, lam)
     assert np.array_equal(a, adv) and np.array_equal(ret, adv + v)
+
+
+def test_upstream_rest_keyframes_stay_near_rest(env, cm):
+    """A coarse EXTERNAL check (it pins no formula): `supine` and `prone` of the reference's `XML/humanoid.xml:212-218` are
+    rest poses authored against MuJoCo itself (root height to 5-6 digits, the contacts the oracle finds there sit 0.24-0.34 mm
+    deep -- the depth of a settled MuJoCo contact, not of a hand-placed body).  Under the oracle they must be near rest too:
+    with zero control the contact forces of the first instant carry the parts that touch (tens of newtons per contact, the
+    order of the body weight in total: a regulariser wrong by the factor 2 mu^2 or 4 of the pyramid would throw the body up at
+    several g), and after 10 s the body has only relaxed the rounding of the authored joint angles -- it has not rolled,
+    bounced away or sunk.  Measured: supine settles 1.0 mm lower with joints within 0.04 rad, prone 5.8 mm / 0.41 rad (arms)."""
+    kf = np.load(GOLD / "reference_keyframes.npz")
+    weight = float(np.sum(cm.body_mass)) * 9.81
+    for idx, dz_max, dq_max in ((3, 2e-3, 0.06), (2, 8e-3, 0.6)):           # supine, prone (file order: squat, stand_on_left_leg, prone, supine)
+        q0 = kf["qpos"][idx].copy()
+        env.set_state(q0, np.zeros(cm.nv), np.zeros(cm.nv), 0, 0)
+        env.set_ctrl(np.zeros(cm.nu))
+        env.forward()
+        dist = env.get("contact_dist")
+        assert len(dist) == 3 and dist.max() < 0 and dist.min() > -3e-3
+        ty, f, J = env.get("efc_type"), env.get("efc_force"), env.get("efc_J").reshape(-1, cm.nv)
+        fz = float((J[:, 2] * f)[ty == ty.max()].sum())                     # net vertical contact force on the root's z dof
+        assert 0.25 * weight < fz < 1.05 * weight, fz                      # limbs still hovering carry nothing yet
+        qacc = env.get("qacc")
+        assert abs(qacc[2]) < 0.5 * 9.81                                    # the trunk is neither thrown up nor in free fall
+        for _ in range(2000):
+            env.mj_step()
+        s = env.get_state()
+        assert abs(s["qpos"][2] - q0[2]) < dz_max and np.abs(s["qpos"][7:] - q0[7:]).max() < dq_max
+        assert np.abs(s["qvel"]).max() < 0.05 and np.linalg.norm(s["qpos"][:2] - q0[:2]) < 0.01
+        assert 2 * np.arccos(min(1.0, abs(float(np.dot(s["qpos"][3:7], q0[3:7]))))) < 0.05   # orientation kept

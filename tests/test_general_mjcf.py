@@ -147,3 +147,47 @@ def test_cuda_build_matches_oracle_on_the_second_model(biped, dtype, tol):
     c = b.counters()
     assert c["contact_overflow"] == 0 and c["bad_state"] == 0
     b.close()
+
+
+@pytest.mark.gpu
+def test_vec_env_and_rollout_on_the_second_model(biped):
+    """The drop-in boundary with `model_path` pointing at another MJCF (custom_env.py:21,53): VecEnv.step results against the
+    oracle's SubprocVecEnv semantics, then the in-library collect_rollouts loop on the 131-column observation."""
+    torch = pytest.importorskip("torch")
+    from mujocoposelearning_b200.policy import MlpPolicy, MlpPolicyParams, RolloutCollector
+    from mujocoposelearning_b200.vec_env import B200HumanoidVecEnv
+    from oracle.oracle import OracleVecEnv
+    cm, ms = biped
+    n, obs_dim = 6, (cm.nq - 2) + cm.nv + 16 * cm.nbody + cm.nv
+    env = B200HumanoidVecEnv({"model_path": str(BIPED), "duration": 0.2, "frame_skip": 3, "reward_config": {"type": "stand"}},
+                             n_envs=n, dtype="f64", seed=2)
+    assert env.observation_space.shape == (obs_dim,) and env.action_space.shape == (cm.nu,)
+    rng = np.random.default_rng(4)
+    noise = rng.uniform(-0.01, 0.01, (n, cm.nq + cm.nv))
+    env.batch.set_reset_noise(noise)
+    ref = OracleVecEnv(ms, cm.nq, cm.nv, cm.nu, n, frame_skip=3, duration=0.2, reward_type=0)
+    obs = env.reset()
+    assert obs.shape == (n, obs_dim) and np.abs(obs - ref.reset(noise)).max() < 1e-9
+    n_done = 0
+    for k in range(20):                                    # 0.2 s = 50 physics steps: the episode ends inside this loop
+        act = rng.uniform(-1, 1, (n, cm.nu)).astype(np.float32)
+        env.batch.set_reset_noise(noise)                   # consumed by the auto-reset of the step that ends the episode
+        obs, rew, dones, infos = env.step(act)
+        ro, rr, rdone, rterm, rtrunc, rinfo = ref.step(act, noise)
+        assert np.array_equal(dones, rdone)
+        assert np.abs(obs - ro).max() < 1e-8 * max(1.0, np.abs(ro).max()) and np.abs(rew - rr).max() < 1e-9
+        n_done += int(dones.sum())
+    assert n_done == n
+    env.close()
+    from mujocoposelearning_b200.batch import HumanoidBatch
+    b = HumanoidBatch(64, model_path=str(BIPED), frame_skip=3, duration=10.0, reward_type="stand", dtype="f32", seed=1)
+    b.reset()
+    pol = MlpPolicy(MlpPolicyParams(obs_dim=obs_dim, act_dim=cm.nu, seed=3), precise=True, seed=5)
+    col = RolloutCollector(b, pol, n_steps=8, cuda_graph=False)
+    col.start_from_current()
+    col.collect()
+    torch.cuda.synchronize()
+    col.check_error()
+    assert col.obs.shape[-1] == obs_dim and col.actions.shape[-1] == cm.nu
+    assert torch.isfinite(col.advantages).all() and torch.isfinite(col.obs).all() and float(col.obs.abs().max()) > 0
+    b.close()

@@ -1332,6 +1332,7 @@ int b2h_ppo_train(B2HPpo* h, const float* obs_dev, const float* actions_dev, con
                   float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev, int64_t* step_inout, void* stream) {
   if (!h || !perm_dev || !step_inout || n_samples <= 0 || n_epochs <= 0 || batch_size <= 0) { g_err_ppo = "b2h_ppo_train: bad argument"; return B2H_EINVAL; }
   const bool p2p = h->comm && h->world > 1 && h->peer_base[h->world - 1];     // attached: gradients summed over the ranks by peer loads
+  h->gathered_idx = nullptr;   // a prefetch left behind by a call that failed half-way must not be taken for this call's first minibatch
   for (int e = 0; e < n_epochs; e++)
     for (int64_t i = 0; i < n_samples; i += batch_size) {
       const int n = (int)std::min<int64_t>(batch_size, n_samples - i);

@@ -60,3 +60,37 @@ def test_flat_asset_equals_reference_xml(cm):
               "geom_pos", "geom_quat", "pair_geom1", "pair_geom2", "pair_solref", "dof_invweight0", "body_invweight0",
               "actuator_gear", "ten_J", "dof_damping", "jnt_stiffness", "dof_armature"):
         np.testing.assert_allclose(getattr(ref, k), getattr(cm, k), rtol=0, atol=1e-12, err_msg=k)
+
+
+def test_body_invweight0_by_an_independent_route(cm, model_struct):
+    """mj_setConst's body_invweight0 (the constant every contact's regulariser R scales with) recomputed without the compiler's
+    cdof algebra: translational Jacobian of each body's inertial frame by finite differences through the ORACLE's kinematics,
+    M from the oracle's CRBA, trace(J M^-1 J^T) / 3.  Ties mjcf._set_const to the definition, not to MuJoCo's numbers."""
+    from oracle.oracle import OracleEnv
+    env = OracleEnv(model_struct, cm.nq, cm.nv, cm.nu)
+    nv, q0, eps = cm.nv, cm.qpos0.copy(), 1e-6
+
+    def fk(q):
+        env.set_state(q, np.zeros(nv), np.zeros(nv), 0, 0)
+        env.forward()
+        return env.get("xipos").reshape(-1, 3).copy()
+    x0 = fk(q0)
+    M = env.get("qM").reshape(nv, nv).copy()
+    assert np.allclose(q0[3:7], [1, 0, 0, 0])               # body-frame rotations of the root = world-frame ones at qpos0
+    J = np.zeros((cm.nbody, 3, nv))
+    for i in range(nv):
+        q = q0.copy()
+        if i < 3:
+            q[i] += eps
+        elif i < 6:
+            q[3], q[4 + (i - 3)] = np.cos(eps / 2), np.sin(eps / 2)
+        else:
+            q[i + 1] += eps
+        J[:, :, i] = (fk(q) - x0) / eps
+    Minv = np.linalg.inv(M)
+    for b in range(1, cm.nbody):
+        tran = np.trace(J[b] @ Minv @ J[b].T) / 3
+        assert abs(tran - cm.body_invweight0[b][0]) < 1e-5 * max(1.0, tran), (b, tran, cm.body_invweight0[b][0])
+    d = np.diag(Minv).copy()
+    d[0:3], d[3:6] = d[0:3].mean(), d[3:6].mean()
+    assert np.abs(d - cm.dof_invweight0).max() < 1e-9 * np.abs(d).max()
